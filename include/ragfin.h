@@ -1,0 +1,121 @@
+/*
+ * ragfin.h - C ABI of the B200-native exact cosine top-k engine.
+ *
+ * This is the drop-in boundary for rag-fin's vector-RAG hot path.  The reference has no
+ * FFI layer of its own: its operator API for this path is the pymilvus 2.3.0 call
+ *
+ *     Collection.search(data, "embedding", {"metric_type": "COSINE"}, limit, output_fields=...)
+ *
+ * made at   retrieve.py:28-34,  vector_rag_mcp/main.py:51-57,
+ *           "chunking_storing (1).py":411-417,  graph_cons.py:275-281
+ * plus the ingest calls  Collection.insert / flush / load  ("chunking_storing (1).py":383-396)
+ * and  Collection.num_entities  (vector_rag_mcp/main.py:113,120,164).
+ * The Python shim `ragfin_b200.milvus_compat.Collection` reproduces that surface and binds
+ * exactly the entry points below through ctypes.
+ *
+ * Conventions: every function returns 0 on success and a negative RAGFIN_E* code on
+ * failure; the message is available from ragfin_last_error() (thread local).  No C++
+ * exception crosses the boundary.  Plain pointers and sizes only.  The engine owns the
+ * device-resident corpus matrix behind the opaque handle; the caller owns every buffer it
+ * passes in.  `stream` is a cudaStream_t cast to void* (NULL = legacy default stream).
+ * A handle may be used from several host threads: searches are serialised against each
+ * other and against add (FastMCP runs tools on a worker pool, vector_rag_mcp/main.py:134).
+ *
+ * There is NO CPU fallback: without a CUDA device every call that touches data fails
+ * with RAGFIN_ECUDA.
+ */
+#ifndef RAGFIN_H
+#define RAGFIN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ragfin ragfin_t;
+
+enum { RAGFIN_F32 = 0, RAGFIN_BF16 = 1, RAGFIN_F16 = 2 };
+
+enum {
+    RAGFIN_OK = 0,
+    RAGFIN_EINVAL = -1,   /* bad argument                                   */
+    RAGFIN_ECUDA = -2,    /* CUDA runtime / driver error, or no device      */
+    RAGFIN_ENOMEM = -3,   /* capacity_rows exceeded or device allocation failed */
+    RAGFIN_EUNSUPPORTED = -4
+};
+
+/* ABI version of this header; bumped on any signature change. */
+#define RAGFIN_ABI_VERSION 1
+int ragfin_abi_version(void);
+
+/* Create an empty collection of `dim`-wide embeddings stored as `dtype` on CUDA device
+ * `device`, with room for `capacity_rows` rows (HBM is reserved up front: one contiguous
+ * row-major [capacity, ld] matrix, ld = dim rounded up to 8).
+ * Replaces: Collection(name, CollectionSchema([... FieldSchema("embedding", FLOAT_VECTOR,
+ * dim=384) ...])) + create_index(COSINE)  - "chunking_storing (1).py":14-29. */
+int ragfin_create(ragfin_t** out, int32_t dim, int32_t dtype, int64_t capacity_rows, int32_t device);
+
+/* Append n fp32 rows ([n, dim] row-major; host memory, or device memory when
+ * src_is_device != 0).  Each row is L2-normalised (fp64 canonical sum) and
+ * rounded once to the storage type by the ingest kernel.  Row ids are insertion ordinals.
+ * Replaces: collection.insert([... embeddings ...]); flush(); load()
+ * - "chunking_storing (1).py":383-396. */
+int ragfin_add(ragfin_t* h, const float* rows, int64_t n, int32_t src_is_device, void* stream);
+
+/* Append rows row0..row0+n of the deterministic synthetic matrix `seed`,
+ * generated on the device and passed through the same ingest kernel.  dup_every /
+ * zero_every (0 = off) plant duplicate and all-zero rows.  Bench/test data only. */
+int ragfin_add_synthetic(ragfin_t* h, uint64_t seed, int64_t row0, int64_t n, int32_t dup_every,
+                         int32_t zero_every, void* stream);
+
+/* Number of rows held.  Replaces: Collection.num_entities - vector_rag_mcp/main.py:164. */
+int ragfin_count(const ragfin_t* h, int64_t* n);
+
+/* Global id of local row 0 (row-sharded corpora: shard r sets its base). Default 0. */
+int ragfin_set_id_base(ragfin_t* h, int64_t id_base);
+
+/* Exact cosine top-k.  q: [nq, dim] fp32 row-major DEVICE memory (raw, un-normalised
+ * queries).  out_ids [nq, k] int64 and out_scores [nq, k] fp32 are DEVICE memory; hits are
+ * in descending score, ties broken by lower id; slots beyond min(k, N) hold id -1 and
+ * score -inf.  Asynchronous on `stream`.  1 <= k <= 16384 (the Milvus limit).
+ * Replaces: Collection.search(q, "embedding", {"metric_type":"COSINE"}, k)
+ * - vector_rag_mcp/main.py:51-57 (and the three other call sites listed above). */
+int ragfin_search(ragfin_t* h, const float* q, int32_t nq, int32_t k, int64_t* out_ids,
+                  float* out_scores, void* stream);
+
+/* Same, with HOST buffers: copies the queries in, searches, copies the hits out and
+ * synchronises.  This is the call the Python shim makes for numpy / list input. */
+int ragfin_search_host(ragfin_t* h, const float* q_host, int32_t nq, int32_t k, int64_t* out_ids_host,
+                       float* out_scores_host);
+
+/* Cross-shard reduce: merge `parts` exact hit lists per query (ids [nq, parts*k] int64,
+ * scores [nq, parts*k] fp32, device memory; -1 ids are padding) into the global top-k,
+ * ordered by (score desc, id asc).  Used after the NCCL all-gather of per-rank hits
+ * (Milvus proxy reduce in the reference deployment). */
+int ragfin_merge_topk(const int64_t* ids, const float* scores, int32_t nq, int32_t parts, int32_t k,
+                      int64_t* out_ids, float* out_scores, int32_t device, void* stream);
+
+/* Copy rows row0..row0+n of the STORED matrix, raw storage bytes [n, ld], to host memory
+ * (test hook for ingest parity).  *ld_out receives the row stride in elements. */
+int ragfin_read_rows(ragfin_t* h, int64_t row0, int64_t n, void* out_host, int32_t* ld_out);
+
+/* Counters of the most recent search on this handle: kernel launches issued, queries that
+ * took the exact-rescan tier (certificate failed), which scoring path ran
+ * (0 = small-batch scan, 1 = tcgen05 GEMM).  Reading queries_rescanned synchronises. */
+typedef struct {
+    int32_t launches;
+    int32_t path;
+    int32_t queries_rescanned;
+    int32_t cand_per_query;   /* K' : candidates kept per query before the exact rescore */
+} ragfin_search_stats;
+int ragfin_last_search_stats(ragfin_t* h, ragfin_search_stats* out);
+
+void ragfin_destroy(ragfin_t* h);
+
+const char* ragfin_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAGFIN_H */

@@ -1,0 +1,384 @@
+// Device kernels of the exact cosine top-k path (everything except the tcgen05 GEMM).
+//
+//   ingest_kernel      K1  L2-normalise + cast at ingest ("chunking_storing (1).py":380-396)
+//   scan_topk_kernel   K2  small-batch HBM-bound scan with fused per-warp top-K' lists
+//   finalize_kernel    K4  merge of per-CTA candidates + exact fp64 rescore + certificate
+//   exact_scan_kernel      tier-2: full canonical fp64 scan for queries whose certificate failed
+//   merge_topk_kernel      cross-shard reduce of exact hit lists (after the NCCL all-gather)
+#pragma once
+#include "common.cuh"
+
+namespace rfk {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanWarps = kScanThreads / kWarp;
+constexpr int kFinThreads = 512;
+constexpr int kFinWarps = kFinThreads / kWarp;
+
+// ---------------------------------------------------------------------------------
+// K1: one warp per row.  n2 = canonical fp64 sum of squares; y = RNE_store(RNE_f32(x * 1/sqrt(n2))).
+// SYNTH: the source row is generated in registers from the counter hash instead of read.
+// dst rows have stride ld (>= dim, multiple of 8); columns [dim, ld) are zero.
+// ---------------------------------------------------------------------------------
+template <int DT, bool SYNTH>
+__global__ void __launch_bounds__(256) ingest_kernel(const float* __restrict__ src, uint64_t synth_key,
+                                                     int64_t synth_row0, int dup_every, int zero_every,
+                                                     int64_t n, int dim, int ld,
+                                                     typename Store<DT>::T* __restrict__ dst) {
+    typedef typename Store<DT>::T T;
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = gw; r < n; r += nw) {
+        uint64_t srow = 0;
+        bool zero = false;
+        const float* x = nullptr;
+        if (SYNTH) {
+            const uint64_t row = (uint64_t)(synth_row0 + r);
+            srow = row;
+            if (dup_every > 1 && row % (uint64_t)dup_every == (uint64_t)(dup_every - 1)) srow = row - 1;
+            zero = zero_every > 1 && row % (uint64_t)zero_every == (uint64_t)(zero_every - 1);
+        } else {
+            x = src + r * (int64_t)dim;
+        }
+        auto elem = [&](int i) -> float {
+            if (SYNTH) return zero ? 0.0f : synth_value(synth_key, srow, dim, i);
+            return x[i];
+        };
+        double acc = 0.0;
+        for (int i = lane; i < dim; i += kWarp) {
+            const double v = (double)elem(i);
+            acc = acc + v * v;
+        }
+        const double n2 = warp_butterfly_f64(acc);
+        const double inv = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
+        T* out = dst + r * (int64_t)ld;
+        for (int i = lane * 2; i < ld; i += 2 * kWarp) {
+            const float y0 = i < dim ? (float)((double)elem(i) * inv) : 0.0f;
+            const float y1 = i + 1 < dim ? (float)((double)elem(i + 1) * inv) : 0.0f;
+            if (DT == 0) {
+                *reinterpret_cast<float2*>(out + i) = make_float2(y0, y1);
+            } else {
+                T pr[2] = {Store<DT>::from_f32(y0), Store<DT>::from_f32(y1)};
+                *reinterpret_cast<uint32_t*>(out + i) = *reinterpret_cast<uint32_t*>(pr);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Transposed warp reduction: every lane holds M partial sums (M a power of two <= 32);
+// afterwards lane l holds the warp-wide total of value index (l >> (5 - log2 M)).
+// log2(M) exchange rounds halve the live values, the remaining rounds are a plain butterfly:
+// M + (5 - log2 M) - 1 shuffles instead of 5 * M.
+// ---------------------------------------------------------------------------------
+template <int C, int OFF>
+struct TransposeReduce {
+    template <int M>
+    __device__ static __forceinline__ void run(float (&v)[M], int lane) {
+        if (C > 1) {
+            const bool upper = (lane & OFF) != 0;
+#pragma unroll
+            for (int i = 0; i < C / 2; ++i) {
+                const float keep = upper ? v[i + C / 2] : v[i];
+                const float send = upper ? v[i] : v[i + C / 2];
+                v[i] = keep + __shfl_xor_sync(kFull, send, OFF);
+            }
+        } else {
+            v[0] = v[0] + __shfl_xor_sync(kFull, v[0], OFF);
+        }
+        TransposeReduce<(C > 1 ? C / 2 : 1), OFF / 2>::run(v, lane);
+    }
+};
+template <int C>
+struct TransposeReduce<C, 0> {
+    template <int M>
+    __device__ static __forceinline__ void run(float (&)[M], int) {}
+};
+__host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x / 2); }
+
+// rows held in flight per warp iteration, by vectors per lane per row
+__host__ __device__ constexpr int scan_rows(int steps) { return steps <= 1 ? 8 : steps <= 3 ? 4 : steps <= 6 ? 2 : 1; }
+
+// ---------------------------------------------------------------------------------
+// K2: small-batch scan.  Each warp streams R rows per iteration with 128-bit
+// ld.global.nc loads (lane l, step j covers elements [(j*32+l)*V, +V)), holds the NQ
+// normalised queries in registers as fp32, accumulates in fp32, reduces with the
+// transposed butterfly and keeps a sorted top-K' key list per (warp, query) in shared
+// memory behind a register threshold, so a row costs one compare in the common case.
+// At the end the CTA merges its warps' lists and writes K' keys per query:
+//   cand[q * cand_q_stride + blockIdx.x * kp + i],  sorted descending, 0 = empty.
+// Algorithmic HBM bytes: n_rows * ld * sizeof(T) (one pass), independent of NQ.
+// ---------------------------------------------------------------------------------
+template <int DT, int NQ, int STEPS>
+__global__ void __launch_bounds__(kScanThreads, NQ >= 4 ? 1 : 2)
+scan_topk_kernel(const void* __restrict__ data, int64_t n_rows, int ld, const float* __restrict__ qhat,
+                 int kp, u64* __restrict__ cand, int64_t cand_q_stride) {
+    typedef Store<DT> S;
+    constexpr int V = S::kVec;
+    constexpr int R = scan_rows(STEPS);
+    constexpr int M = R * NQ;
+    constexpr int SH = 5 - ilog2(M);
+    static_assert(M <= 32, "too many partial sums per lane");
+    extern __shared__ __align__(16) u64 lists[];  // [NQ][kScanWarps][kp]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < NQ * kScanWarps * kp; i += kScanThreads) lists[i] = 0;
+    __syncthreads();
+
+    const int nvec = ld / V;
+    float qreg[NQ][STEPS * V];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int j = 0; j < STEPS; ++j) {
+            const int vi = j * kWarp + lane;
+#pragma unroll
+            for (int e = 0; e < V; ++e) qreg[q][j * V + e] = vi < nvec ? qhat[(size_t)q * ld + vi * V + e] : 0.0f;
+        }
+
+    float tau[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) tau[q] = -INFINITY;
+
+    const char* base = reinterpret_cast<const char*>(data);
+    const size_t row_bytes = (size_t)ld * sizeof(typename S::T);
+    const int64_t chunks = (n_rows + R - 1) / R;
+    const int64_t stride = (int64_t)gridDim.x * kScanWarps;
+    for (int64_t c = (int64_t)blockIdx.x * kScanWarps + warp; c < chunks; c += stride) {
+        const int64_t row0 = c * R;
+        uint4 d[R][STEPS];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int64_t rr = row0 + r;
+            rr = rr < n_rows ? rr : n_rows - 1;
+            const char* rp = base + (size_t)rr * row_bytes;
+#pragma unroll
+            for (int j = 0; j < STEPS; ++j) {
+                const int vi = j * kWarp + lane;
+                d[r][j] = vi < nvec ? ldg_stream(rp + (size_t)vi * 16) : make_uint4(0, 0, 0, 0);
+            }
+        }
+        float acc[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) acc[i] = 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int j = 0; j < STEPS; ++j) {
+                float f[V];
+                S::unpack(d[r][j], f);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                    for (int e = 0; e < V; ++e) acc[r * NQ + q] = fmaf(f[e], qreg[q][j * V + e], acc[r * NQ + q]);
+            }
+        TransposeReduce<M, 16>::run(acc, lane);
+        const float s = acc[0];
+        const int idx = lane >> SH;
+        const int myq = idx % NQ;
+        float mytau = tau[0];
+#pragma unroll
+        for (int q = 1; q < NQ; ++q) mytau = myq == q ? tau[q] : mytau;
+        const bool leader = (lane & ((1 << SH) - 1)) == 0;
+        const bool hit = leader && (row0 + idx / NQ < n_rows) && (s >= mytau);
+        unsigned mask = __ballot_sync(kFull, hit);
+        while (mask) {
+            const int l = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float bs = __shfl_sync(kFull, s, l) + 0.0f;
+            const int bidx = l >> SH;
+            const int q = bidx % NQ;
+            const u64 key = make_key(bs, (uint32_t)(row0 + bidx / NQ));
+            u64* list = lists + (size_t)(q * kScanWarps + warp) * kp;
+            if (key > list[kp - 1]) {
+                warp_list_insert(list, kp, key, lane);
+                const u64 last = list[kp - 1];
+                const float nt = last ? key_score(last) : -INFINITY;
+#pragma unroll
+                for (int qq = 0; qq < NQ; ++qq) tau[qq] = q == qq ? nt : tau[qq];
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int q = 0; q < NQ; ++q) {
+        u64* region = lists + (size_t)q * kScanWarps * kp;
+        block_bitonic_sort_desc(region, kScanWarps * kp, threadIdx.x, kScanThreads);
+        u64* out = cand + (size_t)q * cand_q_stride + (size_t)blockIdx.x * kp;
+        for (int i = threadIdx.x; i < kp; i += kScanThreads) out[i] = region[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Merge `G` descending key lists of length kp into FW per-warp lists, then one sort.
+// wl: shared [kFinWarps][kp].  On return (after __syncthreads) wl[0..kp) is the top-kp.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void merge_lists(const u64* __restrict__ src, int G, int kp, u64* wl) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64* mine = wl + (size_t)warp * kp;
+    for (int i = lane; i < kp; i += kWarp) mine[i] = 0;
+    __syncwarp();
+    for (int l = warp; l < G; l += kFinWarps) {
+        const u64* in = src + (size_t)l * kp;
+        for (int s = 0; s < kp; s += kWarp) {
+            const u64 key = in[s + lane];
+            const unsigned hits = __ballot_sync(kFull, key > mine[kp - 1]);
+            unsigned m = hits;
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const u64 bk = __shfl_sync(kFull, key, b);
+                if (bk > mine[kp - 1]) warp_list_insert(mine, kp, bk, lane);
+            }
+            if (hits != kFull) break;  // list is sorted: nothing further can qualify
+        }
+    }
+    __syncthreads();
+    block_bitonic_sort_desc(wl, kFinWarps * kp, threadIdx.x, kFinThreads);
+}
+
+template <int DT>
+__device__ __forceinline__ double rescore_row(const void* data, int64_t row, int ld, const float* q, int lane) {
+    const typename Store<DT>::T* rp = reinterpret_cast<const typename Store<DT>::T*>(data) + (size_t)row * ld;
+    return canonical_dot_row<DT>(rp, q, ld, lane);
+}
+
+// ---------------------------------------------------------------------------------
+// K4: one CTA per query.
+//  EXACT_IN = false: keys carry APPROXIMATE scores.  Select the top-kp, recompute those
+//    kp dot products canonically in fp64 from the stored values, order by the exact key and
+//    certify: every row outside the candidate set has approx <= tau (the kp-th approx
+//    score) hence exact <= tau + eps; if exact_k > tau + eps the top-k is proven exact.
+//    Otherwise flags[q] = 1 and the query goes to the exact-rescan tier.
+//  EXACT_IN = true: keys already carry exact scores (tier 2); only flagged queries run.
+// ---------------------------------------------------------------------------------
+template <bool EXACT_IN>
+__global__ void __launch_bounds__(kFinThreads)
+finalize_kernel(const u64* __restrict__ cand, int G, int kp, const void* __restrict__ data, int dt,
+                int64_t n_rows, int scanned, int ld, const float* __restrict__ qhat, float eps_const,
+                const float* __restrict__ eps_q, int k, int64_t id_base, int64_t* __restrict__ out_ids,
+                float* __restrict__ out_scores, int* __restrict__ flags, int* __restrict__ flag_count) {
+    extern __shared__ __align__(16) u64 fsm[];  // [kFinWarps][kp] merge lists, then [kp] exact keys
+    const int q = blockIdx.x;
+    if (EXACT_IN && flags[q] == 0) return;
+    u64* wl = fsm;
+    u64* ex = fsm + (size_t)kFinWarps * kp;
+    merge_lists(cand + (size_t)q * G * kp, G, kp, wl);
+
+    const int keff = (int64_t)k < n_rows ? k : (int)n_rows;
+    const u64* fin = wl;
+    if (!EXACT_IN) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const float* qv = qhat + (size_t)q * ld;
+        for (int c = warp; c < kp; c += kFinWarps) {
+            const u64 key = wl[c];
+            u64 ek = 0;
+            if (key) {
+                const uint32_t row = key_row(key);
+                double s;
+                if (dt == 0) s = rescore_row<0>(data, row, ld, qv, lane);
+                else if (dt == 1) s = rescore_row<1>(data, row, ld, qv, lane);
+                else s = rescore_row<2>(data, row, ld, qv, lane);
+                ek = make_key((float)s + 0.0f, row);
+            }
+            if (lane == 0) ex[c] = ek;
+        }
+        __syncthreads();
+        block_bitonic_sort_desc(ex, kp, threadIdx.x, kFinThreads);
+        if (threadIdx.x == 0) {
+            bool ok = scanned && n_rows <= (int64_t)kp;
+            if (!ok && scanned && keff > 0) {
+                const double eps = (double)eps_const + (eps_q ? (double)eps_q[q] : 0.0);
+                const double tau = (double)key_score(wl[kp - 1]);
+                ok = ex[keff - 1] != 0 && (double)key_score(ex[keff - 1]) > tau + eps;
+            }
+            flags[q] = ok ? 0 : 1;
+            if (!ok) atomicAdd(flag_count, 1);
+        }
+        fin = ex;
+    }
+    for (int i = threadIdx.x; i < k; i += kFinThreads) {
+        const u64 key = i < keff ? fin[i] : 0;
+        out_ids[(size_t)q * k + i] = key ? id_base + (int64_t)key_row(key) : -1;
+        out_scores[(size_t)q * k + i] = key ? key_score(key) : -INFINITY;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Tier 2: canonical fp64 score of EVERY row for the flagged queries, exact keys, per-warp
+// lists of kpe entries, CTA merge.  Exits immediately when nothing is flagged.
+// cand_e[(q * gridDim.x + blockIdx.x) * kpe + i]
+// ---------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(kScanThreads)
+exact_scan_kernel(const void* __restrict__ data, int64_t n_rows, int ld, const float* __restrict__ qhat,
+                  int nq, const int* __restrict__ flags, const int* __restrict__ flag_count, int kpe,
+                  u64* __restrict__ cand_e) {
+    if (*flag_count == 0) return;
+    extern __shared__ __align__(16) u64 lists[];  // [kScanWarps][kpe]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const typename Store<DT>::T* base = reinterpret_cast<const typename Store<DT>::T*>(data);
+    for (int q = 0; q < nq; ++q) {
+        if (flags[q] == 0) continue;  // block-uniform
+        for (int i = threadIdx.x; i < kScanWarps * kpe; i += kScanThreads) lists[i] = 0;
+        __syncthreads();
+        u64* mine = lists + (size_t)warp * kpe;
+        const float* qv = qhat + (size_t)q * ld;
+        const int64_t stride = (int64_t)gridDim.x * kScanWarps;
+        for (int64_t r = (int64_t)blockIdx.x * kScanWarps + warp; r < n_rows; r += stride) {
+            const double s = canonical_dot_row<DT>(base + (size_t)r * ld, qv, ld, lane);
+            const u64 key = make_key((float)s + 0.0f, (uint32_t)r);
+            if (key > mine[kpe - 1]) warp_list_insert(mine, kpe, key, lane);
+        }
+        __syncthreads();
+        block_bitonic_sort_desc(lists, kScanWarps * kpe, threadIdx.x, kScanThreads);
+        u64* out = cand_e + ((size_t)q * gridDim.x + blockIdx.x) * kpe;
+        for (int i = threadIdx.x; i < kpe; i += kScanThreads) out[i] = lists[i];
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Cross-shard reduce.  Each part's list is sorted by (score desc, id asc) with -1 padding at
+// the end and all ids are distinct, so the global rank of an element is its own index plus,
+// for every other part, the number of that part's elements that beat it (binary search).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ bool hit_better(float sa, int64_t ia, float sb, int64_t ib) {
+    return sa > sb || (sa == sb && ia < ib);
+}
+__device__ __forceinline__ int count_better(const int64_t* ids, const float* sc, int k, float s, int64_t id) {
+    int lo = 0, hi = k;  // first index whose element does NOT beat (s, id); padding never beats
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const bool b = ids[mid] >= 0 && hit_better(sc[mid], ids[mid], s, id);
+        if (b) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__global__ void merge_topk_kernel(const int64_t* __restrict__ ids, const float* __restrict__ scores, int nq,
+                                  int parts, int k, int64_t* __restrict__ out_ids, float* __restrict__ out_scores) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per_q = (int64_t)parts * k;
+    if (t >= (int64_t)nq * per_q) return;
+    const int q = (int)(t / per_q);
+    const int e = (int)(t % per_q);
+    const int p = e / k, i = e % k;
+    const int64_t* qi = ids + (size_t)q * per_q;
+    const float* qs = scores + (size_t)q * per_q;
+    if (p == 0) {  // slot i of the output: pad it if fewer than i+1 valid hits exist in total
+        int valid = 0;
+        for (int pp = 0; pp < parts; ++pp)
+            valid += count_better(qi + (size_t)pp * k, qs + (size_t)pp * k, k, -INFINITY, INT64_MAX);
+        if (i >= valid) { out_ids[(size_t)q * k + i] = -1; out_scores[(size_t)q * k + i] = -INFINITY; }
+    }
+    const int64_t id = qi[e];
+    if (id < 0) return;
+    const float s = qs[e];
+    int rank = i;
+    for (int pp = 0; pp < parts && rank < k; ++pp)
+        if (pp != p) rank += count_better(qi + (size_t)pp * k, qs + (size_t)pp * k, k, s, id);
+    if (rank < k) { out_ids[(size_t)q * k + rank] = id; out_scores[(size_t)q * k + rank] = s; }
+}
+
+}  // namespace rfk

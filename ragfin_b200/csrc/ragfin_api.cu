@@ -1,0 +1,461 @@
+// C ABI of the engine (include/ragfin.h): handle, workspace, kernel dispatch.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+
+#include "../../include/ragfin.h"
+#include "kernels.cuh"
+
+using namespace rfk;
+
+// ------------------------------------------------------------------------------
+// error plumbing: thread-local message, negative codes, no exceptions across the ABI
+// ------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU_TRY(expr)                                                                               \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(RAGFIN_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),     \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+extern "C" const char* ragfin_last_error(void) { return g_err; }
+extern "C" int ragfin_abi_version(void) { return RAGFIN_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------
+struct Buf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct ragfin {
+    int dim = 0, ld = 0, dtype = 0, device = 0, num_sms = 0;
+    int64_t capacity = 0, count = 0, id_base = 0;
+    void* data = nullptr;  // [capacity, ld] storage, row-major, L2-normalised
+    std::mutex mu;
+    // workspace (grow-only)
+    Buf qhat, cand, cand_e, flags, stage_q, stage_ids, stage_scores, add_stage;
+    cudaEvent_t last_done = nullptr;
+    ragfin_search_stats stats = {0, 0, 0, 0};
+};
+
+static size_t esize(int dtype) { return dtype == RAGFIN_F32 ? 4 : 2; }
+
+static int ensure(Buf& b, size_t bytes) {
+    if (b.bytes >= bytes) return 0;
+    if (b.p) {
+        CU_TRY(cudaDeviceSynchronize());
+        CU_TRY(cudaFree(b.p));
+        b.p = nullptr;
+        b.bytes = 0;
+    }
+    size_t want = bytes + bytes / 4;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        (void)cudaGetLastError();
+        return fail(RAGFIN_ENOMEM, "workspace cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    b.bytes = want;
+    return 0;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; (void)cudaGetLastError(); }
+        ok = cudaSetDevice(dev) == cudaSuccess;
+        if (!ok) (void)cudaGetLastError();
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) (void)cudaSetDevice(prev);
+    }
+};
+
+extern "C" int ragfin_create(ragfin_t** out, int32_t dim, int32_t dtype, int64_t capacity_rows, int32_t device) {
+    if (!out) return fail(RAGFIN_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (dim < 1 || dim > 65536) return fail(RAGFIN_EINVAL, "dim %d out of range [1, 65536]", dim);
+    if (dtype < 0 || dtype > 2) return fail(RAGFIN_EINVAL, "dtype %d is not 0 (f32), 1 (bf16) or 2 (f16)", dtype);
+    if (capacity_rows < 1 || capacity_rows >= (int64_t)0xFFFFFFFF)
+        return fail(RAGFIN_EINVAL, "capacity_rows %lld out of range [1, 2^32-1)", (long long)capacity_rows);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        return fail(RAGFIN_ECUDA, "no CUDA device available (%s); this engine has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= ndev) return fail(RAGFIN_EINVAL, "device %d not in [0, %d)", device, ndev);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(RAGFIN_ECUDA, "cudaSetDevice(%d) failed", device);
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(RAGFIN_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    ragfin* h = new (std::nothrow) ragfin();
+    if (!h) return fail(RAGFIN_ENOMEM, "host allocation failed");
+    h->dim = dim;
+    h->ld = (dim + 7) / 8 * 8;
+    h->dtype = dtype;
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    h->capacity = capacity_rows;
+    const size_t bytes = (size_t)capacity_rows * h->ld * esize(dtype);
+    e = cudaMalloc(&h->data, bytes);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        delete h;
+        return fail(RAGFIN_ENOMEM, "cudaMalloc of %zu bytes for the corpus failed: %s", bytes, cudaGetErrorString(e));
+    }
+    e = cudaEventCreateWithFlags(&h->last_done, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        cudaFree(h->data);
+        delete h;
+        return fail(RAGFIN_ECUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return RAGFIN_OK;
+}
+
+extern "C" void ragfin_destroy(ragfin_t* h) {
+    if (!h) return;
+    DeviceGuard g(h->device);
+    (void)cudaDeviceSynchronize();
+    Buf* bufs[] = {&h->qhat, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage};
+    for (Buf* b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (h->data) cudaFree(h->data);
+    if (h->last_done) cudaEventDestroy(h->last_done);
+    delete h;
+}
+
+extern "C" int ragfin_count(const ragfin_t* h, int64_t* n) {
+    if (!h || !n) return fail(RAGFIN_EINVAL, "NULL argument");
+    *n = h->count;
+    return RAGFIN_OK;
+}
+
+extern "C" int ragfin_set_id_base(ragfin_t* h, int64_t id_base) {
+    if (!h) return fail(RAGFIN_EINVAL, "NULL handle");
+    if (id_base < 0) return fail(RAGFIN_EINVAL, "id_base must be >= 0");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->id_base = id_base;
+    return RAGFIN_OK;
+}
+
+// ------------------------------------------------------------------------------
+// K1 launch
+// ------------------------------------------------------------------------------
+template <bool SYNTH>
+static int launch_ingest(int dtype, const float* src, uint64_t key, int64_t row0, int dup, int zero, int64_t n,
+                         int dim, int ld, void* dst, int num_sms, cudaStream_t st) {
+    if (n == 0) return 0;
+    const int threads = 256, wpb = threads / 32;
+    int64_t blocks = (n + wpb - 1) / wpb;
+    const int64_t cap = (int64_t)num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    switch (dtype) {
+        case 0: ingest_kernel<0, SYNTH><<<(int)blocks, threads, 0, st>>>(src, key, row0, dup, zero, n, dim, ld, (float*)dst); break;
+        case 1: ingest_kernel<1, SYNTH><<<(int)blocks, threads, 0, st>>>(src, key, row0, dup, zero, n, dim, ld, (__nv_bfloat16*)dst); break;
+        default: ingest_kernel<2, SYNTH><<<(int)blocks, threads, 0, st>>>(src, key, row0, dup, zero, n, dim, ld, (__half*)dst); break;
+    }
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int wait_prev(ragfin* h, cudaStream_t st) { CU_TRY(cudaStreamWaitEvent(st, h->last_done, 0)); return 0; }
+static int mark_done(ragfin* h, cudaStream_t st) { CU_TRY(cudaEventRecord(h->last_done, st)); return 0; }
+
+extern "C" int ragfin_add(ragfin_t* h, const float* rows, int64_t n, int32_t src_is_device, void* stream) {
+    if (!h) return fail(RAGFIN_EINVAL, "NULL handle");
+    if (n < 0 || (n > 0 && !rows)) return fail(RAGFIN_EINVAL, "bad rows/n");
+    if (n == 0) return RAGFIN_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->count + n > h->capacity)
+        return fail(RAGFIN_ENOMEM, "add of %lld rows exceeds capacity (%lld of %lld used)", (long long)n,
+                    (long long)h->count, (long long)h->capacity);
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = wait_prev(h, st))) return rc;
+    char* dst = (char*)h->data + (size_t)h->count * h->ld * esize(h->dtype);
+    if (src_is_device) {
+        if ((rc = launch_ingest<false>(h->dtype, rows, 0, 0, 0, 0, n, h->dim, h->ld, dst, h->num_sms, st))) return rc;
+    } else {
+        // staged in slices so that a huge host matrix never needs a device copy of itself
+        const int64_t slice = (int64_t)((256u << 20) / ((size_t)h->dim * 4)) + 1;
+        for (int64_t r0 = 0; r0 < n; r0 += slice) {
+            const int64_t m = n - r0 < slice ? n - r0 : slice;
+            if ((rc = ensure(h->add_stage, (size_t)m * h->dim * 4))) return rc;
+            CU_TRY(cudaMemcpyAsync(h->add_stage.p, rows + (size_t)r0 * h->dim, (size_t)m * h->dim * 4,
+                                   cudaMemcpyHostToDevice, st));
+            if ((rc = launch_ingest<false>(h->dtype, (const float*)h->add_stage.p, 0, 0, 0, 0, m, h->dim, h->ld,
+                                           dst + (size_t)r0 * h->ld * esize(h->dtype), h->num_sms, st)))
+                return rc;
+            CU_TRY(cudaStreamSynchronize(st));  // host buffer and staging slice are reusable on return
+        }
+    }
+    h->count += n;
+    return mark_done(h, st);
+}
+
+extern "C" int ragfin_add_synthetic(ragfin_t* h, uint64_t seed, int64_t row0, int64_t n, int32_t dup_every,
+                                    int32_t zero_every, void* stream) {
+    if (!h) return fail(RAGFIN_EINVAL, "NULL handle");
+    if (n < 0 || row0 < 0) return fail(RAGFIN_EINVAL, "bad row0/n");
+    if (n == 0) return RAGFIN_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->count + n > h->capacity)
+        return fail(RAGFIN_ENOMEM, "add of %lld rows exceeds capacity (%lld of %lld used)", (long long)n,
+                    (long long)h->count, (long long)h->capacity);
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = wait_prev(h, st))) return rc;
+    char* dst = (char*)h->data + (size_t)h->count * h->ld * esize(h->dtype);
+    if ((rc = launch_ingest<true>(h->dtype, nullptr, mix64(seed), row0, dup_every, zero_every, n, h->dim, h->ld, dst,
+                                  h->num_sms, st)))
+        return rc;
+    h->count += n;
+    return mark_done(h, st);
+}
+
+extern "C" int ragfin_read_rows(ragfin_t* h, int64_t row0, int64_t n, void* out_host, int32_t* ld_out) {
+    if (!h || !out_host) return fail(RAGFIN_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (row0 < 0 || n < 0 || row0 + n > h->count) return fail(RAGFIN_EINVAL, "rows [%lld, %lld) outside [0, %lld)",
+                                                               (long long)row0, (long long)(row0 + n), (long long)h->count);
+    DeviceGuard g(h->device);
+    CU_TRY(cudaDeviceSynchronize());
+    const size_t rb = (size_t)h->ld * esize(h->dtype);
+    CU_TRY(cudaMemcpy(out_host, (char*)h->data + (size_t)row0 * rb, (size_t)n * rb, cudaMemcpyDeviceToHost));
+    if (ld_out) *ld_out = h->ld;
+    return RAGFIN_OK;
+}
+
+// ------------------------------------------------------------------------------
+// K2 dispatch
+// ------------------------------------------------------------------------------
+typedef void (*scan_fn)(const void*, int64_t, int, const float*, int, u64*, int64_t);
+static const int kMaxScanCtasPerSm = 4;
+
+template <int DT, int NQ>
+static scan_fn pick_steps(int steps) {
+    switch (steps) {
+        case 1: return scan_topk_kernel<DT, NQ, 1>;
+        case 2: return scan_topk_kernel<DT, NQ, 2>;
+        case 3: return scan_topk_kernel<DT, NQ, 3>;
+        case 4: return scan_topk_kernel<DT, NQ, 4>;
+        case 6: return scan_topk_kernel<DT, NQ, 6>;
+        case 8: return scan_topk_kernel<DT, NQ, 8>;
+    }
+    return nullptr;
+}
+template <int DT>
+static scan_fn pick_nq(int nqt, int steps) {
+    switch (nqt) {
+        case 1: return pick_steps<DT, 1>(steps);
+        case 2: return pick_steps<DT, 2>(steps);
+        case 4: return pick_steps<DT, 4>(steps);
+    }
+    return nullptr;
+}
+static scan_fn pick_scan(int dt, int nqt, int steps) {
+    switch (dt) {
+        case 0: return pick_nq<0>(nqt, steps);
+        case 1: return pick_nq<1>(nqt, steps);
+        case 2: return pick_nq<2>(nqt, steps);
+    }
+    return nullptr;
+}
+static int round_steps(int need) {
+    static const int allowed[] = {1, 2, 3, 4, 6, 8};
+    for (int s : allowed)
+        if (s >= need) return s;
+    return 0;
+}
+
+// candidates kept per query before the exact rescore: k plus a guard band, in lists of 32
+static int cand_per_query(int k) {
+    const int slack = k / 4 > 16 ? k / 4 : 16;
+    const int want = k + slack;
+    for (int kp = 32; kp <= 256; kp <<= 1)
+        if (kp >= want) return kp;
+    return 0;
+}
+
+// |fp32-accumulated dot - exact dot| for unit-norm operands (any summation order), plus the
+// fp32 rounding of the exact score and one ulp so that a tie after rounding cannot hide a row.
+static float eps_fp32_accumulate(int ld) { return (float)((ld + 64) * 5.9604644775390625e-08 * 1.0625 + 4.76837158203125e-07); }
+
+static const int kMaxQueryBatch = 256;  // queries per pass through the pipeline (bounds the workspace)
+
+static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* out_ids, float* out_scores,
+                         cudaStream_t st) {
+    int rc;
+    const int64_t n = h->count;
+    h->stats.launches = 0;
+    h->stats.path = 0;
+    h->stats.queries_rescanned = -1;
+    const int V = h->dtype == 0 ? 4 : 8;
+    const int nvec = h->ld / V;
+    const int steps = round_steps((nvec + 31) / 32);
+    int kp = cand_per_query(k);
+    if (kp == 0) return fail(RAGFIN_EUNSUPPORTED, "k = %d above 224 needs the large-k path (not built yet)", k);
+    h->stats.cand_per_query = kp;
+    const int kpe = (k + 31) / 32 * 32;
+    if ((rc = ensure(h->flags, (size_t)(kMaxQueryBatch + 1) * sizeof(int)))) return rc;
+    int* flags = (int*)h->flags.p;
+    int* flag_count = flags + kMaxQueryBatch;
+    const float eps = eps_fp32_accumulate(h->ld);
+
+    for (int q0 = 0; q0 < nq; q0 += kMaxQueryBatch) {
+        const int nb = nq - q0 < kMaxQueryBatch ? nq - q0 : kMaxQueryBatch;
+        const int nb4 = (nb + 3) / 4 * 4;
+        // 1. normalise the queries (same kernel as ingest, fp32 out, stride ld); pad to 4 with zero rows
+        if ((rc = ensure(h->qhat, (size_t)nb4 * h->ld * sizeof(float)))) return rc;
+        float* qhat = (float*)h->qhat.p;
+        if (nb4 > nb) CU_TRY(cudaMemsetAsync(qhat + (size_t)nb * h->ld, 0, (size_t)(nb4 - nb) * h->ld * sizeof(float), st));
+        if ((rc = launch_ingest<false>(0, q_dev + (size_t)q0 * h->dim, 0, 0, 0, 0, nb, h->dim, h->ld, qhat, h->num_sms, st))) return rc;
+        h->stats.launches++;
+        CU_TRY(cudaMemsetAsync(flags, 0, (size_t)(kMaxQueryBatch + 1) * sizeof(int), st));
+
+        // 2. scan in groups of <= 4 queries.  Candidate layout [nb4][G][kp]; a group whose kernel
+        //    variant fits fewer CTAs than G leaves the surplus lists empty (zeroed here).
+        const int G = h->num_sms * kMaxScanCtasPerSm;
+        const bool scanned = n > 0 && steps > 0;
+        if ((rc = ensure(h->cand, (size_t)nb4 * G * kp * sizeof(u64)))) return rc;
+        CU_TRY(cudaMemsetAsync(h->cand.p, 0, (size_t)nb4 * G * kp * sizeof(u64), st));
+        if (scanned) {
+            for (int g0 = 0; g0 < nb; g0 += 4) {
+                const int left = nb - g0;
+                const int nqt = left >= 3 ? 4 : left;  // 1, 2 or 4 query register sets (3 pads to 4)
+                scan_fn fn = pick_scan(h->dtype, nqt, steps);
+                if (!fn) return fail(RAGFIN_EUNSUPPORTED, "no scan kernel for dtype %d nq %d steps %d", h->dtype, nqt, steps);
+                const size_t smem = (size_t)nqt * kScanWarps * kp * sizeof(u64);
+                CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int per_sm = 0;
+                CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kScanThreads, smem));
+                if (per_sm < 1) return fail(RAGFIN_ECUDA, "scan kernel does not fit on an SM (smem %zu)", smem);
+                if (per_sm > kMaxScanCtasPerSm) per_sm = kMaxScanCtasPerSm;
+                fn<<<h->num_sms * per_sm, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat + (size_t)g0 * h->ld, kp,
+                                                                     (u64*)h->cand.p + (size_t)g0 * G * kp,
+                                                                     (int64_t)G * kp);
+                CU_TRY(cudaGetLastError());
+                h->stats.launches++;
+            }
+        }
+        // 3. merge + exact rescore + certificate (an unscanned, non-empty corpus flags every query)
+        {
+            const size_t smem = ((size_t)kFinWarps * kp + kp) * sizeof(u64);
+            finalize_kernel<false><<<nb, kFinThreads, smem, st>>>(
+                (const u64*)h->cand.p, G, kp, h->data, h->dtype, n, (scanned || n == 0) ? 1 : 0, h->ld, qhat, eps, nullptr,
+                k, h->id_base, out_ids + (size_t)q0 * k, out_scores + (size_t)q0 * k, flags, flag_count);
+            CU_TRY(cudaGetLastError());
+            h->stats.launches++;
+        }
+        // 4. tier 2 (device-side gated: both kernels exit at once when no query is flagged)
+        if (n > 0) {
+            const int Ge = h->num_sms * 2;
+            if ((rc = ensure(h->cand_e, (size_t)nb * Ge * kpe * sizeof(u64)))) return rc;
+            const size_t smem = (size_t)kScanWarps * kpe * sizeof(u64);
+            switch (h->dtype) {
+                case 0: exact_scan_kernel<0><<<Ge, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat, nb, flags, flag_count, kpe, (u64*)h->cand_e.p); break;
+                case 1: exact_scan_kernel<1><<<Ge, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat, nb, flags, flag_count, kpe, (u64*)h->cand_e.p); break;
+                default: exact_scan_kernel<2><<<Ge, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat, nb, flags, flag_count, kpe, (u64*)h->cand_e.p); break;
+            }
+            CU_TRY(cudaGetLastError());
+            const size_t fsm = ((size_t)kFinWarps * kpe + kpe) * sizeof(u64);
+            finalize_kernel<true><<<nb, kFinThreads, fsm, st>>>((const u64*)h->cand_e.p, Ge, kpe, h->data, h->dtype, n, 1, h->ld,
+                                                                qhat, 0.0f, nullptr, k, h->id_base,
+                                                                out_ids + (size_t)q0 * k, out_scores + (size_t)q0 * k,
+                                                                flags, flag_count);
+            CU_TRY(cudaGetLastError());
+            h->stats.launches += 2;
+        }
+    }
+    return 0;
+}
+
+extern "C" int ragfin_search(ragfin_t* h, const float* q, int32_t nq, int32_t k, int64_t* out_ids, float* out_scores,
+                             void* stream) {
+    if (!h) return fail(RAGFIN_EINVAL, "NULL handle");
+    if (nq < 0 || (nq > 0 && (!q || !out_ids || !out_scores))) return fail(RAGFIN_EINVAL, "NULL buffer");
+    if (k < 1 || k > 16384) return fail(RAGFIN_EINVAL, "k = %d outside [1, 16384]", k);
+    if (nq == 0) return RAGFIN_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = wait_prev(h, st))) return rc;
+    if ((rc = search_locked(h, q, nq, k, out_ids, out_scores, st))) return rc;
+    return mark_done(h, st);
+}
+
+extern "C" int ragfin_search_host(ragfin_t* h, const float* q_host, int32_t nq, int32_t k, int64_t* out_ids_host,
+                                  float* out_scores_host) {
+    if (!h) return fail(RAGFIN_EINVAL, "NULL handle");
+    if (nq < 0 || (nq > 0 && (!q_host || !out_ids_host || !out_scores_host))) return fail(RAGFIN_EINVAL, "NULL buffer");
+    if (k < 1 || k > 16384) return fail(RAGFIN_EINVAL, "k = %d outside [1, 16384]", k);
+    if (nq == 0) return RAGFIN_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    cudaStream_t st = 0;
+    int rc;
+    if ((rc = wait_prev(h, st))) return rc;
+    const size_t qb = (size_t)nq * h->dim * sizeof(float), ib = (size_t)nq * k * sizeof(int64_t), sb = (size_t)nq * k * sizeof(float);
+    if ((rc = ensure(h->stage_q, qb)) || (rc = ensure(h->stage_ids, ib)) || (rc = ensure(h->stage_scores, sb))) return rc;
+    CU_TRY(cudaMemcpyAsync(h->stage_q.p, q_host, qb, cudaMemcpyHostToDevice, st));
+    if ((rc = search_locked(h, (const float*)h->stage_q.p, nq, k, (int64_t*)h->stage_ids.p, (float*)h->stage_scores.p, st))) return rc;
+    CU_TRY(cudaMemcpyAsync(out_ids_host, h->stage_ids.p, ib, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(out_scores_host, h->stage_scores.p, sb, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return mark_done(h, st);
+}
+
+extern "C" int ragfin_last_search_stats(ragfin_t* h, ragfin_search_stats* out) {
+    if (!h || !out) return fail(RAGFIN_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    if (h->flags.p) {
+        CU_TRY(cudaDeviceSynchronize());
+        int fc = 0;
+        CU_TRY(cudaMemcpy(&fc, (int*)h->flags.p + kMaxQueryBatch, sizeof(int), cudaMemcpyDeviceToHost));
+        h->stats.queries_rescanned = fc;  // of the last query batch (<= 256 queries)
+    }
+    *out = h->stats;
+    return RAGFIN_OK;
+}
+
+extern "C" int ragfin_merge_topk(const int64_t* ids, const float* scores, int32_t nq, int32_t parts, int32_t k,
+                                 int64_t* out_ids, float* out_scores, int32_t device, void* stream) {
+    if (nq < 0 || parts < 1 || k < 1) return fail(RAGFIN_EINVAL, "bad nq/parts/k");
+    if (nq == 0) return RAGFIN_OK;
+    if (!ids || !scores || !out_ids || !out_scores) return fail(RAGFIN_EINVAL, "NULL buffer");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(RAGFIN_ECUDA, "cudaSetDevice(%d) failed", device);
+    const int64_t total = (int64_t)nq * parts * k;
+    const int threads = 256;
+    merge_topk_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+        ids, scores, nq, parts, k, out_ids, out_scores);
+    CU_TRY(cudaGetLastError());
+    return RAGFIN_OK;
+}

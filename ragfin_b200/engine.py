@@ -1,0 +1,164 @@
+"""Device-resident exact cosine top-k index: the Python face of the C ABI.
+
+`Index` owns one handle (one GPU, one row shard).  Arrays go in and out as numpy (host) or
+torch CUDA tensors (device); torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+
+DTYPE_CODE = {"f32": 0, "fp32": 0, "float32": 0, "bf16": 1, "bfloat16": 1, "f16": 2, "fp16": 2, "float16": 2}
+MAX_TOPK = 16384  # Milvus' own limit on `limit`
+
+
+def _stream_ptr(stream) -> int:
+    if stream is None:
+        import torch
+        return int(torch.cuda.current_stream().cuda_stream)
+    return int(getattr(stream, "cuda_stream", stream))
+
+
+class Index:
+    """Exact cosine top-k over a device-resident, L2-normalised embedding matrix.
+
+    Mirrors what the reference gets from a loaded Milvus collection with a COSINE index
+    (reference "chunking_storing (1).py":14-29, retrieve.py:17-19)."""
+
+    def __init__(self, dim: int, dtype: str = "f32", capacity: int = 1 << 20, device: int = 0):
+        if dtype not in DTYPE_CODE:
+            raise ValueError(f"dtype must be one of {sorted(DTYPE_CODE)}, got {dtype!r}")
+        self._L = _lib.load()
+        self.dim, self.dtype, self.capacity, self.device = int(dim), dtype, int(capacity), int(device)
+        h = ctypes.c_void_p()
+        _lib.check(self._L.ragfin_create(ctypes.byref(h), self.dim, DTYPE_CODE[dtype], self.capacity, self.device))
+        self._h = h
+
+    # -- lifecycle -------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.ragfin_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        n = ctypes.c_int64()
+        _lib.check(self._L.ragfin_count(self._h, ctypes.byref(n)))
+        return int(n.value)
+
+    num_entities = property(__len__)
+
+    def set_id_base(self, base: int) -> None:
+        _lib.check(self._L.ragfin_set_id_base(self._h, int(base)))
+
+    # -- ingest (K1) -----------------------------------------------------------------
+    def add(self, rows, stream=None) -> None:
+        """Append fp32 rows [n, dim]: numpy / nested lists (host) or a torch CUDA tensor."""
+        if hasattr(rows, "is_cuda"):
+            import torch
+            if not rows.is_cuda:
+                rows = rows.numpy()
+            else:
+                if rows.dim() != 2 or rows.shape[1] != self.dim:
+                    raise ValueError(f"rows must be [n, {self.dim}], got {tuple(rows.shape)}")
+                if rows.device.index != self.device:
+                    raise ValueError(f"rows live on cuda:{rows.device.index}, index on cuda:{self.device}")
+                rows = rows.to(torch.float32).contiguous()
+                with torch.cuda.device(self.device):
+                    _lib.check(self._L.ragfin_add(self._h, rows.data_ptr(), rows.shape[0], 1, _stream_ptr(stream)))
+                    torch.cuda.current_stream().synchronize()  # `rows` may be freed by the caller
+                return
+        a = np.ascontiguousarray(rows, dtype=np.float32)
+        if a.ndim == 1:
+            a = a[None, :]
+        if a.ndim != 2 or a.shape[1] != self.dim:
+            raise ValueError(f"rows must be [n, {self.dim}], got {a.shape}")
+        _lib.check(self._L.ragfin_add(self._h, a.ctypes.data, a.shape[0], 0, None))
+
+    def add_synthetic(self, seed: int, row0: int, n: int, dup_every: int = 0, zero_every: int = 0) -> None:
+        _lib.check(self._L.ragfin_add_synthetic(self._h, seed, row0, n, dup_every, zero_every, None))
+
+    def read_rows(self, row0: int, n: int) -> np.ndarray:
+        """Stored rows as fp32 values [n, dim] (test hook for ingest parity)."""
+        ld = (self.dim + 7) // 8 * 8
+        code = DTYPE_CODE[self.dtype]
+        raw = np.empty((n, ld), dtype=np.float32 if code == 0 else np.uint16)
+        ldo = ctypes.c_int32()
+        _lib.check(self._L.ragfin_read_rows(self._h, row0, n, raw.ctypes.data, ctypes.byref(ldo)))
+        assert ldo.value == ld
+        if code == 0:
+            out = raw
+        elif code == 1:
+            out = (raw.astype(np.uint32) << np.uint32(16)).view(np.float32)
+        else:
+            out = raw.view(np.float16).astype(np.float32)
+        assert not out[:, self.dim:].any(), "padding columns must be zero"
+        return np.ascontiguousarray(out[:, :self.dim])
+
+    # -- search ----------------------------------------------------------------------
+    def _check_k(self, k: int) -> int:
+        k = int(k)
+        if not 1 <= k <= MAX_TOPK:
+            raise ValueError(f"top_k must be in [1, {MAX_TOPK}], got {k}")
+        return k
+
+    def search(self, queries, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        """Host path: queries numpy/list [nq, dim] -> (ids int64 [nq, k], scores fp32 [nq, k]).
+        Hits are in descending score, ties to the lower id; slots past min(k, N) hold (-1, -inf)."""
+        k = self._check_k(k)
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be [nq, {self.dim}], got {q.shape}")
+        ids = np.empty((q.shape[0], k), dtype=np.int64)
+        scores = np.empty((q.shape[0], k), dtype=np.float32)
+        _lib.check(self._L.ragfin_search_host(self._h, q.ctypes.data, q.shape[0], k, ids.ctypes.data, scores.ctypes.data))
+        return ids, scores
+
+    def search_device(self, queries, k: int, out_ids=None, out_scores=None, stream=None):
+        """Device path: `queries` is a torch CUDA fp32 tensor [nq, dim]; returns torch CUDA tensors.
+        Asynchronous on the given (default: current) stream."""
+        import torch
+        k = self._check_k(k)
+        if not queries.is_cuda or queries.dtype != torch.float32 or queries.dim() != 2 or queries.shape[1] != self.dim:
+            raise ValueError(f"queries must be a CUDA fp32 tensor [nq, {self.dim}]")
+        queries = queries.contiguous()
+        nq = queries.shape[0]
+        if out_ids is None:
+            out_ids = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
+        if out_scores is None:
+            out_scores = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.ragfin_search(self._h, queries.data_ptr(), nq, k, out_ids.data_ptr(),
+                                             out_scores.data_ptr(), _stream_ptr(stream)))
+        return out_ids, out_scores
+
+    def stats(self) -> dict:
+        s = _lib.SearchStats()
+        _lib.check(self._L.ragfin_last_search_stats(self._h, ctypes.byref(s)))
+        return {"launches": s.launches, "path": s.path, "queries_rescanned": s.queries_rescanned,
+                "cand_per_query": s.cand_per_query}
+
+
+def merge_topk(ids, scores, parts: int, k: int, stream=None):
+    """Cross-shard reduce of exact hit lists: torch CUDA tensors ids int64 / scores fp32 [nq, parts*k]."""
+    import torch
+    L = _lib.load()
+    nq = ids.shape[0]
+    assert ids.shape == (nq, parts * k) and scores.shape == (nq, parts * k)
+    ids, scores = ids.contiguous(), scores.contiguous()
+    out_ids = torch.empty((nq, k), dtype=torch.int64, device=ids.device)
+    out_scores = torch.empty((nq, k), dtype=torch.float32, device=ids.device)
+    _lib.check(L.ragfin_merge_topk(ids.data_ptr(), scores.data_ptr(), nq, parts, k, out_ids.data_ptr(),
+                                   out_scores.data_ptr(), ids.device.index, _stream_ptr(stream)))
+    return out_ids, out_scores

@@ -1,0 +1,58 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/ragfin.h declares, and
+fails loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    from ragfin_b200 import _lib
+    if not os.path.exists(_lib.SO_PATH):
+        ge.build()
+    return _lib.load()
+
+
+def test_header_symbols_are_exported(lib):
+    from ragfin_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "ragfin.h")).read()
+    declared = set(re.findall(r"\b(ragfin_[a-z_]+)\s*\(", hdr))
+    declared.discard("ragfin_t")
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ragfin_abi_version() == int(re.search(r"RAGFIN_ABI_VERSION (\d+)", hdr).group(1))
+
+
+def test_argument_validation_without_device(lib):
+    h = ctypes.c_void_p()
+    assert lib.ragfin_create(ctypes.byref(h), 0, 0, 10, 0) == -1       # EINVAL: dim
+    assert b"dim" in lib.ragfin_last_error()
+    assert lib.ragfin_create(ctypes.byref(h), 8, 7, 10, 0) == -1       # EINVAL: dtype
+    assert lib.ragfin_create(ctypes.byref(h), 8, 0, 0, 0) == -1        # EINVAL: capacity
+    assert lib.ragfin_search(None, None, 1, 1, None, None, None) == -1
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import ragfin_b200
+    with pytest.raises(ragfin_b200.RagfinError) as e:
+        ragfin_b200.Index(384, "f32", 16)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "ragfin_b200")
+    for dp, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dp, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+                assert "ragfin_oracle" not in src.replace("oracle/ragfin_oracle", ""), fn

@@ -1,0 +1,183 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the oracle on the same seeded
+inputs.  Index sets and scores must be BIT-EXACT (ids equal, fp32 score bit patterns equal)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ragfin_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _index(x, dtype, capacity=None):
+    import ragfin_b200
+    idx = ragfin_b200.Index(x.shape[1], dtype, capacity=capacity or max(len(x), 1), device=0)
+    if len(x):
+        idx.add(x)
+    return idx
+
+
+def _assert_same(got, want, what=""):
+    gi, gs = got
+    wi, ws = want
+    assert np.array_equal(gi, wi), f"{what}: ids differ\n{gi}\n{wi}"
+    assert np.array_equal(gs.view(np.uint32), ws.view(np.uint32)), f"{what}: score bits differ\n{gs}\n{ws}"
+
+
+@pytest.mark.parametrize("dtype", O.DTYPES)
+@pytest.mark.parametrize("dim", [384, 768, 1024, 100, 33, 8])
+def test_ingest_is_bit_exact(coracle, dtype, dim):
+    x = O.synth_rows(3, 0, 777, dim, zero_every=17)
+    x[5] *= 1000.0
+    x[6] *= 1e-6
+    idx = _index(x, dtype)
+    got = idx.read_rows(0, 777)
+    want = coracle.normalize_rows(x, dtype)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("dtype", O.DTYPES)
+def test_synthetic_ingest_matches_host_generator(coracle, dtype):
+    import ragfin_b200
+    idx = ragfin_b200.Index(768, dtype, capacity=3000, device=0)
+    idx.add_synthetic(1234, 0, 1000, dup_every=7, zero_every=11)
+    idx.add_synthetic(1234, 1000, 2000, dup_every=7, zero_every=11)   # chunked adds continue the same matrix
+    want = coracle.normalize_rows(O.synth_rows(1234, 0, 3000, 768, 7, 11), dtype)
+    assert np.array_equal(idx.read_rows(0, 3000).view(np.uint32), want.view(np.uint32))
+    assert len(idx) == 3000
+
+
+@pytest.mark.parametrize("dtype", O.DTYPES)
+@pytest.mark.parametrize("dim", [384, 768, 1024])
+@pytest.mark.parametrize("nq,k", [(1, 10), (2, 5), (3, 1), (4, 100), (9, 10)])
+def test_search_matches_oracle(coracle, dtype, dim, nq, k):
+    n = 20000 if dim == 768 else 6000
+    x = O.synth_rows(40 + dim, 0, n, dim, dup_every=97, zero_every=1013)
+    q = O.synth_rows(41 + dim, 0, nq, dim)
+    idx = _index(x, dtype)
+    got = idx.search(q, k)
+    want = coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), k)
+    _assert_same(got, want, f"{dtype} dim={dim} nq={nq} k={k}")
+    assert idx.stats()["launches"] > 0
+
+
+@pytest.mark.parametrize("dtype", O.DTYPES)
+@pytest.mark.parametrize("dim", [100, 33, 8, 2048, 1536])
+def test_search_odd_and_wide_dims(coracle, dtype, dim):
+    x = O.synth_rows(50, 0, 3000, dim)
+    q = O.synth_rows(51, 0, 2, dim)
+    got = _index(x, dtype).search(q, 7)
+    _assert_same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), 7), f"{dtype} dim={dim}")
+
+
+@pytest.mark.parametrize("n", [1, 2, 16, 31, 32, 33, 255, 257])
+def test_small_collections_and_k_above_n(coracle, n):
+    """The reference's real collection has 16 rows and is queried with limit up to 1000
+    (graph_cons.py:279): every row comes back, padded slots are (-1, -inf)."""
+    x = O.synth_rows(60, 0, n, 384)
+    q = O.synth_rows(61, 0, 3, 384)
+    idx = _index(x, "f32")
+    for k in (1, 3, 20, 200):
+        got = idx.search(q, k)
+        want = coracle.cosine_topk(q, coracle.normalize_rows(x, "f32"), k)
+        _assert_same(got, want, f"n={n} k={k}")
+        if k > n:
+            assert (got[0][:, n:] == -1).all() and np.isneginf(got[1][:, n:]).all()
+
+
+def test_empty_collection():
+    import ragfin_b200
+    idx = ragfin_b200.Index(384, "bf16", capacity=8, device=0)
+    ids, sc = idx.search(np.ones((2, 384), np.float32), 3)
+    assert (ids == -1).all() and np.isneginf(sc).all()
+
+
+@pytest.mark.parametrize("dtype", O.DTYPES)
+def test_heavy_duplicates_take_the_exact_tier(coracle, dtype):
+    """300 copies of the best row straddle the candidate guard band: the certificate must fail
+    and the exact rescan tier must still return the lowest ids."""
+    x = O.synth_rows(70, 0, 5000, 768)
+    q = O.synth_rows(71, 0, 2, 768)
+    x[100:400] = q[0] * 3.0
+    x[4000:4100] = q[1]
+    idx = _index(x, dtype)
+    got = idx.search(q, 10)
+    _assert_same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), 10), dtype)
+    assert got[0][0].tolist() == list(range(100, 110))
+    assert idx.stats()["queries_rescanned"] == 2
+
+
+def test_all_rows_identical(coracle):
+    x = np.tile(O.synth_rows(80, 0, 1, 384), (3000, 1))
+    q = O.synth_rows(81, 0, 1, 384)
+    got = _index(x, "bf16").search(q, 5)
+    assert got[0][0].tolist() == [0, 1, 2, 3, 4]
+    _assert_same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, "bf16"), 5))
+
+
+def test_zero_rows_and_zero_query(coracle):
+    x = O.synth_rows(90, 0, 2000, 384, zero_every=4)
+    idx = _index(x, "f16")
+    q = np.zeros((1, 384), np.float32)
+    got = idx.search(q, 5)
+    _assert_same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, "f16"), 5))
+    assert got[0][0].tolist() == [0, 1, 2, 3, 4] and not got[1].any()
+
+
+def test_incremental_add_and_id_base(coracle):
+    x = O.synth_rows(95, 0, 9000, 768)
+    q = O.synth_rows(96, 0, 4, 768)
+    idx = _index(x[:1000], "bf16", capacity=9000)
+    idx.add(x[1000:1001])
+    idx.add(x[1001:])
+    want = coracle.cosine_topk(q, coracle.normalize_rows(x, "bf16"), 10)
+    _assert_same(idx.search(q, 10), want)
+    idx.set_id_base(5_000_000_000)
+    got = idx.search(q, 10)
+    assert np.array_equal(got[0], want[0] + 5_000_000_000)
+
+
+def test_device_path_and_merge(coracle):
+    import torch
+    import ragfin_b200
+    x = O.synth_rows(97, 0, 8000, 768, dup_every=5)
+    q = O.synth_rows(98, 0, 5, 768)
+    want = coracle.cosine_topk(q, coracle.normalize_rows(x, "f16"), 10)
+    qd = torch.from_numpy(q).cuda()
+    shards, outs = [], []
+    for a, b in ((0, 3000), (3000, 3001), (3001, 8000)):
+        s = ragfin_b200.Index(768, "f16", capacity=b - a, device=0)
+        s.add(torch.from_numpy(x[a:b]).cuda())
+        s.set_id_base(a)
+        shards.append(s)
+        outs.append(s.search_device(qd, 10))
+    ids = torch.cat([o[0] for o in outs], dim=1)
+    sc = torch.cat([o[1] for o in outs], dim=1)
+    mi, ms = ragfin_b200.merge_topk(ids, sc, 3, 10)
+    torch.cuda.synchronize()
+    _assert_same((mi.cpu().numpy(), ms.cpu().numpy()), want)
+
+
+def test_golden_fixtures_on_gpu():
+    with open(os.path.join(GOLDEN, "topk_cases.json")) as f:
+        cases = json.load(f)["cases"]
+    for c in cases:
+        x = O.synth_rows(c["seed"], 0, c["n"], c["dim"], c["dup_every"], c["zero_every"])
+        q = O.synth_rows(c["seed"] + 1, 0, c["nq"], c["dim"])
+        ids, sc = _index(x, c["dtype"]).search(q, c["k"])
+        assert ids.tolist() == c["ids"], c["name"]
+        assert sc.view(np.uint32).tolist() == c["score_bits"], c["name"]
+
+
+def test_errors_are_loud():
+    import ragfin_b200
+    idx = ragfin_b200.Index(384, "f32", capacity=4, device=0)
+    with pytest.raises(ragfin_b200.RagfinError):
+        idx.add(np.zeros((5, 384), np.float32))          # over capacity
+    with pytest.raises(ValueError):
+        idx.search(np.zeros((1, 383), np.float32), 3)    # wrong dim
+    with pytest.raises(ValueError):
+        idx.search(np.zeros((1, 384), np.float32), 0)    # top_k < 1
