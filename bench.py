@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py - exact cosine top-k throughput on a synthetic 10M x 768 bf16 corpus (BASELINE.json).
+
+A "step" is one pass of the hot path over one batch of synthetic queries: one exact top-k search
+of `--batch` queries over the whole corpus.  With --gpus N the corpus is row-sharded over N ranks
+(one process per GPU, torchrun), each rank searches its shard and the per-rank hits are
+all-gathered over NCCL and reduced: total work is fixed, so scaling = "strong".
+
+  value     queries/s with the queries already resident in HBM (CUDA events, max over ranks)
+  e2e       queries/s through the public host API: pinned host queries -> H2D -> search ->
+            [all-gather + reduce] -> D2H of (ids, scores), every step
+  roofline  dominant kernel (small-batch scan: HBM; GEMM: tensor), timed live with CUDA events
+            recorded by the library around that kernel on the launching stream
+  cpu_baseline  the reference's CPU retrieval path (oracle/fast_cpu.py port) on this box's cores
+
+`--impl reference` times only that CPU path (rank 0), same metric/config.
+Inputs are far larger than L2 (15.36 GB corpus vs 126 MB), so no L2 flush is needed between steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "exact top-k queries/sec at 10Mx768"
+SEED_CORPUS, SEED_QUERY = 1234, 1235
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="queries per search call")
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--dtype", default="bf16", choices=["f32", "bf16", "f16"])
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="rows of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    rows = f"{a.rows // 1_000_000}M" if a.rows % 1_000_000 == 0 else str(a.rows)
+    return f"synthetic {rows}x{a.dim} {a.dtype} corpus, batch-{a.batch} queries, k={a.k}"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            m = json.load(f)
+        return {"hbm": m["hbm_gbs"], "bf16": m["bf16_tflops"], "bf16_sustained": m.get("bf16_tflops_sustained"),
+                "source": "MEASURED_PEAKS.json"}
+    return {"hbm": 6650.0, "bf16": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi DURING the timed region
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline (oracle port; the only place bench.py executes oracle/)
+# ----------------------------------------------------------------------------------------------
+def cpu_baseline(a, budget_s: float, steps: int | None = None):
+    import numpy as np
+    import torch
+    from oracle import c_oracle, fast_cpu
+    c_oracle.build()
+    rows = min(a.cpu_rows, a.rows)
+    nq = a.batch if a.batch <= 64 else 64           # bounded sample of the query batch
+    x = c_oracle.synth_rows(SEED_CORPUS, 0, rows, a.dim)
+    stored = torch.from_numpy(c_oracle.normalize_rows(x, "f32"))
+    del x
+    q = c_oracle.synth_rows(SEED_QUERY, 0, nq * 4, a.dim)
+    fast_cpu.fast_topk(stored, q[:nq], a.k)          # warm-up
+    times, t_end, i = [], time.perf_counter() + budget_s, 0
+    while (steps is None and time.perf_counter() < t_end) or (steps is not None and i < steps):
+        t0 = time.perf_counter()
+        fast_cpu.fast_topk(stored, q[(i % 4) * nq:(i % 4 + 1) * nq], a.k)
+        times.append(time.perf_counter() - t0)
+        i += 1
+        if steps is None and i >= 400:
+            break
+    per_call = statistics.median(times)
+    qps = nq / per_call * (rows / a.rows)            # linear in corpus rows (brute force)
+    sample = (f"{nq} of {a.batch} queries per call over a {rows}-row fp32 slice of the {a.rows}-row corpus, "
+              f"{len(times)} calls, median; throughput scaled by {rows}/{a.rows} (extrapolated, linear in rows)")
+    return {"value": qps, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
+            "ms_per_call_on_sample": per_call * 1e3}, len(times), per_call
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, n, per_call = cpu_baseline(a, budget_s=0.0, steps=a.steps + a.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "queries/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": a.batch / base["value"] * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "k": a.k, "batch": a.batch,
+                   "note": "reference CPU retrieval path (Milvus/knowhere brute-force COSINE restated: oracle/fast_cpu.py)"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import ragfin_b200
+    from ragfin_b200.sharded import ShardedSearcher, shard_bounds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- corpus: this rank's row shard of the synthetic matrix, generated + ingested on device
+    row0, n_local = shard_bounds(a.rows, world, rank)
+    idx = ragfin_b200.Index(a.dim, a.dtype, capacity=max(n_local, 1), device=local)
+    t0 = time.perf_counter()
+    for r in range(0, n_local, 1_000_000):
+        idx.add_synthetic(SEED_CORPUS, row0 + r, min(1_000_000, n_local - r))
+    idx.set_id_base(row0)
+    torch.cuda.synchronize()
+    ingest_s = time.perf_counter() - t0
+    searcher = ShardedSearcher.for_index(idx)
+
+    # ---- queries: 4 distinct batches, generated on the host with the oracle-identical generator
+    from ragfin_b200.synthetic import synth_rows
+    nbatches = 4
+    q_host = torch.from_numpy(synth_rows(SEED_QUERY, 0, nbatches * a.batch, a.dim)).view(nbatches, a.batch, a.dim).pin_memory()
+    q_dev = q_host.to(dev)
+    out_ids = torch.empty((a.batch, a.k), dtype=torch.int64).pin_memory()
+    out_sc = torch.empty((a.batch, a.k), dtype=torch.float32).pin_memory()
+    q_stage = torch.empty((a.batch, a.dim), dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def e2e_step(i):
+        if world == 1:   # the C-ABI host call: H2D + search + D2H + sync inside ragfin_search_host
+            idx.search(q_host[i % nbatches].numpy(), a.k, out_ids=out_ids.numpy(), out_scores=out_sc.numpy())
+        else:
+            q_stage.copy_(q_host[i % nbatches], non_blocking=True)
+            ids, sc = searcher.search(q_stage, a.k)
+            out_ids.copy_(ids, non_blocking=True)
+            out_sc.copy_(sc, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    # ---- warm-up (both paths)
+    for i in range(a.warmup):
+        searcher.search(q_dev[i % nbatches], a.k)
+    for i in range(max(1, a.warmup // 2)):
+        e2e_step(i)
+    launches_per_step = idx.stats()["launches"] + (1 if world > 1 else 0)
+    rescanned = idx.stats()["queries_rescanned"]
+
+    # ---- timed region 1: device-resident queries
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    idx.profile(True)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(a.steps):
+        searcher.search(q_dev[i % nbatches], a.k)
+    ev1.record()
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    kern_ms, kern_n = idx.profile_read()
+    idx.profile(False)
+
+    # ---- timed region 2: end to end through the host API
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        e2e_step(i)
+    barrier()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
+    clocks = sampler.stop() if rank == 0 else None
+    kern = torch.tensor([kern_ms / max(kern_n, 1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kern, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, kern_avg_ms = float(ms.item()), float(e2e_ms.item()), float(kern.item())
+
+    if rank == 0:
+        peaks = measured_peaks()
+        esize = 4 if a.dtype == "f32" else 2
+        ld = (a.dim + 7) // 8 * 8
+        path = idx.stats()["path"]
+        shard_rows = shard_bounds(a.rows, world, 0)[1]
+        if path == 0:   # HBM-bound scan: algorithmic bytes = one pass over the shard
+            alg = shard_rows * ld * esize
+            achieved = alg / (kern_avg_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": "scan_topk_kernel", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm"], "algorithmic_bytes_per_launch": alg,
+                    "frac_of_nominal_8TBps": achieved / 8000.0}
+        else:           # tensor-bound GEMM: algorithmic flops = 2 * nq * rows * dim
+            alg = 2.0 * a.batch * shard_rows * a.dim
+            achieved = alg / (kern_avg_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "gemm_topk_kernel", "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["bf16"], "algorithmic_flops_per_launch": alg}
+        roof.update({"kernel_ms_avg": kern_avg_ms, "kernel_launches_timed": kern_n, "peak_source": peaks["source"],
+                     "kernel_share_of_step": kern_avg_ms * (kern_n / max(a.steps, 1)) / (ms / a.steps),
+                     "traffic": load_traffic(a)})
+        bi = a.batch * a.dim * 4
+        bo = a.batch * a.k * 12
+        line = {
+            "metric": METRIC, "value": a.batch * a.steps / (ms * 1e-3), "unit": "queries/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+            "config": {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "k": a.k, "batch": a.batch,
+                       "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
+                       "l2": "inputs (corpus shard) larger than L2; no flush needed",
+                       "ingest_s": round(ingest_s, 2), "queries_rescanned_in_warmup": rescanned},
+            "clocks": clocks,
+            "e2e": {"value": a.batch * a.steps / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms / a.steps,
+                    "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo},
+            "gpu_launches": launches_per_step * a.steps,
+            "roofline": roof,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            del idx
+            line["cpu_baseline"] = cpu_baseline(a, budget_s=15.0)[0]
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def load_traffic(a):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    ncu --set full capture of this workload (profiles/traffic.json), else null."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    return t.get(f"{a.rows}x{a.dim}:{a.dtype}:b{a.batch}:k{a.k}")
+
+
+def main():
+    a = parse_args()
+    if a.gpus > 1 and "WORLD_SIZE" not in os.environ:   # convenience: self-launch under torchrun
+        port = 29500 + os.getpid() % 2000
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -89,12 +89,15 @@ int ragfin_search(ragfin_t* h, const float* q, int32_t nq, int32_t k, int64_t* o
 int ragfin_search_host(ragfin_t* h, const float* q_host, int32_t nq, int32_t k, int64_t* out_ids_host,
                        float* out_scores_host);
 
-/* Cross-shard reduce: merge `parts` exact hit lists per query (ids [nq, parts*k] int64,
- * scores [nq, parts*k] fp32, device memory; -1 ids are padding) into the global top-k,
- * ordered by (score desc, id asc).  Used after the NCCL all-gather of per-rank hits
+/* Cross-shard reduce: merge `parts` exact hit lists per query (device memory; -1 ids are
+ * padding) into the global top-k, ordered by (score desc, id asc).  Hit j of part p for query q
+ * is at element  q * query_stride + p * part_stride + j  of `ids` / `scores`: an all-gather
+ * buffer [parts][nq][k] is (part_stride = nq*k, query_stride = k); a concatenation
+ * [nq][parts*k] is (part_stride = k, query_stride = parts*k).  Used after the NCCL all-gather of per-rank hits
  * (Milvus proxy reduce in the reference deployment). */
 int ragfin_merge_topk(const int64_t* ids, const float* scores, int32_t nq, int32_t parts, int32_t k,
-                      int64_t* out_ids, float* out_scores, int32_t device, void* stream);
+                      int64_t part_stride, int64_t query_stride, int64_t* out_ids, float* out_scores,
+                      int32_t device, void* stream);
 
 /* Copy rows row0..row0+n of the STORED matrix, raw storage bytes [n, ld], to host memory
  * (test hook for ingest parity).  *ld_out receives the row stride in elements. */
@@ -110,6 +113,13 @@ typedef struct {
     int32_t cand_per_query;   /* K' : candidates kept per query before the exact rescore */
 } ragfin_search_stats;
 int ragfin_last_search_stats(ragfin_t* h, ragfin_search_stats* out);
+
+/* Measurement hook: when enabled, every search records a CUDA event pair around its dominant
+ * scoring kernel (the scan or the GEMM) on the launching stream.  ragfin_profile_read
+ * synchronises, returns the summed kernel time and the number of timed launches since the last
+ * read, and resets both.  Used by bench.py for the roofline figure; off by default. */
+int ragfin_profile(ragfin_t* h, int32_t enable);
+int ragfin_profile_read(ragfin_t* h, double* total_ms, int32_t* launches);
 
 void ragfin_destroy(ragfin_t* h);
 

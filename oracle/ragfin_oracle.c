@@ -58,19 +58,24 @@ static inline uint64_t mix64(uint64_t z) {
     return z ^ (z >> 31);
 }
 
-void oracle_synth_rows(uint64_t seed, int64_t row0, int64_t n, int32_t dim, int32_t dup_every,
-                       int32_t zero_every, float* out) {
-    const uint64_t key = mix64(seed);
-    for (int64_t r = 0; r < n; ++r) {
-        uint64_t row = (uint64_t)(row0 + r), src = row;
-        if (dup_every > 1 && row % (uint64_t)dup_every == (uint64_t)(dup_every - 1)) src = row - 1;
-        int zero = zero_every > 1 && row % (uint64_t)zero_every == (uint64_t)(zero_every - 1);
-        for (int32_t c = 0; c < dim; ++c) {
-            uint64_t h = mix64((src * (uint64_t)dim + (uint64_t)c) ^ key);
+typedef struct { uint64_t key; int64_t row0; int32_t dim, dup_every, zero_every; float* out; } synth_ctx;
+static void synth_range(int64_t lo, int64_t hi, void* p) {
+    synth_ctx* c = (synth_ctx*)p;
+    for (int64_t r = lo; r < hi; ++r) {
+        uint64_t row = (uint64_t)(c->row0 + r), src = row;
+        if (c->dup_every > 1 && row % (uint64_t)c->dup_every == (uint64_t)(c->dup_every - 1)) src = row - 1;
+        int zero = c->zero_every > 1 && row % (uint64_t)c->zero_every == (uint64_t)(c->zero_every - 1);
+        for (int32_t j = 0; j < c->dim; ++j) {
+            uint64_t h = mix64((src * (uint64_t)c->dim + (uint64_t)j) ^ c->key);
             int64_t s = (int64_t)((h & 0xFFFF) + ((h >> 16) & 0xFFFF) + ((h >> 32) & 0xFFFF) + (h >> 48));
-            out[r * dim + c] = zero ? 0.0f : (float)(s - 131070) * 0x1p-16f;
+            c->out[r * c->dim + j] = zero ? 0.0f : (float)(s - 131070) * 0x1p-16f;
         }
     }
+}
+void oracle_synth_rows(uint64_t seed, int64_t row0, int64_t n, int32_t dim, int32_t dup_every,
+                       int32_t zero_every, float* out) {
+    synth_ctx c = {mix64(seed), row0, dim, dup_every, zero_every, out};
+    parallel_for(n, synth_range, &c);
 }
 
 /* ---------------- storage rounding ---------------- */

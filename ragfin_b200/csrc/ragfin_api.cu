@@ -52,7 +52,19 @@ struct ragfin {
     Buf qhat, cand, cand_e, flags, stage_q, stage_ids, stage_scores, add_stage;
     cudaEvent_t last_done = nullptr;
     ragfin_search_stats stats = {0, 0, 0, 0};
+    // measurement hook (ragfin_profile): event pairs around the dominant kernel
+    bool profiling = false;
+    static const int kProfPairs = 512;
+    cudaEvent_t prof_ev[2 * kProfPairs] = {};
+    int prof_used = 0;
 };
+
+static void prof_begin(ragfin* h, cudaStream_t st) {
+    if (h->profiling && h->prof_used < ragfin::kProfPairs) cudaEventRecord(h->prof_ev[2 * h->prof_used], st);
+}
+static void prof_end(ragfin* h, cudaStream_t st) {
+    if (h->profiling && h->prof_used < ragfin::kProfPairs) { cudaEventRecord(h->prof_ev[2 * h->prof_used + 1], st); h->prof_used++; }
+}
 
 static size_t esize(int dtype) { return dtype == RAGFIN_F32 ? 4 : 2; }
 
@@ -144,6 +156,8 @@ extern "C" void ragfin_destroy(ragfin_t* h) {
         if (b->p) cudaFree(b->p);
     if (h->data) cudaFree(h->data);
     if (h->last_done) cudaEventDestroy(h->last_done);
+    for (cudaEvent_t e : h->prof_ev)
+        if (e) cudaEventDestroy(e);
     delete h;
 }
 
@@ -356,9 +370,11 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
                 CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kScanThreads, smem));
                 if (per_sm < 1) return fail(RAGFIN_ECUDA, "scan kernel does not fit on an SM (smem %zu)", smem);
                 if (per_sm > kMaxScanCtasPerSm) per_sm = kMaxScanCtasPerSm;
+                prof_begin(h, st);
                 fn<<<h->num_sms * per_sm, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat + (size_t)g0 * h->ld, kp,
                                                                      (u64*)h->cand.p + (size_t)g0 * G * kp,
                                                                      (int64_t)G * kp);
+                prof_end(h, st);
                 CU_TRY(cudaGetLastError());
                 h->stats.launches++;
             }
@@ -445,9 +461,39 @@ extern "C" int ragfin_last_search_stats(ragfin_t* h, ragfin_search_stats* out) {
     return RAGFIN_OK;
 }
 
+extern "C" int ragfin_profile(ragfin_t* h, int32_t enable) {
+    if (!h) return fail(RAGFIN_EINVAL, "NULL handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    if (enable && !h->prof_ev[0])
+        for (cudaEvent_t& e : h->prof_ev) CU_TRY(cudaEventCreate(&e));
+    h->profiling = enable != 0;
+    h->prof_used = 0;
+    return RAGFIN_OK;
+}
+
+extern "C" int ragfin_profile_read(ragfin_t* h, double* total_ms, int32_t* launches) {
+    if (!h || !total_ms || !launches) return fail(RAGFIN_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    CU_TRY(cudaDeviceSynchronize());
+    double sum = 0.0;
+    for (int i = 0; i < h->prof_used; ++i) {
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+        sum += ms;
+    }
+    *total_ms = sum;
+    *launches = h->prof_used;
+    h->prof_used = 0;
+    return RAGFIN_OK;
+}
+
 extern "C" int ragfin_merge_topk(const int64_t* ids, const float* scores, int32_t nq, int32_t parts, int32_t k,
-                                 int64_t* out_ids, float* out_scores, int32_t device, void* stream) {
+                                 int64_t part_stride, int64_t query_stride, int64_t* out_ids, float* out_scores,
+                                 int32_t device, void* stream) {
     if (nq < 0 || parts < 1 || k < 1) return fail(RAGFIN_EINVAL, "bad nq/parts/k");
+    if (part_stride < k || query_stride < k) return fail(RAGFIN_EINVAL, "strides must be >= k");
     if (nq == 0) return RAGFIN_OK;
     if (!ids || !scores || !out_ids || !out_scores) return fail(RAGFIN_EINVAL, "NULL buffer");
     DeviceGuard g(device);
@@ -455,7 +501,7 @@ extern "C" int ragfin_merge_topk(const int64_t* ids, const float* scores, int32_
     const int64_t total = (int64_t)nq * parts * k;
     const int threads = 256;
     merge_topk_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
-        ids, scores, nq, parts, k, out_ids, out_scores);
+        ids, scores, nq, parts, k, part_stride, query_stride, out_ids, out_scores);
     CU_TRY(cudaGetLastError());
     return RAGFIN_OK;
 }

@@ -111,17 +111,22 @@ class Index:
             raise ValueError(f"top_k must be in [1, {MAX_TOPK}], got {k}")
         return k
 
-    def search(self, queries, k: int) -> Tuple[np.ndarray, np.ndarray]:
+    def search(self, queries, k: int, out_ids: Optional[np.ndarray] = None,
+               out_scores: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
         """Host path: queries numpy/list [nq, dim] -> (ids int64 [nq, k], scores fp32 [nq, k]).
-        Hits are in descending score, ties to the lower id; slots past min(k, N) hold (-1, -inf)."""
+        Hits are in descending score, ties to the lower id; slots past min(k, N) hold (-1, -inf).
+        `out_ids` / `out_scores` may be caller-owned (e.g. pinned) C-contiguous arrays."""
         k = self._check_k(k)
         q = np.ascontiguousarray(queries, dtype=np.float32)
         if q.ndim == 1:
             q = q[None, :]
         if q.ndim != 2 or q.shape[1] != self.dim:
             raise ValueError(f"queries must be [nq, {self.dim}], got {q.shape}")
-        ids = np.empty((q.shape[0], k), dtype=np.int64)
-        scores = np.empty((q.shape[0], k), dtype=np.float32)
+        ids = out_ids if out_ids is not None else np.empty((q.shape[0], k), dtype=np.int64)
+        scores = out_scores if out_scores is not None else np.empty((q.shape[0], k), dtype=np.float32)
+        if (ids.shape != (q.shape[0], k) or ids.dtype != np.int64 or not ids.flags.c_contiguous
+                or scores.shape != (q.shape[0], k) or scores.dtype != np.float32 or not scores.flags.c_contiguous):
+            raise ValueError("out_ids / out_scores must be C-contiguous int64 / float32 arrays of shape [nq, k]")
         _lib.check(self._L.ragfin_search_host(self._h, q.ctypes.data, q.shape[0], k, ids.ctypes.data, scores.ctypes.data))
         return ids, scores
 
@@ -143,6 +148,16 @@ class Index:
                                              out_scores.data_ptr(), _stream_ptr(stream)))
         return out_ids, out_scores
 
+    def profile(self, enable: bool = True) -> None:
+        """Record CUDA events around the dominant scoring kernel of every search (bench.py)."""
+        _lib.check(self._L.ragfin_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """(summed kernel ms, timed launches) since the last read; synchronises."""
+        ms, n = ctypes.c_double(), ctypes.c_int32()
+        _lib.check(self._L.ragfin_profile_read(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return float(ms.value), int(n.value)
+
     def stats(self) -> dict:
         s = _lib.SearchStats()
         _lib.check(self._L.ragfin_last_search_stats(self._h, ctypes.byref(s)))
@@ -150,15 +165,24 @@ class Index:
                 "cand_per_query": s.cand_per_query}
 
 
-def merge_topk(ids, scores, parts: int, k: int, stream=None):
-    """Cross-shard reduce of exact hit lists: torch CUDA tensors ids int64 / scores fp32 [nq, parts*k]."""
+def merge_topk(ids, scores, parts: int, k: int, stream=None, out_ids=None, out_scores=None):
+    """Cross-shard reduce of exact hit lists (torch CUDA tensors, ids int64 / scores fp32).
+
+    Accepts either the all-gather layout [parts, nq, k] or a concatenation [nq, parts*k]."""
     import torch
     L = _lib.load()
-    nq = ids.shape[0]
-    assert ids.shape == (nq, parts * k) and scores.shape == (nq, parts * k)
     ids, scores = ids.contiguous(), scores.contiguous()
-    out_ids = torch.empty((nq, k), dtype=torch.int64, device=ids.device)
-    out_scores = torch.empty((nq, k), dtype=torch.float32, device=ids.device)
-    _lib.check(L.ragfin_merge_topk(ids.data_ptr(), scores.data_ptr(), nq, parts, k, out_ids.data_ptr(),
-                                   out_scores.data_ptr(), ids.device.index, _stream_ptr(stream)))
+    if ids.dim() == 3:
+        assert ids.shape[0] == parts and ids.shape[2] == k and scores.shape == ids.shape
+        nq, part_stride, query_stride = ids.shape[1], ids.shape[1] * k, k
+    else:
+        nq = ids.shape[0]
+        assert ids.shape == (nq, parts * k) and scores.shape == ids.shape
+        part_stride, query_stride = k, parts * k
+    if out_ids is None:
+        out_ids = torch.empty((nq, k), dtype=torch.int64, device=ids.device)
+    if out_scores is None:
+        out_scores = torch.empty((nq, k), dtype=torch.float32, device=ids.device)
+    _lib.check(L.ragfin_merge_topk(ids.data_ptr(), scores.data_ptr(), nq, parts, k, part_stride, query_stride,
+                                   out_ids.data_ptr(), out_scores.data_ptr(), ids.device.index, _stream_ptr(stream)))
     return out_ids, out_scores

@@ -1,0 +1,58 @@
+"""Row-sharded search over the GPUs of one box: one process per GPU, torch.distributed plumbing.
+
+Partition: rank r owns the contiguous rows [r * ceil(N / W), ...); its local row 0
+has global id `row0`, so "lower id wins" survives the merge.  Every rank searches its shard
+(each rank's hits are already EXACT and ordered), the per-rank [nq, k] hit lists are
+all-gathered (NCCL over NVLink on GPUs; gloo in the CPU tests) and every rank reduces the
+[W, nq, k] buffer to the global top-k.  This replaces the querynode -> proxy reduce a Milvus
+deployment of the reference would do over gRPC.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+
+def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row block of `rank`: (row0, n_local)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError(f"rank {rank} not in [0, {world})")
+    per = -(-n_rows // world)
+    row0 = min(rank * per, n_rows)
+    return row0, min(per, n_rows - row0)
+
+
+class ShardedSearcher:
+    """Search = local top-k on this rank's shard -> all-gather -> global reduce.
+
+    `local_search(queries, k) -> (ids, scores)` and `merge(ids, scores, parts, k)` are injected so
+    that the host logic can be exercised on CPU (gloo) with stand-ins; on a GPU box they are
+    `Index.search_device` and `ragfin_b200.merge_topk` (see `for_index`)."""
+
+    def __init__(self, local_search: Callable, merge: Callable, group=None):
+        import torch.distributed as dist
+        self._dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.local_search = local_search
+        self.merge = merge
+        self._gather_ids = None
+        self._gather_scores = None
+
+    @classmethod
+    def for_index(cls, index, group=None) -> "ShardedSearcher":
+        from .engine import merge_topk
+        return cls(index.search_device, merge_topk, group)
+
+    def search(self, queries, k: int):
+        import torch
+        ids, scores = self.local_search(queries, k)
+        if self.world == 1:
+            return ids, scores
+        shape = (self.world,) + tuple(ids.shape)
+        if self._gather_ids is None or tuple(self._gather_ids.shape) != shape or self._gather_ids.device != ids.device:
+            self._gather_ids = torch.empty(shape, dtype=ids.dtype, device=ids.device)
+            self._gather_scores = torch.empty(shape, dtype=scores.dtype, device=scores.device)
+        self._dist.all_gather_into_tensor(self._gather_ids, ids.contiguous(), group=self.group)
+        self._dist.all_gather_into_tensor(self._gather_scores, scores.contiguous(), group=self.group)
+        return self.merge(self._gather_ids, self._gather_scores, self.world, k)

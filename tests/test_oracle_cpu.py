@@ -138,3 +138,24 @@ def test_golden_chunk_collection(coracle):
         assert [g["chunks"][i]["id"] for i in ids[qi]] == want["top3_ids"]
         assert sc[qi].view(np.uint32).tolist() == want["top3_score_bits"]
     assert math.isfinite(float(sc.max()))
+
+
+def test_product_generator_matches_oracle_generator():
+    from ragfin_b200.synthetic import synth_rows
+    a = synth_rows(1234, 123456789, 700, 768, dup_every=7, zero_every=11)
+    b = O.synth_rows(1234, 123456789, 700, 768, dup_every=7, zero_every=11)
+    assert np.array_equal(a, b)
+
+
+def test_fast_cpu_port_within_1e5_of_canonical(coracle):
+    """The timed CPU baseline (faiss-style sgemv / blocked sgemm + topk) agrees with the canonical
+    oracle: same index sets on tie-free data and scores within 1e-5 relative."""
+    import torch
+    from oracle import fast_cpu
+    st = coracle.normalize_rows(O.synth_rows(31, 0, 70000, 384), "f32")
+    for nq in (3, 24):
+        q = O.synth_rows(32, 0, nq, 384)
+        wi, ws = coracle.cosine_topk(q, st, 10)
+        gi, gs = fast_cpu.fast_topk(torch.from_numpy(st), q, 10)
+        assert np.array_equal(np.sort(gi, axis=1), np.sort(wi, axis=1))
+        assert np.allclose(gs, ws, rtol=1e-5, atol=1e-7)
