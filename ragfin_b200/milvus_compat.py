@@ -1,0 +1,441 @@
+"""pymilvus-shaped front end over the B200 engine: the reference's operator API for the hot path.
+
+The reference reaches its vector store only through this subset of pymilvus 2.3.0
+(reference vector_rag_mcp/requirements.txt:2); each name below behaves like the pymilvus
+object the reference uses, so a maintainer switches with
+
+    from ragfin_b200.milvus_compat import connections, Collection, CollectionSchema, FieldSchema, DataType, utility
+
+  connections.connect                      retrieve.py:17, vector_rag_mcp/main.py:43, "chunking_storing (1).py":11
+  FieldSchema / CollectionSchema / DataType  "chunking_storing (1).py":14-28
+  utility.has_collection / drop_collection  "chunking_storing (1).py":25-26
+  Collection(name[, schema])               retrieve.py:18, "chunking_storing (1).py":28
+  .create_index(field, params)             "chunking_storing (1).py":29      (metric must be COSINE)
+  .insert(column-major data)               "chunking_storing (1).py":383-394
+  .flush() / .load()                       "chunking_storing (1).py":395-396, retrieve.py:19
+  .num_entities                            vector_rag_mcp/main.py:113,120,164, test_vector.py:29
+  .search(data, anns_field, param, limit, output_fields=)   retrieve.py:28-34, vector_rag_mcp/main.py:51-57,
+                                           "chunking_storing (1).py":411-417, graph_cons.py:275-281
+  .query(expr, output_fields=, limit=)     test_vector.py:35-39, graph_cons.py:308-311
+
+Hits expose .id, .distance, .score, .entity.<field> and .entity.get(field) exactly as the
+call sites read them (retrieve.py:39-43, graph_cons.py:287-292).  Scalar columns live on the
+host; only the embedding column goes to the GPU.  Row id = insertion ordinal; equal scores
+resolve to the earlier-inserted row.
+
+The engine is exact: index_type / nlist / nprobe are accepted and ignored.
+"""
+from __future__ import annotations
+
+import re
+import threading
+from enum import IntEnum
+from typing import Any, Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+
+MAX_LIMIT = 16384  # Milvus' cap on `limit`
+
+
+class MilvusException(Exception):
+    """Mirror of pymilvus.exceptions.MilvusException (code, message)."""
+
+    def __init__(self, code: int = 1, message: str = ""):
+        super().__init__(f"<MilvusException: (code={code}, message={message})>")
+        self.code, self.message = code, message
+
+
+class SchemaNotReadyException(MilvusException):
+    pass
+
+
+class ParamError(MilvusException):
+    pass
+
+
+class DataType(IntEnum):
+    NONE = 0
+    BOOL = 1
+    INT8 = 2
+    INT16 = 3
+    INT32 = 4
+    INT64 = 5
+    FLOAT = 10
+    DOUBLE = 11
+    STRING = 20
+    VARCHAR = 21
+    JSON = 23
+    BINARY_VECTOR = 100
+    FLOAT_VECTOR = 101
+
+
+class FieldSchema:
+    def __init__(self, name: str, dtype: DataType, description: str = "", **kwargs):
+        self.name, self.dtype, self.description = name, DataType(dtype), description
+        self.is_primary = bool(kwargs.get("is_primary", False))
+        self.auto_id = bool(kwargs.get("auto_id", False))
+        self.max_length = kwargs.get("max_length")
+        self.dim = kwargs.get("dim")
+        self.params = {k: v for k, v in kwargs.items() if k in ("max_length", "dim")}
+        if self.dtype == DataType.FLOAT_VECTOR and (not isinstance(self.dim, int) or self.dim < 1):
+            raise ParamError(message=f"FLOAT_VECTOR field {name!r} needs dim >= 1")
+
+    def __repr__(self):
+        return f"FieldSchema({self.name!r}, {self.dtype.name}, {self.params})"
+
+
+class CollectionSchema:
+    def __init__(self, fields: Sequence[FieldSchema], description: str = "", **kwargs):
+        self.fields, self.description = list(fields), description
+        names = [f.name for f in self.fields]
+        if len(set(names)) != len(names):
+            raise ParamError(message="duplicate field names")
+        prim = [f for f in self.fields if f.is_primary]
+        if len(prim) != 1:
+            raise SchemaNotReadyException(message="exactly one primary field is required")
+        vec = [f for f in self.fields if f.dtype == DataType.FLOAT_VECTOR]
+        if len(vec) != 1:
+            raise SchemaNotReadyException(message="exactly one FLOAT_VECTOR field is supported")
+        self.primary_field, self.vector_field = prim[0], vec[0]
+
+
+class _Connections:
+    """connections.connect("default", host=..., port=...): there is no server; the alias records
+    which CUDA device collections are created on (kwarg `device`, default 0)."""
+
+    def __init__(self):
+        self._alias: Dict[str, dict] = {}
+
+    def connect(self, alias: str = "default", **kwargs):
+        self._alias[alias] = dict(kwargs)
+
+    def disconnect(self, alias: str = "default"):
+        self._alias.pop(alias, None)
+
+    def has_connection(self, alias: str = "default") -> bool:
+        return alias in self._alias
+
+    def device(self, alias: str = "default") -> int:
+        return int(self._alias.get(alias, {}).get("device", 0))
+
+
+connections = _Connections()
+
+_REGISTRY: Dict[str, "_Store"] = {}
+_REG_LOCK = threading.Lock()
+
+# engine defaults for collections created through the shim (override per collection with kwargs)
+DEFAULTS = {"storage_dtype": "f32", "initial_capacity": 4096}
+
+
+def _default_index_factory(dim: int, dtype: str, capacity: int, device: int):
+    from .engine import Index
+    return Index(dim, dtype, capacity=capacity, device=device)
+
+
+class _Store:
+    """State of one named collection (what the Milvus server would hold)."""
+
+    def __init__(self, name, schema, storage_dtype, capacity, device, index_factory):
+        self.name, self.schema = name, schema
+        self.storage_dtype, self.capacity, self.device = storage_dtype, capacity, device
+        self.index_factory = index_factory
+        self.columns: Dict[str, list] = {f.name: [] for f in schema.fields if f.dtype != DataType.FLOAT_VECTOR}
+        self.raw: List[np.ndarray] = []       # fp32 embedding blocks as inserted (host copy)
+        self.pending: List[np.ndarray] = []   # inserted, not yet flushed to the device
+        self.n_inserted = 0
+        self.index = None
+        self.metric: Optional[str] = None
+        self.pk_to_row: Dict[Any, int] = {}
+        self.lock = threading.RLock()
+
+    def flush(self):
+        with self.lock:
+            if not self.pending:
+                return
+            need = self.n_inserted
+            if self.index is None or need > self.capacity:
+                while self.capacity < need:
+                    self.capacity *= 2
+                if self.index is not None:
+                    self.index.close()
+                self.index = self.index_factory(self.schema.vector_field.dim, self.storage_dtype, self.capacity, self.device)
+                blocks = self.raw            # re-ingest everything from the host copy
+            else:
+                blocks = self.pending
+            for b in blocks:
+                self.index.add(b)
+            self.pending = []
+
+
+class _Utility:
+    def has_collection(self, name: str, using: str = "default") -> bool:
+        return name in _REGISTRY
+
+    def drop_collection(self, name: str, using: str = "default") -> None:
+        with _REG_LOCK:
+            st = _REGISTRY.pop(name, None)
+        if st is not None and st.index is not None:
+            st.index.close()
+
+    def list_collections(self, using: str = "default") -> List[str]:
+        return sorted(_REGISTRY)
+
+
+utility = _Utility()
+
+
+class Entity:
+    """hit.entity: attribute access (retrieve.py:40-42) and .get() (graph_cons.py:288-291)."""
+
+    def __init__(self, fields: Dict[str, Any]):
+        self.__dict__["fields"] = fields
+
+    def __getattr__(self, name):
+        try:
+            return self.__dict__["fields"][name]
+        except KeyError:
+            raise MilvusException(message=f"Field {name} is not in return entity") from None
+
+    def get(self, name, default=None):
+        return self.__dict__["fields"].get(name, default)
+
+    def to_dict(self):
+        return dict(self.__dict__["fields"])
+
+    def __repr__(self):
+        return f"Entity({self.__dict__['fields']!r})"
+
+
+class Hit:
+    __slots__ = ("id", "distance", "entity")
+
+    def __init__(self, pk, distance: float, entity: Entity):
+        self.id, self.distance, self.entity = pk, distance, entity
+
+    @property
+    def score(self) -> float:
+        return self.distance
+
+    def to_dict(self):
+        return {"id": self.id, "distance": self.distance, "entity": self.entity.to_dict()}
+
+    def __repr__(self):
+        return f"id: {self.id}, distance: {self.distance}, entity: {self.entity.to_dict()}"
+
+
+class Hits(list):
+    @property
+    def ids(self):
+        return [h.id for h in self]
+
+    @property
+    def distances(self):
+        return [h.distance for h in self]
+
+
+class SearchResult(list):
+    """results[0] is the Hits of the first query (retrieve.py:38)."""
+
+
+class MutationResult:
+    def __init__(self, primary_keys):
+        self.primary_keys = list(primary_keys)
+        self.insert_count = len(self.primary_keys)
+
+
+_EXPR_IN = re.compile(r"^\s*(\w+)\s+in\s+\[(.*)\]\s*$", re.S)
+_EXPR_EQ = re.compile(r"^\s*(\w+)\s*==\s*(.+?)\s*$", re.S)
+
+
+def _parse_literal(tok: str):
+    tok = tok.strip()
+    if len(tok) >= 2 and tok[0] == tok[-1] and tok[0] in "\"'":
+        return tok[1:-1]
+    try:
+        return int(tok)
+    except ValueError:
+        return float(tok)
+
+
+class Collection:
+    def __init__(self, name: str, schema: Optional[CollectionSchema] = None, using: str = "default", **kwargs):
+        self.name, self._using = name, using
+        with _REG_LOCK:
+            st = _REGISTRY.get(name)
+            if st is None:
+                if schema is None:
+                    raise SchemaNotReadyException(
+                        message=f"Collection '{name}' not exist, or you can pass in schema to create one.")
+                st = _Store(name, schema,
+                            kwargs.get("storage_dtype", DEFAULTS["storage_dtype"]),
+                            int(kwargs.get("initial_capacity", DEFAULTS["initial_capacity"])),
+                            int(kwargs.get("device", connections.device(using))),
+                            kwargs.get("index_factory", _default_index_factory))
+                _REGISTRY[name] = st
+        self._st = st
+
+    # -- schema / index ---------------------------------------------------------------
+    @property
+    def schema(self) -> CollectionSchema:
+        return self._st.schema
+
+    @property
+    def description(self) -> str:
+        return self._st.schema.description
+
+    def create_index(self, field_name: str, index_params: Optional[dict] = None, **kwargs):
+        if field_name != self._st.schema.vector_field.name:
+            raise MilvusException(message=f"cannot create index on non-vector field {field_name!r}")
+        metric = str((index_params or {}).get("metric_type", "COSINE")).upper()
+        if metric != "COSINE":
+            raise MilvusException(message=f"metric_type {metric} is not supported: this engine serves COSINE only")
+        self._st.metric = metric      # index_type / nlist are irrelevant: the search is exact
+
+    def has_index(self, **kwargs) -> bool:
+        return self._st.metric is not None
+
+    # -- ingest -----------------------------------------------------------------------
+    def insert(self, data, partition_name=None, timeout=None, **kwargs) -> MutationResult:
+        st = self._st
+        fields = st.schema.fields
+        if isinstance(data, dict):
+            data = [data]
+        if len(data) > 0 and isinstance(data[0], dict):          # row-major list of dicts
+            cols = [[row[f.name] for row in data] for f in fields]
+        else:                                                     # column-major, schema field order
+            cols = list(data)
+        if len(cols) != len(fields):
+            raise ParamError(message=f"expected {len(fields)} columns ({[f.name for f in fields]}), got {len(cols)}")
+        n = len(cols[0])
+        if any(len(c) != n for c in cols):
+            raise ParamError(message="all columns must have the same number of rows")
+        vi = fields.index(st.schema.vector_field)
+        emb = np.ascontiguousarray(cols[vi], dtype=np.float32)
+        if n and (emb.ndim != 2 or emb.shape != (n, st.schema.vector_field.dim)):
+            raise ParamError(message=f"embedding column must be [{n}, {st.schema.vector_field.dim}], got {emb.shape}")
+        pk_name = st.schema.primary_field.name
+        pks = list(cols[fields.index(st.schema.primary_field)])
+        with st.lock:
+            for pk in pks:
+                if pk in st.pk_to_row:
+                    raise MilvusException(message=f"duplicate primary key {pk!r}")
+            for f, c in zip(fields, cols):
+                if f.dtype == DataType.FLOAT_VECTOR:
+                    continue
+                if f.dtype == DataType.VARCHAR and f.max_length:
+                    for v in c:
+                        if len(str(v)) > f.max_length:
+                            raise MilvusException(message=f"length of varchar field {f.name} exceeds max length {f.max_length}")
+                st.columns[f.name].extend(c)
+            for j, pk in enumerate(pks):
+                st.pk_to_row[pk] = st.n_inserted + j
+            if n:
+                st.raw.append(emb)
+                st.pending.append(emb)
+            st.n_inserted += n
+        assert pk_name in st.columns
+        return MutationResult(pks)
+
+    def flush(self, timeout=None, **kwargs):
+        self._st.flush()
+
+    def load(self, partition_names=None, replica_number=1, timeout=None, **kwargs):
+        self._st.flush()
+
+    def release(self, timeout=None, **kwargs):
+        pass
+
+    def drop(self, timeout=None, **kwargs):
+        utility.drop_collection(self.name)
+
+    @property
+    def num_entities(self) -> int:
+        st = self._st
+        return st.n_inserted - sum(len(b) for b in st.pending)
+
+    @property
+    def is_empty(self) -> bool:
+        return self.num_entities == 0
+
+    # -- hot path ---------------------------------------------------------------------
+    def search(self, data, anns_field: str, param: dict, limit: int, expr: Optional[str] = None,
+               partition_names=None, output_fields: Optional[List[str]] = None, timeout=None,
+               round_decimal: int = -1, **kwargs) -> SearchResult:
+        st = self._st
+        if anns_field != st.schema.vector_field.name:
+            raise MilvusException(message=f"failed to get field schema by name: fieldName({anns_field}) not found")
+        metric = str((param or {}).get("metric_type", st.metric or "COSINE")).upper()
+        if metric != "COSINE":
+            raise MilvusException(message=f"metric type not match: expected=COSINE, actual={metric}")
+        if not isinstance(limit, (int, np.integer)) or not 1 <= int(limit) <= MAX_LIMIT:
+            raise MilvusException(message=f"`limit` value {limit} is illegal: topk [1, {MAX_LIMIT}]")
+        if expr:
+            raise MilvusException(message="filtered search (expr) is not supported yet")
+        out_fields = list(output_fields or [])
+        for f in out_fields:
+            if f not in st.columns:
+                raise MilvusException(message=f"field {f} not exist")
+        q = np.ascontiguousarray(data, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != st.schema.vector_field.dim:
+            raise MilvusException(message=f"vector dimension mismatch: expected {st.schema.vector_field.dim}, got {q.shape}")
+        with st.lock:
+            st.flush()
+            res = SearchResult()
+            if st.index is None or st.n_inserted == 0:
+                for _ in range(q.shape[0]):
+                    res.append(Hits())
+                return res
+            ids, scores = st.index.search(q, int(limit))
+            pk_col = st.columns[st.schema.primary_field.name]
+            for qi in range(q.shape[0]):
+                hits = Hits()
+                for row, sc in zip(ids[qi].tolist(), scores[qi].tolist()):
+                    if row < 0:
+                        break
+                    d = float(sc) if round_decimal < 0 else round(float(sc), round_decimal)
+                    hits.append(Hit(pk_col[row], d, Entity({f: st.columns[f][row] for f in out_fields})))
+                res.append(hits)
+            return res
+
+    # -- scalar lookups (host side; "next" row N1) --------------------------------------
+    def query(self, expr: str = "", output_fields: Optional[List[str]] = None, partition_names=None,
+              timeout=None, limit: Optional[int] = None, offset: int = 0, **kwargs) -> List[dict]:
+        st = self._st
+        pk_name = st.schema.primary_field.name
+        out_fields = list(output_fields or [])
+        if pk_name not in out_fields:
+            out_fields = [pk_name] + out_fields
+        for f in out_fields:
+            if f not in st.columns:
+                raise MilvusException(message=f"field {f} not exist")
+        with st.lock:
+            n = self.num_entities
+            expr = (expr or "").strip()
+            if expr == "":
+                if limit is None:
+                    raise MilvusException(message="empty expression should be used with limit")
+                rows = list(range(n))
+            else:
+                m_in, m_eq = _EXPR_IN.match(expr), _EXPR_EQ.match(expr)
+                if m_in:
+                    field = m_in.group(1)
+                    body = m_in.group(2).strip()
+                    wanted = [_parse_literal(t) for t in re.findall(r"\"[^\"]*\"|'[^']*'|[^,\s]+", body)] if body else []
+                elif m_eq:
+                    field, wanted = m_eq.group(1), [_parse_literal(m_eq.group(2))]
+                else:
+                    raise MilvusException(message=f"cannot parse expression: {expr}")
+                if field not in st.columns:
+                    raise MilvusException(message=f"field {field} not exist")
+                if field == pk_name:
+                    rows = sorted(r for r in (st.pk_to_row.get(w) for w in wanted) if r is not None and r < n)
+                else:
+                    ws = set(wanted)
+                    rows = [r for r in range(n) if st.columns[field][r] in ws]
+            rows = rows[offset:]
+            if limit is not None:
+                rows = rows[:int(limit)]
+            return [{f: st.columns[f][r] for f in out_fields} for r in rows]

@@ -49,10 +49,12 @@ class ShardedSearcher:
         ids, scores = self.local_search(queries, k)
         if self.world == 1:
             return ids, scores
-        shape = (self.world,) + tuple(ids.shape)
+        nq = ids.shape[0]
+        shape = (self.world * nq, k)          # concatenation along dim 0 == [world][nq][k] in memory
         if self._gather_ids is None or tuple(self._gather_ids.shape) != shape or self._gather_ids.device != ids.device:
             self._gather_ids = torch.empty(shape, dtype=ids.dtype, device=ids.device)
             self._gather_scores = torch.empty(shape, dtype=scores.dtype, device=scores.device)
         self._dist.all_gather_into_tensor(self._gather_ids, ids.contiguous(), group=self.group)
         self._dist.all_gather_into_tensor(self._gather_scores, scores.contiguous(), group=self.group)
-        return self.merge(self._gather_ids, self._gather_scores, self.world, k)
+        return self.merge(self._gather_ids.view(self.world, nq, k), self._gather_scores.view(self.world, nq, k),
+                          self.world, k)

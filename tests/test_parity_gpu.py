@@ -181,3 +181,40 @@ def test_errors_are_loud():
         idx.search(np.zeros((1, 383), np.float32), 3)    # wrong dim
     with pytest.raises(ValueError):
         idx.search(np.zeros((1, 384), np.float32), 0)    # top_k < 1
+
+
+def test_reference_call_sites_through_the_shim(coracle):
+    """Ingest + search exactly as "chunking_storing (1).py":11-29,376-417 and vector_rag_mcp/main.py:48-70
+    do, through the pymilvus-shaped shim on the real engine."""
+    from ragfin_b200 import milvus_compat as mc
+    from ragfin_b200.vector_rag import HashingEncoder, VectorRAG
+    with open(os.path.join(GOLDEN, "fin_chunks_collection.json")) as f:
+        g = json.load(f)
+    F, D = mc.FieldSchema, mc.DataType
+    fields = [F("id", D.VARCHAR, max_length=100, is_primary=True), F("text", D.VARCHAR, max_length=4000),
+              F("embedding", D.FLOAT_VECTOR, dim=384), F("period", D.VARCHAR, max_length=20),
+              F("chunk_type", D.VARCHAR, max_length=30), F("statement_type", D.VARCHAR, max_length=30),
+              F("primary_value", D.DOUBLE)]
+    mc.connections.connect("default", host="localhost", port="19530")
+    if mc.utility.has_collection("fin_chunks"):
+        mc.utility.drop_collection("fin_chunks")
+    col = mc.Collection("fin_chunks", mc.CollectionSchema(fields, "Financial complete context chunks"))
+    col.create_index("embedding", {"index_type": "IVF_FLAT", "metric_type": "COSINE", "params": {"nlist": 128}})
+    ch = g["chunks"]
+    emb = O.synth_rows(g["seed"], 0, 16, 384)
+    col.insert([[c["id"] for c in ch], [c["id"] + " text" for c in ch], emb.tolist(), [c["period"] for c in ch],
+                [c["chunk_type"] for c in ch], ["consolidated"] * 16, [1.0] * 16])
+    col.flush()
+    col.load()
+    assert col.num_entities == 16
+    q = O.synth_rows(g["seed"] + 1, 0, 5, 384)
+    for qi, want in enumerate(g["queries"]):
+        hits = col.search(q[qi:qi + 1], "embedding", {"metric_type": "COSINE"}, 3, output_fields=["text", "period", "chunk_type"])[0]
+        assert [h.id for h in hits] == want["top3_ids"]
+        assert [np.float32(h.score).view(np.uint32).item() for h in hits] == want["top3_score_bits"]
+    allhits = col.search(q[:1], "embedding", {"metric_type": "COSINE"}, limit=1000, output_fields=["id"])[0]
+    assert len(allhits) == 16
+    rag = VectorRAG(HashingEncoder(384), collection=col)
+    env = rag.search_vectors("net profit Q1", 3)
+    assert env["status"] == "success" and env["result_count"] == 3
+    mc.utility.drop_collection("fin_chunks")

@@ -1,0 +1,184 @@
+"""CPU suite for the reference-shaped host layer (pymilvus-compatible shim + VectorRAG mirror).
+The engine is replaced by an oracle-backed stand-in through the shim's index_factory hook, so the
+host logic (columns, hits, query expressions, envelopes) is what is under test here."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ragfin_oracle as O
+from ragfin_b200 import milvus_compat as mc
+from ragfin_b200.vector_rag import HashingEncoder, VectorRAG, merge_hybrid, validate_search_request
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+class OracleIndex:
+    """Stand-in with the `Index` surface the shim uses (add / search / close)."""
+
+    def __init__(self, dim, dtype, capacity, device):
+        self.dim, self.dtype, self.capacity = dim, dtype, capacity
+        self.rows = np.zeros((0, dim), np.float32)
+        self.closed = False
+
+    def add(self, rows):
+        assert len(self.rows) + len(rows) <= self.capacity
+        self.rows = np.concatenate([self.rows, O.normalize_rows(rows, self.dtype)])
+
+    def search(self, q, k):
+        return O.cosine_topk(q, self.rows, k)
+
+    def close(self):
+        self.closed = True
+
+
+def reference_fields(dim=384):
+    F, D = mc.FieldSchema, mc.DataType
+    return [F("id", D.VARCHAR, max_length=100, is_primary=True), F("text", D.VARCHAR, max_length=4000),
+            F("embedding", D.FLOAT_VECTOR, dim=dim), F("period", D.VARCHAR, max_length=20),
+            F("chunk_type", D.VARCHAR, max_length=30), F("statement_type", D.VARCHAR, max_length=30),
+            F("primary_value", D.DOUBLE)]
+
+
+def build_collection(name="fin_chunks", factory=OracleIndex, **kw):
+    """The reference's ingest script, "chunking_storing (1).py":11-29 and 376-396, on the golden chunk metadata."""
+    with open(os.path.join(GOLDEN, "fin_chunks_collection.json")) as f:
+        g = json.load(f)
+    mc.connections.connect("default", host="localhost", port="19530")
+    if mc.utility.has_collection(name):
+        mc.utility.drop_collection(name)
+    col = mc.Collection(name, mc.CollectionSchema(reference_fields(), "Financial complete context chunks"),
+                        index_factory=factory, **kw)
+    col.create_index("embedding", {"index_type": "IVF_FLAT", "metric_type": "COSINE", "params": {"nlist": 128}})
+    chunks = g["chunks"]
+    texts = [f"{c['period']} {c['chunk_type']} text of {c['id']}" for c in chunks]
+    emb = O.synth_rows(g["seed"], 0, 16, 384)
+    data = [[c["id"] for c in chunks], texts, emb.tolist(), [c["period"] for c in chunks],
+            [c["chunk_type"] for c in chunks], ["consolidated"] * 16, [float(i) for i in range(16)]]
+    mr = col.insert(data)
+    assert mr.insert_count == 16
+    assert col.num_entities == 0          # pymilvus counts flushed rows
+    col.flush()
+    col.load()
+    return col, g
+
+
+def test_ingest_and_search_like_the_reference():
+    col, g = build_collection()
+    assert col.num_entities == 16
+    q = O.synth_rows(g["seed"] + 1, 0, 5, 384)
+    for qi, want in enumerate(g["queries"]):
+        res = col.search(q[qi:qi + 1], "embedding", {"metric_type": "COSINE"}, 3,
+                         output_fields=["text", "period", "chunk_type"])
+        hits = res[0]
+        assert [h.id for h in hits] == want["top3_ids"]
+        assert [np.float32(h.score).view(np.uint32).item() for h in hits] == want["top3_score_bits"]
+        assert hits[0].distance == hits[0].score and hits[0].entity.period.startswith("Q")
+        assert hits[0].entity.get("chunk_type") == hits[0].entity.chunk_type
+        with pytest.raises(mc.MilvusException):
+            hits[0].entity.statement_type     # not requested in output_fields
+
+
+def test_limit_keyword_and_limit_above_n_returns_all_rows():
+    col, g = build_collection()
+    q = O.synth_rows(g["seed"] + 1, 0, 1, 384)
+    res = col.search(q, "embedding", {"metric_type": "COSINE"}, limit=1000, output_fields=["id", "text", "period", "chunk_type"])
+    assert len(res) == 1 and len(res[0]) == 16
+    sc = [h.score for h in res[0]]
+    assert sc == sorted(sc, reverse=True)
+    assert sorted(h.entity.get("id") for h in res[0]) == sorted(c["id"] for c in g["chunks"])
+
+
+def test_search_argument_errors():
+    col, g = build_collection()
+    q = np.zeros((1, 384), np.float32)
+    for bad in (0, 16385, "3"):
+        with pytest.raises(mc.MilvusException):
+            col.search(q, "embedding", {"metric_type": "COSINE"}, bad)
+    with pytest.raises(mc.MilvusException):
+        col.search(q, "embedding", {"metric_type": "L2"}, 3)
+    with pytest.raises(mc.MilvusException):
+        col.search(q, "vector", {"metric_type": "COSINE"}, 3)
+    with pytest.raises(mc.MilvusException):
+        col.search(np.zeros((1, 383), np.float32), "embedding", {"metric_type": "COSINE"}, 3)
+    with pytest.raises(mc.MilvusException):
+        col.search(q, "embedding", {"metric_type": "COSINE"}, 3, output_fields=["nope"])
+    with pytest.raises(mc.MilvusException):
+        col.create_index("embedding", {"metric_type": "L2"})
+
+
+def test_query_expressions():
+    col, g = build_collection()
+    rows = col.query(expr="", limit=3, output_fields=["id", "period", "chunk_type", "statement_type"])   # test_vector.py:35-39
+    assert [r["id"] for r in rows] == [c["id"] for c in g["chunks"][:3]]
+    ids = [g["chunks"][5]["id"], g["chunks"][2]["id"], "missing"]
+    expr = f"id in {str(ids)}".replace("'", '"')                                                        # graph_cons.py:306-311
+    rows = col.query(expr=expr, output_fields=["id", "text", "period", "chunk_type"])
+    assert [r.get("id") for r in rows] == [g["chunks"][2]["id"], g["chunks"][5]["id"]]
+    rows = col.query(expr='period == "Q2_FY2024"', output_fields=["chunk_type"])
+    assert len(rows) == 4
+    with pytest.raises(mc.MilvusException):
+        col.query(expr="")
+    with pytest.raises(mc.MilvusException):
+        col.query(expr="id like 'x%'")
+
+
+def test_open_existing_and_missing_collection():
+    build_collection("fin_chunks")
+    again = mc.Collection("fin_chunks")
+    again.load()
+    assert again.num_entities == 16
+    with pytest.raises(mc.SchemaNotReadyException):
+        mc.Collection("does_not_exist")
+    mc.utility.drop_collection("fin_chunks")
+    assert not mc.utility.has_collection("fin_chunks")
+
+
+def test_growth_reingests_from_host_copy_and_duplicate_pk():
+    made = []
+
+    def factory(*a):
+        made.append(OracleIndex(*a))
+        return made[-1]
+
+    mc.utility.drop_collection("grow")
+    col = mc.Collection("grow", mc.CollectionSchema(reference_fields(64)), index_factory=factory, initial_capacity=4)
+    x = O.synth_rows(5, 0, 11, 64)
+    for a, b in ((0, 3), (3, 4), (4, 11)):
+        col.insert([[f"c{i}" for i in range(a, b)], ["t"] * (b - a), x[a:b], ["p"] * (b - a), ["k"] * (b - a),
+                    ["s"] * (b - a), [0.0] * (b - a)])
+        col.flush()
+    assert len(made) == 2 and made[0].closed and made[1].capacity == 16
+    assert np.array_equal(made[1].rows, O.normalize_rows(x, "f32"))
+    with pytest.raises(mc.MilvusException):
+        col.insert([["c3"], ["t"], x[:1], ["p"], ["k"], ["s"], [0.0]])
+    res = col.search(x[7:8] * 3.0, "embedding", {"metric_type": "COSINE"}, 1)
+    assert res[0][0].id == "c7" and abs(res[0][0].score - 1.0) < 1e-6
+
+
+def test_vector_rag_mirror_and_tool_envelope():
+    col, g = build_collection()
+    rag = VectorRAG(HashingEncoder(384), collection=col)
+    ctx = rag.search("net profit Q1", top_k=3)                                  # test_vector.py:97-100
+    assert [c["rank"] for c in ctx] == [1, 2, 3]
+    assert set(ctx[0]) == {"rank", "text", "period", "chunk_type", "statement_type", "primary_value", "score"}
+    assert isinstance(ctx[0]["score"], float) and ctx[0]["score"] >= ctx[1]["score"] >= ctx[2]["score"]
+    env = rag.search_vectors("net profit Q1", 3)
+    assert env["status"] == "success" and env["result_count"] == 3 and env["results"] == ctx
+    bad = rag.search_vectors("net profit Q1", 0)
+    assert bad["status"] == "error" and "limit" in bad["message"] and bad["query"] == "net profit Q1"
+    assert rag.get_collection_stats() == {"status": "success", "collection_name": "fin_chunks", "total_chunks": 16}
+    tup = rag.retrieve_contexts("net profit Q1", top_k=5)
+    assert len(tup) == 5 and tup[0][0] == ctx[0]["text"]
+    hv = rag.hybrid_vector_chunks("net profit Q1")
+    assert len(hv) == 16 and hv[0]["id"] in [c["id"] for c in g["chunks"]]
+    merged = merge_hybrid(hv[:2], [{"id": hv[1]["id"], "score": 1.0}, {"id": "g1", "score": 1.0}])
+    assert [m["id"] for m in merged] == [hv[0]["id"], hv[1]["id"], "g1"]
+
+
+def test_rest_request_bounds():
+    assert validate_search_request("net profit Q1") == 3
+    for q, k in (("abc", 3), ("net profit", 0), ("net profit", 21)):
+        with pytest.raises(ValueError):
+            validate_search_request(q, k)
