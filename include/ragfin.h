@@ -121,6 +121,14 @@ int ragfin_last_search_stats(ragfin_t* h, ragfin_search_stats* out);
 int ragfin_profile(ragfin_t* h, int32_t enable);
 int ragfin_profile_read(ragfin_t* h, double* total_ms, int32_t* launches);
 
+/* Dispatch knob: query batches of at least `min_nq` rows take the tcgen05 tensor-core path, smaller
+ * ones the HBM-bound scan (default 9).  Both paths return identical results. */
+int ragfin_set_gemm_min_batch(ragfin_t* h, int32_t min_nq);
+
+/* Test hook: raw (approximate, fp32-accumulated) tensor-core scores of nq queries against every
+ * stored row, out_scores_dev [nq, count] device memory.  Validates the TMA / tcgen05 plumbing. */
+int ragfin_debug_gemm_scores(ragfin_t* h, const float* q_dev, int32_t nq, float* out_scores_dev, void* stream);
+
 void ragfin_destroy(ragfin_t* h);
 
 const char* ragfin_last_error(void);

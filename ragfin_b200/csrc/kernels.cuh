@@ -214,7 +214,7 @@ scan_topk_kernel(const void* __restrict__ data, int64_t n_rows, int ld, const fl
 // Merge `G` descending key lists of length kp into FW per-warp lists, then one sort.
 // wl: shared [kFinWarps][kp].  On return (after __syncthreads) wl[0..kp) is the top-kp.
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ void merge_lists(const u64* __restrict__ src, int G, int kp, u64* wl) {
+__device__ __forceinline__ void merge_lists(const u64* __restrict__ src, int G, int kp, u64* wl, bool sorted_lists) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u64* mine = wl + (size_t)warp * kp;
     for (int i = lane; i < kp; i += kWarp) mine[i] = 0;
@@ -231,7 +231,7 @@ __device__ __forceinline__ void merge_lists(const u64* __restrict__ src, int G, 
                 const u64 bk = __shfl_sync(kFull, key, b);
                 if (bk > mine[kp - 1]) warp_list_insert(mine, kp, bk, lane);
             }
-            if (hits != kFull) break;  // list is sorted: nothing further can qualify
+            if (sorted_lists && hits != kFull) break;  // sorted list: nothing further can qualify
         }
     }
     __syncthreads();
@@ -256,7 +256,7 @@ __device__ __forceinline__ double rescore_row(const void* data, int64_t row, int
 template <bool EXACT_IN>
 __global__ void __launch_bounds__(kFinThreads)
 finalize_kernel(const u64* __restrict__ cand, int G, int kp, const void* __restrict__ data, int dt,
-                int64_t n_rows, int scanned, int ld, const float* __restrict__ qhat, float eps_const,
+                int64_t n_rows, int scanned, int sorted_lists, int ld, const float* __restrict__ qhat, float eps_const,
                 const float* __restrict__ eps_q, int k, int64_t id_base, int64_t* __restrict__ out_ids,
                 float* __restrict__ out_scores, int* __restrict__ flags, int* __restrict__ flag_count) {
     extern __shared__ __align__(16) u64 fsm[];  // [kFinWarps][kp] merge lists, then [kp] exact keys
@@ -264,7 +264,7 @@ finalize_kernel(const u64* __restrict__ cand, int G, int kp, const void* __restr
     if (EXACT_IN && flags[q] == 0) return;
     u64* wl = fsm;
     u64* ex = fsm + (size_t)kFinWarps * kp;
-    merge_lists(cand + (size_t)q * G * kp, G, kp, wl);
+    merge_lists(cand + (size_t)q * G * kp, G, kp, wl, sorted_lists != 0);
 
     const int keff = (int64_t)k < n_rows ? k : (int)n_rows;
     const u64* fin = wl;

@@ -9,6 +9,7 @@
 
 #include "../../include/ragfin.h"
 #include "kernels.cuh"
+#include "gemm.cuh"
 
 using namespace rfk;
 
@@ -49,7 +50,8 @@ struct ragfin {
     void* data = nullptr;  // [capacity, ld] storage, row-major, L2-normalised
     std::mutex mu;
     // workspace (grow-only)
-    Buf qhat, cand, cand_e, flags, stage_q, stage_ids, stage_scores, add_stage;
+    Buf qhat, q16, eps_q, gtau, cand, cand_e, flags, stage_q, stage_ids, stage_scores, add_stage;
+    int gemm_min_nq = 9;      // query batches of at least this many rows take the tcgen05 path
     cudaEvent_t last_done = nullptr;
     ragfin_search_stats stats = {0, 0, 0, 0};
     // measurement hook (ragfin_profile): event pairs around the dominant kernel
@@ -151,7 +153,7 @@ extern "C" void ragfin_destroy(ragfin_t* h) {
     if (!h) return;
     DeviceGuard g(h->device);
     (void)cudaDeviceSynchronize();
-    Buf* bufs[] = {&h->qhat, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage};
+    Buf* bufs[] = {&h->qhat, &h->q16, &h->eps_q, &h->gtau, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage};
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->data) cudaFree(h->data);
@@ -320,7 +322,144 @@ static int cand_per_query(int k) {
 // fp32 rounding of the exact score and one ulp so that a tie after rounding cannot hide a row.
 static float eps_fp32_accumulate(int ld) { return (float)((ld + 64) * 5.9604644775390625e-08 * 1.0625 + 4.76837158203125e-07); }
 
-static const int kMaxQueryBatch = 256;  // queries per pass through the pipeline (bounds the workspace)
+static const int kMaxQueryBatch = 4096;  // queries per pass through the pipeline (bounds the workspace)
+
+// ------------------------------------------------------------------------------
+// K3 host side: tensor maps (driver entry point, no -lcuda), slice plan, launch
+// ------------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn get_encode_tiled() {
+    static encode_tiled_fn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (encode_tiled_fn)p;
+        else
+            (void)cudaGetLastError();
+    });
+    return fn;
+}
+
+// [rows, ld] row-major matrix of `dtype`; box = 128 bytes of K x box_rows rows, 128-byte swizzle, zero OOB fill
+static int make_map(CUtensorMap* map, int dtype, const void* base, int64_t rows, int ld, int box_rows) {
+    encode_tiled_fn enc = get_encode_tiled();
+    if (!enc) return fail(RAGFIN_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const CUtensorMapDataType dt = dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                   : dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * esize(dtype)};
+    const cuuint32_t box[2] = {(cuuint32_t)(kGKBytes / esize(dtype)), (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RAGFIN_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+struct GemmPlan {
+    int QT, S, stages, grid;
+    int64_t rows_per_slice;
+};
+
+// Items are (query tile, slice).  Pick the number of waves w (items per CTA) whose slice count S = floor(SMs*w/QT)
+// leaves the fewest CTAs idle, with at least one 256-row tile per slice.
+static GemmPlan plan_gemm(int nq, int64_t n, int num_sms, int kp) {
+    GemmPlan p;
+    p.QT = (nq + kGM - 1) / kGM;
+    const int64_t n_tiles = (n + kGN - 1) / kGN;
+    double best = 1e300;
+    int bestS = 1;
+    for (int w = 1; w <= 8; ++w) {
+        int64_t S = (int64_t)num_sms * w / p.QT;
+        if (S < 1) S = 1;
+        if (S > n_tiles) S = n_tiles;
+        const int64_t tps = (n_tiles + S - 1) / S;
+        S = (n_tiles + tps - 1) / tps;
+        const int64_t items = (int64_t)p.QT * S;
+        const double cost = (double)((items + num_sms - 1) / num_sms) * (double)tps + 0.02 * w;
+        if (cost < best) { best = cost; bestS = (int)S; }
+    }
+    const int64_t tps = (n_tiles + bestS - 1) / bestS;
+    p.S = (int)((n_tiles + tps - 1) / tps);
+    p.rows_per_slice = tps * kGN;
+    p.stages = kp <= 32 ? 4 : kp <= 64 ? 3 : 2;
+    const int64_t items = (int64_t)p.QT * p.S;
+    p.grid = (int)(items < num_sms ? items : num_sms);
+    return p;
+}
+
+static bool gemm_supported(const ragfin* h, int kp) { return kp <= 128 && h->count > 0; }
+
+// Scores the nb normalised queries in h->qhat against the corpus on the tensor cores.  Fills
+// h->cand as [nb][S][kp] (unsorted lists) and h->eps_q; returns S through *G.  dump != null: write raw scores instead.
+static int run_gemm(ragfin* h, int nb, int kp, int* G, float* dump, cudaStream_t st) {
+    int rc;
+    const int64_t n = h->count;
+    const GemmPlan p = plan_gemm(nb, n, h->num_sms, kp);
+    const float* qhat = (const float*)h->qhat.p;
+    const void* a_base = qhat;
+    if ((rc = ensure(h->eps_q, (size_t)nb * sizeof(float)))) return rc;
+    if (h->dtype != 0) {
+        if ((rc = ensure(h->q16, (size_t)nb * h->ld * 2))) return rc;
+        const int wpb = 8;
+        if (h->dtype == 1)
+            qconv_kernel<1><<<(nb + wpb - 1) / wpb, wpb * 32, 0, st>>>(qhat, nb, h->ld, (__nv_bfloat16*)h->q16.p, (float*)h->eps_q.p);
+        else
+            qconv_kernel<2><<<(nb + wpb - 1) / wpb, wpb * 32, 0, st>>>(qhat, nb, h->ld, (__half*)h->q16.p, (float*)h->eps_q.p);
+        CU_TRY(cudaGetLastError());
+        h->stats.launches++;
+        a_base = h->q16.p;
+    } else {
+        CU_TRY(cudaMemsetAsync(h->eps_q.p, 0, (size_t)nb * sizeof(float), st));
+    }
+    CUtensorMap tmA, tmB;
+    if ((rc = make_map(&tmA, h->dtype, a_base, nb, h->ld, kGM))) return rc;
+    if ((rc = make_map(&tmB, h->dtype, h->data, n, h->ld, kGN))) return rc;
+    if (!dump) {
+        if ((rc = ensure(h->cand, (size_t)nb * p.S * kp * sizeof(u64)))) return rc;
+    }
+    GemmArgs a;
+    a.idesc = make_idesc(h->dtype == 0 ? 2 : h->dtype == 1 ? 1 : 0);
+    a.k_elems = kGKBytes / (int)esize(h->dtype);
+    a.num_kblocks = (h->ld + a.k_elems - 1) / a.k_elems;
+    a.nq = nb;
+    a.n_rows = n;
+    a.QT = p.QT;
+    a.S = p.S;
+    a.rows_per_slice = p.rows_per_slice;
+    a.stages = p.stages;
+    a.kp = kp;
+    if ((rc = ensure(h->gtau, (size_t)nb * sizeof(uint32_t)))) return rc;
+    CU_TRY(cudaMemsetAsync(h->gtau.p, 0, (size_t)nb * sizeof(uint32_t), st));
+    a.cand = (u64*)h->cand.p;
+    a.gtau = (uint32_t*)h->gtau.p;
+    a.dump = dump;
+    const size_t smem = gemm_smem_bytes(p.stages, kp);
+    typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const GemmArgs);
+    gemm_fn fn = h->dtype == 0 ? (dump ? gemm_topk_kernel<1, true> : gemm_topk_kernel<1, false>)
+                               : (dump ? gemm_topk_kernel<0, true> : gemm_topk_kernel<0, false>);
+    CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_begin(h, st);
+    fn<<<p.grid, kGemmThreads, smem, st>>>(tmA, tmB, a);
+    prof_end(h, st);
+    CU_TRY(cudaGetLastError());
+    h->stats.launches++;
+    *G = p.S;
+    return 0;
+}
+
+// |tensor-core score - exact score| beyond the query rounding term: fp32 accumulation inside the tensor
+// core (bounded generously: truncating adds) and, for tf32, the truncation of both operands to 10 mantissa bits.
+static float eps_gemm_const(int dtype, int ld) {
+    double e = (ld + 64) * 4.76837158203125e-07 * 1.0625 + 4.76837158203125e-07;   // (ld+64) * 2^-21
+    if (dtype == 0) e += 2.0 * 9.765625e-04 * 1.0625;                               // 2 * 2^-10
+    return (float)e;
+}
 
 static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* out_ids, float* out_scores,
                          cudaStream_t st) {
@@ -339,7 +478,6 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
     if ((rc = ensure(h->flags, (size_t)(kMaxQueryBatch + 1) * sizeof(int)))) return rc;
     int* flags = (int*)h->flags.p;
     int* flag_count = flags + kMaxQueryBatch;
-    const float eps = eps_fp32_accumulate(h->ld);
 
     for (int q0 = 0; q0 < nq; q0 += kMaxQueryBatch) {
         const int nb = nq - q0 < kMaxQueryBatch ? nq - q0 : kMaxQueryBatch;
@@ -352,39 +490,54 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
         h->stats.launches++;
         CU_TRY(cudaMemsetAsync(flags, 0, (size_t)(kMaxQueryBatch + 1) * sizeof(int), st));
 
-        // 2. scan in groups of <= 4 queries.  Candidate layout [nb4][G][kp]; a group whose kernel
-        //    variant fits fewer CTAs than G leaves the surplus lists empty (zeroed here).
-        const int G = h->num_sms * kMaxScanCtasPerSm;
-        const bool scanned = n > 0 && steps > 0;
-        if ((rc = ensure(h->cand, (size_t)nb4 * G * kp * sizeof(u64)))) return rc;
-        CU_TRY(cudaMemsetAsync(h->cand.p, 0, (size_t)nb4 * G * kp * sizeof(u64), st));
-        if (scanned) {
-            for (int g0 = 0; g0 < nb; g0 += 4) {
-                const int left = nb - g0;
-                const int nqt = left >= 3 ? 4 : left;  // 1, 2 or 4 query register sets (3 pads to 4)
-                scan_fn fn = pick_scan(h->dtype, nqt, steps);
-                if (!fn) return fail(RAGFIN_EUNSUPPORTED, "no scan kernel for dtype %d nq %d steps %d", h->dtype, nqt, steps);
-                const size_t smem = (size_t)nqt * kScanWarps * kp * sizeof(u64);
-                CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                int per_sm = 0;
-                CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kScanThreads, smem));
-                if (per_sm < 1) return fail(RAGFIN_ECUDA, "scan kernel does not fit on an SM (smem %zu)", smem);
-                if (per_sm > kMaxScanCtasPerSm) per_sm = kMaxScanCtasPerSm;
-                prof_begin(h, st);
-                fn<<<h->num_sms * per_sm, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat + (size_t)g0 * h->ld, kp,
-                                                                     (u64*)h->cand.p + (size_t)g0 * G * kp,
-                                                                     (int64_t)G * kp);
-                prof_end(h, st);
-                CU_TRY(cudaGetLastError());
-                h->stats.launches++;
+        int G = 0, sorted_lists = 1;
+        bool scanned = false;
+        float eps = 0.f;
+        const float* eps_q = nullptr;
+        if (nb >= h->gemm_min_nq && gemm_supported(h, kp)) {
+            // 2a. tensor-core path
+            if ((rc = run_gemm(h, nb, kp, &G, nullptr, st))) return rc;
+            h->stats.path = 1;
+            sorted_lists = 0;
+            scanned = true;
+            eps = eps_gemm_const(h->dtype, h->ld);
+            eps_q = (const float*)h->eps_q.p;
+        } else {
+            // 2b. scan in groups of <= 4 queries.  Candidate layout [nb4][G][kp]; a group whose kernel
+            //     variant fits fewer CTAs than G leaves the surplus lists empty (zeroed here).
+            G = h->num_sms * kMaxScanCtasPerSm;
+            scanned = n > 0 && steps > 0;
+            eps = eps_fp32_accumulate(h->ld);
+            if ((rc = ensure(h->cand, (size_t)nb4 * G * kp * sizeof(u64)))) return rc;
+            CU_TRY(cudaMemsetAsync(h->cand.p, 0, (size_t)nb4 * G * kp * sizeof(u64), st));
+            if (scanned) {
+                for (int g0 = 0; g0 < nb; g0 += 4) {
+                    const int left = nb - g0;
+                    const int nqt = left >= 3 ? 4 : left;  // 1, 2 or 4 query register sets (3 pads to 4)
+                    scan_fn fn = pick_scan(h->dtype, nqt, steps);
+                    if (!fn) return fail(RAGFIN_EUNSUPPORTED, "no scan kernel for dtype %d nq %d steps %d", h->dtype, nqt, steps);
+                    const size_t smem = (size_t)nqt * kScanWarps * kp * sizeof(u64);
+                    CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    int per_sm = 0;
+                    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kScanThreads, smem));
+                    if (per_sm < 1) return fail(RAGFIN_ECUDA, "scan kernel does not fit on an SM (smem %zu)", smem);
+                    if (per_sm > kMaxScanCtasPerSm) per_sm = kMaxScanCtasPerSm;
+                    prof_begin(h, st);
+                    fn<<<h->num_sms * per_sm, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat + (size_t)g0 * h->ld, kp,
+                                                                         (u64*)h->cand.p + (size_t)g0 * G * kp,
+                                                                         (int64_t)G * kp);
+                    prof_end(h, st);
+                    CU_TRY(cudaGetLastError());
+                    h->stats.launches++;
+                }
             }
         }
         // 3. merge + exact rescore + certificate (an unscanned, non-empty corpus flags every query)
         {
             const size_t smem = ((size_t)kFinWarps * kp + kp) * sizeof(u64);
             finalize_kernel<false><<<nb, kFinThreads, smem, st>>>(
-                (const u64*)h->cand.p, G, kp, h->data, h->dtype, n, (scanned || n == 0) ? 1 : 0, h->ld, qhat, eps, nullptr,
-                k, h->id_base, out_ids + (size_t)q0 * k, out_scores + (size_t)q0 * k, flags, flag_count);
+                (const u64*)h->cand.p, G, kp, h->data, h->dtype, n, (scanned || n == 0) ? 1 : 0, sorted_lists, h->ld, qhat,
+                eps, eps_q, k, h->id_base, out_ids + (size_t)q0 * k, out_scores + (size_t)q0 * k, flags, flag_count);
             CU_TRY(cudaGetLastError());
             h->stats.launches++;
         }
@@ -400,7 +553,7 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
             }
             CU_TRY(cudaGetLastError());
             const size_t fsm = ((size_t)kFinWarps * kpe + kpe) * sizeof(u64);
-            finalize_kernel<true><<<nb, kFinThreads, fsm, st>>>((const u64*)h->cand_e.p, Ge, kpe, h->data, h->dtype, n, 1, h->ld,
+            finalize_kernel<true><<<nb, kFinThreads, fsm, st>>>((const u64*)h->cand_e.p, Ge, kpe, h->data, h->dtype, n, 1, 1, h->ld,
                                                                 qhat, 0.0f, nullptr, k, h->id_base,
                                                                 out_ids + (size_t)q0 * k, out_scores + (size_t)q0 * k,
                                                                 flags, flag_count);
@@ -409,6 +562,30 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
         }
     }
     return 0;
+}
+
+// Test hook: raw tensor-core scores [nq, count] of the queries against every row (device memory out).
+extern "C" int ragfin_debug_gemm_scores(ragfin_t* h, const float* q_dev, int32_t nq, float* out_scores_dev, void* stream) {
+    if (!h || !q_dev || !out_scores_dev || nq < 1) return fail(RAGFIN_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (h->count == 0) return fail(RAGFIN_EINVAL, "empty collection");
+    if ((rc = wait_prev(h, st))) return rc;
+    if ((rc = ensure(h->qhat, (size_t)nq * h->ld * sizeof(float)))) return rc;
+    if ((rc = launch_ingest<false>(0, q_dev, 0, 0, 0, 0, nq, h->dim, h->ld, (float*)h->qhat.p, h->num_sms, st))) return rc;
+    int G = 0;
+    if ((rc = run_gemm(h, nq, 32, &G, out_scores_dev, st))) return rc;
+    return mark_done(h, st);
+}
+
+// Dispatch knob: query batches of at least `min_nq` rows use the tcgen05 path (default 9; INT32_MAX = never).
+extern "C" int ragfin_set_gemm_min_batch(ragfin_t* h, int32_t min_nq) {
+    if (!h || min_nq < 1) return fail(RAGFIN_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->gemm_min_nq = min_nq;
+    return RAGFIN_OK;
 }
 
 extern "C" int ragfin_search(ragfin_t* h, const float* q, int32_t nq, int32_t k, int64_t* out_ids, float* out_scores,

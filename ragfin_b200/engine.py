@@ -148,6 +148,20 @@ class Index:
                                              out_scores.data_ptr(), _stream_ptr(stream)))
         return out_ids, out_scores
 
+    def set_gemm_min_batch(self, min_nq: int) -> None:
+        """Query batches of at least `min_nq` rows use the tcgen05 path (default 9)."""
+        _lib.check(self._L.ragfin_set_gemm_min_batch(self._h, int(min_nq)))
+
+    def debug_gemm_scores(self, queries):
+        """Test hook: raw tensor-core scores [nq, N] (torch CUDA fp32) of CUDA fp32 queries [nq, dim]."""
+        import torch
+        queries = queries.contiguous()
+        out = torch.empty((queries.shape[0], len(self)), dtype=torch.float32, device=queries.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.ragfin_debug_gemm_scores(self._h, queries.data_ptr(), queries.shape[0], out.data_ptr(),
+                                                        _stream_ptr(None)))
+        return out
+
     def profile(self, enable: bool = True) -> None:
         """Record CUDA events around the dominant scoring kernel of every search (bench.py)."""
         _lib.check(self._L.ragfin_profile(self._h, 1 if enable else 0))

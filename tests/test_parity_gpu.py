@@ -218,3 +218,83 @@ def test_reference_call_sites_through_the_shim(coracle):
     env = rag.search_vectors("net profit Q1", 3)
     assert env["status"] == "success" and env["result_count"] == 3
     mc.utility.drop_collection("fin_chunks")
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core path (query batches >= 9 rows)
+# ------------------------------------------------------------------------------------------------
+def _rounded_operands(idx, q, dtype):
+    stored = idx.read_rows(0, len(idx))
+    qhat = O.normalize_rows(q, "f32")
+    if dtype == "f32":      # kind::tf32 reads the top 19 bits of each fp32 operand
+        trunc = lambda a: (np.ascontiguousarray(a).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+        return trunc(stored), trunc(qhat)
+    return stored, O.round_to_storage(qhat, dtype)
+
+
+@pytest.mark.parametrize("dtype,dim,n,nq", [("bf16", 768, 5000, 130), ("f16", 384, 777, 9), ("bf16", 100, 3000, 128),
+                                             ("f32", 768, 2100, 40), ("f16", 1024, 9000, 257)])
+def test_gemm_raw_scores_match_matmul(dtype, dim, n, nq):
+    import torch
+    x = O.synth_rows(5, 0, n, dim)
+    q = O.synth_rows(6, 0, nq, dim)
+    idx = _index(x, dtype)
+    got = idx.debug_gemm_scores(torch.from_numpy(q).cuda()).cpu()
+    rows, qs = _rounded_operands(idx, q, dtype)
+    ref = (torch.from_numpy(qs).double() @ torch.from_numpy(rows).double().T).float()
+    assert (got - ref).abs().max().item() < 2e-6      # exact products, fp32 accumulation
+
+
+@pytest.mark.parametrize("dtype", O.DTYPES)
+@pytest.mark.parametrize("nq,k", [(9, 10), (128, 5), (129, 1), (300, 10), (64, 100)])
+def test_gemm_search_matches_oracle(coracle, dtype, nq, k):
+    x = O.synth_rows(140, 0, 30000, 768, dup_every=97, zero_every=1013)
+    q = O.synth_rows(141, 0, nq, 768)
+    idx = _index(x, dtype)
+    got = idx.search(q, k)
+    assert idx.stats()["path"] == 1
+    _assert_same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), k), f"gemm {dtype} nq={nq} k={k}")
+
+
+@pytest.mark.parametrize("dtype,dim", [("bf16", 384), ("f16", 100), ("f32", 1024), ("bf16", 33), ("f32", 8)])
+def test_gemm_search_other_dims(coracle, dtype, dim):
+    x = O.synth_rows(150, 0, 7001, dim)
+    q = O.synth_rows(151, 0, 33, dim)
+    idx = _index(x, dtype)
+    got = idx.search(q, 10)
+    assert idx.stats()["path"] == 1
+    _assert_same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), 10), f"gemm {dtype} dim={dim}")
+
+
+def test_gemm_and_scan_paths_agree_and_knob_works(coracle):
+    x = O.synth_rows(160, 0, 20000, 768, dup_every=50)
+    q = O.synth_rows(161, 0, 20, 768)
+    idx = _index(x, "bf16")
+    a = idx.search(q, 10)
+    assert idx.stats()["path"] == 1
+    idx.set_gemm_min_batch(1 << 30)
+    b = idx.search(q, 10)
+    assert idx.stats()["path"] == 0
+    _assert_same(a, b, "gemm vs scan")
+    _assert_same(a, coracle.cosine_topk(q, coracle.normalize_rows(x, "bf16"), 10))
+
+
+def test_gemm_heavy_duplicates_take_the_exact_tier(coracle):
+    x = O.synth_rows(170, 0, 6000, 768)
+    q = O.synth_rows(171, 0, 12, 768)
+    x[100:400] = q[0] * 3.0
+    x[4000:4100] = q[5]
+    idx = _index(x, "bf16")
+    got = idx.search(q, 10)
+    assert idx.stats()["path"] == 1 and idx.stats()["queries_rescanned"] == 2
+    _assert_same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, "bf16"), 10))
+    assert got[0][0].tolist() == list(range(100, 110))
+
+
+def test_gemm_small_collection_and_k_above_n(coracle):
+    x = O.synth_rows(180, 0, 16, 384)
+    q = O.synth_rows(181, 0, 40, 384)
+    idx = _index(x, "f32")
+    got = idx.search(q, 20)
+    assert idx.stats()["path"] == 1
+    _assert_same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, "f32"), 20))
