@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--dtype", default="bf16", choices=["f32", "bf16", "f16"])
     ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--also-batch", type=int, default=4096,
+                    help="second regime measured in the same run and reported under 'regimes' (0 = off)")
     ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="rows of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -173,6 +175,7 @@ def run_ours(a):
     import torch.distributed as dist
     import ragfin_b200
     from ragfin_b200.sharded import ShardedSearcher, shard_bounds
+    from ragfin_b200.synthetic import synth_rows
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -194,106 +197,113 @@ def run_ours(a):
     torch.cuda.synchronize()
     ingest_s = time.perf_counter() - t0
     searcher = ShardedSearcher.for_index(idx)
-
-    # ---- queries: 4 distinct batches, generated on the host with the oracle-identical generator
-    from ragfin_b200.synthetic import synth_rows
-    nbatches = 4
-    q_host = torch.from_numpy(synth_rows(SEED_QUERY, 0, nbatches * a.batch, a.dim)).view(nbatches, a.batch, a.dim).pin_memory()
-    q_dev = q_host.to(dev)
-    out_ids = torch.empty((a.batch, a.k), dtype=torch.int64).pin_memory()
-    out_sc = torch.empty((a.batch, a.k), dtype=torch.float32).pin_memory()
-    q_stage = torch.empty((a.batch, a.dim), dtype=torch.float32, device=dev)
+    peaks = measured_peaks()
+    esize = 4 if a.dtype == "f32" else 2
+    ld = (a.dim + 7) // 8 * 8
+    shard_rows = shard_bounds(a.rows, world, 0)[1]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def e2e_step(i):
-        if world == 1:   # the C-ABI host call: H2D + search + D2H + sync inside ragfin_search_host
-            idx.search(q_host[i % nbatches].numpy(), a.k, out_ids=out_ids.numpy(), out_scores=out_sc.numpy())
-        else:
-            q_stage.copy_(q_host[i % nbatches], non_blocking=True)
-            ids, sc = searcher.search(q_stage, a.k)
-            out_ids.copy_(ids, non_blocking=True)
-            out_sc.copy_(sc, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+    def measure(batch, steps, warmup):
+        """One regime: device-resident timing (value), host end-to-end timing (e2e), live kernel timing (roofline)."""
+        nbatches = 4
+        q_host = torch.from_numpy(synth_rows(SEED_QUERY, 0, nbatches * batch, a.dim)).view(nbatches, batch, a.dim).pin_memory()
+        q_dev = q_host.to(dev)
+        out_ids = torch.empty((batch, a.k), dtype=torch.int64).pin_memory()
+        out_sc = torch.empty((batch, a.k), dtype=torch.float32).pin_memory()
+        q_stage = torch.empty((batch, a.dim), dtype=torch.float32, device=dev)
 
-    # ---- warm-up (both paths)
-    for i in range(a.warmup):
-        searcher.search(q_dev[i % nbatches], a.k)
-    for i in range(max(1, a.warmup // 2)):
-        e2e_step(i)
-    launches_per_step = idx.stats()["launches"] + (1 if world > 1 else 0)
-    rescanned = idx.stats()["queries_rescanned"]
+        def e2e_step(i):
+            if world == 1:   # the C-ABI host call: H2D + search + D2H + sync inside ragfin_search_host
+                idx.search(q_host[i % nbatches].numpy(), a.k, out_ids=out_ids.numpy(), out_scores=out_sc.numpy())
+            else:
+                q_stage.copy_(q_host[i % nbatches], non_blocking=True)
+                ids, sc = searcher.search(q_stage, a.k)
+                out_ids.copy_(ids, non_blocking=True)
+                out_sc.copy_(sc, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
 
-    # ---- timed region 1: device-resident queries
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    idx.profile(True)
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for i in range(a.steps):
-        searcher.search(q_dev[i % nbatches], a.k)
-    ev1.record()
-    barrier()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-    kern_ms, kern_n = idx.profile_read()
-    idx.profile(False)
+        for i in range(warmup):
+            searcher.search(q_dev[i % nbatches], a.k)
+        for i in range(max(1, warmup // 2)):
+            e2e_step(i)
+        st = idx.stats()
+        launches_per_step = st["launches"] + (1 if world > 1 else 0)
 
-    # ---- timed region 2: end to end through the host API
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(a.steps):
-        e2e_step(i)
-    barrier()
-    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
-    clocks = sampler.stop() if rank == 0 else None
-    kern = torch.tensor([kern_ms / max(kern_n, 1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(kern, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, kern_avg_ms = float(ms.item()), float(e2e_ms.item()), float(kern.item())
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        idx.profile(True)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(steps):
+            searcher.search(q_dev[i % nbatches], a.k)
+        ev1.record()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        kern_ms, kern_n = idx.profile_read()
+        idx.profile(False)
 
-    if rank == 0:
-        peaks = measured_peaks()
-        esize = 4 if a.dtype == "f32" else 2
-        ld = (a.dim + 7) // 8 * 8
-        path = idx.stats()["path"]
-        shard_rows = shard_bounds(a.rows, world, 0)[1]
-        if path == 0:   # HBM-bound scan: algorithmic bytes = one pass over the shard
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            e2e_step(i)
+        barrier()
+        e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
+        clocks = sampler.stop() if rank == 0 else None
+        kern = torch.tensor([kern_ms / max(kern_n, 1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(kern, op=dist.ReduceOp.MAX)
+        ms, e2e_ms, kern_avg_ms = float(ms.item()), float(e2e_ms.item()), float(kern.item())
+        launches_of_kernel_per_step = kern_n / max(steps, 1)
+        if st["path"] == 0:   # HBM-bound scan: algorithmic bytes = one pass over the shard per launch
             alg = shard_rows * ld * esize
             achieved = alg / (kern_avg_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": "scan_topk_kernel", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": achieved / peaks["hbm"], "algorithmic_bytes_per_launch": alg,
                     "frac_of_nominal_8TBps": achieved / 8000.0}
-        else:           # tensor-bound GEMM: algorithmic flops = 2 * nq * rows * dim
-            alg = 2.0 * a.batch * shard_rows * a.dim
+        else:                 # tensor-bound GEMM: algorithmic flops = 2 * nq * shard rows * dim per launch
+            alg = 2.0 * batch * shard_rows * a.dim
             achieved = alg / (kern_avg_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "gemm_topk_kernel", "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["bf16"], "algorithmic_flops_per_launch": alg}
+            roof = {"bound": "tensor", "kernel": "gemm_topk_kernel", "achieved": achieved, "peak": peaks["bf16"],
+                    "unit": "TFLOP/s", "frac": achieved / peaks["bf16"], "algorithmic_flops_per_launch": alg,
+                    "frac_of_sustained_peak": achieved / peaks["bf16_sustained"] if peaks.get("bf16_sustained") else None}
         roof.update({"kernel_ms_avg": kern_avg_ms, "kernel_launches_timed": kern_n, "peak_source": peaks["source"],
-                     "kernel_share_of_step": kern_avg_ms * (kern_n / max(a.steps, 1)) / (ms / a.steps),
-                     "traffic": load_traffic(a)})
-        bi = a.batch * a.dim * 4
-        bo = a.batch * a.k * 12
+                     "kernel_share_of_step": kern_avg_ms * launches_of_kernel_per_step / (ms / steps),
+                     "traffic": load_traffic(a, batch)})
+        return {
+            "value": batch * steps / (ms * 1e-3), "unit": "queries/s", "batch": batch, "steps": steps,
+            "ms_per_step": ms / steps, "clocks": clocks,
+            "e2e": {"value": batch * steps / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms / steps,
+                    "h2d_bytes_per_step": batch * a.dim * 4, "d2h_bytes_per_step": batch * a.k * 12},
+            "gpu_launches": launches_per_step * steps, "roofline": roof,
+            "queries_rescanned_last_step": st["queries_rescanned"],
+        }
+
+    main = measure(a.batch, a.steps, a.warmup)
+    other = None
+    if a.also_batch and a.also_batch != a.batch:
+        other = measure(a.also_batch, max(5, a.steps // 10), a.warmup)
+
+    if rank == 0:
         line = {
-            "metric": METRIC, "value": a.batch * a.steps / (ms * 1e-3), "unit": "queries/s", "n_gpus": world,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "metric": METRIC, "value": main["value"], "unit": "queries/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
             "config": {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "k": a.k, "batch": a.batch,
                        "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
                        "l2": "inputs (corpus shard) larger than L2; no flush needed",
-                       "ingest_s": round(ingest_s, 2), "queries_rescanned_in_warmup": rescanned},
-            "clocks": clocks,
-            "e2e": {"value": a.batch * a.steps / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms / a.steps,
-                    "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo},
-            "gpu_launches": launches_per_step * a.steps,
-            "roofline": roof,
+                       "ingest_s": round(ingest_s, 2), "queries_rescanned_last_step": main["queries_rescanned_last_step"]},
+            "clocks": main["clocks"], "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "roofline": main["roofline"],
         }
+        if other is not None:
+            line["regimes"] = {f"batch_{other['batch']}": other}
         if world == 1 and not a.no_cpu_baseline:
             del idx
             line["cpu_baseline"] = cpu_baseline(a, budget_s=15.0)[0]
@@ -303,7 +313,7 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
-def load_traffic(a):
+def load_traffic(a, batch):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
     ncu --set full capture of this workload (profiles/traffic.json), else null."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -311,7 +321,7 @@ def load_traffic(a):
         return None
     with open(p) as f:
         t = json.load(f)
-    return t.get(f"{a.rows}x{a.dim}:{a.dtype}:b{a.batch}:k{a.k}")
+    return t.get(f"{a.rows}x{a.dim}:{a.dtype}:b{batch}:k{a.k}")
 
 
 def main():

@@ -102,7 +102,8 @@ template <int DT>
 __device__ __forceinline__ double canonical_dot_row(const typename Store<DT>::T* __restrict__ row,
                                                     const float* __restrict__ q, int dim, int lane) {
     double acc = 0.0;
-    for (int i = lane; i < dim; i += kWarp)
+#pragma unroll 8
+    for (int i = lane; i < dim; i += kWarp)   // loads batch up; the fp64 adds stay in increasing-i order
         acc = acc + (double)Store<DT>::to_f32(row[i]) * (double)q[i];
     return warp_butterfly_f64(acc);
 }

@@ -154,11 +154,15 @@ struct GemmArgs {
 };
 
 // Per-query candidate list of one epilogue thread: kp keys in shared memory (column layout
-// lists[e * 128 + m]), unsorted; once full, `tau_key` is its minimum and a new key replaces it.
+// lists[e * 128 + m]), unsorted; once full, `tau_key` is its minimum and a better key replaces it.
+// `tau_s` is the score a row needs to be worth looking at: max(list minimum, global bound), where
+// the global bound gtau[q] is the best list-minimum any CTA has published for this query - a valid
+// lower bound of the global K'-th approximate score, so rows below it can never be candidates.
 struct CandState {
     int cnt, minpos;
     u64 tau_key;
-    float tau_s;     // scores below this cannot enter: max(list minimum, global bound)
+    float tau_s;
+    uint32_t* gptr;   // &gtau[q], or null for padding lanes
 };
 __device__ __noinline__ void cand_insert(CandState& st, u64* lists, int m, int kp, float s, uint32_t row) {
     const u64 key = make_key(s + 0.0f, row);
@@ -179,7 +183,11 @@ __device__ __noinline__ void cand_insert(CandState& st, u64* lists, int m, int k
     }
     st.tau_key = mn;
     st.minpos = mp;
-    st.tau_s = fmaxf(st.tau_s, key_score(mn));
+    const float t = key_score(mn);
+    if (t > st.tau_s) {
+        st.tau_s = t;
+        if (st.gptr) atomicMax(st.gptr, float_to_ordered(t));   // publish: every CTA sweeping this query tightens
+    }
 }
 
 template <int KIND, bool DUMP>
@@ -289,9 +297,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             st.cnt = 0;
             st.minpos = 0;
             st.tau_key = 0;
-            st.tau_s = -INFINITY;
+            st.tau_s = q < a.nq ? -INFINITY : INFINITY;   // padding lanes of a partial query tile never collect
+            st.gptr = (!DUMP && q < a.nq) ? a.gtau + q : nullptr;
             for (int t = 0; t < ntiles; ++t) {
-                if (!DUMP) {   // bound published by the slices of this query that finished earlier
+                if (!DUMP) {   // bound published by the other CTAs sweeping this query
                     const uint32_t g = __ldcg(a.gtau + qc);
                     if (g) st.tau_s = fmaxf(st.tau_s, ordered_to_float(g));
                 }
@@ -318,13 +327,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     float mx = __uint_as_float(v[0]);
 #pragma unroll
                     for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-                    if (mx >= st.tau_s) {          // rare per thread: spill this chunk and walk it
-                        float w[32];
+                    if (mx >= st.tau_s) {          // rare per thread; every v[j] stays in its register
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) w[j] = __uint_as_float(v[j]);
-#pragma unroll 1
                         for (int j = 0; j < 32; ++j) {
-                            const float sc = w[j];
+                            const float sc = __uint_as_float(v[j]);
                             if (sc >= st.tau_s && c * 32 + j < valid)
                                 cand_insert(st, lists, m, kp, sc, (uint32_t)(trow + c * 32 + j));
                         }
@@ -337,7 +343,6 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (!DUMP && q < a.nq) {
                 u64* out = a.cand + ((size_t)q * a.S + sl) * kp;
                 for (int e = 0; e < kp; ++e) out[e] = e < st.cnt ? lists[(size_t)e * kGM + m] : 0ull;
-                if (st.cnt == kp) atomicMax(a.gtau + q, float_to_ordered(key_score(st.tau_key)));
             }
         }
     }

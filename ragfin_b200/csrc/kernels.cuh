@@ -253,18 +253,93 @@ __device__ __forceinline__ double rescore_row(const void* data, int64_t row, int
 //    Otherwise flags[q] = 1 and the query goes to the exact-rescan tier.
 //  EXACT_IN = true: keys already carry exact scores (tier 2); only flagged queries run.
 // ---------------------------------------------------------------------------------
+constexpr int kFinCap = 4096;     // survivor buffer, keys (>= kFinWarps * 256 so the fallback merge fits)
+constexpr int kFinHeads = 1024;   // most candidate lists per query the head-threshold shortcut handles
+
+// Top-kp of G candidate lists into buf[0..kp) (descending), without touching most of the input:
+//  * sorted lists (scan / exact tier): the kp-th largest list HEAD is a lower bound of the kp-th
+//    largest key overall (kp heads are >= it), so only each list's prefix above it can matter;
+//  * unsorted lists (tensor-core path): the bound is gtau[q], the best list minimum published
+//    during the sweep.
+// Survivors are appended to shared memory and bitonic-sorted; if they overflow (adversarial input)
+// the streaming per-warp merge below is used instead.
+__device__ __forceinline__ void select_top(const u64* __restrict__ src, int G, int kp, bool sorted_lists, u64 bound,
+                                           u64* buf, u64* heads, int* s_cnt, u64* s_tau) {
+    const int tid = threadIdx.x;
+    if (tid == 0) { *s_cnt = 0; *s_tau = bound; }
+    if (sorted_lists && G >= kp && G <= kFinHeads) {
+        for (int i = tid; i < G; i += kFinThreads) heads[i] = src[(size_t)i * kp];
+        __syncthreads();
+        for (int i = tid; i < G; i += kFinThreads) {
+            const u64 my = heads[i];
+            if (my == 0) continue;
+            int r = 0;
+            for (int j = 0; j < G; ++j) r += heads[j] > my;
+            if (r == kp - 1) *s_tau = my;   // keys are unique: exactly one thread writes
+        }
+    }
+    __syncthreads();
+    const u64 tau0 = *s_tau;
+    if (sorted_lists) {
+        for (int l = tid; l < G; l += kFinThreads) {
+            const u64* in = src + (size_t)l * kp;
+            for (int e = 0; e < kp; ++e) {
+                const u64 key = in[e];
+                if (key == 0 || key < tau0) break;
+                const int pos = atomicAdd(s_cnt, 1);
+                if (pos < kFinCap) buf[pos] = key;
+            }
+        }
+    } else {
+        for (int i = tid; i < G * kp; i += kFinThreads) {
+            const u64 key = src[i];
+            if (key != 0 && key >= tau0) {
+                const int pos = atomicAdd(s_cnt, 1);
+                if (pos < kFinCap) buf[pos] = key;
+            }
+        }
+    }
+    __syncthreads();
+    const int n = *s_cnt;
+    if (n > kFinCap) {   // overflow: streaming merge over everything
+        __syncthreads();
+        merge_lists(src, G, kp, buf, sorted_lists);
+        return;
+    }
+    int P = kp;
+    while (P < n) P <<= 1;
+    for (int i = n + tid; i < P; i += kFinThreads) buf[i] = 0;
+    __syncthreads();
+    block_bitonic_sort_desc(buf, P, tid, kFinThreads);
+}
+
+// ---------------------------------------------------------------------------------
+// K4: one CTA per query.
+//  EXACT_IN = false: keys carry APPROXIMATE scores.  Select the top-kp, recompute those
+//    kp dot products canonically in fp64 from the stored values, order by the exact key and
+//    certify: every row outside the candidate set has approx <= tau (the kp-th approx
+//    score) hence exact <= tau + eps; if exact_k > tau + eps the top-k is proven exact.
+//    Otherwise flags[q] = 1 and the query goes to the exact-rescan tier.
+//  EXACT_IN = true: keys already carry exact scores (tier 2); only flagged queries run.
+// ---------------------------------------------------------------------------------
 template <bool EXACT_IN>
 __global__ void __launch_bounds__(kFinThreads)
 finalize_kernel(const u64* __restrict__ cand, int G, int kp, const void* __restrict__ data, int dt,
-                int64_t n_rows, int scanned, int sorted_lists, int ld, const float* __restrict__ qhat, float eps_const,
+                int64_t n_rows, int scanned, int sorted_lists, const uint32_t* __restrict__ gtau, int ld,
+                const float* __restrict__ qhat, float eps_const,
                 const float* __restrict__ eps_q, int k, int64_t id_base, int64_t* __restrict__ out_ids,
                 float* __restrict__ out_scores, int* __restrict__ flags, int* __restrict__ flag_count) {
-    extern __shared__ __align__(16) u64 fsm[];  // [kFinWarps][kp] merge lists, then [kp] exact keys
+    __shared__ __align__(16) u64 buf[kFinCap];
+    __shared__ __align__(16) u64 ex[256];
+    __shared__ __align__(16) u64 heads[kFinHeads];
+    __shared__ int s_cnt;
+    __shared__ u64 s_tau;
     const int q = blockIdx.x;
     if (EXACT_IN && flags[q] == 0) return;
-    u64* wl = fsm;
-    u64* ex = fsm + (size_t)kFinWarps * kp;
-    merge_lists(cand + (size_t)q * G * kp, G, kp, wl, sorted_lists != 0);
+    u64 bound = 0;
+    if (!sorted_lists && gtau != nullptr) bound = (u64)gtau[q] << 32;   // key >= bound  <=>  score >= published bound
+    select_top(cand + (size_t)q * G * kp, G, kp, sorted_lists != 0, bound, buf, heads, &s_cnt, &s_tau);
+    const u64* wl = buf;
 
     const int keff = (int64_t)k < n_rows ? k : (int)n_rows;
     const u64* fin = wl;

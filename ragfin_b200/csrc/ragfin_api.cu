@@ -472,9 +472,11 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
     const int nvec = h->ld / V;
     const int steps = round_steps((nvec + 31) / 32);
     int kp = cand_per_query(k);
-    if (kp == 0) return fail(RAGFIN_EUNSUPPORTED, "k = %d above 224 needs the large-k path (not built yet)", k);
+    if (kp == 0 && n <= 256) kp = 256;   // every row is a candidate: any k (graph_cons.py:279 asks limit=1000 of 16 rows)
+    if (kp == 0)
+        return fail(RAGFIN_EUNSUPPORTED, "k = %d above 224 on a corpus of more than 256 rows needs the large-k path (not built yet)", k);
     h->stats.cand_per_query = kp;
-    const int kpe = (k + 31) / 32 * 32;
+    const int kpe = k > 256 ? 256 : (k + 31) / 32 * 32;   // k > 256 only occurs with n <= 256
     if ((rc = ensure(h->flags, (size_t)(kMaxQueryBatch + 1) * sizeof(int)))) return rc;
     int* flags = (int*)h->flags.p;
     int* flag_count = flags + kMaxQueryBatch;
@@ -488,7 +490,7 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
         if (nb4 > nb) CU_TRY(cudaMemsetAsync(qhat + (size_t)nb * h->ld, 0, (size_t)(nb4 - nb) * h->ld * sizeof(float), st));
         if ((rc = launch_ingest<false>(0, q_dev + (size_t)q0 * h->dim, 0, 0, 0, 0, nb, h->dim, h->ld, qhat, h->num_sms, st))) return rc;
         h->stats.launches++;
-        CU_TRY(cudaMemsetAsync(flags, 0, (size_t)(kMaxQueryBatch + 1) * sizeof(int), st));
+        CU_TRY(cudaMemsetAsync(flag_count, 0, sizeof(int), st));   // flags[q] itself is written by finalize for every q
 
         int G = 0, sorted_lists = 1;
         bool scanned = false;
@@ -505,15 +507,17 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
         } else {
             // 2b. scan in groups of <= 4 queries.  Candidate layout [nb4][G][kp]; a group whose kernel
             //     variant fits fewer CTAs than G leaves the surplus lists empty (zeroed here).
-            G = h->num_sms * kMaxScanCtasPerSm;
+            //     Every group of a batch uses the same grid (the smallest occupancy among the variants used), so
+            //     the candidate buffer is exactly [nb4][G][kp] and every list is written by its CTA.
             scanned = n > 0 && steps > 0;
             eps = eps_fp32_accumulate(h->ld);
-            if ((rc = ensure(h->cand, (size_t)nb4 * G * kp * sizeof(u64)))) return rc;
-            CU_TRY(cudaMemsetAsync(h->cand.p, 0, (size_t)nb4 * G * kp * sizeof(u64), st));
+            G = 1;
             if (scanned) {
-                for (int g0 = 0; g0 < nb; g0 += 4) {
-                    const int left = nb - g0;
-                    const int nqt = left >= 3 ? 4 : left;  // 1, 2 or 4 query register sets (3 pads to 4)
+                int per_sm_min = kMaxScanCtasPerSm;
+                const int last = nb - (nb - 1) / 4 * 4;                      // queries in the last group: 1..4
+                const int variants[2] = {nb > 4 ? 4 : 0, last >= 3 ? 4 : last};  // every group but the last uses 4
+                for (int nqt : variants) {
+                    if (nqt == 0) continue;
                     scan_fn fn = pick_scan(h->dtype, nqt, steps);
                     if (!fn) return fail(RAGFIN_EUNSUPPORTED, "no scan kernel for dtype %d nq %d steps %d", h->dtype, nqt, steps);
                     const size_t smem = (size_t)nqt * kScanWarps * kp * sizeof(u64);
@@ -521,11 +525,22 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
                     int per_sm = 0;
                     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kScanThreads, smem));
                     if (per_sm < 1) return fail(RAGFIN_ECUDA, "scan kernel does not fit on an SM (smem %zu)", smem);
-                    if (per_sm > kMaxScanCtasPerSm) per_sm = kMaxScanCtasPerSm;
+                    if (per_sm < per_sm_min) per_sm_min = per_sm;
+                }
+                G = h->num_sms * per_sm_min;
+            }
+            if ((rc = ensure(h->cand, (size_t)nb4 * G * kp * sizeof(u64)))) return rc;
+            if (!scanned) CU_TRY(cudaMemsetAsync(h->cand.p, 0, (size_t)nb4 * G * kp * sizeof(u64), st));
+            if (scanned) {
+                for (int g0 = 0; g0 < nb; g0 += 4) {
+                    const int left = nb - g0;
+                    const int nqt = left >= 3 ? 4 : left;  // 1, 2 or 4 query register sets (3 pads to 4)
+                    scan_fn fn = pick_scan(h->dtype, nqt, steps);
+                    const size_t smem = (size_t)nqt * kScanWarps * kp * sizeof(u64);
                     prof_begin(h, st);
-                    fn<<<h->num_sms * per_sm, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat + (size_t)g0 * h->ld, kp,
-                                                                         (u64*)h->cand.p + (size_t)g0 * G * kp,
-                                                                         (int64_t)G * kp);
+                    fn<<<G, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat + (size_t)g0 * h->ld, kp,
+                                                       (u64*)h->cand.p + (size_t)g0 * G * kp,
+                                                       (int64_t)G * kp);
                     prof_end(h, st);
                     CU_TRY(cudaGetLastError());
                     h->stats.launches++;
@@ -534,10 +549,9 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
         }
         // 3. merge + exact rescore + certificate (an unscanned, non-empty corpus flags every query)
         {
-            const size_t smem = ((size_t)kFinWarps * kp + kp) * sizeof(u64);
-            finalize_kernel<false><<<nb, kFinThreads, smem, st>>>(
-                (const u64*)h->cand.p, G, kp, h->data, h->dtype, n, (scanned || n == 0) ? 1 : 0, sorted_lists, h->ld, qhat,
-                eps, eps_q, k, h->id_base, out_ids + (size_t)q0 * k, out_scores + (size_t)q0 * k, flags, flag_count);
+            finalize_kernel<false><<<nb, kFinThreads, 0, st>>>(
+                (const u64*)h->cand.p, G, kp, h->data, h->dtype, n, (scanned || n == 0) ? 1 : 0, sorted_lists,
+                sorted_lists ? nullptr : (const uint32_t*)h->gtau.p, h->ld, qhat, eps, eps_q, k, h->id_base, out_ids + (size_t)q0 * k, out_scores + (size_t)q0 * k, flags, flag_count);
             CU_TRY(cudaGetLastError());
             h->stats.launches++;
         }
@@ -552,9 +566,8 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
                 default: exact_scan_kernel<2><<<Ge, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat, nb, flags, flag_count, kpe, (u64*)h->cand_e.p); break;
             }
             CU_TRY(cudaGetLastError());
-            const size_t fsm = ((size_t)kFinWarps * kpe + kpe) * sizeof(u64);
-            finalize_kernel<true><<<nb, kFinThreads, fsm, st>>>((const u64*)h->cand_e.p, Ge, kpe, h->data, h->dtype, n, 1, 1, h->ld,
-                                                                qhat, 0.0f, nullptr, k, h->id_base,
+            finalize_kernel<true><<<nb, kFinThreads, 0, st>>>((const u64*)h->cand_e.p, Ge, kpe, h->data, h->dtype, n, 1, 1, nullptr,
+                                                              h->ld, qhat, 0.0f, nullptr, k, h->id_base,
                                                                 out_ids + (size_t)q0 * k, out_scores + (size_t)q0 * k,
                                                                 flags, flag_count);
             CU_TRY(cudaGetLastError());

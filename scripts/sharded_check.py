@@ -1,0 +1,41 @@
+"""Multi-GPU parity: run under torchrun (one rank per GPU).  Every rank ingests its row shard of the same
+synthetic matrix, the sharded search (local exact top-k -> NCCL all-gather -> reduce) must equal the oracle's
+unsharded answer bit for bit on every rank."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import ragfin_b200
+from oracle import c_oracle as C, ragfin_oracle as O
+from ragfin_b200.sharded import ShardedSearcher, shard_bounds
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ok = True
+for dtype, dim, n, nq, k in [("bf16", 768, 50001, 1, 10), ("f16", 768, 30000, 4, 100), ("f32", 384, 9000, 40, 5),
+                             ("bf16", 768, 7, 3, 10), ("bf16", 1024, 40000, 300, 10)]:
+    row0, cnt = shard_bounds(n, world, rank)
+    idx = ragfin_b200.Index(dim, dtype, capacity=max(cnt, 1), device=local)
+    if cnt:
+        idx.add_synthetic(500, row0, cnt, dup_every=53)
+    idx.set_id_base(row0)
+    s = ShardedSearcher.for_index(idx)
+    q = O.synth_rows(501, 0, nq, dim)
+    ids, sc = s.search(torch.from_numpy(q).cuda(), k)
+    torch.cuda.synchronize()
+    wi, ws = C.cosine_topk(q, C.normalize_rows(O.synth_rows(500, 0, n, dim, dup_every=53), dtype), k)
+    same = np.array_equal(ids.cpu().numpy(), wi) and np.array_equal(sc.cpu().numpy().view(np.uint32), ws.view(np.uint32))
+    ok &= same
+    if rank == 0:
+        print(f"sharded x{world} {dtype} dim={dim} n={n} nq={nq} k={k}: parity={same}", flush=True)
+t = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(t, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("SHARDED CHECK", "OK" if t.item() == 1 else "FAILED", flush=True)
+dist.destroy_process_group()
+sys.exit(0 if t.item() == 1 else 1)
