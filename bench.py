@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--also-batch", type=int, default=4096,
                     help="second regime measured in the same run and reported under 'regimes' (0 = off)")
+    ap.add_argument("--gemm-cluster", type=int, default=0, help="tcgen05 path cluster size: 0 auto, 1, 2 or 4")
     ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="rows of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -194,6 +195,7 @@ def run_ours(a):
     for r in range(0, n_local, 1_000_000):
         idx.add_synthetic(SEED_CORPUS, row0 + r, min(1_000_000, n_local - r))
     idx.set_id_base(row0)
+    idx.set_gemm_cluster(a.gemm_cluster)
     torch.cuda.synchronize()
     ingest_s = time.perf_counter() - t0
     searcher = ShardedSearcher.for_index(idx)

@@ -46,7 +46,7 @@ enum {
 };
 
 /* ABI version of this header; bumped on any signature change. */
-#define RAGFIN_ABI_VERSION 1
+#define RAGFIN_ABI_VERSION 2
 int ragfin_abi_version(void);
 
 /* Create an empty collection of `dim`-wide embeddings stored as `dtype` on CUDA device
@@ -91,13 +91,15 @@ int ragfin_search_host(ragfin_t* h, const float* q_host, int32_t nq, int32_t k, 
 
 /* Cross-shard reduce: merge `parts` exact hit lists per query (device memory; -1 ids are
  * padding) into the global top-k, ordered by (score desc, id asc).  Hit j of part p for query q
- * is at element  q * query_stride + p * part_stride + j  of `ids` / `scores`: an all-gather
- * buffer [parts][nq][k] is (part_stride = nq*k, query_stride = k); a concatenation
- * [nq][parts*k] is (part_stride = k, query_stride = parts*k).  Used after the NCCL all-gather of per-rank hits
+ * is at element  q * query_stride + p * ids_part_stride + j  of `ids` and
+ * q * query_stride + p * scores_part_stride + j  of `scores`: an all-gather buffer
+ * [parts][nq][k] has both part strides nq*k and query_stride k; a concatenation [nq][parts*k] has
+ * part strides k and query_stride parts*k; a packed per-rank record {ids[nq*k] | scores[nq*k]} of
+ * B bytes (one all-gather) has ids_part_stride B/8 and scores_part_stride B/4.  Used after the NCCL all-gather of per-rank hits
  * (Milvus proxy reduce in the reference deployment). */
 int ragfin_merge_topk(const int64_t* ids, const float* scores, int32_t nq, int32_t parts, int32_t k,
-                      int64_t part_stride, int64_t query_stride, int64_t* out_ids, float* out_scores,
-                      int32_t device, void* stream);
+                      int64_t ids_part_stride, int64_t scores_part_stride, int64_t query_stride,
+                      int64_t* out_ids, float* out_scores, int32_t device, void* stream);
 
 /* Copy rows row0..row0+n of the STORED matrix, raw storage bytes [n, ld], to host memory
  * (test hook for ingest parity).  *ld_out receives the row stride in elements. */
@@ -124,6 +126,10 @@ int ragfin_profile_read(ragfin_t* h, double* total_ms, int32_t* launches);
 /* Dispatch knob: query batches of at least `min_nq` rows take the tcgen05 tensor-core path, smaller
  * ones the HBM-bound scan (default 9).  Both paths return identical results. */
 int ragfin_set_gemm_min_batch(ragfin_t* h, int32_t min_nq);
+
+/* Tuning knob: thread-block cluster size of the tcgen05 path along the query-tile axis (corpus tiles
+ * are TMA-multicast across the cluster).  0 = automatic (default), else 1, 2 or 4. */
+int ragfin_set_gemm_cluster(ragfin_t* h, int32_t cluster);
 
 /* Test hook: raw (approximate, fp32-accumulated) tensor-core scores of nq queries against every
  * stored row, out_scores_dev [nq, count] device memory.  Validates the TMA / tcgen05 plumbing. */

@@ -73,6 +73,28 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar,
+                                               uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(cta_mask)
+                 : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -190,7 +212,10 @@ __device__ __noinline__ void cand_insert(CandState& st, u64* lists, int m, int k
     }
 }
 
-template <int KIND, bool DUMP>
+// C = thread-block cluster size along the query-tile axis: the C CTAs of a cluster hold C different
+// query tiles and sweep the same corpus slice in lockstep; each loads 1/C of every corpus tile and
+// TMA-multicasts it into all C shared memories, so a corpus tile leaves L2 once per cluster.
+template <int KIND, bool DUMP, int C>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs a) {
     extern __shared__ uint8_t gsm_raw[];
@@ -211,8 +236,14 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = C > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << C) - 1u);
+    const int cluster_id = blockIdx.x / C, n_clusters = gridDim.x / C;
+    const int n_groups = (a.QT + C - 1) / C;        // groups of C query tiles
     if (threadIdx.x == 0) {
-        for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        // empty[s] collects one tcgen05.commit from every CTA of the cluster: a slot may be refilled (by
+        // multicast into all C CTAs) only when all C tensor cores are done reading it
+        for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), C); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -222,18 +253,20 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    if (C > 1) cluster_sync_all();   // peers' barriers must be initialised before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int n_items = a.QT * a.S;
+    const int n_items = n_groups * a.S;
     const int nkb = a.num_kblocks;
 
     if (warp == 0) {
         if (lane == 0) {   // ===== TMA producer =====
             int stage = 0;
             uint32_t phase = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int qt = item % a.QT, sl = item / a.QT;
+            constexpr int kSubRows = kGN / C;   // corpus rows this CTA fetches (and multicasts) per tile
+            for (int item = cluster_id; item < n_items; item += n_clusters) {
+                const int qt = (item % n_groups) * C + (int)crank, sl = item / n_groups;
                 const long long r0 = (long long)sl * a.rows_per_slice;
                 long long r1 = r0 + a.rows_per_slice;
                 if (r1 > a.n_rows) r1 = a.n_rows;
@@ -241,10 +274,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int t = 0; t < ntiles; ++t) {
                     for (int kb = 0; kb < nkb; ++kb) {
                         mbar_wait(empty_bar(stage), phase ^ 1u);
-                        mbar_expect_tx(full_bar(stage), kStageBytes);
+                        mbar_expect_tx(full_bar(stage), kStageBytes);   // own A tile + the whole B tile (C parts)
                         tma_load_2d(smA + (uint32_t)stage * kABytes, &tmA, kb * a.k_elems, qt * kGM, full_bar(stage));
-                        tma_load_2d(smB + (uint32_t)stage * kBBytes, &tmB, kb * a.k_elems, (int)(r0 + (long long)t * kGN),
-                                    full_bar(stage));
+                        const uint32_t bdst = smB + (uint32_t)stage * kBBytes + crank * (uint32_t)(kSubRows * kGKBytes);
+                        const int brow = (int)(r0 + (long long)t * kGN) + (int)crank * kSubRows;
+                        if (C > 1) tma_load_2d_mc(bdst, &tmB, kb * a.k_elems, brow, full_bar(stage), cmask);
+                        else tma_load_2d(bdst, &tmB, kb * a.k_elems, brow, full_bar(stage));
                         if (++stage == stages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -254,8 +289,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {   // ===== MMA issuer =====
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int sl = item / a.QT;
+            for (int item = cluster_id; item < n_items; item += n_clusters) {
+                const int sl = item / n_groups;
                 const long long r0 = (long long)sl * a.rows_per_slice;
                 long long r1 = r0 + a.rows_per_slice;
                 if (r1 > a.n_rows) r1 = a.n_rows;
@@ -272,7 +307,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                         for (int k4 = 0; k4 < kGKBytes / 32; ++k4)   // 32 B of K per instruction: +2 in 16-byte units
                             tc_mma<KIND>(d_tmem, ad + 2u * k4, bd + 2u * k4, a.idesc, (uint32_t)((kb | k4) != 0));
-                        tc_commit(empty_bar(stage));
+                        if (C > 1) tc_commit_mc(empty_bar(stage), cmask);
+                        else tc_commit(empty_bar(stage));
                         if (++stage == stages) { stage = 0; phase ^= 1u; }
                     }
                     tc_commit(tfull_bar(acc));
@@ -285,8 +321,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int m = quarter * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int qt = item % a.QT, sl = item / a.QT;
+        for (int item = cluster_id; item < n_items; item += n_clusters) {
+            const int qt = (item % n_groups) * C + (int)crank, sl = item / n_groups;
             const long long r0 = (long long)sl * a.rows_per_slice;
             long long r1 = r0 + a.rows_per_slice;
             if (r1 > a.n_rows) r1 = a.n_rows;
@@ -299,13 +335,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             st.tau_key = 0;
             st.tau_s = q < a.nq ? -INFINITY : INFINITY;   // padding lanes of a partial query tile never collect
             st.gptr = (!DUMP && q < a.nq) ? a.gtau + q : nullptr;
+            uint32_t g_next = DUMP ? 0u : __ldcg(a.gtau + qc);
             for (int t = 0; t < ntiles; ++t) {
-                if (!DUMP) {   // bound published by the other CTAs sweeping this query
-                    const uint32_t g = __ldcg(a.gtau + qc);
-                    if (g) st.tau_s = fmaxf(st.tau_s, ordered_to_float(g));
+                if (!DUMP) {   // bound published by the other CTAs sweeping this query (loaded one tile ahead)
+                    const uint32_t g = g_next;
+                    if (g && q < a.nq) st.tau_s = fmaxf(st.tau_s, ordered_to_float(g));
                 }
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
+                if (!DUMP) g_next = __ldcg(a.gtau + qc);
                 const long long trow = r0 + (long long)t * kGN;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kGN;
                 const int valid = r1 - trow < kGN ? (int)(r1 - trow) : kGN;   // rows of this tile inside the corpus
@@ -348,6 +386,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    if (C > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast into it or arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");

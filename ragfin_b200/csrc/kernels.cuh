@@ -432,7 +432,7 @@ __device__ __forceinline__ int count_better(const int64_t* ids, const float* sc,
     return lo;
 }
 __global__ void merge_topk_kernel(const int64_t* __restrict__ ids, const float* __restrict__ scores, int nq,
-                                  int parts, int k, int64_t part_stride, int64_t query_stride,
+                                  int parts, int k, int64_t ips, int64_t sps, int64_t query_stride,
                                   int64_t* __restrict__ out_ids, float* __restrict__ out_scores) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t per_q = (int64_t)parts * k;
@@ -445,15 +445,15 @@ __global__ void merge_topk_kernel(const int64_t* __restrict__ ids, const float* 
     if (p == 0) {  // slot i of the output: pad it if fewer than i+1 valid hits exist in total
         int valid = 0;
         for (int pp = 0; pp < parts; ++pp)
-            valid += count_better(qi + (size_t)pp * part_stride, qs + (size_t)pp * part_stride, k, -INFINITY, INT64_MAX);
+            valid += count_better(qi + (size_t)pp * ips, qs + (size_t)pp * sps, k, -INFINITY, INT64_MAX);
         if (i >= valid) { out_ids[(size_t)q * k + i] = -1; out_scores[(size_t)q * k + i] = -INFINITY; }
     }
-    const int64_t id = qi[(size_t)p * part_stride + i];
+    const int64_t id = qi[(size_t)p * ips + i];
     if (id < 0) return;
-    const float s = qs[(size_t)p * part_stride + i];
+    const float s = qs[(size_t)p * sps + i];
     int rank = i;
     for (int pp = 0; pp < parts && rank < k; ++pp)
-        if (pp != p) rank += count_better(qi + (size_t)pp * part_stride, qs + (size_t)pp * part_stride, k, s, id);
+        if (pp != p) rank += count_better(qi + (size_t)pp * ips, qs + (size_t)pp * sps, k, s, id);
     if (rank < k) { out_ids[(size_t)q * k + rank] = id; out_scores[(size_t)q * k + rank] = s; }
 }
 

@@ -52,6 +52,7 @@ struct ragfin {
     // workspace (grow-only)
     Buf qhat, q16, eps_q, gtau, cand, cand_e, flags, stage_q, stage_ids, stage_scores, add_stage;
     int gemm_min_nq = 9;      // query batches of at least this many rows take the tcgen05 path
+    int gemm_cluster = 0;     // 0 = choose by batch size; 1, 2 or 4 = force
     cudaEvent_t last_done = nullptr;
     ragfin_search_stats stats = {0, 0, 0, 0};
     // measurement hook (ragfin_profile): event pairs around the dominant kernel
@@ -362,25 +363,28 @@ static int make_map(CUtensorMap* map, int dtype, const void* base, int64_t rows,
 }
 
 struct GemmPlan {
-    int QT, S, stages, grid;
+    int QT, S, stages, grid, C;
     int64_t rows_per_slice;
 };
 
 // Items are (query tile, slice).  Pick the number of waves w (items per CTA) whose slice count S = floor(SMs*w/QT)
 // leaves the fewest CTAs idle, with at least one 256-row tile per slice.
-static GemmPlan plan_gemm(int nq, int64_t n, int num_sms, int kp) {
+static GemmPlan plan_gemm(int nq, int64_t n, int num_sms, int kp, int C) {
     GemmPlan p;
+    p.C = C;
     p.QT = (nq + kGM - 1) / kGM;
+    const int groups = (p.QT + C - 1) / C;   // work items are (group of C query tiles, slice), one per cluster
+    num_sms /= C;                            // = clusters that can be resident
     const int64_t n_tiles = (n + kGN - 1) / kGN;
     double best = 1e300;
     int bestS = 1;
     for (int w = 1; w <= 8; ++w) {
-        int64_t S = (int64_t)num_sms * w / p.QT;
+        int64_t S = (int64_t)num_sms * w / groups;
         if (S < 1) S = 1;
         if (S > n_tiles) S = n_tiles;
         const int64_t tps = (n_tiles + S - 1) / S;
         S = (n_tiles + tps - 1) / tps;
-        const int64_t items = (int64_t)p.QT * S;
+        const int64_t items = (int64_t)groups * S;
         const double cost = (double)((items + num_sms - 1) / num_sms) * (double)tps + 0.02 * w;
         if (cost < best) { best = cost; bestS = (int)S; }
     }
@@ -388,8 +392,8 @@ static GemmPlan plan_gemm(int nq, int64_t n, int num_sms, int kp) {
     p.S = (int)((n_tiles + tps - 1) / tps);
     p.rows_per_slice = tps * kGN;
     p.stages = kp <= 32 ? 4 : kp <= 64 ? 3 : 2;
-    const int64_t items = (int64_t)p.QT * p.S;
-    p.grid = (int)(items < num_sms ? items : num_sms);
+    const int64_t items = (int64_t)groups * p.S;
+    p.grid = (int)(items < num_sms ? items : num_sms) * C;
     return p;
 }
 
@@ -400,7 +404,41 @@ static bool gemm_supported(const ragfin* h, int kp) { return kp <= 128 && h->cou
 static int run_gemm(ragfin* h, int nb, int kp, int* G, float* dump, cudaStream_t st) {
     int rc;
     const int64_t n = h->count;
-    const GemmPlan p = plan_gemm(nb, n, h->num_sms, kp);
+    // cluster size along the query-tile axis: multicast pays once several query tiles share a slice
+    const int QT0 = (nb + kGM - 1) / kGM;
+    int C = h->gemm_cluster ? h->gemm_cluster : (QT0 >= 8 ? 4 : QT0 >= 2 ? 2 : 1);
+    typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const GemmArgs);
+    auto pick = [&](int c) -> gemm_fn {
+        const bool d = dump != nullptr;
+        if (h->dtype == 0) {
+            if (c == 4) return d ? gemm_topk_kernel<1, true, 4> : gemm_topk_kernel<1, false, 4>;
+            if (c == 2) return d ? gemm_topk_kernel<1, true, 2> : gemm_topk_kernel<1, false, 2>;
+            return d ? gemm_topk_kernel<1, true, 1> : gemm_topk_kernel<1, false, 1>;
+        }
+        if (c == 4) return d ? gemm_topk_kernel<0, true, 4> : gemm_topk_kernel<0, false, 4>;
+        if (c == 2) return d ? gemm_topk_kernel<0, true, 2> : gemm_topk_kernel<0, false, 2>;
+        return d ? gemm_topk_kernel<0, true, 1> : gemm_topk_kernel<0, false, 1>;
+    };
+    const int stages0 = kp <= 32 ? 4 : kp <= 64 ? 3 : 2;
+    const size_t smem = gemm_smem_bytes(stages0, kp);
+    gemm_fn fn = pick(C);
+    CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int resident_clusters = h->num_sms;
+    if (C > 1) {   // how many clusters of C CTAs the device can hold at once (GPC packing may strand SMs)
+        cudaLaunchConfig_t qc = {};
+        qc.gridDim = dim3(h->num_sms / C * C);
+        qc.blockDim = dim3(kGemmThreads);
+        qc.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        qc.attrs = at; qc.numAttrs = 1;
+        int nc = 0;
+        CU_TRY(cudaOccupancyMaxActiveClusters(&nc, (const void*)fn, &qc));
+        if (nc < 1) { C = 1; fn = pick(1); CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
+        else resident_clusters = nc;
+    }
+    const GemmPlan p = plan_gemm(nb, n, C > 1 ? resident_clusters * C : h->num_sms, kp, C);
     const float* qhat = (const float*)h->qhat.p;
     const void* a_base = qhat;
     if ((rc = ensure(h->eps_q, (size_t)nb * sizeof(float)))) return rc;
@@ -419,7 +457,7 @@ static int run_gemm(ragfin* h, int nb, int kp, int* G, float* dump, cudaStream_t
     }
     CUtensorMap tmA, tmB;
     if ((rc = make_map(&tmA, h->dtype, a_base, nb, h->ld, kGM))) return rc;
-    if ((rc = make_map(&tmB, h->dtype, h->data, n, h->ld, kGN))) return rc;
+    if ((rc = make_map(&tmB, h->dtype, h->data, n, h->ld, kGN / C))) return rc;   // each CTA fetches 1/C of a tile
     if (!dump) {
         if ((rc = ensure(h->cand, (size_t)nb * p.S * kp * sizeof(u64)))) return rc;
     }
@@ -439,14 +477,20 @@ static int run_gemm(ragfin* h, int nb, int kp, int* G, float* dump, cudaStream_t
     a.cand = (u64*)h->cand.p;
     a.gtau = (uint32_t*)h->gtau.p;
     a.dump = dump;
-    const size_t smem = gemm_smem_bytes(p.stages, kp);
-    typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const GemmArgs);
-    gemm_fn fn = h->dtype == 0 ? (dump ? gemm_topk_kernel<1, true> : gemm_topk_kernel<1, false>)
-                               : (dump ? gemm_topk_kernel<0, true> : gemm_topk_kernel<0, false>);
-    CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    prof_begin(h, st);
-    fn<<<p.grid, kGemmThreads, smem, st>>>(tmA, tmB, a);
-    prof_end(h, st);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(p.grid);
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        prof_begin(h, st);
+        CU_TRY(cudaLaunchKernelEx(&cfg, fn, tmA, tmB, a));
+        prof_end(h, st);
+    }
     CU_TRY(cudaGetLastError());
     h->stats.launches++;
     *G = p.S;
@@ -601,6 +645,14 @@ extern "C" int ragfin_set_gemm_min_batch(ragfin_t* h, int32_t min_nq) {
     return RAGFIN_OK;
 }
 
+// Tuning knob: thread-block cluster size of the tcgen05 path (0 = automatic, else 1, 2 or 4).
+extern "C" int ragfin_set_gemm_cluster(ragfin_t* h, int32_t cluster) {
+    if (!h || !(cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4)) return fail(RAGFIN_EINVAL, "cluster must be 0, 1, 2 or 4");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->gemm_cluster = cluster;
+    return RAGFIN_OK;
+}
+
 extern "C" int ragfin_search(ragfin_t* h, const float* q, int32_t nq, int32_t k, int64_t* out_ids, float* out_scores,
                              void* stream) {
     if (!h) return fail(RAGFIN_EINVAL, "NULL handle");
@@ -680,10 +732,10 @@ extern "C" int ragfin_profile_read(ragfin_t* h, double* total_ms, int32_t* launc
 }
 
 extern "C" int ragfin_merge_topk(const int64_t* ids, const float* scores, int32_t nq, int32_t parts, int32_t k,
-                                 int64_t part_stride, int64_t query_stride, int64_t* out_ids, float* out_scores,
-                                 int32_t device, void* stream) {
+                                 int64_t ids_part_stride, int64_t scores_part_stride, int64_t query_stride,
+                                 int64_t* out_ids, float* out_scores, int32_t device, void* stream) {
     if (nq < 0 || parts < 1 || k < 1) return fail(RAGFIN_EINVAL, "bad nq/parts/k");
-    if (part_stride < k || query_stride < k) return fail(RAGFIN_EINVAL, "strides must be >= k");
+    if (ids_part_stride < k || scores_part_stride < k || query_stride < k) return fail(RAGFIN_EINVAL, "strides must be >= k");
     if (nq == 0) return RAGFIN_OK;
     if (!ids || !scores || !out_ids || !out_scores) return fail(RAGFIN_EINVAL, "NULL buffer");
     DeviceGuard g(device);
@@ -691,7 +743,7 @@ extern "C" int ragfin_merge_topk(const int64_t* ids, const float* scores, int32_
     const int64_t total = (int64_t)nq * parts * k;
     const int threads = 256;
     merge_topk_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
-        ids, scores, nq, parts, k, part_stride, query_stride, out_ids, out_scores);
+        ids, scores, nq, parts, k, ids_part_stride, scores_part_stride, query_stride, out_ids, out_scores);
     CU_TRY(cudaGetLastError());
     return RAGFIN_OK;
 }

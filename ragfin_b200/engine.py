@@ -152,6 +152,10 @@ class Index:
         """Query batches of at least `min_nq` rows use the tcgen05 path (default 9)."""
         _lib.check(self._L.ragfin_set_gemm_min_batch(self._h, int(min_nq)))
 
+    def set_gemm_cluster(self, cluster: int) -> None:
+        """Thread-block cluster size of the tcgen05 path (0 = automatic, else 1, 2 or 4)."""
+        _lib.check(self._L.ragfin_set_gemm_cluster(self._h, int(cluster)))
+
     def debug_gemm_scores(self, queries):
         """Test hook: raw tensor-core scores [nq, N] (torch CUDA fp32) of CUDA fp32 queries [nq, dim]."""
         import torch
@@ -184,7 +188,6 @@ def merge_topk(ids, scores, parts: int, k: int, stream=None, out_ids=None, out_s
 
     Accepts either the all-gather layout [parts, nq, k] or a concatenation [nq, parts*k]."""
     import torch
-    L = _lib.load()
     ids, scores = ids.contiguous(), scores.contiguous()
     if ids.dim() == 3:
         assert ids.shape[0] == parts and ids.shape[2] == k and scores.shape == ids.shape
@@ -193,10 +196,36 @@ def merge_topk(ids, scores, parts: int, k: int, stream=None, out_ids=None, out_s
         nq = ids.shape[0]
         assert ids.shape == (nq, parts * k) and scores.shape == ids.shape
         part_stride, query_stride = k, parts * k
+    return _merge_raw(ids.data_ptr(), scores.data_ptr(), nq, parts, k, part_stride, part_stride, query_stride,
+                      ids.device, stream, out_ids, out_scores)
+
+
+def _merge_raw(ids_ptr, scores_ptr, nq, parts, k, ids_ps, scores_ps, qs, device, stream=None, out_ids=None, out_scores=None):
+    import torch
+    L = _lib.load()
     if out_ids is None:
-        out_ids = torch.empty((nq, k), dtype=torch.int64, device=ids.device)
+        out_ids = torch.empty((nq, k), dtype=torch.int64, device=device)
     if out_scores is None:
-        out_scores = torch.empty((nq, k), dtype=torch.float32, device=ids.device)
-    _lib.check(L.ragfin_merge_topk(ids.data_ptr(), scores.data_ptr(), nq, parts, k, part_stride, query_stride,
-                                   out_ids.data_ptr(), out_scores.data_ptr(), ids.device.index, _stream_ptr(stream)))
+        out_scores = torch.empty((nq, k), dtype=torch.float32, device=device)
+    _lib.check(L.ragfin_merge_topk(ids_ptr, scores_ptr, nq, parts, k, ids_ps, scores_ps, qs,
+                                   out_ids.data_ptr(), out_scores.data_ptr(), device.index, _stream_ptr(stream)))
     return out_ids, out_scores
+
+
+class PackedHits:
+    """One byte buffer per rank holding {ids int64 [nq, k] | scores fp32 [nq, k]} (padded to 16 B) so that the
+    cross-shard exchange is a single all-gather; `gathered` is the [world, record] receive buffer."""
+
+    def __init__(self, nq: int, k: int, world: int, device):
+        import torch
+        self.nq, self.k, self.world = nq, k, world
+        self.record = (nq * k * 12 + 15) // 16 * 16
+        self.local = torch.empty(self.record, dtype=torch.uint8, device=device)
+        self.gathered = torch.empty(world * self.record, dtype=torch.uint8, device=device)
+        self.ids = self.local[: nq * k * 8].view(torch.int64).view(nq, k)
+        self.scores = self.local[nq * k * 8: nq * k * 12].view(torch.float32).view(nq, k)
+
+    def merge(self, stream=None):
+        base = self.gathered.data_ptr()
+        return _merge_raw(base, base + self.nq * self.k * 8, self.nq, self.world, self.k, self.record // 8,
+                          self.record // 4, self.k, self.gathered.device, stream)

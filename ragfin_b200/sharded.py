@@ -26,9 +26,11 @@ class ShardedSearcher:
 
     `local_search(queries, k) -> (ids, scores)` and `merge(ids, scores, parts, k)` are injected so
     that the host logic can be exercised on CPU (gloo) with stand-ins; on a GPU box they are
-    `Index.search_device` and `ragfin_b200.merge_topk` (see `for_index`)."""
+    `Index.search_device` and `ragfin_b200.merge_topk` (see `for_index`).  With `packed_factory`
+    (GPU path) the local hits are written straight into one packed record per rank, so the exchange
+    is a single NCCL all-gather of nq*k*12 bytes."""
 
-    def __init__(self, local_search: Callable, merge: Callable, group=None):
+    def __init__(self, local_search: Callable, merge: Callable, group=None, packed_factory: Optional[Callable] = None):
         import torch.distributed as dist
         self._dist = dist
         self.group = group
@@ -36,20 +38,30 @@ class ShardedSearcher:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.local_search = local_search
         self.merge = merge
+        self.packed_factory = packed_factory
+        self._packed = {}
         self._gather_ids = None
         self._gather_scores = None
 
     @classmethod
     def for_index(cls, index, group=None) -> "ShardedSearcher":
-        from .engine import merge_topk
-        return cls(index.search_device, merge_topk, group)
+        from .engine import PackedHits, merge_topk
+        return cls(index.search_device, merge_topk, group, packed_factory=PackedHits)
 
     def search(self, queries, k: int):
         import torch
-        ids, scores = self.local_search(queries, k)
         if self.world == 1:
-            return ids, scores
-        nq = ids.shape[0]
+            return self.local_search(queries, k)
+        nq = queries.shape[0]
+        if self.packed_factory is not None:
+            key = (nq, k)
+            ph = self._packed.get(key)
+            if ph is None:
+                ph = self._packed[key] = self.packed_factory(nq, k, self.world, queries.device)
+            self.local_search(queries, k, out_ids=ph.ids, out_scores=ph.scores)
+            self._dist.all_gather_into_tensor(ph.gathered, ph.local, group=self.group)
+            return ph.merge()
+        ids, scores = self.local_search(queries, k)
         shape = (self.world * nq, k)          # concatenation along dim 0 == [world][nq][k] in memory
         if self._gather_ids is None or tuple(self._gather_ids.shape) != shape or self._gather_ids.device != ids.device:
             self._gather_ids = torch.empty(shape, dtype=ids.dtype, device=ids.device)

@@ -298,3 +298,17 @@ def test_gemm_small_collection_and_k_above_n(coracle):
     got = idx.search(q, 20)
     assert idx.stats()["path"] == 1
     _assert_same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, "f32"), 20))
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4])
+@pytest.mark.parametrize("dtype,nq", [("bf16", 300), ("f16", 129), ("f32", 513), ("bf16", 40)])
+def test_gemm_cluster_multicast_variants(coracle, cluster, dtype, nq):
+    """Thread-block clusters with TMA multicast of the corpus tile: same bits for every cluster size, including
+    query-tile counts that do not divide the cluster (padding tiles)."""
+    x = O.synth_rows(190, 0, 26000, 768, dup_every=211)
+    q = O.synth_rows(191, 0, nq, 768)
+    idx = _index(x, dtype)
+    idx.set_gemm_cluster(cluster)
+    got = idx.search(q, 10)
+    assert idx.stats()["path"] == 1
+    _assert_same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), 10), f"cluster={cluster} {dtype} nq={nq}")
