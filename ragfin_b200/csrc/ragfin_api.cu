@@ -385,7 +385,8 @@ static GemmPlan plan_gemm(int nq, int64_t n, int num_sms, int kp, int C) {
         const int64_t tps = (n_tiles + S - 1) / S;
         S = (n_tiles + tps - 1) / tps;
         const int64_t items = (int64_t)groups * S;
-        const double cost = (double)((items + num_sms - 1) / num_sms) * (double)tps + 0.02 * w;
+        // sweep length in tiles, plus a per-item charge: every extra slice of a query restarts its candidate list
+        const double cost = (double)((items + num_sms - 1) / num_sms) * ((double)tps + 24.0);
         if (cost < best) { best = cost; bestS = (int)S; }
     }
     const int64_t tps = (n_tiles + bestS - 1) / bestS;
