@@ -78,7 +78,8 @@ int ragfin_set_id_base(ragfin_t* h, int64_t id_base);
 /* Exact cosine top-k.  q: [nq, dim] fp32 row-major DEVICE memory (raw, un-normalised
  * queries).  out_ids [nq, k] int64 and out_scores [nq, k] fp32 are DEVICE memory; hits are
  * in descending score, ties broken by lower id; slots beyond min(k, N) hold id -1 and
- * score -inf.  Asynchronous on `stream`.  1 <= k <= 16384 (the Milvus limit).
+ * score -inf.  Asynchronous on `stream` for k <= 224; larger k (up to 16384, the Milvus limit) takes
+ * an exact radix-select path that synchronises the stream once per query.
  * Replaces: Collection.search(q, "embedding", {"metric_type":"COSINE"}, k)
  * - vector_rag_mcp/main.py:51-57 (and the three other call sites listed above). */
 int ragfin_search(ragfin_t* h, const float* q, int32_t nq, int32_t k, int64_t* out_ids,
@@ -107,7 +108,7 @@ int ragfin_read_rows(ragfin_t* h, int64_t row0, int64_t n, void* out_host, int32
 
 /* Counters of the most recent search on this handle: kernel launches issued, queries that
  * took the exact-rescan tier (certificate failed), which scoring path ran
- * (0 = small-batch scan, 1 = tcgen05 GEMM).  Reading queries_rescanned synchronises. */
+ * (0 = small-batch scan, 1 = tcgen05 GEMM, 2 = large-k radix select).  Reading queries_rescanned synchronises. */
 typedef struct {
     int32_t launches;
     int32_t path;

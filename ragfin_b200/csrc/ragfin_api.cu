@@ -10,6 +10,7 @@
 #include "../../include/ragfin.h"
 #include "kernels.cuh"
 #include "gemm.cuh"
+#include "bigk.cuh"
 
 using namespace rfk;
 
@@ -50,7 +51,7 @@ struct ragfin {
     void* data = nullptr;  // [capacity, ld] storage, row-major, L2-normalised
     std::mutex mu;
     // workspace (grow-only)
-    Buf qhat, q16, eps_q, gtau, cand, cand_e, flags, stage_q, stage_ids, stage_scores, add_stage;
+    Buf qhat, q16, eps_q, gtau, bk_scores, bk_state, bk_keys, cand, cand_e, flags, stage_q, stage_ids, stage_scores, add_stage;
     int gemm_min_nq = 9;      // query batches of at least this many rows take the tcgen05 path
     int gemm_cluster = 0;     // 0 = choose by batch size; 1, 2 or 4 = force
     cudaEvent_t last_done = nullptr;
@@ -154,7 +155,7 @@ extern "C" void ragfin_destroy(ragfin_t* h) {
     if (!h) return;
     DeviceGuard g(h->device);
     (void)cudaDeviceSynchronize();
-    Buf* bufs[] = {&h->qhat, &h->q16, &h->eps_q, &h->gtau, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage};
+    Buf* bufs[] = {&h->qhat, &h->q16, &h->eps_q, &h->gtau, &h->bk_scores, &h->bk_state, &h->bk_keys, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage};
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->data) cudaFree(h->data);
@@ -506,6 +507,51 @@ static float eps_gemm_const(int dtype, int ld) {
     return (float)e;
 }
 
+// ------------------------------------------------------------------------------
+// Large-k path: exact scores of every row, radix select of the k-th key, rank sort.  One query at a time.
+// ------------------------------------------------------------------------------
+static int search_bigk(ragfin* h, const float* q_dev, int nq, int k, int64_t* out_ids, float* out_scores, cudaStream_t st) {
+    int rc;
+    const int64_t n = h->count;
+    const int m = (int64_t)k < n ? k : (int)n;   // hits that exist
+    h->stats.path = 2;
+    h->stats.cand_per_query = m;
+    h->stats.queries_rescanned = 0;
+    if ((rc = ensure(h->qhat, (size_t)h->ld * sizeof(float)))) return rc;
+    if ((rc = ensure(h->bk_scores, (size_t)n * sizeof(float)))) return rc;
+    if ((rc = ensure(h->bk_state, sizeof(RadixState)))) return rc;
+    if ((rc = ensure(h->bk_keys, (size_t)m * sizeof(u64)))) return rc;
+    float* qhat = (float*)h->qhat.p;
+    float* scores = (float*)h->bk_scores.p;
+    RadixState* state = (RadixState*)h->bk_state.p;
+    u64* keys = (u64*)h->bk_keys.p;
+    const int blocks = h->num_sms * 8;
+    for (int q = 0; q < nq; ++q) {
+        if ((rc = launch_ingest<false>(0, q_dev + (size_t)q * h->dim, 0, 0, 0, 0, 1, h->dim, h->ld, qhat, h->num_sms, st))) return rc;
+        switch (h->dtype) {
+            case 0: score_all_kernel<0><<<blocks, 256, 0, st>>>(h->data, n, h->ld, qhat, scores); break;
+            case 1: score_all_kernel<1><<<blocks, 256, 0, st>>>(h->data, n, h->ld, qhat, scores); break;
+            default: score_all_kernel<2><<<blocks, 256, 0, st>>>(h->data, n, h->ld, qhat, scores); break;
+        }
+        CU_TRY(cudaGetLastError());
+        RadixState init;
+        memset(&init, 0, sizeof(init));
+        init.remaining = m;
+        CU_TRY(cudaMemcpyAsync(state, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaStreamSynchronize(st));   // `init` lives on this stack frame
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            radix_hist_kernel<<<blocks, 256, 0, st>>>(scores, n, shift, state);
+            radix_pick_kernel<<<1, 32, 0, st>>>(shift, state);
+        }
+        compact_kernel<<<blocks, 256, 0, st>>>(scores, n, state, keys, m);
+        const int span = m > k ? m : k;
+        rank_sort_kernel<<<(span + 255) / 256, 256, 0, st>>>(keys, m, k, h->id_base, out_ids + (size_t)q * k, out_scores + (size_t)q * k);
+        CU_TRY(cudaGetLastError());
+        h->stats.launches += 20;
+    }
+    return 0;
+}
+
 static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* out_ids, float* out_scores,
                          cudaStream_t st) {
     int rc;
@@ -518,8 +564,7 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
     const int steps = round_steps((nvec + 31) / 32);
     int kp = cand_per_query(k);
     if (kp == 0 && n <= 256) kp = 256;   // every row is a candidate: any k (graph_cons.py:279 asks limit=1000 of 16 rows)
-    if (kp == 0)
-        return fail(RAGFIN_EUNSUPPORTED, "k = %d above 224 on a corpus of more than 256 rows needs the large-k path (not built yet)", k);
+    if (kp == 0) return search_bigk(h, q_dev, nq, k, out_ids, out_scores, st);
     h->stats.cand_per_query = kp;
     const int kpe = k > 256 ? 256 : (k + 31) / 32 * 32;   // k > 256 only occurs with n <= 256
     if ((rc = ensure(h->flags, (size_t)(kMaxQueryBatch + 1) * sizeof(int)))) return rc;
@@ -694,7 +739,7 @@ extern "C" int ragfin_last_search_stats(ragfin_t* h, ragfin_search_stats* out) {
     if (!h || !out) return fail(RAGFIN_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard g(h->device);
-    if (h->flags.p) {
+    if (h->flags.p && h->stats.path != 2) {
         CU_TRY(cudaDeviceSynchronize());
         int fc = 0;
         CU_TRY(cudaMemcpy(&fc, (int*)h->flags.p + kMaxQueryBatch, sizeof(int), cudaMemcpyDeviceToHost));

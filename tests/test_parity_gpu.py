@@ -312,3 +312,37 @@ def test_gemm_cluster_multicast_variants(coracle, cluster, dtype, nq):
     got = idx.search(q, 10)
     assert idx.stats()["path"] == 1
     _assert_same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), 10), f"cluster={cluster} {dtype} nq={nq}")
+
+
+# ------------------------------------------------------------------------------------------------
+# large-k path (k > 224 on corpora of more than 256 rows; Milvus allows limit up to 16384)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,n,k,nq", [("f32", 3000, 300, 2), ("bf16", 20000, 1000, 3), ("f16", 9000, 5000, 1),
+                                          ("bf16", 700, 1000, 2), ("f32", 40000, 16384, 1)])
+def test_large_k_matches_oracle(coracle, dtype, n, k, nq):
+    x = O.synth_rows(200, 0, n, 384, dup_every=37, zero_every=501)
+    q = O.synth_rows(201, 0, nq, 384)
+    idx = _index(x, dtype)
+    got = idx.search(q, k)
+    assert idx.stats()["path"] == 2
+    _assert_same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), k), f"large-k {dtype} n={n} k={k}")
+    if k > n:
+        assert (got[0][:, n:] == -1).all() and np.isneginf(got[1][:, n:]).all()
+
+
+def test_hybrid_limit_1000_through_the_shim_on_a_larger_collection(coracle):
+    """graph_cons.py:275-281 asks limit=1000; on a collection larger than that it must return exactly 1000 ranked hits."""
+    from ragfin_b200 import milvus_compat as mc
+    F, D = mc.FieldSchema, mc.DataType
+    mc.utility.drop_collection("big")
+    col = mc.Collection("big", mc.CollectionSchema([F("id", D.VARCHAR, max_length=100, is_primary=True),
+                                                     F("embedding", D.FLOAT_VECTOR, dim=384)]), storage_dtype="bf16")
+    x = O.synth_rows(210, 0, 5000, 384)
+    col.insert([[f"c{i}" for i in range(5000)], x])
+    col.load()
+    q = O.synth_rows(211, 0, 1, 384)
+    hits = col.search(q, "embedding", {"metric_type": "COSINE"}, limit=1000, output_fields=["id"])[0]
+    wi, ws = coracle.cosine_topk(q, coracle.normalize_rows(x, "bf16"), 1000)
+    assert [h.entity.get("id") for h in hits] == [f"c{i}" for i in wi[0]]
+    assert np.array_equal(np.array([h.score for h in hits], np.float32).view(np.uint32), ws[0].view(np.uint32))
+    mc.utility.drop_collection("big")
