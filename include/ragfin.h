@@ -124,8 +124,16 @@ int ragfin_last_search_stats(ragfin_t* h, ragfin_search_stats* out);
 int ragfin_profile(ragfin_t* h, int32_t enable);
 int ragfin_profile_read(ragfin_t* h, double* total_ms, int32_t* launches);
 
+/* Persistence of the device-resident matrix (stands in for Milvus' flush()/load() durability,
+ * "chunking_storing (1).py":395-396, retrieve.py:18-19).  File = 64-byte header {magic "RAGFINB2", version,
+ * dim, ld, dtype, count, id_base} + the stored rows [count, ld] exactly as they sit in HBM, so a
+ * reloaded collection returns bit-identical results without re-normalising.
+ * ragfin_load creates a new handle on `device` with room for max(capacity_rows, count) rows. */
+int ragfin_save(ragfin_t* h, const char* path);
+int ragfin_load(ragfin_t** out, const char* path, int64_t capacity_rows, int32_t device);
+
 /* Dispatch knob: query batches of at least `min_nq` rows take the tcgen05 tensor-core path, smaller
- * ones the HBM-bound scan (default 9).  Both paths return identical results. */
+ * ones the HBM-bound scan (default 5).  Both paths return identical results. */
 int ragfin_set_gemm_min_batch(ragfin_t* h, int32_t min_nq);
 
 /* Tuning knob: thread-block cluster size of the tcgen05 path along the query-tile axis (corpus tiles

@@ -113,7 +113,7 @@ __host__ __device__ constexpr int scan_rows(int steps) { return steps <= 1 ? 8 :
 template <int DT, int NQ, int STEPS>
 __global__ void __launch_bounds__(kScanThreads, NQ >= 4 ? 1 : 2)
 scan_topk_kernel(const void* __restrict__ data, int64_t n_rows, int ld, const float* __restrict__ qhat,
-                 int kp, u64* __restrict__ cand, int64_t cand_q_stride) {
+                 int nq_valid, int kp, u64* __restrict__ cand, int64_t cand_q_stride) {
     typedef Store<DT> S;
     constexpr int V = S::kVec;
     constexpr int R = scan_rows(STEPS);
@@ -137,9 +137,9 @@ scan_topk_kernel(const void* __restrict__ data, int64_t n_rows, int ld, const fl
             for (int e = 0; e < V; ++e) qreg[q][j * V + e] = vi < nvec ? qhat[(size_t)q * ld + vi * V + e] : 0.0f;
         }
 
-    float tau[NQ];
+    float tau[NQ];   // padding queries (zero rows beyond nq_valid) never collect
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) tau[q] = -INFINITY;
+    for (int q = 0; q < NQ; ++q) tau[q] = q < nq_valid ? -INFINITY : INFINITY;
 
     const char* base = reinterpret_cast<const char*>(data);
     const size_t row_bytes = (size_t)ld * sizeof(typename S::T);

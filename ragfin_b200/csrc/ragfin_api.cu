@@ -52,7 +52,7 @@ struct ragfin {
     std::mutex mu;
     // workspace (grow-only)
     Buf qhat, q16, eps_q, gtau, bk_scores, bk_state, bk_keys, cand, cand_e, flags, stage_q, stage_ids, stage_scores, add_stage;
-    int gemm_min_nq = 9;      // query batches of at least this many rows take the tcgen05 path
+    int gemm_min_nq = 5;      // query batches of at least this many rows take the tcgen05 path
     int gemm_cluster = 0;     // 0 = choose by batch size; 1, 2 or 4 = force
     cudaEvent_t last_done = nullptr;
     ragfin_search_stats stats = {0, 0, 0, 0};
@@ -272,7 +272,7 @@ extern "C" int ragfin_read_rows(ragfin_t* h, int64_t row0, int64_t n, void* out_
 // ------------------------------------------------------------------------------
 // K2 dispatch
 // ------------------------------------------------------------------------------
-typedef void (*scan_fn)(const void*, int64_t, int, const float*, int, u64*, int64_t);
+typedef void (*scan_fn)(const void*, int64_t, int, const float*, int, int, u64*, int64_t);
 static const int kMaxScanCtasPerSm = 4;
 
 template <int DT, int NQ>
@@ -628,7 +628,7 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
                     scan_fn fn = pick_scan(h->dtype, nqt, steps);
                     const size_t smem = (size_t)nqt * kScanWarps * kp * sizeof(u64);
                     prof_begin(h, st);
-                    fn<<<G, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat + (size_t)g0 * h->ld, kp,
+                    fn<<<G, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat + (size_t)g0 * h->ld, left < nqt ? left : nqt, kp,
                                                        (u64*)h->cand.p + (size_t)g0 * G * kp,
                                                        (int64_t)G * kp);
                     prof_end(h, st);
@@ -667,6 +667,79 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
     return 0;
 }
 
+// ------------------------------------------------------------------------------
+// persistence
+// ------------------------------------------------------------------------------
+struct FileHeader {
+    char magic[8];
+    uint32_t version, dim, ld, dtype;
+    int64_t count, id_base;
+    uint8_t pad[24];
+};
+static_assert(sizeof(FileHeader) == 64, "header is 64 bytes");
+
+extern "C" int ragfin_save(ragfin_t* h, const char* path) {
+    if (!h || !path) return fail(RAGFIN_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    CU_TRY(cudaDeviceSynchronize());
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(RAGFIN_EINVAL, "cannot open %s for writing", path);
+    FileHeader hd;
+    memset(&hd, 0, sizeof(hd));
+    memcpy(hd.magic, "RAGFINB2", 8);
+    hd.version = 1; hd.dim = (uint32_t)h->dim; hd.ld = (uint32_t)h->ld; hd.dtype = (uint32_t)h->dtype;
+    hd.count = h->count; hd.id_base = h->id_base;
+    int rc = 0;
+    if (fwrite(&hd, sizeof(hd), 1, f) != 1) rc = fail(RAGFIN_EINVAL, "write to %s failed", path);
+    const size_t rb = (size_t)h->ld * esize(h->dtype);
+    const int64_t slice = (int64_t)((64u << 20) / rb) + 1;
+    void* host = nullptr;
+    if (!rc && cudaMallocHost(&host, (size_t)slice * rb) != cudaSuccess) { (void)cudaGetLastError(); rc = fail(RAGFIN_ENOMEM, "pinned staging allocation failed"); }
+    for (int64_t r0 = 0; !rc && r0 < h->count; r0 += slice) {
+        const int64_t m = h->count - r0 < slice ? h->count - r0 : slice;
+        if (cudaMemcpy(host, (char*)h->data + (size_t)r0 * rb, (size_t)m * rb, cudaMemcpyDeviceToHost) != cudaSuccess) { (void)cudaGetLastError(); rc = fail(RAGFIN_ECUDA, "device read failed"); break; }
+        if (fwrite(host, rb, (size_t)m, f) != (size_t)m) rc = fail(RAGFIN_EINVAL, "write to %s failed", path);
+    }
+    if (host) cudaFreeHost(host);
+    if (fclose(f) != 0 && !rc) rc = fail(RAGFIN_EINVAL, "close of %s failed", path);
+    return rc;
+}
+
+extern "C" int ragfin_load(ragfin_t** out, const char* path, int64_t capacity_rows, int32_t device) {
+    if (!out || !path) return fail(RAGFIN_EINVAL, "NULL argument");
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(RAGFIN_EINVAL, "cannot open %s", path);
+    FileHeader hd;
+    if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, "RAGFINB2", 8) != 0 || hd.version != 1 || hd.dtype > 2 ||
+        hd.ld != (hd.dim + 7) / 8 * 8 || hd.count < 0) {
+        fclose(f);
+        return fail(RAGFIN_EINVAL, "%s is not a ragfin matrix file", path);
+    }
+    ragfin* h = nullptr;
+    const int64_t cap = capacity_rows > hd.count ? capacity_rows : (hd.count > 0 ? hd.count : 1);
+    int rc = ragfin_create(&h, (int32_t)hd.dim, (int32_t)hd.dtype, cap, device);
+    if (rc) { fclose(f); return rc; }
+    DeviceGuard g(device);
+    const size_t rb = (size_t)h->ld * esize(h->dtype);
+    const int64_t slice = (int64_t)((64u << 20) / rb) + 1;
+    void* host = nullptr;
+    if (cudaMallocHost(&host, (size_t)slice * rb) != cudaSuccess) { (void)cudaGetLastError(); rc = fail(RAGFIN_ENOMEM, "pinned staging allocation failed"); }
+    for (int64_t r0 = 0; !rc && r0 < hd.count; r0 += slice) {
+        const int64_t m = hd.count - r0 < slice ? hd.count - r0 : slice;
+        if (fread(host, rb, (size_t)m, f) != (size_t)m) { rc = fail(RAGFIN_EINVAL, "%s is truncated", path); break; }
+        if (cudaMemcpy((char*)h->data + (size_t)r0 * rb, host, (size_t)m * rb, cudaMemcpyHostToDevice) != cudaSuccess) { (void)cudaGetLastError(); rc = fail(RAGFIN_ECUDA, "device write failed"); }
+    }
+    if (host) cudaFreeHost(host);
+    fclose(f);
+    if (rc) { ragfin_destroy(h); return rc; }
+    h->count = hd.count;
+    h->id_base = hd.id_base;
+    *out = h;
+    return RAGFIN_OK;
+}
+
 // Test hook: raw tensor-core scores [nq, count] of the queries against every row (device memory out).
 extern "C" int ragfin_debug_gemm_scores(ragfin_t* h, const float* q_dev, int32_t nq, float* out_scores_dev, void* stream) {
     if (!h || !q_dev || !out_scores_dev || nq < 1) return fail(RAGFIN_EINVAL, "bad argument");
@@ -683,7 +756,7 @@ extern "C" int ragfin_debug_gemm_scores(ragfin_t* h, const float* q_dev, int32_t
     return mark_done(h, st);
 }
 
-// Dispatch knob: query batches of at least `min_nq` rows use the tcgen05 path (default 9; INT32_MAX = never).
+// Dispatch knob: query batches of at least `min_nq` rows use the tcgen05 path (default 5; INT32_MAX = never).
 extern "C" int ragfin_set_gemm_min_batch(ragfin_t* h, int32_t min_nq) {
     if (!h || min_nq < 1) return fail(RAGFIN_EINVAL, "bad argument");
     std::lock_guard<std::mutex> lk(h->mu);

@@ -38,6 +38,25 @@ class Index:
         _lib.check(self._L.ragfin_create(ctypes.byref(h), self.dim, DTYPE_CODE[dtype], self.capacity, self.device))
         self._h = h
 
+    # -- persistence -----------------------------------------------------------------
+    def save(self, path: str) -> None:
+        """Write the stored (normalised, rounded) matrix to `path`; `Index.load` restores it bit for bit."""
+        _lib.check(self._L.ragfin_save(self._h, str(path).encode()))
+
+    @classmethod
+    def load(cls, path: str, capacity: int = 0, device: int = 0) -> "Index":
+        L = _lib.load()
+        h = ctypes.c_void_p()
+        _lib.check(L.ragfin_load(ctypes.byref(h), str(path).encode(), int(capacity), int(device)))
+        self = cls.__new__(cls)
+        self._L, self._h, self.device = L, h, int(device)
+        with open(path, "rb") as f:
+            hd = f.read(64)
+        self.dim = int.from_bytes(hd[12:16], "little")
+        self.dtype = ("f32", "bf16", "f16")[int.from_bytes(hd[20:24], "little")]
+        self.capacity = max(int(capacity), int.from_bytes(hd[24:32], "little", signed=True), 1)
+        return self
+
     # -- lifecycle -------------------------------------------------------------------
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -149,7 +168,7 @@ class Index:
         return out_ids, out_scores
 
     def set_gemm_min_batch(self, min_nq: int) -> None:
-        """Query batches of at least `min_nq` rows use the tcgen05 path (default 9)."""
+        """Query batches of at least `min_nq` rows use the tcgen05 path (default 5)."""
         _lib.check(self._L.ragfin_set_gemm_min_batch(self._h, int(min_nq)))
 
     def set_gemm_cluster(self, cluster: int) -> None:

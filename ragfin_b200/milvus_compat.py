@@ -154,6 +154,8 @@ class _Store:
             if not self.pending:
                 return
             need = self.n_inserted
+            if self.raw is None and need > self.capacity:
+                raise MilvusException(message="collection was loaded from disk with a fixed capacity; reload with a larger one")
             if self.index is None or need > self.capacity:
                 while self.capacity < need:
                     self.capacity *= 2
@@ -166,6 +168,44 @@ class _Store:
             for b in blocks:
                 self.index.add(b)
             self.pending = []
+
+
+def save_collection(name: str, directory: str) -> None:
+    """Durability stand-in for a Milvus flush: `<dir>/<name>.ragfin` (device matrix) + `<dir>/<name>.columns.json`."""
+    import json, os
+    st = _REGISTRY[name]
+    with st.lock:
+        st.flush()
+        os.makedirs(directory, exist_ok=True)
+        if st.index is not None:
+            st.index.save(os.path.join(directory, name + ".ragfin"))
+        fields = [{"name": f.name, "dtype": int(f.dtype), "is_primary": f.is_primary, "params": f.params} for f in st.schema.fields]
+        with open(os.path.join(directory, name + ".columns.json"), "w") as f:
+            json.dump({"fields": fields, "description": st.schema.description, "columns": st.columns,
+                       "n": st.n_inserted, "storage_dtype": st.storage_dtype, "metric": st.metric}, f)
+
+
+def load_collection(name: str, directory: str, device: int = 0, using: str = "default") -> "Collection":
+    """Re-open a saved collection without re-embedding or re-normalising (results are bit-identical)."""
+    import json, os
+    from .engine import Index
+    with open(os.path.join(directory, name + ".columns.json")) as f:
+        meta = json.load(f)
+    fields = [FieldSchema(x["name"], DataType(x["dtype"]), is_primary=x["is_primary"], **x["params"]) for x in meta["fields"]]
+    utility.drop_collection(name)
+    col = Collection(name, CollectionSchema(fields, meta["description"]), using=using, storage_dtype=meta["storage_dtype"], device=device)
+    st = col._st
+    st.columns = meta["columns"]
+    st.n_inserted = int(meta["n"])
+    st.metric = meta["metric"]
+    pk = st.schema.primary_field.name
+    st.pk_to_row = {v: i for i, v in enumerate(st.columns[pk])}
+    mpath = os.path.join(directory, name + ".ragfin")
+    if st.n_inserted and os.path.exists(mpath):
+        st.index = Index.load(mpath, capacity=max(st.capacity, st.n_inserted), device=device)
+        st.capacity = st.index.capacity
+        st.raw = None          # the original fp32 rows are gone: growth past capacity is refused after a reload
+    return col
 
 
 class _Utility:
@@ -331,7 +371,8 @@ class Collection:
             for j, pk in enumerate(pks):
                 st.pk_to_row[pk] = st.n_inserted + j
             if n:
-                st.raw.append(emb)
+                if st.raw is not None:
+                    st.raw.append(emb)
                 st.pending.append(emb)
             st.n_inserted += n
         assert pk_name in st.columns

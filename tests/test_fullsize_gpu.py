@@ -44,7 +44,7 @@ def test_full_size_properties(corpus, coracle):
     idx.set_gemm_min_batch(1 << 30)
     ids_s, sc_s = idx.search(q[:8], K)
     assert idx.stats()["path"] == 0
-    idx.set_gemm_min_batch(9)
+    idx.set_gemm_min_batch(5)
     ids_g, sc_g = idx.search(q, K)
     assert idx.stats()["path"] == 1
     assert np.array_equal(ids_s, ids_g[:8]) and np.array_equal(sc_s.view(np.uint32), sc_g[:8].view(np.uint32))

@@ -346,3 +346,47 @@ def test_hybrid_limit_1000_through_the_shim_on_a_larger_collection(coracle):
     assert [h.entity.get("id") for h in hits] == [f"c{i}" for i in wi[0]]
     assert np.array_equal(np.array([h.score for h in hits], np.float32).view(np.uint32), ws[0].view(np.uint32))
     mc.utility.drop_collection("big")
+
+
+def test_save_load_roundtrip_is_bit_identical(coracle, tmp_path):
+    import ragfin_b200
+    x = O.synth_rows(220, 0, 12345, 768, dup_every=17)
+    q = O.synth_rows(221, 0, 12, 768)
+    idx = _index(x, "bf16")
+    idx.set_id_base(777)
+    want = idx.search(q, 10)
+    path = str(tmp_path / "corpus.ragfin")
+    idx.save(path)
+    idx.close()
+    back = ragfin_b200.Index.load(path, capacity=20000, device=0)
+    assert len(back) == 12345 and back.dim == 768 and back.dtype == "bf16"
+    _assert_same(back.search(q, 10), want, "reloaded")
+    assert np.array_equal(back.read_rows(0, 100).view(np.uint32), coracle.normalize_rows(x[:100], "bf16").view(np.uint32))
+    back.add(x[:5])                    # still appendable up to the new capacity
+    assert len(back) == 12350
+    with pytest.raises(ragfin_b200.RagfinError):
+        ragfin_b200.Index.load(str(tmp_path / "missing.ragfin"))
+    (tmp_path / "junk.ragfin").write_bytes(b"not a matrix" * 10)
+    with pytest.raises(ragfin_b200.RagfinError):
+        ragfin_b200.Index.load(str(tmp_path / "junk.ragfin"))
+
+
+def test_collection_save_and_reload_through_the_shim(tmp_path):
+    from ragfin_b200 import milvus_compat as mc
+    F, D = mc.FieldSchema, mc.DataType
+    mc.utility.drop_collection("persist")
+    col = mc.Collection("persist", mc.CollectionSchema([F("id", D.VARCHAR, max_length=100, is_primary=True),
+                                                         F("embedding", D.FLOAT_VECTOR, dim=384), F("period", D.VARCHAR, max_length=20)]))
+    x = O.synth_rows(230, 0, 300, 384)
+    col.insert([[f"c{i}" for i in range(300)], x, [f"Q{i % 4 + 1}_FY2024" for i in range(300)]])
+    col.flush()
+    q = O.synth_rows(231, 0, 2, 384)
+    before = [[(h.id, h.score, h.entity.period) for h in hits] for hits in col.search(q, "embedding", {"metric_type": "COSINE"}, 5, output_fields=["period"])]
+    mc.save_collection("persist", str(tmp_path))
+    mc.utility.drop_collection("persist")
+    col2 = mc.load_collection("persist", str(tmp_path))
+    assert col2.num_entities == 300 and mc.Collection("persist").num_entities == 300
+    after = [[(h.id, h.score, h.entity.period) for h in hits] for hits in col2.search(q, "embedding", {"metric_type": "COSINE"}, 5, output_fields=["period"])]
+    assert before == after
+    assert col2.query(expr='id in ["c7"]', output_fields=["period"]) == [{"id": "c7", "period": "Q4_FY2024"}]
+    mc.utility.drop_collection("persist")
