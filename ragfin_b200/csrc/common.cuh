@@ -102,9 +102,16 @@ template <int DT>
 __device__ __forceinline__ double canonical_dot_row(const typename Store<DT>::T* __restrict__ row,
                                                     const float* __restrict__ q, int dim, int lane) {
     double acc = 0.0;
-#pragma unroll 8
-    for (int i = lane; i < dim; i += kWarp)   // loads batch up; the fp64 adds stay in increasing-i order
-        acc = acc + (double)Store<DT>::to_f32(row[i]) * (double)q[i];
+    int i = lane;
+    for (; i + 23 * kWarp < dim; i += 24 * kWarp) {   // 24 loads in flight (one 768-wide row); adds stay in increasing-i order
+        float a[24], b[24];
+#pragma unroll
+        for (int u = 0; u < 24; ++u) { a[u] = Store<DT>::to_f32(row[i + u * kWarp]); b[u] = q[i + u * kWarp]; }
+#pragma unroll
+        for (int u = 0; u < 24; ++u) acc = acc + (double)a[u] * (double)b[u];
+    }
+#pragma unroll 4
+    for (; i < dim; i += kWarp) acc = acc + (double)Store<DT>::to_f32(row[i]) * (double)q[i];
     return warp_butterfly_f64(acc);
 }
 

@@ -12,7 +12,7 @@ namespace rfk {
 
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / kWarp;
-constexpr int kFinThreads = 512;
+constexpr int kFinThreads = 1024;
 constexpr int kFinWarps = kFinThreads / kWarp;
 
 // ---------------------------------------------------------------------------------
@@ -216,26 +216,30 @@ scan_topk_kernel(const void* __restrict__ data, int64_t n_rows, int ld, const fl
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void merge_lists(const u64* __restrict__ src, int G, int kp, u64* wl, bool sorted_lists) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u64* mine = wl + (size_t)warp * kp;
-    for (int i = lane; i < kp; i += kWarp) mine[i] = 0;
-    __syncwarp();
-    for (int l = warp; l < G; l += kFinWarps) {
-        const u64* in = src + (size_t)l * kp;
-        for (int s = 0; s < kp; s += kWarp) {
-            const u64 key = in[s + lane];
-            const unsigned hits = __ballot_sync(kFull, key > mine[kp - 1]);
-            unsigned m = hits;
-            while (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                const u64 bk = __shfl_sync(kFull, key, b);
-                if (bk > mine[kp - 1]) warp_list_insert(mine, kp, bk, lane);
+    int mw = 4096 / kp;                       // merging warps: their lists must fit the 4096-key buffer
+    if (mw > kFinWarps) mw = kFinWarps;
+    if (warp < mw) {
+        u64* mine = wl + (size_t)warp * kp;
+        for (int i = lane; i < kp; i += kWarp) mine[i] = 0;
+        __syncwarp();
+        for (int l = warp; l < G; l += mw) {
+            const u64* in = src + (size_t)l * kp;
+            for (int s = 0; s < kp; s += kWarp) {
+                const u64 key = in[s + lane];
+                const unsigned hits = __ballot_sync(kFull, key > mine[kp - 1]);
+                unsigned m = hits;
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    const u64 bk = __shfl_sync(kFull, key, b);
+                    if (bk > mine[kp - 1]) warp_list_insert(mine, kp, bk, lane);
+                }
+                if (sorted_lists && hits != kFull) break;  // sorted list: nothing further can qualify
             }
-            if (sorted_lists && hits != kFull) break;  // sorted list: nothing further can qualify
         }
     }
     __syncthreads();
-    block_bitonic_sort_desc(wl, kFinWarps * kp, threadIdx.x, kFinThreads);
+    block_bitonic_sort_desc(wl, mw * kp, threadIdx.x, kFinThreads);
 }
 
 template <int DT>
@@ -253,7 +257,7 @@ __device__ __forceinline__ double rescore_row(const void* data, int64_t row, int
 //    Otherwise flags[q] = 1 and the query goes to the exact-rescan tier.
 //  EXACT_IN = true: keys already carry exact scores (tier 2); only flagged queries run.
 // ---------------------------------------------------------------------------------
-constexpr int kFinCap = 4096;     // survivor buffer, keys (>= kFinWarps * 256 so the fallback merge fits)
+constexpr int kFinCap = 4096;     // survivor buffer, keys; the fallback merge uses kFinCap / kp warps
 constexpr int kFinHeads = 1024;   // most candidate lists per query the head-threshold shortcut handles
 
 // Top-kp of G candidate lists into buf[0..kp) (descending), without touching most of the input:
