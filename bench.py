@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--also-batch", type=int, default=4096,
                     help="second regime measured in the same run and reported under 'regimes' (0 = off)")
     ap.add_argument("--gemm-cluster", type=int, default=0, help="tcgen05 path cluster size: 0 auto, 1, 2 or 4")
+    ap.add_argument("--gemm-variant", type=int, default=-1, help="tcgen05 kernel: 0 auto, 1 streaming, 2 A-stationary (-1 = library default)")
     ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="rows of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -196,6 +197,8 @@ def run_ours(a):
         idx.add_synthetic(SEED_CORPUS, row0 + r, min(1_000_000, n_local - r))
     idx.set_id_base(row0)
     idx.set_gemm_cluster(a.gemm_cluster)
+    if a.gemm_variant >= 0:
+        idx.set_gemm_variant(a.gemm_variant)
     torch.cuda.synchronize()
     ingest_s = time.perf_counter() - t0
     searcher = ShardedSearcher.for_index(idx)

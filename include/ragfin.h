@@ -140,6 +140,11 @@ int ragfin_set_gemm_min_batch(ragfin_t* h, int32_t min_nq);
  * are TMA-multicast across the cluster).  0 = automatic (default), else 1, 2 or 4. */
 int ragfin_set_gemm_cluster(ragfin_t* h, int32_t cluster);
 
+/* Tuning knob: tcgen05 kernel variant. 1 = streaming (query and corpus tiles through shared memory, any
+ * dtype / width); 2 = A-stationary (query tile resident in tensor memory; 16-bit storage, dim <= 768);
+ * 0 = automatic.  Results are identical. */
+int ragfin_set_gemm_variant(ragfin_t* h, int32_t variant);
+
 /* Test hook: raw (approximate, fp32-accumulated) tensor-core scores of nq queries against every
  * stored row, out_scores_dev [nq, count] device memory.  Validates the TMA / tcgen05 plumbing. */
 int ragfin_debug_gemm_scores(ragfin_t* h, const float* q_dev, int32_t nq, float* out_scores_dev, void* stream);

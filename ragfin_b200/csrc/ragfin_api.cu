@@ -10,6 +10,7 @@
 #include "../../include/ragfin.h"
 #include "kernels.cuh"
 #include "gemm.cuh"
+#include "gemm_astat.cuh"
 #include "bigk.cuh"
 
 using namespace rfk;
@@ -54,6 +55,7 @@ struct ragfin {
     Buf qhat, q16, eps_q, gtau, bk_scores, bk_state, bk_keys, cand, cand_e, flags, stage_q, stage_ids, stage_scores, add_stage;
     int gemm_min_nq = 5;      // query batches of at least this many rows take the tcgen05 path
     int gemm_cluster = 0;     // 0 = choose by batch size; 1, 2 or 4 = force
+    int gemm_variant = 1;     // 0 = automatic, 1 = streaming (A and B through shared memory), 2 = A-stationary (A in TMEM)
     cudaEvent_t last_done = nullptr;
     ragfin_search_stats stats = {0, 0, 0, 0};
     // measurement hook (ragfin_profile): event pairs around the dominant kernel
@@ -499,6 +501,96 @@ static int run_gemm(ragfin* h, int nb, int kp, int* G, float* dump, cudaStream_t
     return 0;
 }
 
+static bool astat_supported(const ragfin* h, int kp) {
+    return h->dtype != 0 && h->ld <= 2 * kAColsMax && (kp == 32 || kp == 64 || kp == 128) && h->count > 0;
+}
+
+// A-stationary tcgen05 path (gemm_astat.cuh): same contract as run_gemm.
+static int run_gemm_astat(ragfin* h, int nb, int kp, int* G, float* dump, cudaStream_t st) {
+    int rc;
+    const int64_t n = h->count;
+    const int QT0 = (nb + kGM - 1) / kGM;
+    int C = h->gemm_cluster ? h->gemm_cluster : (QT0 >= 8 ? 4 : QT0 >= 2 ? 2 : 1);
+    typedef void (*astat_fn)(const CUtensorMap, const AstatArgs);
+    auto pick = [&](int c) -> astat_fn {
+        if (dump) return gemm_astat_kernel<true, 1>;
+        return c == 4 ? gemm_astat_kernel<false, 4> : c == 2 ? gemm_astat_kernel<false, 2> : gemm_astat_kernel<false, 1>;
+    };
+    if (dump) C = 1;
+    const size_t smem = astat_smem_bytes(kp);
+    astat_fn fn = pick(C);
+    CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int resident_clusters = h->num_sms;
+    if (C > 1) {
+        cudaLaunchConfig_t qc = {};
+        qc.gridDim = dim3(h->num_sms / C * C);
+        qc.blockDim = dim3(kGemmThreads);
+        qc.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        qc.attrs = at; qc.numAttrs = 1;
+        int nc = 0;
+        CU_TRY(cudaOccupancyMaxActiveClusters(&nc, (const void*)fn, &qc));
+        if (nc < 1) { C = 1; fn = pick(1); CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
+        else resident_clusters = nc;
+    }
+    const GemmPlan p = plan_gemm(nb, n, C > 1 ? resident_clusters * C : h->num_sms, kp, C);
+    const float* qhat = (const float*)h->qhat.p;
+    if ((rc = ensure(h->eps_q, (size_t)nb * sizeof(float)))) return rc;
+    if ((rc = ensure(h->q16, (size_t)nb * h->ld * 2))) return rc;
+    const int wpb = 8;
+    if (h->dtype == 1)
+        qconv_kernel<1><<<(nb + wpb - 1) / wpb, wpb * 32, 0, st>>>(qhat, nb, h->ld, (__nv_bfloat16*)h->q16.p, (float*)h->eps_q.p);
+    else
+        qconv_kernel<2><<<(nb + wpb - 1) / wpb, wpb * 32, 0, st>>>(qhat, nb, h->ld, (__half*)h->q16.p, (float*)h->eps_q.p);
+    CU_TRY(cudaGetLastError());
+    h->stats.launches++;
+    CUtensorMap tmB;
+    if ((rc = make_map(&tmB, h->dtype, h->data, n, h->ld, kSN / C))) return rc;
+    if (!dump) {
+        if ((rc = ensure(h->cand, (size_t)nb * p.S * kp * sizeof(u64)))) return rc;
+    }
+    if ((rc = ensure(h->gtau, (size_t)nb * sizeof(uint32_t)))) return rc;
+    CU_TRY(cudaMemsetAsync(h->gtau.p, 0, (size_t)nb * sizeof(uint32_t), st));
+    AstatArgs a;
+    a.idesc = make_idesc_n(h->dtype == 1 ? 1 : 0, kSN);
+    a.num_kblocks = (h->ld + 63) / 64;
+    a.ld = h->ld;
+    a.nq = nb;
+    a.n_rows = n;
+    a.QT = p.QT;
+    a.S = p.S;
+    a.rows_per_slice = p.rows_per_slice;
+    a.slots = astat_slots(kp);
+    a.kp = kp;
+    a.q16 = (const uint16_t*)h->q16.p;
+    a.cand = (u64*)h->cand.p;
+    a.gtau = (uint32_t*)h->gtau.p;
+    a.dump = dump;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    prof_begin(h, st);
+    CU_TRY(cudaLaunchKernelEx(&cfg, fn, tmB, a));
+    prof_end(h, st);
+    CU_TRY(cudaGetLastError());
+    h->stats.launches++;
+    *G = p.S;
+    return 0;
+}
+
+static bool use_astat(const ragfin* h, int kp) {
+    if (h->gemm_variant == 1) return false;
+    return astat_supported(h, kp);   // variant 2 (forced) and 0 (automatic) both need eligibility
+}
+
 // |tensor-core score - exact score| beyond the query rounding term: fp32 accumulation inside the tensor
 // core (bounded generously: truncating adds) and, for tf32, the truncation of both operands to 10 mantissa bits.
 static float eps_gemm_const(int dtype, int ld) {
@@ -588,7 +680,8 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
         const float* eps_q = nullptr;
         if (nb >= h->gemm_min_nq && gemm_supported(h, kp)) {
             // 2a. tensor-core path
-            if ((rc = run_gemm(h, nb, kp, &G, nullptr, st))) return rc;
+            if (use_astat(h, kp)) { if ((rc = run_gemm_astat(h, nb, kp, &G, nullptr, st))) return rc; }
+            else if ((rc = run_gemm(h, nb, kp, &G, nullptr, st))) return rc;
             h->stats.path = 1;
             sorted_lists = 0;
             scanned = true;
@@ -752,7 +845,8 @@ extern "C" int ragfin_debug_gemm_scores(ragfin_t* h, const float* q_dev, int32_t
     if ((rc = ensure(h->qhat, (size_t)nq * h->ld * sizeof(float)))) return rc;
     if ((rc = launch_ingest<false>(0, q_dev, 0, 0, 0, 0, nq, h->dim, h->ld, (float*)h->qhat.p, h->num_sms, st))) return rc;
     int G = 0;
-    if ((rc = run_gemm(h, nq, 32, &G, out_scores_dev, st))) return rc;
+    if (use_astat(h, 32)) { if ((rc = run_gemm_astat(h, nq, 32, &G, out_scores_dev, st))) return rc; }
+    else if ((rc = run_gemm(h, nq, 32, &G, out_scores_dev, st))) return rc;
     return mark_done(h, st);
 }
 
@@ -761,6 +855,14 @@ extern "C" int ragfin_set_gemm_min_batch(ragfin_t* h, int32_t min_nq) {
     if (!h || min_nq < 1) return fail(RAGFIN_EINVAL, "bad argument");
     std::lock_guard<std::mutex> lk(h->mu);
     h->gemm_min_nq = min_nq;
+    return RAGFIN_OK;
+}
+
+// Tuning knob: which tcgen05 kernel serves large batches (0 automatic, 1 streaming, 2 A-stationary when eligible).
+extern "C" int ragfin_set_gemm_variant(ragfin_t* h, int32_t variant) {
+    if (!h || variant < 0 || variant > 2) return fail(RAGFIN_EINVAL, "variant must be 0, 1 or 2");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->gemm_variant = variant;
     return RAGFIN_OK;
 }
 

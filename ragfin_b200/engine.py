@@ -175,6 +175,10 @@ class Index:
         """Thread-block cluster size of the tcgen05 path (0 = automatic, else 1, 2 or 4)."""
         _lib.check(self._L.ragfin_set_gemm_cluster(self._h, int(cluster)))
 
+    def set_gemm_variant(self, variant: int) -> None:
+        """tcgen05 kernel variant: 0 automatic, 1 streaming, 2 A-stationary (query tile in tensor memory)."""
+        _lib.check(self._L.ragfin_set_gemm_variant(self._h, int(variant)))
+
     def debug_gemm_scores(self, queries):
         """Test hook: raw tensor-core scores [nq, N] (torch CUDA fp32) of CUDA fp32 queries [nq, dim]."""
         import torch

@@ -390,3 +390,27 @@ def test_collection_save_and_reload_through_the_shim(tmp_path):
     assert before == after
     assert col2.query(expr='id in ["c7"]', output_fields=["period"]) == [{"id": "c7", "period": "Q4_FY2024"}]
     mc.utility.drop_collection("persist")
+
+
+@pytest.mark.parametrize("cluster", [1, 4])
+@pytest.mark.parametrize("dtype,dim,nq", [("bf16", 768, 300), ("f16", 384, 40), ("bf16", 100, 129)])
+def test_gemm_a_stationary_variant(coracle, cluster, dtype, dim, nq):
+    """Experimental tcgen05 variant with the query tile resident in tensor memory (A from TMEM)."""
+    x = O.synth_rows(240, 0, 21000, dim, dup_every=211)
+    q = O.synth_rows(241, 0, nq, dim)
+    idx = _index(x, dtype)
+    idx.set_gemm_variant(2)
+    idx.set_gemm_cluster(cluster)
+    got = idx.search(q, 10)
+    assert idx.stats()["path"] == 1
+    _assert_same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), 10), f"astat {dtype} dim={dim} nq={nq}")
+
+
+def test_more_queries_than_one_pipeline_pass(coracle):
+    """nq above the 4096-query workspace bound is processed in several passes."""
+    x = O.synth_rows(250, 0, 3000, 128)
+    q = O.synth_rows(251, 0, 4096 + 130, 128)
+    idx = _index(x, "f16")
+    got = idx.search(q, 3)
+    want = coracle.cosine_topk(q, coracle.normalize_rows(x, "f16"), 3)
+    _assert_same(got, want, "nq=4226")
