@@ -90,6 +90,17 @@ int ragfin_search(ragfin_t* h, const float* q, int32_t nq, int32_t k, int64_t* o
 int ragfin_search_host(ragfin_t* h, const float* q_host, int32_t nq, int32_t k, int64_t* out_ids_host,
                        float* out_scores_host);
 
+/* Scalar-filtered search (Milvus `search(..., expr=...)`; "next" row N1 of the scope table): only rows
+ * whose bit is set in `allow_bits` (ceil(count / 32) little-endian 32-bit words, bit r of word r/32 = row r)
+ * may be returned; n_allowed = number of set bits.  The bitmask is consumed inside the top-k epilogues, the
+ * corpus is still read once.  Results equal the unfiltered search restricted to the allowed rows.
+ * _filtered: device bitmask, asynchronous; _filtered_host: host buffers, synchronous. */
+int ragfin_search_filtered(ragfin_t* h, const float* q, int32_t nq, int32_t k, const uint32_t* allow_bits_dev,
+                           int64_t n_allowed, int64_t* out_ids, float* out_scores, void* stream);
+int ragfin_search_filtered_host(ragfin_t* h, const float* q_host, int32_t nq, int32_t k,
+                                const uint32_t* allow_bits_host, int64_t n_allowed, int64_t* out_ids_host,
+                                float* out_scores_host);
+
 /* Cross-shard reduce: merge `parts` exact hit lists per query (device memory; -1 ids are
  * padding) into the global top-k, ordered by (score desc, id asc).  Hit j of part p for query q
  * is at element  q * query_stride + p * ids_part_stride + j  of `ids` and

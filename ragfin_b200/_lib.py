@@ -15,7 +15,7 @@ SO_PATH = os.path.join(CSRC, "libragfin.so")
 # every symbol include/ragfin.h declares
 SYMBOLS = (
     "ragfin_abi_version", "ragfin_create", "ragfin_add", "ragfin_add_synthetic", "ragfin_count",
-    "ragfin_set_id_base", "ragfin_search", "ragfin_search_host", "ragfin_merge_topk", "ragfin_read_rows",
+    "ragfin_set_id_base", "ragfin_search", "ragfin_search_host", "ragfin_search_filtered", "ragfin_search_filtered_host", "ragfin_merge_topk", "ragfin_read_rows",
     "ragfin_last_search_stats", "ragfin_profile", "ragfin_profile_read", "ragfin_save", "ragfin_load", "ragfin_set_gemm_min_batch", "ragfin_set_gemm_cluster", "ragfin_set_gemm_variant", "ragfin_debug_gemm_scores", "ragfin_destroy", "ragfin_last_error",
 )
 
@@ -54,6 +54,8 @@ def load() -> ctypes.CDLL:
     L.ragfin_set_id_base.argtypes = [vp, i64]
     L.ragfin_search.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     L.ragfin_search_host.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.ragfin_search_filtered.argtypes = [vp, vp, i32, i32, vp, i64, vp, vp, vp]
+    L.ragfin_search_filtered_host.argtypes = [vp, vp, i32, i32, vp, i64, vp, vp]
     L.ragfin_merge_topk.argtypes = [vp, vp, i32, i32, i32, i64, i64, i64, vp, vp, i32, vp]
     L.ragfin_profile.argtypes = [vp, i32]
     L.ragfin_save.argtypes = [vp, ctypes.c_char_p]

@@ -12,11 +12,16 @@ namespace rfk {
 
 template <int DT>
 __global__ void __launch_bounds__(256) score_all_kernel(const void* __restrict__ data, int64_t n_rows, int ld,
-                                                        const float* __restrict__ qhat, float* __restrict__ scores) {
+                                                        const float* __restrict__ qhat, float* __restrict__ scores,
+                                                        const uint32_t* __restrict__ allow) {
     const int lane = threadIdx.x & 31;
     const typename Store<DT>::T* base = reinterpret_cast<const typename Store<DT>::T*>(data);
     const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows; r += stride) {
+        if (allow != nullptr && !row_allowed(allow, r)) {   // filtered out: below every real score
+            if (lane == 0) scores[r] = -INFINITY;
+            continue;
+        }
         const double s = canonical_dot_row<DT>(base + (size_t)r * ld, qhat, ld, lane);
         if (lane == 0) scores[r] = (float)s + 0.0f;
     }

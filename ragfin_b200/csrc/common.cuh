@@ -79,6 +79,11 @@ template <> struct Store<2> {
     }
 };
 
+// scalar filter: bit r of `allow` set <=> row r may be returned
+__device__ __forceinline__ bool row_allowed(const uint32_t* __restrict__ allow, long long row) {
+    return (__ldg(allow + (row >> 5)) >> (row & 31)) & 1u;
+}
+
 // streaming 128-bit load: read-only path, do not allocate in L1 (corpus is read once per scan)
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
     uint4 r;

@@ -172,6 +172,7 @@ struct GemmArgs {
     int kp;
     u64* cand;              // [nq][S][kp]
     uint32_t* gtau;         // [nq] ordered-uint lower bound of the global K'-th approximate score (atomicMax)
+    const uint32_t* allow;  // scalar filter bitmask over rows, or null
     float* dump;            // DUMP only: [nq][n_rows] raw scores
 };
 
@@ -369,7 +370,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float sc = __uint_as_float(v[j]);
-                            if (sc >= st.tau_s && c * 32 + j < valid)
+                            if (sc >= st.tau_s && c * 32 + j < valid && (a.allow == nullptr || row_allowed(a.allow, trow + c * 32 + j)))
                                 cand_insert(st, lists, m, kp, sc, (uint32_t)(trow + c * 32 + j));
                         }
                     }

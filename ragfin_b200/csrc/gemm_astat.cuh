@@ -63,6 +63,7 @@ struct AstatArgs {
     const uint16_t* q16;    // [nq][ld] queries rounded to the storage type
     u64* cand;              // [nq][S][kp]
     uint32_t* gtau;
+    const uint32_t* allow;  // scalar filter bitmask over rows, or null
     float* dump;
 };
 
@@ -243,7 +244,7 @@ gemm_astat_kernel(const __grid_constant__ CUtensorMap tmB, const AstatArgs a) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float sc = __uint_as_float(v[j]);
-                            if (sc >= st.tau_s && c * 32 + j < valid)
+                            if (sc >= st.tau_s && c * 32 + j < valid && (a.allow == nullptr || row_allowed(a.allow, trow + c * 32 + j)))
                                 cand_insert(st, lists, m, kp, sc, (uint32_t)(trow + c * 32 + j));
                         }
                     }

@@ -113,7 +113,8 @@ __host__ __device__ constexpr int scan_rows(int steps) { return steps <= 1 ? 8 :
 template <int DT, int NQ, int STEPS>
 __global__ void __launch_bounds__(kScanThreads, NQ >= 4 ? 1 : 2)
 scan_topk_kernel(const void* __restrict__ data, int64_t n_rows, int ld, const float* __restrict__ qhat,
-                 int nq_valid, int kp, u64* __restrict__ cand, int64_t cand_q_stride) {
+                 int nq_valid, int kp, u64* __restrict__ cand, int64_t cand_q_stride,
+                 const uint32_t* __restrict__ allow) {
     typedef Store<DT> S;
     constexpr int V = S::kVec;
     constexpr int R = scan_rows(STEPS);
@@ -189,6 +190,7 @@ scan_topk_kernel(const void* __restrict__ data, int64_t n_rows, int ld, const fl
             const float bs = __shfl_sync(kFull, s, l) + 0.0f;
             const int bidx = l >> SH;
             const int q = bidx % NQ;
+            if (allow != nullptr && !row_allowed(allow, row0 + bidx / NQ)) continue;   // scalar filter (warp-uniform)
             const u64 key = make_key(bs, (uint32_t)(row0 + bidx / NQ));
             u64* list = lists + (size_t)(q * kScanWarps + warp) * kp;
             if (key > list[kp - 1]) {
@@ -393,7 +395,7 @@ template <int DT>
 __global__ void __launch_bounds__(kScanThreads)
 exact_scan_kernel(const void* __restrict__ data, int64_t n_rows, int ld, const float* __restrict__ qhat,
                   int nq, const int* __restrict__ flags, const int* __restrict__ flag_count, int kpe,
-                  u64* __restrict__ cand_e) {
+                  u64* __restrict__ cand_e, const uint32_t* __restrict__ allow) {
     if (*flag_count == 0) return;
     extern __shared__ __align__(16) u64 lists[];  // [kScanWarps][kpe]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -406,6 +408,7 @@ exact_scan_kernel(const void* __restrict__ data, int64_t n_rows, int ld, const f
         const float* qv = qhat + (size_t)q * ld;
         const int64_t stride = (int64_t)gridDim.x * kScanWarps;
         for (int64_t r = (int64_t)blockIdx.x * kScanWarps + warp; r < n_rows; r += stride) {
+            if (allow != nullptr && !row_allowed(allow, r)) continue;
             const double s = canonical_dot_row<DT>(base + (size_t)r * ld, qv, ld, lane);
             const u64 key = make_key((float)s + 0.0f, (uint32_t)r);
             if (key > mine[kpe - 1]) warp_list_insert(mine, kpe, key, lane);

@@ -52,9 +52,11 @@ struct ragfin {
     void* data = nullptr;  // [capacity, ld] storage, row-major, L2-normalised
     std::mutex mu;
     // workspace (grow-only)
-    Buf qhat, q16, eps_q, gtau, bk_scores, bk_state, bk_keys, cand, cand_e, flags, stage_q, stage_ids, stage_scores, add_stage;
+    Buf qhat, q16, eps_q, gtau, allow, bk_scores, bk_state, bk_keys, cand, cand_e, flags, stage_q, stage_ids, stage_scores, add_stage;
     int gemm_min_nq = 5;      // query batches of at least this many rows take the tcgen05 path
     int gemm_cluster = 0;     // 0 = choose by batch size; 1, 2 or 4 = force
+    const uint32_t* cur_allow = nullptr;   // scalar filter of the search in flight (device bitmask), else null
+    int64_t cur_allowed = 0;               // rows it allows
     int gemm_variant = 1;     // 0 = automatic, 1 = streaming (A and B through shared memory), 2 = A-stationary (A in TMEM)
     cudaEvent_t last_done = nullptr;
     ragfin_search_stats stats = {0, 0, 0, 0};
@@ -157,7 +159,7 @@ extern "C" void ragfin_destroy(ragfin_t* h) {
     if (!h) return;
     DeviceGuard g(h->device);
     (void)cudaDeviceSynchronize();
-    Buf* bufs[] = {&h->qhat, &h->q16, &h->eps_q, &h->gtau, &h->bk_scores, &h->bk_state, &h->bk_keys, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage};
+    Buf* bufs[] = {&h->qhat, &h->q16, &h->eps_q, &h->gtau, &h->allow, &h->bk_scores, &h->bk_state, &h->bk_keys, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage};
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->data) cudaFree(h->data);
@@ -274,7 +276,7 @@ extern "C" int ragfin_read_rows(ragfin_t* h, int64_t row0, int64_t n, void* out_
 // ------------------------------------------------------------------------------
 // K2 dispatch
 // ------------------------------------------------------------------------------
-typedef void (*scan_fn)(const void*, int64_t, int, const float*, int, int, u64*, int64_t);
+typedef void (*scan_fn)(const void*, int64_t, int, const float*, int, int, u64*, int64_t, const uint32_t*);
 static const int kMaxScanCtasPerSm = 4;
 
 template <int DT, int NQ>
@@ -480,6 +482,7 @@ static int run_gemm(ragfin* h, int nb, int kp, int* G, float* dump, cudaStream_t
     CU_TRY(cudaMemsetAsync(h->gtau.p, 0, (size_t)nb * sizeof(uint32_t), st));
     a.cand = (u64*)h->cand.p;
     a.gtau = (uint32_t*)h->gtau.p;
+    a.allow = h->cur_allow;
     a.dump = dump;
     {
         cudaLaunchConfig_t cfg = {};
@@ -567,6 +570,7 @@ static int run_gemm_astat(ragfin* h, int nb, int kp, int* G, float* dump, cudaSt
     a.q16 = (const uint16_t*)h->q16.p;
     a.cand = (u64*)h->cand.p;
     a.gtau = (uint32_t*)h->gtau.p;
+    a.allow = h->cur_allow;
     a.dump = dump;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.grid);
@@ -605,7 +609,8 @@ static float eps_gemm_const(int dtype, int ld) {
 static int search_bigk(ragfin* h, const float* q_dev, int nq, int k, int64_t* out_ids, float* out_scores, cudaStream_t st) {
     int rc;
     const int64_t n = h->count;
-    const int m = (int64_t)k < n ? k : (int)n;   // hits that exist
+    const int64_t n_eff = h->cur_allow ? h->cur_allowed : n;
+    const int m = (int64_t)k < n_eff ? k : (int)n_eff;   // hits that exist
     h->stats.path = 2;
     h->stats.cand_per_query = m;
     h->stats.queries_rescanned = 0;
@@ -621,9 +626,9 @@ static int search_bigk(ragfin* h, const float* q_dev, int nq, int k, int64_t* ou
     for (int q = 0; q < nq; ++q) {
         if ((rc = launch_ingest<false>(0, q_dev + (size_t)q * h->dim, 0, 0, 0, 0, 1, h->dim, h->ld, qhat, h->num_sms, st))) return rc;
         switch (h->dtype) {
-            case 0: score_all_kernel<0><<<blocks, 256, 0, st>>>(h->data, n, h->ld, qhat, scores); break;
-            case 1: score_all_kernel<1><<<blocks, 256, 0, st>>>(h->data, n, h->ld, qhat, scores); break;
-            default: score_all_kernel<2><<<blocks, 256, 0, st>>>(h->data, n, h->ld, qhat, scores); break;
+            case 0: score_all_kernel<0><<<blocks, 256, 0, st>>>(h->data, n, h->ld, qhat, scores, h->cur_allow); break;
+            case 1: score_all_kernel<1><<<blocks, 256, 0, st>>>(h->data, n, h->ld, qhat, scores, h->cur_allow); break;
+            default: score_all_kernel<2><<<blocks, 256, 0, st>>>(h->data, n, h->ld, qhat, scores, h->cur_allow); break;
         }
         CU_TRY(cudaGetLastError());
         RadixState init;
@@ -635,7 +640,7 @@ static int search_bigk(ragfin* h, const float* q_dev, int nq, int k, int64_t* ou
             radix_hist_kernel<<<blocks, 256, 0, st>>>(scores, n, shift, state);
             radix_pick_kernel<<<1, 32, 0, st>>>(shift, state);
         }
-        compact_kernel<<<blocks, 256, 0, st>>>(scores, n, state, keys, m);
+        if (m > 0) compact_kernel<<<blocks, 256, 0, st>>>(scores, n, state, keys, m);
         const int span = m > k ? m : k;
         rank_sort_kernel<<<(span + 255) / 256, 256, 0, st>>>(keys, m, k, h->id_base, out_ids + (size_t)q * k, out_scores + (size_t)q * k);
         CU_TRY(cudaGetLastError());
@@ -654,6 +659,7 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
     const int V = h->dtype == 0 ? 4 : 8;
     const int nvec = h->ld / V;
     const int steps = round_steps((nvec + 31) / 32);
+    const int64_t n_eff = h->cur_allow ? h->cur_allowed : n;   // rows a hit may come from
     int kp = cand_per_query(k);
     if (kp == 0 && n <= 256) kp = 256;   // every row is a candidate: any k (graph_cons.py:279 asks limit=1000 of 16 rows)
     if (kp == 0) return search_bigk(h, q_dev, nq, k, out_ids, out_scores, st);
@@ -723,7 +729,7 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
                     prof_begin(h, st);
                     fn<<<G, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat + (size_t)g0 * h->ld, left < nqt ? left : nqt, kp,
                                                        (u64*)h->cand.p + (size_t)g0 * G * kp,
-                                                       (int64_t)G * kp);
+                                                       (int64_t)G * kp, h->cur_allow);
                     prof_end(h, st);
                     CU_TRY(cudaGetLastError());
                     h->stats.launches++;
@@ -733,7 +739,7 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
         // 3. merge + exact rescore + certificate (an unscanned, non-empty corpus flags every query)
         {
             finalize_kernel<false><<<nb, kFinThreads, 0, st>>>(
-                (const u64*)h->cand.p, G, kp, h->data, h->dtype, n, (scanned || n == 0) ? 1 : 0, sorted_lists,
+                (const u64*)h->cand.p, G, kp, h->data, h->dtype, n_eff, (scanned || n == 0) ? 1 : 0, sorted_lists,
                 sorted_lists ? nullptr : (const uint32_t*)h->gtau.p, h->ld, qhat, eps, eps_q, k, h->id_base, out_ids + (size_t)q0 * k, out_scores + (size_t)q0 * k, flags, flag_count);
             CU_TRY(cudaGetLastError());
             h->stats.launches++;
@@ -744,12 +750,12 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
             if ((rc = ensure(h->cand_e, (size_t)nb * Ge * kpe * sizeof(u64)))) return rc;
             const size_t smem = (size_t)kScanWarps * kpe * sizeof(u64);
             switch (h->dtype) {
-                case 0: exact_scan_kernel<0><<<Ge, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat, nb, flags, flag_count, kpe, (u64*)h->cand_e.p); break;
-                case 1: exact_scan_kernel<1><<<Ge, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat, nb, flags, flag_count, kpe, (u64*)h->cand_e.p); break;
-                default: exact_scan_kernel<2><<<Ge, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat, nb, flags, flag_count, kpe, (u64*)h->cand_e.p); break;
+                case 0: exact_scan_kernel<0><<<Ge, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat, nb, flags, flag_count, kpe, (u64*)h->cand_e.p, h->cur_allow); break;
+                case 1: exact_scan_kernel<1><<<Ge, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat, nb, flags, flag_count, kpe, (u64*)h->cand_e.p, h->cur_allow); break;
+                default: exact_scan_kernel<2><<<Ge, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat, nb, flags, flag_count, kpe, (u64*)h->cand_e.p, h->cur_allow); break;
             }
             CU_TRY(cudaGetLastError());
-            finalize_kernel<true><<<nb, kFinThreads, 0, st>>>((const u64*)h->cand_e.p, Ge, kpe, h->data, h->dtype, n, 1, 1, nullptr,
+            finalize_kernel<true><<<nb, kFinThreads, 0, st>>>((const u64*)h->cand_e.p, Ge, kpe, h->data, h->dtype, n_eff, 1, 1, nullptr,
                                                               h->ld, qhat, 0.0f, nullptr, k, h->id_base,
                                                                 out_ids + (size_t)q0 * k, out_scores + (size_t)q0 * k,
                                                                 flags, flag_count);
@@ -904,6 +910,63 @@ extern "C" int ragfin_search_host(ragfin_t* h, const float* q_host, int32_t nq, 
     if ((rc = ensure(h->stage_q, qb)) || (rc = ensure(h->stage_ids, ib)) || (rc = ensure(h->stage_scores, sb))) return rc;
     CU_TRY(cudaMemcpyAsync(h->stage_q.p, q_host, qb, cudaMemcpyHostToDevice, st));
     if ((rc = search_locked(h, (const float*)h->stage_q.p, nq, k, (int64_t*)h->stage_ids.p, (float*)h->stage_scores.p, st))) return rc;
+    CU_TRY(cudaMemcpyAsync(out_ids_host, h->stage_ids.p, ib, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(out_scores_host, h->stage_scores.p, sb, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return mark_done(h, st);
+}
+
+// Scalar-filtered search: bit r of allow_bits (ceil(count / 32) 32-bit words) set <=> row r may be returned.
+static int set_filter(ragfin* h, const uint32_t* allow_bits, int64_t n_allowed, int bits_on_device, cudaStream_t st) {
+    if (!allow_bits) { h->cur_allow = nullptr; h->cur_allowed = 0; return 0; }
+    if (n_allowed < 0 || n_allowed > h->count) return fail(RAGFIN_EINVAL, "n_allowed %lld outside [0, %lld]", (long long)n_allowed, (long long)h->count);
+    if (bits_on_device) { h->cur_allow = allow_bits; h->cur_allowed = n_allowed; return 0; }
+    const size_t words = (size_t)((h->count + 31) / 32);
+    int rc;
+    if ((rc = ensure(h->allow, (words ? words : 1) * sizeof(uint32_t)))) return rc;
+    CU_TRY(cudaMemcpyAsync(h->allow.p, allow_bits, words * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    h->cur_allow = (const uint32_t*)h->allow.p;
+    h->cur_allowed = n_allowed;
+    return 0;
+}
+
+extern "C" int ragfin_search_filtered(ragfin_t* h, const float* q, int32_t nq, int32_t k, const uint32_t* allow_bits_dev,
+                                      int64_t n_allowed, int64_t* out_ids, float* out_scores, void* stream) {
+    if (!h) return fail(RAGFIN_EINVAL, "NULL handle");
+    if (nq < 0 || (nq > 0 && (!q || !out_ids || !out_scores))) return fail(RAGFIN_EINVAL, "NULL buffer");
+    if (k < 1 || k > 16384) return fail(RAGFIN_EINVAL, "k = %d outside [1, 16384]", k);
+    if (nq == 0) return RAGFIN_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = wait_prev(h, st))) return rc;
+    if ((rc = set_filter(h, allow_bits_dev, n_allowed, 1, st))) return rc;
+    rc = search_locked(h, q, nq, k, out_ids, out_scores, st);
+    h->cur_allow = nullptr;
+    if (rc) return rc;
+    return mark_done(h, st);
+}
+
+extern "C" int ragfin_search_filtered_host(ragfin_t* h, const float* q_host, int32_t nq, int32_t k,
+                                           const uint32_t* allow_bits_host, int64_t n_allowed, int64_t* out_ids_host,
+                                           float* out_scores_host) {
+    if (!h) return fail(RAGFIN_EINVAL, "NULL handle");
+    if (nq < 0 || (nq > 0 && (!q_host || !out_ids_host || !out_scores_host))) return fail(RAGFIN_EINVAL, "NULL buffer");
+    if (k < 1 || k > 16384) return fail(RAGFIN_EINVAL, "k = %d outside [1, 16384]", k);
+    if (nq == 0) return RAGFIN_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    cudaStream_t st = 0;
+    int rc;
+    if ((rc = wait_prev(h, st))) return rc;
+    const size_t qb = (size_t)nq * h->dim * sizeof(float), ib = (size_t)nq * k * sizeof(int64_t), sb = (size_t)nq * k * sizeof(float);
+    if ((rc = ensure(h->stage_q, qb)) || (rc = ensure(h->stage_ids, ib)) || (rc = ensure(h->stage_scores, sb))) return rc;
+    if ((rc = set_filter(h, allow_bits_host, n_allowed, 0, st))) return rc;
+    CU_TRY(cudaMemcpyAsync(h->stage_q.p, q_host, qb, cudaMemcpyHostToDevice, st));
+    rc = search_locked(h, (const float*)h->stage_q.p, nq, k, (int64_t*)h->stage_ids.p, (float*)h->stage_scores.p, st);
+    h->cur_allow = nullptr;
+    if (rc) return rc;
     CU_TRY(cudaMemcpyAsync(out_ids_host, h->stage_ids.p, ib, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(out_scores_host, h->stage_scores.p, sb, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));

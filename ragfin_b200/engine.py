@@ -131,10 +131,11 @@ class Index:
         return k
 
     def search(self, queries, k: int, out_ids: Optional[np.ndarray] = None,
-               out_scores: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
+               out_scores: Optional[np.ndarray] = None, allow: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
         """Host path: queries numpy/list [nq, dim] -> (ids int64 [nq, k], scores fp32 [nq, k]).
         Hits are in descending score, ties to the lower id; slots past min(k, N) hold (-1, -inf).
-        `out_ids` / `out_scores` may be caller-owned (e.g. pinned) C-contiguous arrays."""
+        `out_ids` / `out_scores` may be caller-owned (e.g. pinned) C-contiguous arrays.
+        `allow`: optional bool array [N]; only rows with allow[r] may be returned (scalar-filtered search)."""
         k = self._check_k(k)
         q = np.ascontiguousarray(queries, dtype=np.float32)
         if q.ndim == 1:
@@ -146,6 +147,17 @@ class Index:
         if (ids.shape != (q.shape[0], k) or ids.dtype != np.int64 or not ids.flags.c_contiguous
                 or scores.shape != (q.shape[0], k) or scores.dtype != np.float32 or not scores.flags.c_contiguous):
             raise ValueError("out_ids / out_scores must be C-contiguous int64 / float32 arrays of shape [nq, k]")
+        if allow is not None:
+            mask = np.ascontiguousarray(allow, dtype=bool)
+            if mask.shape != (len(self),):
+                raise ValueError(f"allow must be a bool array of shape [{len(self)}], got {mask.shape}")
+            packed = np.packbits(mask, bitorder="little")
+            packed = np.concatenate([packed, np.zeros((-len(packed)) % 4, np.uint8)]).view(np.uint32)
+            if packed.size == 0:
+                packed = np.zeros(1, np.uint32)
+            _lib.check(self._L.ragfin_search_filtered_host(self._h, q.ctypes.data, q.shape[0], k, packed.ctypes.data,
+                                                           int(mask.sum()), ids.ctypes.data, scores.ctypes.data))
+            return ids, scores
         _lib.check(self._L.ragfin_search_host(self._h, q.ctypes.data, q.shape[0], k, ids.ctypes.data, scores.ctypes.data))
         return ids, scores
 

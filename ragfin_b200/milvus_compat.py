@@ -411,8 +411,6 @@ class Collection:
             raise MilvusException(message=f"metric type not match: expected=COSINE, actual={metric}")
         if not isinstance(limit, (int, np.integer)) or not 1 <= int(limit) <= MAX_LIMIT:
             raise MilvusException(message=f"`limit` value {limit} is illegal: topk [1, {MAX_LIMIT}]")
-        if expr:
-            raise MilvusException(message="filtered search (expr) is not supported yet")
         out_fields = list(output_fields or [])
         for f in out_fields:
             if f not in st.columns:
@@ -429,7 +427,12 @@ class Collection:
                 for _ in range(q.shape[0]):
                     res.append(Hits())
                 return res
-            ids, scores = st.index.search(q, int(limit))
+            if expr and expr.strip():     # scalar filter -> row bitmask consumed inside the top-k epilogues
+                allow = np.zeros(st.n_inserted, dtype=bool)
+                allow[self._rows_matching(expr.strip(), st.n_inserted)] = True
+                ids, scores = st.index.search(q, int(limit), allow=allow)
+            else:
+                ids, scores = st.index.search(q, int(limit))
             pk_col = st.columns[st.schema.primary_field.name]
             for qi in range(q.shape[0]):
                 hits = Hits()
@@ -440,6 +443,26 @@ class Collection:
                     hits.append(Hit(pk_col[row], d, Entity({f: st.columns[f][row] for f in out_fields})))
                 res.append(hits)
             return res
+
+    def _rows_matching(self, expr: str, n: int) -> List[int]:
+        """Rows (ascending) among the first n that satisfy `field in [...]` or `field == literal`."""
+        st = self._st
+        pk_name = st.schema.primary_field.name
+        m_in, m_eq = _EXPR_IN.match(expr), _EXPR_EQ.match(expr)
+        if m_in:
+            field = m_in.group(1)
+            body = m_in.group(2).strip()
+            wanted = [_parse_literal(t) for t in re.findall(r"\"[^\"]*\"|'[^']*'|[^,\s]+", body)] if body else []
+        elif m_eq:
+            field, wanted = m_eq.group(1), [_parse_literal(m_eq.group(2))]
+        else:
+            raise MilvusException(message=f"cannot parse expression: {expr}")
+        if field not in st.columns:
+            raise MilvusException(message=f"field {field} not exist")
+        if field == pk_name:
+            return sorted(r for r in (st.pk_to_row.get(w) for w in wanted) if r is not None and r < n)
+        ws = set(wanted)
+        return [r for r in range(n) if st.columns[field][r] in ws]
 
     # -- scalar lookups (host side; "next" row N1) --------------------------------------
     def query(self, expr: str = "", output_fields: Optional[List[str]] = None, partition_names=None,
@@ -460,22 +483,7 @@ class Collection:
                     raise MilvusException(message="empty expression should be used with limit")
                 rows = list(range(n))
             else:
-                m_in, m_eq = _EXPR_IN.match(expr), _EXPR_EQ.match(expr)
-                if m_in:
-                    field = m_in.group(1)
-                    body = m_in.group(2).strip()
-                    wanted = [_parse_literal(t) for t in re.findall(r"\"[^\"]*\"|'[^']*'|[^,\s]+", body)] if body else []
-                elif m_eq:
-                    field, wanted = m_eq.group(1), [_parse_literal(m_eq.group(2))]
-                else:
-                    raise MilvusException(message=f"cannot parse expression: {expr}")
-                if field not in st.columns:
-                    raise MilvusException(message=f"field {field} not exist")
-                if field == pk_name:
-                    rows = sorted(r for r in (st.pk_to_row.get(w) for w in wanted) if r is not None and r < n)
-                else:
-                    ws = set(wanted)
-                    rows = [r for r in range(n) if st.columns[field][r] in ws]
+                rows = self._rows_matching(expr, n)
             rows = rows[offset:]
             if limit is not None:
                 rows = rows[:int(limit)]

@@ -414,3 +414,43 @@ def test_more_queries_than_one_pipeline_pass(coracle):
     got = idx.search(q, 3)
     want = coracle.cosine_topk(q, coracle.normalize_rows(x, "f16"), 3)
     _assert_same(got, want, "nq=4226")
+
+
+# ------------------------------------------------------------------------------------------------
+# scalar-filtered search (row bitmask consumed in the top-k epilogues)
+# ------------------------------------------------------------------------------------------------
+def _oracle_filtered(coracle, q, stored, allow, k):
+    rows = np.flatnonzero(allow)
+    ids, sc = coracle.cosine_topk(q, stored[rows], k) if len(rows) else (np.full((len(q), k), -1, np.int64), np.full((len(q), k), -np.inf, np.float32))
+    return np.where(ids >= 0, rows[np.clip(ids, 0, None)] if len(rows) else -1, -1), sc
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+@pytest.mark.parametrize("nq,k,keep", [(1, 10, 0.5), (3, 5, 0.01), (40, 10, 0.3), (2, 300, 0.2), (2, 10, 0.0), (300, 10, 0.9)])
+def test_filtered_search_matches_oracle_on_allowed_rows(coracle, dtype, nq, k, keep):
+    n = 12000
+    x = O.synth_rows(260, 0, n, 384, dup_every=41)
+    q = O.synth_rows(261, 0, nq, 384)
+    allow = np.random.default_rng(5).random(n) < keep
+    idx = _index(x, dtype)
+    got = idx.search(q, k, allow=allow)
+    want = _oracle_filtered(coracle, q, coracle.normalize_rows(x, dtype), allow, k)
+    _assert_same(got, want, f"filtered {dtype} nq={nq} k={k} keep={keep}")
+    valid = got[0][got[0] >= 0]
+    assert allow[valid].all()
+
+
+def test_filtered_search_through_the_shim():
+    from ragfin_b200 import milvus_compat as mc
+    F, D = mc.FieldSchema, mc.DataType
+    mc.utility.drop_collection("filt")
+    col = mc.Collection("filt", mc.CollectionSchema([F("id", D.VARCHAR, max_length=100, is_primary=True),
+                                                      F("embedding", D.FLOAT_VECTOR, dim=384), F("period", D.VARCHAR, max_length=20)]))
+    x = O.synth_rows(270, 0, 2000, 384)
+    col.insert([[f"c{i}" for i in range(2000)], x, [f"Q{i % 4 + 1}_FY2024" for i in range(2000)]])
+    col.load()
+    q = O.synth_rows(271, 0, 1, 384)
+    hits = col.search(q, "embedding", {"metric_type": "COSINE"}, 7, expr='period == "Q3_FY2024"', output_fields=["period"])[0]
+    allhits = col.search(q, "embedding", {"metric_type": "COSINE"}, 2000, output_fields=["period"])[0]
+    assert len(hits) == 7 and [h.id for h in hits] == [h.id for h in allhits if h.entity.period == "Q3_FY2024"][:7]
+    mc.utility.drop_collection("filt")

@@ -26,8 +26,12 @@ class OracleIndex:
         assert len(self.rows) + len(rows) <= self.capacity
         self.rows = np.concatenate([self.rows, O.normalize_rows(rows, self.dtype)])
 
-    def search(self, q, k):
-        return O.cosine_topk(q, self.rows, k)
+    def search(self, q, k, allow=None):
+        if allow is None:
+            return O.cosine_topk(q, self.rows, k)
+        rows = np.flatnonzero(allow)
+        ids, sc = O.cosine_topk(q, self.rows[rows], k)
+        return np.where(ids >= 0, rows[np.clip(ids, 0, None)] if len(rows) else -1, -1), sc
 
     def close(self):
         self.closed = True
@@ -182,3 +186,18 @@ def test_rest_request_bounds():
     for q, k in (("abc", 3), ("net profit", 0), ("net profit", 21)):
         with pytest.raises(ValueError):
             validate_search_request(q, k)
+
+
+def test_filtered_search_expr():
+    col, g = build_collection()
+    q = O.synth_rows(g["seed"] + 1, 0, 1, 384)
+    hits = col.search(q, "embedding", {"metric_type": "COSINE"}, 10, expr='period == "Q2_FY2024"', output_fields=["period"])[0]
+    assert len(hits) == 4 and all(h.entity.period == "Q2_FY2024" for h in hits)
+    allhits = col.search(q, "embedding", {"metric_type": "COSINE"}, 16, output_fields=["period"])[0]
+    assert [h.id for h in hits] == [h.id for h in allhits if h.entity.period == "Q2_FY2024"]
+    ids = [g["chunks"][3]["id"], g["chunks"][9]["id"]]
+    hits = col.search(q, "embedding", {"metric_type": "COSINE"}, 5, expr=f"id in {ids}".replace("'", '"'))[0]
+    assert sorted(h.id for h in hits) == sorted(ids)
+    assert col.search(q, "embedding", {"metric_type": "COSINE"}, 5, expr='period == "none"')[0] == []
+    with pytest.raises(mc.MilvusException):
+        col.search(q, "embedding", {"metric_type": "COSINE"}, 5, expr="period like 'Q%'")
