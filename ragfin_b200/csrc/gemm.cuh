@@ -186,8 +186,10 @@ struct CandState {
     u64 tau_key;
     float tau_s;
     uint32_t* gptr;   // &gtau[q], or null for padding lanes
+    const uint32_t* allow;   // scalar filter bitmask, or null
 };
 __device__ __noinline__ void cand_insert(CandState& st, u64* lists, int m, int kp, float s, uint32_t row) {
+    if (st.allow != nullptr && !row_allowed(st.allow, row)) return;   // filtered out (checked here, off the scan loop)
     const u64 key = make_key(s + 0.0f, row);
     if (st.cnt < kp) {
         lists[(size_t)st.cnt * kGM + m] = key;
@@ -336,6 +338,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             st.tau_key = 0;
             st.tau_s = q < a.nq ? -INFINITY : INFINITY;   // padding lanes of a partial query tile never collect
             st.gptr = (!DUMP && q < a.nq) ? a.gtau + q : nullptr;
+            st.allow = a.allow;
             uint32_t g_next = DUMP ? 0u : __ldcg(a.gtau + qc);
             for (int t = 0; t < ntiles; ++t) {
                 if (!DUMP) {   // bound published by the other CTAs sweeping this query (loaded one tile ahead)
@@ -363,15 +366,31 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                         continue;
                     }
-                    float mx = __uint_as_float(v[0]);
+                    if (valid < c * 32 + 32) {   // last tile of a slice only: rows past the corpus must never qualify
 #pragma unroll
-                    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                        for (int j = 0; j < 32; ++j)
+                            if (c * 32 + j >= valid) v[j] = 0x7FC00000u;   // NaN: fails every >= test, ignored by fmaxf
+                    }
+                    // maxima of the four groups of 8 columns, then of the chunk: one compare in the common case
+                    float gmx[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        float t = fmaxf(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1]));
+#pragma unroll
+                        for (int j = 2; j < 8; ++j) t = fmaxf(t, __uint_as_float(v[g * 8 + j]));
+                        gmx[g] = t;
+                    }
+                    const float mx = fmaxf(fmaxf(gmx[0], gmx[1]), fmaxf(gmx[2], gmx[3]));
                     if (mx >= st.tau_s) {          // rare per thread; every v[j] stays in its register
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float sc = __uint_as_float(v[j]);
-                            if (sc >= st.tau_s && c * 32 + j < valid && (a.allow == nullptr || row_allowed(a.allow, trow + c * 32 + j)))
-                                cand_insert(st, lists, m, kp, sc, (uint32_t)(trow + c * 32 + j));
+                        for (int g = 0; g < 4; ++g) {
+                            if (gmx[g] >= st.tau_s) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float sc = __uint_as_float(v[g * 8 + j]);
+                                    if (sc >= st.tau_s) cand_insert(st, lists, m, kp, sc, (uint32_t)(trow + c * 32 + g * 8 + j));
+                                }
+                            }
                         }
                     }
                 }

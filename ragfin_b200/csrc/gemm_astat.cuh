@@ -210,6 +210,7 @@ gemm_astat_kernel(const __grid_constant__ CUtensorMap tmB, const AstatArgs a) {
             st.tau_key = 0;
             st.tau_s = q < a.nq ? -INFINITY : INFINITY;
             st.gptr = (!DUMP && q < a.nq) ? a.gtau + q : nullptr;
+            st.allow = a.allow;
             uint32_t g_next = DUMP ? 0u : __ldcg(a.gtau + qc);
             for (int t = 0; t < ntiles; ++t) {
                 if (!DUMP && (t & 3) == 0) {   // refresh the published bound every 256 rows
@@ -237,15 +238,31 @@ gemm_astat_kernel(const __grid_constant__ CUtensorMap tmB, const AstatArgs a) {
                         }
                         continue;
                     }
-                    float mx = __uint_as_float(v[0]);
+                    if (valid < c * 32 + 32) {   // last tile of a slice only: rows past the corpus must never qualify
 #pragma unroll
-                    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-                    if (mx >= st.tau_s) {
+                        for (int j = 0; j < 32; ++j)
+                            if (c * 32 + j >= valid) v[j] = 0x7FC00000u;   // NaN: fails every >= test, ignored by fmaxf
+                    }
+                    // maxima of the four groups of 8 columns, then of the chunk: one compare in the common case
+                    float gmx[4];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float sc = __uint_as_float(v[j]);
-                            if (sc >= st.tau_s && c * 32 + j < valid && (a.allow == nullptr || row_allowed(a.allow, trow + c * 32 + j)))
-                                cand_insert(st, lists, m, kp, sc, (uint32_t)(trow + c * 32 + j));
+                    for (int g = 0; g < 4; ++g) {
+                        float t = fmaxf(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1]));
+#pragma unroll
+                        for (int j = 2; j < 8; ++j) t = fmaxf(t, __uint_as_float(v[g * 8 + j]));
+                        gmx[g] = t;
+                    }
+                    const float mx = fmaxf(fmaxf(gmx[0], gmx[1]), fmaxf(gmx[2], gmx[3]));
+                    if (mx >= st.tau_s) {          // rare per thread; every v[j] stays in its register
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (gmx[g] >= st.tau_s) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float sc = __uint_as_float(v[g * 8 + j]);
+                                    if (sc >= st.tau_s) cand_insert(st, lists, m, kp, sc, (uint32_t)(trow + c * 32 + g * 8 + j));
+                                }
+                            }
                         }
                     }
                 }
