@@ -353,7 +353,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int valid = r1 - trow < kGN ? (int)(r1 - trow) : kGN;   // rows of this tile inside the corpus
                 uint32_t vb[2][32];
                 tmem_ld32_async(taddr, vb[0]);
-#pragma unroll
+#pragma unroll 2   // two chunks per iteration keep vb[c & 1] in fixed registers; a full unroll is 138 KB of code
                 for (int c = 0; c < kGN / 32; ++c) {
                     uint32_t(&v)[32] = vb[c & 1];
                     tmem_wait32(v);
