@@ -73,20 +73,68 @@ def measured_peaks():
 # clocks: sample nvidia-smi DURING the timed region
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
+    """Polls NVML in-process (about every 2 ms) while the timed region runs, so that even a three-step
+    batch-1 region (7 ms) is sampled; falls back to an `nvidia-smi -lms` child if NVML is unavailable."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.sm, self.mx, self.reasons, self.power = [], [], set(), []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.nvml = None
+
+    def _nvml_handle(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.gpu
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+
+    def _poll(self, pynvml, h):
+        bits = {pynvml.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+                pynvml.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                pynvml.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                pynvml.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
+        try:
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)))
+        except Exception:
+            pass
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for b, nm in bits.items():
+                    if r & b:
+                        self.reasons.add(nm)
+                self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1e3)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
         try:
+            pynvml, h = self._nvml_handle()
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, args=(pynvml, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
         except OSError:
             self.proc = None
 
@@ -95,15 +143,20 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None,
+                    "reasons": sorted(self.reasons), "source": "nvml, 2 ms poll over the timed regions"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
@@ -113,11 +166,11 @@ class ClockSampler:
                 mx.append(float(f[1]))
             except ValueError:
                 continue
-            for nm, v in zip(names, f[3:7]):
+            for nm, v in zip(self.NAMES, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 20"}
 
 
 # ----------------------------------------------------------------------------------------------

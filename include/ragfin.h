@@ -156,6 +156,11 @@ int ragfin_set_gemm_cluster(ragfin_t* h, int32_t cluster);
  * 0 = automatic.  Results are identical. */
 int ragfin_set_gemm_variant(ragfin_t* h, int32_t variant);
 
+/* Tuning knob: the tensor-core path first scores an evenly strided ~1 % sample of corpus tiles and seeds every
+ * query's candidate threshold with the K'-th largest per-tile maximum (a valid lower bound of the global K'-th
+ * score).  1 = on (default), 0 = off.  Results are identical; only the epilogue's bookkeeping cost changes. */
+int ragfin_set_bound_pass(ragfin_t* h, int32_t enable);
+
 /* Test hook: raw (approximate, fp32-accumulated) tensor-core scores of nq queries against every
  * stored row, out_scores_dev [nq, count] device memory.  Validates the TMA / tcgen05 plumbing. */
 int ragfin_debug_gemm_scores(ragfin_t* h, const float* q_dev, int32_t nq, float* out_scores_dev, void* stream);

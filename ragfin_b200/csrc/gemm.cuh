@@ -173,7 +173,11 @@ struct GemmArgs {
     u64* cand;              // [nq][S][kp]
     uint32_t* gtau;         // [nq] ordered-uint lower bound of the global K'-th approximate score (atomicMax)
     const uint32_t* allow;  // scalar filter bitmask over rows, or null
-    float* dump;            // DUMP only: [nq][n_rows] raw scores
+    float* dump;            // MODE 1: [nq][n_rows] raw scores.  MODE 2: [nq][S * bound_tps] per-tile score maxima
+    int bound_tps;          // MODE 2: sample tiles per item ("slice" sl covers sample tiles [sl * bound_tps, +bound_tps))
+    int bound_tiles;        // MODE 2: sample tiles in total
+    long long bound_stride; // MODE 2: sample tile j is corpus tile j * bound_stride
+    int dbg;                // timing experiments only (RAGFIN_GEMM_DEBUG): 1 skip epilogue filter, 2 skip MMAs, 4 skip A loads, 8 skip B loads
 };
 
 // Per-query candidate list of one epilogue thread: kp keys in shared memory (column layout
@@ -215,10 +219,14 @@ __device__ __noinline__ void cand_insert(CandState& st, u64* lists, int m, int k
     }
 }
 
+// MODE: 0 = collect candidates; 1 = dump raw scores (test hook); 2 = bound pass: score an evenly strided SAMPLE
+// of corpus tiles and write each query's maximum per sample tile.  The K'-th largest of those block maxima is a
+// valid lower bound of the K'-th best score over the whole corpus (K' distinct rows reach it), so the collecting
+// pass can start every list with a tight threshold instead of warming up on its own slice.
 // C = thread-block cluster size along the query-tile axis: the C CTAs of a cluster hold C different
 // query tiles and sweep the same corpus slice in lockstep; each loads 1/C of every corpus tile and
 // TMA-multicasts it into all C shared memories, so a corpus tile leaves L2 once per cluster.
-template <int KIND, bool DUMP, int C>
+template <int KIND, int MODE, int C>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs a) {
     extern __shared__ uint8_t gsm_raw[];
@@ -262,6 +270,22 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int n_items = n_groups * a.S;
     const int nkb = a.num_kblocks;
+    // rows of an item: first row of its tile 0, distance between consecutive tiles, end of the corpus part it may touch
+    auto item_geom = [&](int sl, long long& r0, long long& r1, long long& step) -> int {
+        if (MODE == 2) {
+            const int j0 = sl * a.bound_tps;
+            const int nt = a.bound_tiles - j0 < a.bound_tps ? a.bound_tiles - j0 : a.bound_tps;
+            step = a.bound_stride * kGN;
+            r0 = (long long)j0 * step;
+            r1 = a.n_rows;
+            return nt > 0 ? nt : 0;
+        }
+        step = kGN;
+        r0 = (long long)sl * a.rows_per_slice;
+        r1 = r0 + a.rows_per_slice;
+        if (r1 > a.n_rows) r1 = a.n_rows;
+        return r1 > r0 ? (int)((r1 - r0 + kGN - 1) / kGN) : 0;
+    };
 
     if (warp == 0) {
         if (lane == 0) {   // ===== TMA producer =====
@@ -270,18 +294,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             constexpr int kSubRows = kGN / C;   // corpus rows this CTA fetches (and multicasts) per tile
             for (int item = cluster_id; item < n_items; item += n_clusters) {
                 const int qt = (item % n_groups) * C + (int)crank, sl = item / n_groups;
-                const long long r0 = (long long)sl * a.rows_per_slice;
-                long long r1 = r0 + a.rows_per_slice;
-                if (r1 > a.n_rows) r1 = a.n_rows;
-                const int ntiles = r1 > r0 ? (int)((r1 - r0 + kGN - 1) / kGN) : 0;
+                long long r0, r1, step;
+                const int ntiles = item_geom(sl, r0, r1, step);
                 for (int t = 0; t < ntiles; ++t) {
                     for (int kb = 0; kb < nkb; ++kb) {
                         mbar_wait(empty_bar(stage), phase ^ 1u);
-                        mbar_expect_tx(full_bar(stage), kStageBytes);   // own A tile + the whole B tile (C parts)
-                        tma_load_2d(smA + (uint32_t)stage * kABytes, &tmA, kb * a.k_elems, qt * kGM, full_bar(stage));
+                        mbar_expect_tx(full_bar(stage), ((a.dbg & 4) ? 0 : kABytes) + ((a.dbg & 8) ? 0 : kBBytes));   // own A tile + the whole B tile (C parts)
+                        if (!(a.dbg & 4)) tma_load_2d(smA + (uint32_t)stage * kABytes, &tmA, kb * a.k_elems, qt * kGM, full_bar(stage));
                         const uint32_t bdst = smB + (uint32_t)stage * kBBytes + crank * (uint32_t)(kSubRows * kGKBytes);
-                        const int brow = (int)(r0 + (long long)t * kGN) + (int)crank * kSubRows;
-                        if (C > 1) tma_load_2d_mc(bdst, &tmB, kb * a.k_elems, brow, full_bar(stage), cmask);
+                        const int brow = (int)(r0 + (long long)t * step) + (int)crank * kSubRows;
+                        if (a.dbg & 8) {}
+                        else if (C > 1) tma_load_2d_mc(bdst, &tmB, kb * a.k_elems, brow, full_bar(stage), cmask);
                         else tma_load_2d(bdst, &tmB, kb * a.k_elems, brow, full_bar(stage));
                         if (++stage == stages) { stage = 0; phase ^= 1u; }
                     }
@@ -294,10 +317,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t phase = 0, acc_phase = 0;
             for (int item = cluster_id; item < n_items; item += n_clusters) {
                 const int sl = item / n_groups;
-                const long long r0 = (long long)sl * a.rows_per_slice;
-                long long r1 = r0 + a.rows_per_slice;
-                if (r1 > a.n_rows) r1 = a.n_rows;
-                const int ntiles = r1 > r0 ? (int)((r1 - r0 + kGN - 1) / kGN) : 0;
+                long long r0, r1, step;
+                const int ntiles = item_geom(sl, r0, r1, step);
                 for (int t = 0; t < ntiles; ++t) {
                     mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                     tc_fence_after();
@@ -309,7 +330,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const uint64_t bd = make_smem_desc(smB + (uint32_t)stage * kBBytes);
 #pragma unroll
                         for (int k4 = 0; k4 < kGKBytes / 32; ++k4)   // 32 B of K per instruction: +2 in 16-byte units
-                            tc_mma<KIND>(d_tmem, ad + 2u * k4, bd + 2u * k4, a.idesc, (uint32_t)((kb | k4) != 0));
+                            if (!(a.dbg & 2)) tc_mma<KIND>(d_tmem, ad + 2u * k4, bd + 2u * k4, a.idesc, (uint32_t)((kb | k4) != 0));
                         if (C > 1) tc_commit_mc(empty_bar(stage), cmask);
                         else tc_commit(empty_bar(stage));
                         if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -326,10 +347,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t acc_phase = 0;
         for (int item = cluster_id; item < n_items; item += n_clusters) {
             const int qt = (item % n_groups) * C + (int)crank, sl = item / n_groups;
-            const long long r0 = (long long)sl * a.rows_per_slice;
-            long long r1 = r0 + a.rows_per_slice;
-            if (r1 > a.n_rows) r1 = a.n_rows;
-            const int ntiles = r1 > r0 ? (int)((r1 - r0 + kGN - 1) / kGN) : 0;
+            long long r0, r1, step;
+            const int ntiles = item_geom(sl, r0, r1, step);
             const int q = qt * kGM + m;
             const int qc = q < a.nq ? q : a.nq - 1;
             CandState st;
@@ -337,28 +356,30 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             st.minpos = 0;
             st.tau_key = 0;
             st.tau_s = q < a.nq ? -INFINITY : INFINITY;   // padding lanes of a partial query tile never collect
-            st.gptr = (!DUMP && q < a.nq) ? a.gtau + q : nullptr;
+            st.gptr = (MODE == 0 && q < a.nq) ? a.gtau + q : nullptr;
             st.allow = a.allow;
-            uint32_t g_next = DUMP ? 0u : __ldcg(a.gtau + qc);
+            uint32_t g_next = MODE != 0 ? 0u : __ldcg(a.gtau + qc);
             for (int t = 0; t < ntiles; ++t) {
-                if (!DUMP) {   // bound published by the other CTAs sweeping this query (loaded one tile ahead)
+                if (MODE == 0) {   // bound published by the other CTAs sweeping this query (loaded one tile ahead)
                     const uint32_t g = g_next;
                     if (g && q < a.nq) st.tau_s = fmaxf(st.tau_s, ordered_to_float(g));
                 }
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
-                if (!DUMP) g_next = __ldcg(a.gtau + qc);
-                const long long trow = r0 + (long long)t * kGN;
+                if (MODE == 0) g_next = __ldcg(a.gtau + qc);
+                const long long trow = r0 + (long long)t * step;
+                float tile_mx = -INFINITY;   // MODE 2
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kGN;
                 const int valid = r1 - trow < kGN ? (int)(r1 - trow) : kGN;   // rows of this tile inside the corpus
                 uint32_t vb[2][32];
+                if (a.dbg & 1) { tc_fence_before(); mbar_arrive(tempty_bar(acc)); if (++acc == 2) { acc = 0; acc_phase ^= 1u; } continue; }
                 tmem_ld32_async(taddr, vb[0]);
 #pragma unroll 2   // two chunks per iteration keep vb[c & 1] in fixed registers; a full unroll is 138 KB of code
                 for (int c = 0; c < kGN / 32; ++c) {
                     uint32_t(&v)[32] = vb[c & 1];
                     tmem_wait32(v);
                     if (c + 1 < kGN / 32) tmem_ld32_async(taddr + (uint32_t)(c + 1) * 32, vb[(c + 1) & 1]);
-                    if (DUMP) {
+                    if (MODE == 1) {
                         if (q < a.nq) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
@@ -381,6 +402,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         gmx[g] = t;
                     }
                     const float mx = fmaxf(fmaxf(gmx[0], gmx[1]), fmaxf(gmx[2], gmx[3]));
+                    if (MODE == 2) { tile_mx = fmaxf(tile_mx, mx); continue; }
                     if (mx >= st.tau_s) {          // rare per thread; every v[j] stays in its register
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
@@ -397,8 +419,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tc_fence_before();
                 mbar_arrive(tempty_bar(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                if (MODE == 2 && q < a.nq) a.dump[(size_t)q * a.bound_tiles + (size_t)sl * a.bound_tps + t] = tile_mx;
             }
-            if (!DUMP && q < a.nq) {
+            if (MODE == 0 && q < a.nq) {
                 u64* out = a.cand + ((size_t)q * a.S + sl) * kp;
                 for (int e = 0; e < kp; ++e) out[e] = e < st.cnt ? lists[(size_t)e * kGM + m] : 0ull;
             }
@@ -411,6 +434,22 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
+}
+
+// ---- bound pass, second half: gtau[q] = the kp-th largest of the query's nb per-tile maxima (rank counting) ------
+__global__ void __launch_bounds__(1024) bound_select_kernel(const float* __restrict__ bmax, int nb, int kp, uint32_t* __restrict__ gtau) {
+    __shared__ uint32_t v[1024];
+    const int q = blockIdx.x, i = threadIdx.x;
+    v[i] = i < nb ? float_to_ordered(bmax[(size_t)q * nb + i] + 0.0f) : 0u;
+    __syncthreads();
+    if (i >= nb) return;
+    const uint32_t mine = v[i];
+    int rank = 0;
+    for (int j = 0; j < nb; ++j) {
+        const uint32_t o = v[j];
+        rank += (o > mine) || (o == mine && j < i);
+    }
+    if (rank == kp - 1) gtau[q] = mine;
 }
 
 // ---- query conversion for the f16-kind path: q16 = RNE(qhat), eps_q = |qhat - q16|_2 ------------------

@@ -2,6 +2,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -52,11 +53,12 @@ struct ragfin {
     void* data = nullptr;  // [capacity, ld] storage, row-major, L2-normalised
     std::mutex mu;
     // workspace (grow-only)
-    Buf qhat, q16, eps_q, gtau, allow, bk_scores, bk_state, bk_keys, cand, cand_e, flags, stage_q, stage_ids, stage_scores, add_stage;
+    Buf qhat, q16, eps_q, gtau, bmax, allow, bk_scores, bk_state, bk_keys, cand, cand_e, flags, stage_q, stage_ids, stage_scores, add_stage;
     int gemm_min_nq = 5;      // query batches of at least this many rows take the tcgen05 path
     int gemm_cluster = 0;     // 0 = choose by batch size; 1, 2 or 4 = force
     const uint32_t* cur_allow = nullptr;   // scalar filter of the search in flight (device bitmask), else null
     int64_t cur_allowed = 0;               // rows it allows
+    bool use_bound_pass = true;   // tcgen05 path: sample pass that seeds the per-query thresholds (RAGFIN_NO_BOUND_PASS=1 disables)
     int gemm_variant = 1;     // 0 = automatic, 1 = streaming (A and B through shared memory), 2 = A-stationary (A in TMEM)
     cudaEvent_t last_done = nullptr;
     ragfin_search_stats stats = {0, 0, 0, 0};
@@ -137,6 +139,7 @@ extern "C" int ragfin_create(ragfin_t** out, int32_t dim, int32_t dtype, int64_t
     h->dtype = dtype;
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
+    { const char* e = getenv("RAGFIN_NO_BOUND_PASS"); if (e && atoi(e)) h->use_bound_pass = false; }
     h->capacity = capacity_rows;
     const size_t bytes = (size_t)capacity_rows * h->ld * esize(dtype);
     e = cudaMalloc(&h->data, bytes);
@@ -159,7 +162,7 @@ extern "C" void ragfin_destroy(ragfin_t* h) {
     if (!h) return;
     DeviceGuard g(h->device);
     (void)cudaDeviceSynchronize();
-    Buf* bufs[] = {&h->qhat, &h->q16, &h->eps_q, &h->gtau, &h->allow, &h->bk_scores, &h->bk_state, &h->bk_keys, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage};
+    Buf* bufs[] = {&h->qhat, &h->q16, &h->eps_q, &h->gtau, &h->bmax, &h->allow, &h->bk_scores, &h->bk_state, &h->bk_keys, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage};
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->data) cudaFree(h->data);
@@ -414,20 +417,20 @@ static int run_gemm(ragfin* h, int nb, int kp, int* G, float* dump, cudaStream_t
     const int QT0 = (nb + kGM - 1) / kGM;
     int C = h->gemm_cluster ? h->gemm_cluster : (QT0 >= 8 ? 4 : QT0 >= 2 ? 2 : 1);
     typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const GemmArgs);
-    auto pick = [&](int c) -> gemm_fn {
-        const bool d = dump != nullptr;
+    auto pick = [&](int c, int mode) -> gemm_fn {
         if (h->dtype == 0) {
-            if (c == 4) return d ? gemm_topk_kernel<1, true, 4> : gemm_topk_kernel<1, false, 4>;
-            if (c == 2) return d ? gemm_topk_kernel<1, true, 2> : gemm_topk_kernel<1, false, 2>;
-            return d ? gemm_topk_kernel<1, true, 1> : gemm_topk_kernel<1, false, 1>;
+            if (c == 4) return mode == 0 ? gemm_topk_kernel<1, 0, 4> : mode == 1 ? gemm_topk_kernel<1, 1, 4> : gemm_topk_kernel<1, 2, 4>;
+            if (c == 2) return mode == 0 ? gemm_topk_kernel<1, 0, 2> : mode == 1 ? gemm_topk_kernel<1, 1, 2> : gemm_topk_kernel<1, 2, 2>;
+            return mode == 0 ? gemm_topk_kernel<1, 0, 1> : mode == 1 ? gemm_topk_kernel<1, 1, 1> : gemm_topk_kernel<1, 2, 1>;
         }
-        if (c == 4) return d ? gemm_topk_kernel<0, true, 4> : gemm_topk_kernel<0, false, 4>;
-        if (c == 2) return d ? gemm_topk_kernel<0, true, 2> : gemm_topk_kernel<0, false, 2>;
-        return d ? gemm_topk_kernel<0, true, 1> : gemm_topk_kernel<0, false, 1>;
+        if (c == 4) return mode == 0 ? gemm_topk_kernel<0, 0, 4> : mode == 1 ? gemm_topk_kernel<0, 1, 4> : gemm_topk_kernel<0, 2, 4>;
+        if (c == 2) return mode == 0 ? gemm_topk_kernel<0, 0, 2> : mode == 1 ? gemm_topk_kernel<0, 1, 2> : gemm_topk_kernel<0, 2, 2>;
+        return mode == 0 ? gemm_topk_kernel<0, 0, 1> : mode == 1 ? gemm_topk_kernel<0, 1, 1> : gemm_topk_kernel<0, 2, 1>;
     };
     const int stages0 = kp <= 32 ? 4 : kp <= 64 ? 3 : 2;
     const size_t smem = gemm_smem_bytes(stages0, kp);
-    gemm_fn fn = pick(C);
+    const int mode = dump ? 1 : 0;
+    gemm_fn fn = pick(C, mode);
     CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int resident_clusters = h->num_sms;
     if (C > 1) {   // how many clusters of C CTAs the device can hold at once (GPC packing may strand SMs)
@@ -441,15 +444,19 @@ static int run_gemm(ragfin* h, int nb, int kp, int* G, float* dump, cudaStream_t
         qc.attrs = at; qc.numAttrs = 1;
         int nc = 0;
         CU_TRY(cudaOccupancyMaxActiveClusters(&nc, (const void*)fn, &qc));
-        if (nc < 1) { C = 1; fn = pick(1); CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
+        if (nc < 1) { C = 1; fn = pick(1, mode); CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
         else resident_clusters = nc;
     }
     const GemmPlan p = plan_gemm(nb, n, C > 1 ? resident_clusters * C : h->num_sms, kp, C);
+    // A operand: the query tiles, padded with zero rows to whole tiles (search_locked zeroes qhat's padding; the
+    // 16-bit copy is zeroed here) so that no TMA box of the A operand is partly out of bounds
+    const int nb_pad = p.QT * kGM;
     const float* qhat = (const float*)h->qhat.p;
     const void* a_base = qhat;
     if ((rc = ensure(h->eps_q, (size_t)nb * sizeof(float)))) return rc;
     if (h->dtype != 0) {
-        if ((rc = ensure(h->q16, (size_t)nb * h->ld * 2))) return rc;
+        if ((rc = ensure(h->q16, (size_t)nb_pad * h->ld * 2))) return rc;
+        if (nb_pad > nb) CU_TRY(cudaMemsetAsync((char*)h->q16.p + (size_t)nb * h->ld * 2, 0, (size_t)(nb_pad - nb) * h->ld * 2, st));
         const int wpb = 8;
         if (h->dtype == 1)
             qconv_kernel<1><<<(nb + wpb - 1) / wpb, wpb * 32, 0, st>>>(qhat, nb, h->ld, (__nv_bfloat16*)h->q16.p, (float*)h->eps_q.p);
@@ -462,7 +469,7 @@ static int run_gemm(ragfin* h, int nb, int kp, int* G, float* dump, cudaStream_t
         CU_TRY(cudaMemsetAsync(h->eps_q.p, 0, (size_t)nb * sizeof(float), st));
     }
     CUtensorMap tmA, tmB;
-    if ((rc = make_map(&tmA, h->dtype, a_base, nb, h->ld, kGM))) return rc;
+    if ((rc = make_map(&tmA, h->dtype, a_base, nb_pad, h->ld, kGM))) return rc;
     if ((rc = make_map(&tmB, h->dtype, h->data, n, h->ld, kGN / C))) return rc;   // each CTA fetches 1/C of a tile
     if (!dump) {
         if ((rc = ensure(h->cand, (size_t)nb * p.S * kp * sizeof(u64)))) return rc;
@@ -484,20 +491,54 @@ static int run_gemm(ragfin* h, int nb, int kp, int* G, float* dump, cudaStream_t
     a.gtau = (uint32_t*)h->gtau.p;
     a.allow = h->cur_allow;
     a.dump = dump;
-    {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(p.grid);
-        cfg.blockDim = dim3(kGemmThreads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        prof_begin(h, st);
-        CU_TRY(cudaLaunchKernelEx(&cfg, fn, tmA, tmB, a));
-        prof_end(h, st);
+    a.bound_tps = 0; a.bound_tiles = 0; a.bound_stride = 0;
+    { const char* e = getenv("RAGFIN_GEMM_DEBUG"); a.dbg = e ? atoi(e) : 0; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+
+    // Bound pass: score an evenly strided sample of corpus tiles (about 1 %), take each query's maximum per sample
+    // tile and publish the kp-th largest of them as the starting threshold gtau[q] - a valid lower bound of the
+    // global kp-th score.  Without it every (CTA, query) list warms up on its own slice, which costs more than the
+    // whole HBM-bound sweep at 16..512 queries.  Skipped under a scalar filter (maxima would count excluded rows).
+    const int64_t n_tiles = (n + kGN - 1) / kGN;
+    const int groups = (p.QT + C - 1) / C;
+    const int clusters = C > 1 ? resident_clusters : h->num_sms;
+    if (!dump && h->use_bound_pass && h->cur_allow == nullptr && n_tiles >= 4 * (int64_t)kp) {
+        int64_t want = n_tiles / 96;
+        if (want < 2 * kp) want = 2 * kp;
+        if (want > 1024) want = 1024;
+        int slots = clusters / groups;          // clusters each group of query tiles can occupy at once
+        if (slots < 1) slots = 1;
+        int Sb = want < slots ? (int)want : slots;
+        int tps = (int)((want + Sb - 1) / Sb);
+        while ((int64_t)Sb * tps > 1024) --tps;
+        GemmArgs b = a;
+        b.S = Sb;
+        b.bound_tps = tps;
+        b.bound_tiles = Sb * tps;
+        b.bound_stride = (n_tiles - 1) / b.bound_tiles;   // the last (possibly partial) tile is never sampled
+        if (b.bound_stride < 1) b.bound_stride = 1;
+        if ((rc = ensure(h->bmax, (size_t)nb * b.bound_tiles * sizeof(float)))) return rc;
+        b.dump = (float*)h->bmax.p;
+        gemm_fn bfn = pick(C, 2);
+        CU_TRY(cudaFuncSetAttribute(bfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t items = (int64_t)groups * Sb;
+        cfg.gridDim = dim3((unsigned)(items < clusters ? items : clusters) * C);
+        CU_TRY(cudaLaunchKernelEx(&cfg, bfn, tmA, tmB, b));
+        bound_select_kernel<<<nb, 1024, 0, st>>>((const float*)h->bmax.p, b.bound_tiles, kp, (uint32_t*)h->gtau.p);
+        CU_TRY(cudaGetLastError());
+        h->stats.launches += 2;
     }
+    cfg.gridDim = dim3(p.grid);
+    prof_begin(h, st);
+    CU_TRY(cudaLaunchKernelEx(&cfg, fn, tmA, tmB, a));
+    prof_end(h, st);
     CU_TRY(cudaGetLastError());
     h->stats.launches++;
     *G = p.S;
@@ -672,10 +713,12 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
     for (int q0 = 0; q0 < nq; q0 += kMaxQueryBatch) {
         const int nb = nq - q0 < kMaxQueryBatch ? nq - q0 : kMaxQueryBatch;
         const int nb4 = (nb + 3) / 4 * 4;
-        // 1. normalise the queries (same kernel as ingest, fp32 out, stride ld); pad to 4 with zero rows
-        if ((rc = ensure(h->qhat, (size_t)nb4 * h->ld * sizeof(float)))) return rc;
+        const bool via_gemm = nb >= h->gemm_min_nq && gemm_supported(h, kp);
+        const int nbq = via_gemm ? (nb + kGM - 1) / kGM * kGM : nb4;   // tensor-core path: whole 128-query tiles
+        // 1. normalise the queries (same kernel as ingest, fp32 out, stride ld); pad with zero rows
+        if ((rc = ensure(h->qhat, (size_t)nbq * h->ld * sizeof(float)))) return rc;
         float* qhat = (float*)h->qhat.p;
-        if (nb4 > nb) CU_TRY(cudaMemsetAsync(qhat + (size_t)nb * h->ld, 0, (size_t)(nb4 - nb) * h->ld * sizeof(float), st));
+        if (nbq > nb) CU_TRY(cudaMemsetAsync(qhat + (size_t)nb * h->ld, 0, (size_t)(nbq - nb) * h->ld * sizeof(float), st));
         if ((rc = launch_ingest<false>(0, q_dev + (size_t)q0 * h->dim, 0, 0, 0, 0, nb, h->dim, h->ld, qhat, h->num_sms, st))) return rc;
         h->stats.launches++;
         CU_TRY(cudaMemsetAsync(flag_count, 0, sizeof(int), st));   // flags[q] itself is written by finalize for every q
@@ -684,7 +727,7 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
         bool scanned = false;
         float eps = 0.f;
         const float* eps_q = nullptr;
-        if (nb >= h->gemm_min_nq && gemm_supported(h, kp)) {
+        if (via_gemm) {
             // 2a. tensor-core path
             if (use_astat(h, kp)) { if ((rc = run_gemm_astat(h, nb, kp, &G, nullptr, st))) return rc; }
             else if ((rc = run_gemm(h, nb, kp, &G, nullptr, st))) return rc;
@@ -848,7 +891,9 @@ extern "C" int ragfin_debug_gemm_scores(ragfin_t* h, const float* q_dev, int32_t
     int rc;
     if (h->count == 0) return fail(RAGFIN_EINVAL, "empty collection");
     if ((rc = wait_prev(h, st))) return rc;
-    if ((rc = ensure(h->qhat, (size_t)nq * h->ld * sizeof(float)))) return rc;
+    const int nqp = (nq + kGM - 1) / kGM * kGM;
+    if ((rc = ensure(h->qhat, (size_t)nqp * h->ld * sizeof(float)))) return rc;
+    if (nqp > nq) CU_TRY(cudaMemsetAsync((float*)h->qhat.p + (size_t)nq * h->ld, 0, (size_t)(nqp - nq) * h->ld * sizeof(float), st));
     if ((rc = launch_ingest<false>(0, q_dev, 0, 0, 0, 0, nq, h->dim, h->ld, (float*)h->qhat.p, h->num_sms, st))) return rc;
     int G = 0;
     if (use_astat(h, 32)) { if ((rc = run_gemm_astat(h, nq, 32, &G, out_scores_dev, st))) return rc; }
@@ -861,6 +906,14 @@ extern "C" int ragfin_set_gemm_min_batch(ragfin_t* h, int32_t min_nq) {
     if (!h || min_nq < 1) return fail(RAGFIN_EINVAL, "bad argument");
     std::lock_guard<std::mutex> lk(h->mu);
     h->gemm_min_nq = min_nq;
+    return RAGFIN_OK;
+}
+
+// Tuning knob: the tcgen05 path's threshold-seeding sample pass (default on; results are identical either way).
+extern "C" int ragfin_set_bound_pass(ragfin_t* h, int32_t enable) {
+    if (!h) return fail(RAGFIN_EINVAL, "NULL handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->use_bound_pass = enable != 0;
     return RAGFIN_OK;
 }
 

@@ -191,6 +191,10 @@ class Index:
         """tcgen05 kernel variant: 0 automatic, 1 streaming, 2 A-stationary (query tile in tensor memory)."""
         _lib.check(self._L.ragfin_set_gemm_variant(self._h, int(variant)))
 
+    def set_bound_pass(self, enable: bool) -> None:
+        """tcgen05 path: threshold-seeding sample pass on/off (default on; results identical)."""
+        _lib.check(self._L.ragfin_set_bound_pass(self._h, 1 if enable else 0))
+
     def debug_gemm_scores(self, queries):
         """Test hook: raw tensor-core scores [nq, N] (torch CUDA fp32) of CUDA fp32 queries [nq, dim]."""
         import torch

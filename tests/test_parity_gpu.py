@@ -266,6 +266,36 @@ def test_gemm_search_other_dims(coracle, dtype, dim):
     _assert_same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), 10), f"gemm {dtype} dim={dim}")
 
 
+@pytest.mark.parametrize("dtype", O.DTYPES)
+@pytest.mark.parametrize("n,dim,nq,k", [(70000, 128, 17, 10), (70000, 128, 300, 10), (150000, 64, 130, 100), (40001, 256, 1030, 1)])
+def test_gemm_bound_pass_seeds_thresholds_without_changing_results(coracle, dtype, n, dim, nq, k):
+    """Corpora of >= 4 K' tiles run the sample ("bound") pass first: two more launches, identical hits."""
+    x = O.synth_rows(190, 0, n, dim, dup_every=89, zero_every=2011)
+    q = O.synth_rows(191, 0, nq, dim)
+    idx = _index(x, dtype)
+    with_bound = idx.search(q, k)
+    st = idx.stats()
+    assert st["path"] == 1
+    idx.set_bound_pass(False)
+    without = idx.search(q, k)
+    assert idx.stats()["launches"] == st["launches"] - 2 * ((nq + 4095) // 4096), "the bound pass did not run"
+    _assert_same(with_bound, without, "bound pass on vs off")
+    _assert_same(with_bound, coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), k), f"bound {dtype} n={n} nq={nq} k={k}")
+
+
+def test_gemm_bound_pass_with_heavy_duplicates(coracle):
+    x = O.synth_rows(192, 0, 70000, 128)
+    q = O.synth_rows(193, 0, 20, 128)
+    x[100:400] = q[0] * 3.0          # 300 copies of the best row of query 0: certificate fails, exact tier answers
+    x[30000:30040] = q[5]            # 40 copies: K' = 32 of them fill the list, ties broken by row id
+    x[512::1024] = q[7]              # one copy in every fourth tile
+    idx = _index(x, "bf16")
+    got = idx.search(q, 10)
+    assert idx.stats()["path"] == 1
+    _assert_same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, "bf16"), 10))
+    assert got[0][0].tolist() == list(range(100, 110))
+
+
 def test_gemm_and_scan_paths_agree_and_knob_works(coracle):
     x = O.synth_rows(160, 0, 20000, 768, dup_every=50)
     q = O.synth_rows(161, 0, 20, 768)
