@@ -320,10 +320,13 @@ def run_ours(a):
             dist.all_reduce(kern, op=dist.ReduceOp.MAX)
         ms, e2e_ms, kern_avg_ms = float(ms.item()), float(e2e_ms.item()), float(kern.item())
         launches_of_kernel_per_step = kern_n / max(steps, 1)
-        if st["path"] == 0:   # HBM-bound scan: algorithmic bytes = one pass over the shard per launch
+        # intensity of one pass = 2*nq*N*D flops over N*ld*esize bytes; below the ridge (peak flops / peak bytes,
+        # ~257 queries for bf16) the tensor-core kernel is HBM-bound like the scan
+        ridge = peaks["bf16"] * 1e12 / (peaks["hbm"] * 1e9)
+        if st["path"] == 0 or 2.0 * batch / esize < ridge:   # algorithmic bytes = one pass over the shard per launch
             alg = shard_rows * ld * esize
             achieved = alg / (kern_avg_ms * 1e-3) / 1e9
-            roof = {"bound": "hbm", "kernel": "scan_topk_kernel", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
+            roof = {"bound": "hbm", "kernel": "scan_topk_kernel" if st["path"] == 0 else "gemm_topk_kernel", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": achieved / peaks["hbm"], "algorithmic_bytes_per_launch": alg,
                     "frac_of_nominal_8TBps": achieved / 8000.0}
         else:                 # tensor-bound GEMM: algorithmic flops = 2 * nq * shard rows * dim per launch

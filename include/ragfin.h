@@ -161,6 +161,13 @@ int ragfin_set_gemm_variant(ragfin_t* h, int32_t variant);
  * score).  1 = on (default), 0 = off.  Results are identical; only the epilogue's bookkeeping cost changes. */
 int ragfin_set_bound_pass(ragfin_t* h, int32_t enable);
 
+/* Tuning knob: with the bound pass on, unfiltered searches over corpora of at least 1024 * k rows run the
+ * tensor-core sweep in "append" mode: every row whose approximate score reaches (k-th largest sample maximum -
+ * 2 * error bound) is appended to a per-query buffer, and the finalize step sorts, cuts at (k-th approximate score -
+ * 2 * error bound) and rescans those rows exactly - exact by construction, no certificate.  1 = on (default),
+ * 0 = per-query K' lists in shared memory + certificate.  Results are identical. */
+int ragfin_set_append_mode(ragfin_t* h, int32_t enable);
+
 /* Test hook: raw (approximate, fp32-accumulated) tensor-core scores of nq queries against every
  * stored row, out_scores_dev [nq, count] device memory.  Validates the TMA / tcgen05 plumbing. */
 int ragfin_debug_gemm_scores(ragfin_t* h, const float* q_dev, int32_t nq, float* out_scores_dev, void* stream);

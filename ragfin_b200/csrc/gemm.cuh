@@ -173,10 +173,13 @@ struct GemmArgs {
     u64* cand;              // [nq][S][kp]
     uint32_t* gtau;         // [nq] ordered-uint lower bound of the global K'-th approximate score (atomicMax)
     const uint32_t* allow;  // scalar filter bitmask over rows, or null
-    float* dump;            // MODE 1: [nq][n_rows] raw scores.  MODE 2: [nq][S * bound_tps] per-tile score maxima
-    int bound_tps;          // MODE 2: sample tiles per item ("slice" sl covers sample tiles [sl * bound_tps, +bound_tps))
+    float* dump;            // MODE 1: [nq][n_rows] raw scores.  MODE 2: [nq][S] block maxima (one block per "slice")
+    int bound_tps;          // MODE 2: sample tiles per block ("slice" sl covers sample tiles [sl * bound_tps, +bound_tps))
     int bound_tiles;        // MODE 2: sample tiles in total
     long long bound_stride; // MODE 2: sample tile j is corpus tile j * bound_stride
+    const float* thr;       // MODE 3: [nq] collection threshold (a row is appended when its score >= thr[q])
+    uint32_t* cnt;          // MODE 3: [nq] rows appended so far (may exceed cap: overflow, the query goes to tier 2)
+    int cap;                // MODE 3: capacity of one query's append buffer, cand = [nq][cap]
     int dbg;                // timing experiments only (RAGFIN_GEMM_DEBUG): 1 skip epilogue filter, 2 skip MMAs, 4 skip A loads, 8 skip B loads
 };
 
@@ -219,10 +222,13 @@ __device__ __noinline__ void cand_insert(CandState& st, u64* lists, int m, int k
     }
 }
 
-// MODE: 0 = collect candidates; 1 = dump raw scores (test hook); 2 = bound pass: score an evenly strided SAMPLE
-// of corpus tiles and write each query's maximum per sample tile.  The K'-th largest of those block maxima is a
-// valid lower bound of the K'-th best score over the whole corpus (K' distinct rows reach it), so the collecting
-// pass can start every list with a tight threshold instead of warming up on its own slice.
+// MODE: 0 = collect candidates in per-query lists (shared memory, K' best of the slice); 1 = dump raw scores (test
+// hook); 2 = bound pass: score an evenly strided SAMPLE of corpus tiles and write each query's maximum per block of
+// sample tiles.  The j-th largest of those block maxima is a valid lower bound of the j-th best score over the
+// whole corpus (j distinct rows reach it), so the collecting pass starts with a tight threshold instead of warming
+// up on its own slice.  3 = append: every row whose score reaches the query's fixed threshold thr[q] (bound pass:
+// k-th largest block maximum minus twice the error bound) is appended to the query's buffer in global memory - no
+// lists, no shared memory, nothing to maintain; finalize_append_kernel selects and rescans exactly.
 // C = thread-block cluster size along the query-tile axis: the C CTAs of a cluster hold C different
 // query tiles and sweep the same corpus slice in lockstep; each loads 1/C of every corpus tile and
 // TMA-multicasts it into all C shared memories, so a corpus tile leaves L2 once per cluster.
@@ -358,6 +364,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             st.tau_s = q < a.nq ? -INFINITY : INFINITY;   // padding lanes of a partial query tile never collect
             st.gptr = (MODE == 0 && q < a.nq) ? a.gtau + q : nullptr;
             st.allow = a.allow;
+            float tile_mx = -INFINITY;   // MODE 2: maximum over the block's sample tiles
+            const float thr3 = (MODE == 3 && q < a.nq) ? __ldg(a.thr + qc) : INFINITY;   // padding lanes never append
+            uint32_t* const cnt3 = MODE == 3 ? a.cnt + qc : nullptr;
+            u64* const buf3 = MODE == 3 ? a.cand + (size_t)qc * a.cap : nullptr;
             uint32_t g_next = MODE != 0 ? 0u : __ldcg(a.gtau + qc);
             for (int t = 0; t < ntiles; ++t) {
                 if (MODE == 0) {   // bound published by the other CTAs sweeping this query (loaded one tile ahead)
@@ -368,7 +378,6 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tc_fence_after();
                 if (MODE == 0) g_next = __ldcg(a.gtau + qc);
                 const long long trow = r0 + (long long)t * step;
-                float tile_mx = -INFINITY;   // MODE 2
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kGN;
                 const int valid = r1 - trow < kGN ? (int)(r1 - trow) : kGN;   // rows of this tile inside the corpus
                 uint32_t vb[2][32];
@@ -403,6 +412,24 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     const float mx = fmaxf(fmaxf(gmx[0], gmx[1]), fmaxf(gmx[2], gmx[3]));
                     if (MODE == 2) { tile_mx = fmaxf(tile_mx, mx); continue; }
+                    if (MODE == 3) {
+                        if (mx >= thr3) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                if (gmx[g] >= thr3) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float sc = __uint_as_float(v[g * 8 + j]);
+                                        if (sc >= thr3) {   // one atomic per appended row (measured: reserving slots in blocks is no faster)
+                                            const uint32_t pos = atomicAdd(cnt3, 1u);
+                                            if (pos < (uint32_t)a.cap) buf3[pos] = make_key(sc + 0.0f, (uint32_t)(trow + c * 32 + g * 8 + j));
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        continue;
+                    }
                     if (mx >= st.tau_s) {          // rare per thread; every v[j] stays in its register
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
@@ -419,8 +446,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tc_fence_before();
                 mbar_arrive(tempty_bar(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-                if (MODE == 2 && q < a.nq) a.dump[(size_t)q * a.bound_tiles + (size_t)sl * a.bound_tps + t] = tile_mx;
             }
+            if (MODE == 2 && q < a.nq) a.dump[(size_t)q * a.S + sl] = tile_mx;
             if (MODE == 0 && q < a.nq) {
                 u64* out = a.cand + ((size_t)q * a.S + sl) * kp;
                 for (int e = 0; e < kp; ++e) out[e] = e < st.cnt ? lists[(size_t)e * kGM + m] : 0ull;
@@ -436,20 +463,34 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
-// ---- bound pass, second half: gtau[q] = the kp-th largest of the query's nb per-tile maxima (rank counting) ------
-__global__ void __launch_bounds__(1024) bound_select_kernel(const float* __restrict__ bmax, int nb, int kp, uint32_t* __restrict__ gtau) {
+// ---- bound pass, second half: the rank-th largest (1-based) of the query's nb block maxima, by rank counting ---
+// gtau != null (list mode): gtau[q] = that value as an ordered uint.
+// thr  != null (append mode): thr[q] = value - 2 * (eps_const + eps_q[q]) - 2^-22, cnt[q] = 0.  Every row whose
+//   exact score can be among the k best has an approximate score >= thr[q]:  exact_k >= approx_k - eps and
+//   approx >= exact - eps, and value <= approx_k (rank = k).
+__global__ void __launch_bounds__(1024) bound_select_kernel(const float* __restrict__ bmax, int nb, int rank,
+                                                            uint32_t* __restrict__ gtau, float* __restrict__ thr,
+                                                            uint32_t* __restrict__ cnt, float eps_const,
+                                                            const float* __restrict__ eps_q) {
     __shared__ uint32_t v[1024];
     const int q = blockIdx.x, i = threadIdx.x;
     v[i] = i < nb ? float_to_ordered(bmax[(size_t)q * nb + i] + 0.0f) : 0u;
+    if (i == 0 && cnt != nullptr) cnt[q] = 0u;
     __syncthreads();
     if (i >= nb) return;
     const uint32_t mine = v[i];
-    int rank = 0;
+    int r = 0;
     for (int j = 0; j < nb; ++j) {
         const uint32_t o = v[j];
-        rank += (o > mine) || (o == mine && j < i);
+        r += (o > mine) || (o == mine && j < i);
     }
-    if (rank == kp - 1) gtau[q] = mine;
+    if (r == rank - 1) {
+        if (gtau != nullptr) gtau[q] = mine;
+        if (thr != nullptr) {
+            const float e = eps_const + (eps_q ? eps_q[q] : 0.0f);
+            thr[q] = __fsub_rd(__fsub_rd(ordered_to_float(mine), __fmul_ru(2.0f, e)), 2.384185791015625e-07f);
+        }
+    }
 }
 
 // ---- query conversion for the f16-kind path: q16 = RNE(qhat), eps_q = |qhat - q16|_2 ------------------

@@ -387,6 +387,80 @@ finalize_kernel(const u64* __restrict__ cand, int G, int kp, const void* __restr
 }
 
 // ---------------------------------------------------------------------------------
+// K4 for the append mode of the tensor-core path: one CTA per query.
+//   buf[q][0..m)  keys (approximate score, row) of EVERY row whose approximate score reached thr[q]
+// With eps >= |approx - exact| for every row:  T = k-th largest approximate score (it is in the buffer, because
+// thr <= T - 2 eps), and every row of the exact top-k has approx >= T - 2 eps.  So: sort, cut at T - 2 eps,
+// recompute those rows canonically in fp64, order by the exact key, emit k.  Unconditionally exact - there is no
+// certificate to fail; only an overflowing buffer (m > cap, or more than kAppendRescore rows above the cut:
+// massive duplication) sends the query to tier 2.
+// ---------------------------------------------------------------------------------
+constexpr int kAppendRescore = 2048;   // most rows one query may rescore exactly
+
+__global__ void __launch_bounds__(kFinThreads)
+finalize_append_kernel(const u64* __restrict__ buf, const uint32_t* __restrict__ cnt, int cap,
+                       const void* __restrict__ data, int dt, int64_t n_rows, int ld, const float* __restrict__ qhat,
+                       float eps_const, const float* __restrict__ eps_q, int k, int64_t id_base,
+                       int64_t* __restrict__ out_ids, float* __restrict__ out_scores, int* __restrict__ flags,
+                       int* __restrict__ flag_count) {
+    extern __shared__ __align__(16) u64 fsm[];   // [P >= m keys][kAppendRescore exact keys]
+    __shared__ int s_c2;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const uint32_t m32 = cnt[q];
+    const int keff = (int64_t)k < n_rows ? k : (int)n_rows;
+    bool bad = m32 > (uint32_t)cap;
+    const int m = bad ? 0 : (int)m32;
+    int P = 32;
+    while (P < m) P <<= 1;
+    u64* keys = fsm;
+    u64* ex = fsm + P;
+    const u64* in = buf + (size_t)q * cap;
+    for (int i = tid; i < P; i += kFinThreads) keys[i] = i < m ? in[i] : 0ull;
+    if (tid == 0) s_c2 = 0;
+    __syncthreads();
+    if (!bad) block_bitonic_sort_desc(keys, P, tid, kFinThreads);
+    if (!bad && keff > 0 && (m < keff || keys[keff - 1] == 0ull)) bad = true;   // fewer than k rows collected: cannot happen with a valid bound
+    int c2 = 0;
+    if (!bad && keff > 0) {
+        const float eps = eps_const + (eps_q ? eps_q[q] : 0.0f);
+        const float cut = __fsub_rd(__fsub_rd(key_score(keys[keff - 1]), __fmul_ru(2.0f, eps)), 2.384185791015625e-07f);
+        for (int i = tid; i < m; i += kFinThreads) {   // sorted by score: the rows above the cut are a prefix
+            const bool in_i = keys[i] != 0ull && key_score(keys[i]) >= cut;
+            const bool in_n = i + 1 < m && keys[i + 1] != 0ull && key_score(keys[i + 1]) >= cut;
+            if (in_i && !in_n) s_c2 = i + 1;
+        }
+        __syncthreads();
+        c2 = s_c2;
+        if (c2 > kAppendRescore) bad = true;
+    }
+    if (bad) {   // block-uniform
+        if (tid == 0) { flags[q] = 1; atomicAdd(flag_count, 1); }
+        return;
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    const float* qv = qhat + (size_t)q * ld;
+    for (int c = warp; c < c2; c += kFinWarps) {
+        const uint32_t row = key_row(keys[c]);
+        double sc;
+        if (dt == 0) sc = rescore_row<0>(data, row, ld, qv, lane);
+        else if (dt == 1) sc = rescore_row<1>(data, row, ld, qv, lane);
+        else sc = rescore_row<2>(data, row, ld, qv, lane);
+        if (lane == 0) ex[c] = make_key((float)sc + 0.0f, row);
+    }
+    int P2 = 32;
+    while (P2 < c2) P2 <<= 1;
+    for (int i = c2 + tid; i < P2; i += kFinThreads) ex[i] = 0ull;
+    __syncthreads();
+    block_bitonic_sort_desc(ex, P2, tid, kFinThreads);
+    for (int i = tid; i < k; i += kFinThreads) {
+        const u64 key = i < keff ? ex[i] : 0;
+        out_ids[(size_t)q * k + i] = key ? id_base + (int64_t)key_row(key) : -1;
+        out_scores[(size_t)q * k + i] = key ? key_score(key) : -INFINITY;
+    }
+    if (tid == 0) flags[q] = 0;
+}
+
+// ---------------------------------------------------------------------------------
 // Tier 2: canonical fp64 score of EVERY row for the flagged queries, exact keys, per-warp
 // lists of kpe entries, CTA merge.  Exits immediately when nothing is flagged.
 // cand_e[(q * gridDim.x + blockIdx.x) * kpe + i]

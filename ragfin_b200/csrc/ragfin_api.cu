@@ -53,11 +53,12 @@ struct ragfin {
     void* data = nullptr;  // [capacity, ld] storage, row-major, L2-normalised
     std::mutex mu;
     // workspace (grow-only)
-    Buf qhat, q16, eps_q, gtau, bmax, allow, bk_scores, bk_state, bk_keys, cand, cand_e, flags, stage_q, stage_ids, stage_scores, add_stage;
-    int gemm_min_nq = 5;      // query batches of at least this many rows take the tcgen05 path
+    Buf qhat, q16, eps_q, gtau, bmax, acnt, athr, allow, bk_scores, bk_state, bk_keys, cand, cand_e, flags, stage_q, stage_ids, stage_scores, add_stage;
+    int gemm_min_nq = 3;      // query batches of at least this many rows take the tcgen05 path (1-2: HBM-bound scan)
     int gemm_cluster = 0;     // 0 = choose by batch size; 1, 2 or 4 = force
     const uint32_t* cur_allow = nullptr;   // scalar filter of the search in flight (device bitmask), else null
     int64_t cur_allowed = 0;               // rows it allows
+    bool use_append = true;       // tcgen05 path: append mode (threshold from the bound pass, no lists) when eligible
     bool use_bound_pass = true;   // tcgen05 path: sample pass that seeds the per-query thresholds (RAGFIN_NO_BOUND_PASS=1 disables)
     int gemm_variant = 1;     // 0 = automatic, 1 = streaming (A and B through shared memory), 2 = A-stationary (A in TMEM)
     cudaEvent_t last_done = nullptr;
@@ -162,7 +163,7 @@ extern "C" void ragfin_destroy(ragfin_t* h) {
     if (!h) return;
     DeviceGuard g(h->device);
     (void)cudaDeviceSynchronize();
-    Buf* bufs[] = {&h->qhat, &h->q16, &h->eps_q, &h->gtau, &h->bmax, &h->allow, &h->bk_scores, &h->bk_state, &h->bk_keys, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage};
+    Buf* bufs[] = {&h->qhat, &h->q16, &h->eps_q, &h->gtau, &h->bmax, &h->acnt, &h->athr, &h->allow, &h->bk_scores, &h->bk_state, &h->bk_keys, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage};
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->data) cudaFree(h->data);
@@ -406,30 +407,78 @@ static GemmPlan plan_gemm(int nq, int64_t n, int num_sms, int kp, int C) {
     return p;
 }
 
+// |tensor-core score - exact score| beyond the query rounding term: fp32 accumulation inside the tensor
+// core (bounded generously: truncating adds) and, for tf32, the truncation of both operands to 10 mantissa bits.
+static float eps_gemm_const(int dtype, int ld) {
+    double e = (ld + 64) * 4.76837158203125e-07 * 1.0625 + 4.76837158203125e-07;   // (ld+64) * 2^-21
+    if (dtype == 0) e += 2.0 * 9.765625e-04 * 1.0625;                               // 2 * 2^-10
+    return (float)e;
+}
+
 static bool gemm_supported(const ragfin* h, int kp) { return kp <= 128 && h->count > 0; }
 
 // Scores the nb normalised queries in h->qhat against the corpus on the tensor cores.  Fills
 // h->cand as [nb][S][kp] (unsorted lists) and h->eps_q; returns S through *G.  dump != null: write raw scores instead.
-static int run_gemm(ragfin* h, int nb, int kp, int* G, float* dump, cudaStream_t st) {
+static const int kAppendCap = 16384;   // append mode: keys one query may collect before it overflows to tier 2
+static const int kAppendMaxK = 256;    // largest k the append mode serves (tier 2, its overflow path, keeps 256 keys)
+
+// Append mode needs the bound pass (no scalar filter) and at least 4 k corpus tiles to draw 2 k sample blocks from.
+static bool append_eligible(const ragfin* h, int k) {
+    const int64_t n_tiles = (h->count + kGN - 1) / kGN;
+    return h->use_bound_pass && h->use_append && h->cur_allow == nullptr && k <= kAppendMaxK && n_tiles >= 4 * (int64_t)k;
+}
+
+// Scores the nb normalised queries in h->qhat against the corpus on the tensor cores and leaves per-query candidates
+// for the finalize step: list mode fills h->cand as [nb][S][kp] (unsorted lists, S returned through *G); append
+// mode (*appended = true) fills h->cand as [nb][kAppendCap] with h->acnt[q] keys each.  dump != null: raw scores.
+static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, float* dump, cudaStream_t st) {
     int rc;
     const int64_t n = h->count;
+    *appended = false;
     // cluster size along the query-tile axis: multicast pays once several query tiles share a slice
     const int QT0 = (nb + kGM - 1) / kGM;
-    int C = h->gemm_cluster ? h->gemm_cluster : (QT0 >= 8 ? 4 : QT0 >= 2 ? 2 : 1);
+    // measured on 10M x 768 bf16 (profiles/r01): pairs use all 148 SMs and win from 1024 queries up (49.7 vs 53.1 ms
+    // at 4096); quads strand 16 SMs but read each corpus tile once, which wins at 3-7 query tiles (6.35 vs 6.80 ms at 512)
+    int C = h->gemm_cluster ? h->gemm_cluster : (QT0 >= 8 ? 2 : QT0 >= 3 ? 4 : QT0 >= 2 ? 2 : 1);
     typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const GemmArgs);
+#define RF_PICK_MODE(KIND, CC) (mode == 0 ? gemm_topk_kernel<KIND, 0, CC> : mode == 1 ? gemm_topk_kernel<KIND, 1, CC> : mode == 2 ? gemm_topk_kernel<KIND, 2, CC> : gemm_topk_kernel<KIND, 3, CC>)
     auto pick = [&](int c, int mode) -> gemm_fn {
-        if (h->dtype == 0) {
-            if (c == 4) return mode == 0 ? gemm_topk_kernel<1, 0, 4> : mode == 1 ? gemm_topk_kernel<1, 1, 4> : gemm_topk_kernel<1, 2, 4>;
-            if (c == 2) return mode == 0 ? gemm_topk_kernel<1, 0, 2> : mode == 1 ? gemm_topk_kernel<1, 1, 2> : gemm_topk_kernel<1, 2, 2>;
-            return mode == 0 ? gemm_topk_kernel<1, 0, 1> : mode == 1 ? gemm_topk_kernel<1, 1, 1> : gemm_topk_kernel<1, 2, 1>;
-        }
-        if (c == 4) return mode == 0 ? gemm_topk_kernel<0, 0, 4> : mode == 1 ? gemm_topk_kernel<0, 1, 4> : gemm_topk_kernel<0, 2, 4>;
-        if (c == 2) return mode == 0 ? gemm_topk_kernel<0, 0, 2> : mode == 1 ? gemm_topk_kernel<0, 1, 2> : gemm_topk_kernel<0, 2, 2>;
-        return mode == 0 ? gemm_topk_kernel<0, 0, 1> : mode == 1 ? gemm_topk_kernel<0, 1, 1> : gemm_topk_kernel<0, 2, 1>;
+        if (h->dtype == 0) return c == 4 ? RF_PICK_MODE(1, 4) : c == 2 ? RF_PICK_MODE(1, 2) : RF_PICK_MODE(1, 1);
+        return c == 4 ? RF_PICK_MODE(0, 4) : c == 2 ? RF_PICK_MODE(0, 2) : RF_PICK_MODE(0, 1);
     };
-    const int stages0 = kp <= 32 ? 4 : kp <= 64 ? 3 : 2;
-    const size_t smem = gemm_smem_bytes(stages0, kp);
-    const int mode = dump ? 1 : 0;
+#undef RF_PICK_MODE
+    // Sample ("bound") pass geometry.  nblk blocks of g sample tiles each, evenly strided over the corpus; the
+    // rank-th largest block maximum bounds the rank-th best score from below.  Needs at least twice as many blocks
+    // as the rank and samples at most half of the corpus; skipped under a scalar filter (the maxima would count
+    // excluded rows) and for the dump hook.
+    const int64_t n_tiles = (n + kGN - 1) / kGN;
+    const bool can_bound = !dump && h->use_bound_pass && h->cur_allow == nullptr;
+    const bool append = !dump && append_eligible(h, k);
+    const bool bound = append || (can_bound && n_tiles >= 4 * (int64_t)kp);
+    const int rank = append ? k : kp;
+    int nblk = 0, g = 1;
+    int64_t bstride = 1;
+    if (bound) {
+        // blocks: 16 x rank keeps the rank best sample rows in distinct blocks (expected collisions rank / 32)
+        int64_t want_blk = 16 * (int64_t)rank;
+        if (want_blk < 256) want_blk = 256;
+        if (want_blk > 1024) want_blk = 1024;
+        nblk = (int)(n_tiles / 2 < want_blk ? n_tiles / 2 : want_blk);
+        // sample enough rows that a query expects to collect well under kAppendCap rows: ~1.6 * k / fraction
+        double frac = append ? (double)k / 5000.0 : 0.0;
+        if (frac < 1.0 / 96.0) frac = 1.0 / 96.0;
+        int64_t sample = (int64_t)(frac * (double)n_tiles);
+        if (sample < nblk) sample = nblk;
+        if (sample > n_tiles / 2) sample = n_tiles / 2;
+        g = (int)((sample + nblk - 1) / nblk);
+        while (g > 1 && (int64_t)nblk * g > n_tiles / 2) --g;
+        bstride = (n_tiles - 1) / ((int64_t)nblk * g);   // the last (possibly partial) tile is never sampled
+        if (bstride < 1) bstride = 1;
+    }
+    const int stages0 = append ? 4 : kp <= 32 ? 4 : kp <= 64 ? 3 : 2;
+    const int kp_smem = append ? 0 : kp;      // append mode keeps no lists in shared memory
+    const size_t smem = gemm_smem_bytes(stages0, kp_smem);
+    const int mode = dump ? 1 : append ? 3 : 0;
     gemm_fn fn = pick(C, mode);
     CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int resident_clusters = h->num_sms;
@@ -447,7 +496,8 @@ static int run_gemm(ragfin* h, int nb, int kp, int* G, float* dump, cudaStream_t
         if (nc < 1) { C = 1; fn = pick(1, mode); CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
         else resident_clusters = nc;
     }
-    const GemmPlan p = plan_gemm(nb, n, C > 1 ? resident_clusters * C : h->num_sms, kp, C);
+    GemmPlan p = plan_gemm(nb, n, C > 1 ? resident_clusters * C : h->num_sms, kp, C);
+    p.stages = stages0;
     // A operand: the query tiles, padded with zero rows to whole tiles (search_locked zeroes qhat's padding; the
     // 16-bit copy is zeroed here) so that no TMA box of the A operand is partly out of bounds
     const int nb_pad = p.QT * kGM;
@@ -471,7 +521,11 @@ static int run_gemm(ragfin* h, int nb, int kp, int* G, float* dump, cudaStream_t
     CUtensorMap tmA, tmB;
     if ((rc = make_map(&tmA, h->dtype, a_base, nb_pad, h->ld, kGM))) return rc;
     if ((rc = make_map(&tmB, h->dtype, h->data, n, h->ld, kGN / C))) return rc;   // each CTA fetches 1/C of a tile
-    if (!dump) {
+    if (append) {
+        if ((rc = ensure(h->cand, (size_t)nb * kAppendCap * sizeof(u64)))) return rc;
+        if ((rc = ensure(h->acnt, (size_t)nb * sizeof(uint32_t)))) return rc;
+        if ((rc = ensure(h->athr, (size_t)nb * sizeof(float)))) return rc;
+    } else if (!dump) {
         if ((rc = ensure(h->cand, (size_t)nb * p.S * kp * sizeof(u64)))) return rc;
     }
     GemmArgs a;
@@ -484,14 +538,15 @@ static int run_gemm(ragfin* h, int nb, int kp, int* G, float* dump, cudaStream_t
     a.S = p.S;
     a.rows_per_slice = p.rows_per_slice;
     a.stages = p.stages;
-    a.kp = kp;
+    a.kp = kp_smem;
     if ((rc = ensure(h->gtau, (size_t)nb * sizeof(uint32_t)))) return rc;
-    CU_TRY(cudaMemsetAsync(h->gtau.p, 0, (size_t)nb * sizeof(uint32_t), st));
+    if (!append) CU_TRY(cudaMemsetAsync(h->gtau.p, 0, (size_t)nb * sizeof(uint32_t), st));
     a.cand = (u64*)h->cand.p;
     a.gtau = (uint32_t*)h->gtau.p;
     a.allow = h->cur_allow;
     a.dump = dump;
     a.bound_tps = 0; a.bound_tiles = 0; a.bound_stride = 0;
+    a.thr = (const float*)h->athr.p; a.cnt = (uint32_t*)h->acnt.p; a.cap = kAppendCap;
     { const char* e = getenv("RAGFIN_GEMM_DEBUG"); a.dbg = e ? atoi(e) : 0; }
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(kGemmThreads);
@@ -502,36 +557,24 @@ static int run_gemm(ragfin* h, int nb, int kp, int* G, float* dump, cudaStream_t
     at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
 
-    // Bound pass: score an evenly strided sample of corpus tiles (about 1 %), take each query's maximum per sample
-    // tile and publish the kp-th largest of them as the starting threshold gtau[q] - a valid lower bound of the
-    // global kp-th score.  Without it every (CTA, query) list warms up on its own slice, which costs more than the
-    // whole HBM-bound sweep at 16..512 queries.  Skipped under a scalar filter (maxima would count excluded rows).
-    const int64_t n_tiles = (n + kGN - 1) / kGN;
-    const int groups = (p.QT + C - 1) / C;
-    const int clusters = C > 1 ? resident_clusters : h->num_sms;
-    if (!dump && h->use_bound_pass && h->cur_allow == nullptr && n_tiles >= 4 * (int64_t)kp) {
-        int64_t want = n_tiles / 96;
-        if (want < 2 * kp) want = 2 * kp;
-        if (want > 1024) want = 1024;
-        int slots = clusters / groups;          // clusters each group of query tiles can occupy at once
-        if (slots < 1) slots = 1;
-        int Sb = want < slots ? (int)want : slots;
-        int tps = (int)((want + Sb - 1) / Sb);
-        while ((int64_t)Sb * tps > 1024) --tps;
+    if (bound) {
+        const int groups = (p.QT + C - 1) / C;
+        const int clusters = C > 1 ? resident_clusters : h->num_sms;
         GemmArgs b = a;
-        b.S = Sb;
-        b.bound_tps = tps;
-        b.bound_tiles = Sb * tps;
-        b.bound_stride = (n_tiles - 1) / b.bound_tiles;   // the last (possibly partial) tile is never sampled
-        if (b.bound_stride < 1) b.bound_stride = 1;
-        if ((rc = ensure(h->bmax, (size_t)nb * b.bound_tiles * sizeof(float)))) return rc;
+        b.S = nblk;                 // one item per (group of query tiles, block)
+        b.bound_tps = g;
+        b.bound_tiles = nblk * g;
+        b.bound_stride = bstride;
+        if ((rc = ensure(h->bmax, (size_t)nb * nblk * sizeof(float)))) return rc;
         b.dump = (float*)h->bmax.p;
         gemm_fn bfn = pick(C, 2);
         CU_TRY(cudaFuncSetAttribute(bfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int64_t items = (int64_t)groups * Sb;
+        const int64_t items = (int64_t)groups * nblk;
         cfg.gridDim = dim3((unsigned)(items < clusters ? items : clusters) * C);
         CU_TRY(cudaLaunchKernelEx(&cfg, bfn, tmA, tmB, b));
-        bound_select_kernel<<<nb, 1024, 0, st>>>((const float*)h->bmax.p, b.bound_tiles, kp, (uint32_t*)h->gtau.p);
+        bound_select_kernel<<<nb, 1024, 0, st>>>((const float*)h->bmax.p, nblk, rank, append ? nullptr : (uint32_t*)h->gtau.p,
+                                                 append ? (float*)h->athr.p : nullptr, append ? (uint32_t*)h->acnt.p : nullptr,
+                                                 eps_gemm_const(h->dtype, h->ld), (const float*)h->eps_q.p);
         CU_TRY(cudaGetLastError());
         h->stats.launches += 2;
     }
@@ -542,6 +585,7 @@ static int run_gemm(ragfin* h, int nb, int kp, int* G, float* dump, cudaStream_t
     CU_TRY(cudaGetLastError());
     h->stats.launches++;
     *G = p.S;
+    *appended = append;
     return 0;
 }
 
@@ -636,14 +680,6 @@ static bool use_astat(const ragfin* h, int kp) {
     return astat_supported(h, kp);   // variant 2 (forced) and 0 (automatic) both need eligibility
 }
 
-// |tensor-core score - exact score| beyond the query rounding term: fp32 accumulation inside the tensor
-// core (bounded generously: truncating adds) and, for tf32, the truncation of both operands to 10 mantissa bits.
-static float eps_gemm_const(int dtype, int ld) {
-    double e = (ld + 64) * 4.76837158203125e-07 * 1.0625 + 4.76837158203125e-07;   // (ld+64) * 2^-21
-    if (dtype == 0) e += 2.0 * 9.765625e-04 * 1.0625;                               // 2 * 2^-10
-    return (float)e;
-}
-
 // ------------------------------------------------------------------------------
 // Large-k path: exact scores of every row, radix select of the k-th key, rank sort.  One query at a time.
 // ------------------------------------------------------------------------------
@@ -703,9 +739,12 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
     const int64_t n_eff = h->cur_allow ? h->cur_allowed : n;   // rows a hit may come from
     int kp = cand_per_query(k);
     if (kp == 0 && n <= 256) kp = 256;   // every row is a candidate: any k (graph_cons.py:279 asks limit=1000 of 16 rows)
-    if (kp == 0) return search_bigk(h, q_dev, nq, k, out_ids, out_scores, st);
+    const bool ap = append_eligible(h, k) && nq >= h->gemm_min_nq;   // tensor-core append mode: no K' lists needed
+    if (kp == 0 && !ap) return search_bigk(h, q_dev, nq, k, out_ids, out_scores, st);
+    if (kp == 0) kp = 256;
     h->stats.cand_per_query = kp;
-    const int kpe = k > 256 ? 256 : (k + 31) / 32 * 32;   // k > 256 only occurs with n <= 256
+    int kpe = 32;                                          // tier-2 list length: a power of two (bitonic merges)
+    while (kpe < k && kpe < 256) kpe <<= 1;                // k > 256 only occurs with n <= 256
     if ((rc = ensure(h->flags, (size_t)(kMaxQueryBatch + 1) * sizeof(int)))) return rc;
     int* flags = (int*)h->flags.p;
     int* flag_count = flags + kMaxQueryBatch;
@@ -713,7 +752,7 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
     for (int q0 = 0; q0 < nq; q0 += kMaxQueryBatch) {
         const int nb = nq - q0 < kMaxQueryBatch ? nq - q0 : kMaxQueryBatch;
         const int nb4 = (nb + 3) / 4 * 4;
-        const bool via_gemm = nb >= h->gemm_min_nq && gemm_supported(h, kp);
+        const bool via_gemm = nb >= h->gemm_min_nq && (gemm_supported(h, kp) || (ap && h->count > 0));
         const int nbq = via_gemm ? (nb + kGM - 1) / kGM * kGM : nb4;   // tensor-core path: whole 128-query tiles
         // 1. normalise the queries (same kernel as ingest, fp32 out, stride ld); pad with zero rows
         if ((rc = ensure(h->qhat, (size_t)nbq * h->ld * sizeof(float)))) return rc;
@@ -724,13 +763,13 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
         CU_TRY(cudaMemsetAsync(flag_count, 0, sizeof(int), st));   // flags[q] itself is written by finalize for every q
 
         int G = 0, sorted_lists = 1;
-        bool scanned = false;
+        bool scanned = false, appended = false;
         float eps = 0.f;
         const float* eps_q = nullptr;
         if (via_gemm) {
             // 2a. tensor-core path
-            if (use_astat(h, kp)) { if ((rc = run_gemm_astat(h, nb, kp, &G, nullptr, st))) return rc; }
-            else if ((rc = run_gemm(h, nb, kp, &G, nullptr, st))) return rc;
+            if (!ap && use_astat(h, kp)) { if ((rc = run_gemm_astat(h, nb, kp, &G, nullptr, st))) return rc; }
+            else if ((rc = run_gemm(h, nb, k, kp, &G, &appended, nullptr, st))) return rc;
             h->stats.path = 1;
             sorted_lists = 0;
             scanned = true;
@@ -780,7 +819,15 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
             }
         }
         // 3. merge + exact rescore + certificate (an unscanned, non-empty corpus flags every query)
-        {
+        if (appended) {
+            const size_t fsm = (size_t)(kAppendCap + kAppendRescore) * sizeof(u64);
+            CU_TRY(cudaFuncSetAttribute(finalize_append_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+            finalize_append_kernel<<<nb, kFinThreads, fsm, st>>>(
+                (const u64*)h->cand.p, (const uint32_t*)h->acnt.p, kAppendCap, h->data, h->dtype, n_eff, h->ld, qhat, eps, eps_q, k,
+                h->id_base, out_ids + (size_t)q0 * k, out_scores + (size_t)q0 * k, flags, flag_count);
+            CU_TRY(cudaGetLastError());
+            h->stats.launches++;
+        } else {
             finalize_kernel<false><<<nb, kFinThreads, 0, st>>>(
                 (const u64*)h->cand.p, G, kp, h->data, h->dtype, n_eff, (scanned || n == 0) ? 1 : 0, sorted_lists,
                 sorted_lists ? nullptr : (const uint32_t*)h->gtau.p, h->ld, qhat, eps, eps_q, k, h->id_base, out_ids + (size_t)q0 * k, out_scores + (size_t)q0 * k, flags, flag_count);
@@ -897,11 +944,11 @@ extern "C" int ragfin_debug_gemm_scores(ragfin_t* h, const float* q_dev, int32_t
     if ((rc = launch_ingest<false>(0, q_dev, 0, 0, 0, 0, nq, h->dim, h->ld, (float*)h->qhat.p, h->num_sms, st))) return rc;
     int G = 0;
     if (use_astat(h, 32)) { if ((rc = run_gemm_astat(h, nq, 32, &G, out_scores_dev, st))) return rc; }
-    else if ((rc = run_gemm(h, nq, 32, &G, out_scores_dev, st))) return rc;
+    else { bool ap = false; if ((rc = run_gemm(h, nq, 10, 32, &G, &ap, out_scores_dev, st))) return rc; }
     return mark_done(h, st);
 }
 
-// Dispatch knob: query batches of at least `min_nq` rows use the tcgen05 path (default 5; INT32_MAX = never).
+// Dispatch knob: query batches of at least `min_nq` rows use the tcgen05 path (default 3; INT32_MAX = never).
 extern "C" int ragfin_set_gemm_min_batch(ragfin_t* h, int32_t min_nq) {
     if (!h || min_nq < 1) return fail(RAGFIN_EINVAL, "bad argument");
     std::lock_guard<std::mutex> lk(h->mu);
@@ -914,6 +961,14 @@ extern "C" int ragfin_set_bound_pass(ragfin_t* h, int32_t enable) {
     if (!h) return fail(RAGFIN_EINVAL, "NULL handle");
     std::lock_guard<std::mutex> lk(h->mu);
     h->use_bound_pass = enable != 0;
+    return RAGFIN_OK;
+}
+
+// Tuning knob: append mode of the tcgen05 path (default on; needs the bound pass; results are identical).
+extern "C" int ragfin_set_append_mode(ragfin_t* h, int32_t enable) {
+    if (!h) return fail(RAGFIN_EINVAL, "NULL handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->use_append = enable != 0;
     return RAGFIN_OK;
 }
 

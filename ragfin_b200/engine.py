@@ -195,6 +195,10 @@ class Index:
         """tcgen05 path: threshold-seeding sample pass on/off (default on; results identical)."""
         _lib.check(self._L.ragfin_set_bound_pass(self._h, 1 if enable else 0))
 
+    def set_append_mode(self, enable: bool) -> None:
+        """tcgen05 path: append mode (no lists, threshold from the bound pass) on/off (default on; results identical)."""
+        _lib.check(self._L.ragfin_set_append_mode(self._h, 1 if enable else 0))
+
     def debug_gemm_scores(self, queries):
         """Test hook: raw tensor-core scores [nq, N] (torch CUDA fp32) of CUDA fp32 queries [nq, dim]."""
         import torch

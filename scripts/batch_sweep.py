@@ -9,7 +9,9 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--rows", type=int, default=10_000_000)
 ap.add_argument("--dim", type=int, default=768)
 ap.add_argument("--dtype", default="bf16")
-ap.add_argument("--k", type=int, default=10)
+ap.add_argument("--k", default="10", help="comma-separated k values")
+ap.add_argument("--cluster", default="0", help="comma-separated tcgen05 cluster sizes (0 = automatic)")
+ap.add_argument("--out", default="gpurun_out/batch_sweep.json")
 ap.add_argument("--batches", default="1,2,3,4,5,6,8,9,12,16,32,64,128,256,512,1024,2048,4096")
 ap.add_argument("--paths", default="auto")
 a = ap.parse_args()
@@ -18,19 +20,24 @@ for r in range(0, a.rows, 1_000_000):
     idx.add_synthetic(1234, r, min(1_000_000, a.rows - r))
 out = []
 for path in a.paths.split(","):
-    idx.set_gemm_min_batch({"auto": 5, "scan": 1 << 30, "gemm": 2}.get(path, 9) if not path.isdigit() else int(path))
-    for b in [int(x) for x in a.batches.split(",")]:
-        if path == "scan" and b > 16:
-            continue
-        q = torch.from_numpy(synth_rows(1235, 0, b, a.dim)).cuda()
-        for _ in range(3):
-            idx.search_device(q, a.k)
-        ts = []
-        for _ in range(7):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); idx.search_device(q, a.k); e1.record(); torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        ms = statistics.median(ts)
-        out.append({"path": path, "used": idx.stats()["path"], "batch": b, "ms": round(ms, 3), "qps": round(b / ms * 1e3, 1)})
-        print(out[-1], flush=True)
-json.dump(out, open("gpurun_out/batch_sweep.json", "w"), indent=1)
+    idx.set_gemm_min_batch({"auto": 3, "scan": 1 << 30, "gemm": 2}.get(path, 9) if not path.isdigit() else int(path))
+    for cluster in [int(x) for x in a.cluster.split(",")]:
+        idx.set_gemm_cluster(cluster)
+        for k in [int(x) for x in a.k.split(",")]:
+            for b in [int(x) for x in a.batches.split(",")]:
+                if path == "scan" and b > 16:
+                    continue
+                q = torch.from_numpy(synth_rows(1235, 0, b, a.dim)).cuda()
+                for _ in range(3):
+                    idx.search_device(q, k)
+                ts = []
+                for _ in range(7):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); idx.search_device(q, k); e1.record(); torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                ms = statistics.median(ts)
+                st = idx.stats()
+                out.append({"path": path, "used": st["path"], "cluster": cluster, "k": k, "batch": b, "ms": round(ms, 3),
+                            "qps": round(b / ms * 1e3, 1), "rescanned": st["queries_rescanned"]})
+                print(out[-1], flush=True)
+json.dump(out, open(a.out, "w"), indent=1)

@@ -44,7 +44,7 @@ def test_full_size_properties(corpus, coracle):
     idx.set_gemm_min_batch(1 << 30)
     ids_s, sc_s = idx.search(q[:8], K)
     assert idx.stats()["path"] == 0
-    idx.set_gemm_min_batch(5)
+    idx.set_gemm_min_batch(3)
     ids_g, sc_g = idx.search(q, K)
     assert idx.stats()["path"] == 1
     assert np.array_equal(ids_s, ids_g[:8]) and np.array_equal(sc_s.view(np.uint32), sc_g[:8].view(np.uint32))
@@ -89,3 +89,19 @@ def test_full_size_properties(corpus, coracle):
     mi, ms = ragfin_b200.merge_topk(torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs]), 2, K)
     torch.cuda.synchronize()
     assert np.array_equal(mi.cpu().numpy(), ids_g[:16]) and np.array_equal(ms.cpu().numpy().view(np.uint32), sc_g[:16].view(np.uint32))
+
+
+def test_full_size_k100_stays_on_the_fast_path(corpus, coracle):
+    """k = 100 over 10M bf16 rows: the gap between the 100th and the 128th score is about the size of the rigorous
+    bf16-query error bound, so K' = 128 lists fail their certificate for most queries; append mode has no certificate
+    and must answer every query without the exact tier - and agree with the HBM scan path bit for bit."""
+    idx, q = corpus
+    idx.set_gemm_min_batch(3)
+    ids_g, sc_g = idx.search(q[:16], 100)
+    st = idx.stats()
+    assert st["path"] == 1 and st["queries_rescanned"] == 0
+    idx.set_gemm_min_batch(1 << 30)
+    ids_s, sc_s = idx.search(q[:4], 100)
+    assert idx.stats()["path"] == 0
+    idx.set_gemm_min_batch(3)
+    assert np.array_equal(ids_s, ids_g[:4]) and np.array_equal(sc_s.view(np.uint32), sc_g[:4].view(np.uint32))

@@ -267,20 +267,29 @@ def test_gemm_search_other_dims(coracle, dtype, dim):
 
 
 @pytest.mark.parametrize("dtype", O.DTYPES)
-@pytest.mark.parametrize("n,dim,nq,k", [(70000, 128, 17, 10), (70000, 128, 300, 10), (150000, 64, 130, 100), (40001, 256, 1030, 1)])
-def test_gemm_bound_pass_seeds_thresholds_without_changing_results(coracle, dtype, n, dim, nq, k):
-    """Corpora of >= 4 K' tiles run the sample ("bound") pass first: two more launches, identical hits."""
+@pytest.mark.parametrize("n,dim,nq,k", [(70000, 128, 17, 10), (70000, 128, 300, 10), (150000, 64, 130, 100), (40001, 256, 1030, 1),
+                                        (260000, 32, 5, 224)])
+def test_gemm_append_and_bound_modes_agree_with_the_oracle(coracle, dtype, n, dim, nq, k):
+    """Large unfiltered corpora run the sample ("bound") pass and then the append-mode sweep (no lists, exact by
+    construction).  Turning append mode off falls back to K' lists seeded by the bound pass; turning the bound pass
+    off as well gives the plain list sweep.  All three must return the oracle's hits bit for bit."""
     x = O.synth_rows(190, 0, n, dim, dup_every=89, zero_every=2011)
     q = O.synth_rows(191, 0, nq, dim)
+    want = coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), k)
     idx = _index(x, dtype)
-    with_bound = idx.search(q, k)
+    appended = idx.search(q, k)
     st = idx.stats()
-    assert st["path"] == 1
-    idx.set_bound_pass(False)
-    without = idx.search(q, k)
-    assert idx.stats()["launches"] == st["launches"] - 2 * ((nq + 4095) // 4096), "the bound pass did not run"
-    _assert_same(with_bound, without, "bound pass on vs off")
-    _assert_same(with_bound, coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), k), f"bound {dtype} n={n} nq={nq} k={k}")
+    assert st["path"] == 1 and st["queries_rescanned"] == 0
+    _assert_same(appended, want, f"append {dtype} n={n} nq={nq} k={k}")
+    idx.set_append_mode(False)
+    seeded = idx.search(q, k)
+    _assert_same(seeded, want, f"bound+lists {dtype} n={n} nq={nq} k={k}")
+    if k <= 100:    # beyond K' = 128 only append mode reaches the tensor cores; the fallback is the large-k path
+        assert idx.stats()["path"] == 1 and idx.stats()["launches"] == st["launches"]
+        idx.set_bound_pass(False)
+        plain = idx.search(q, k)
+        assert idx.stats()["launches"] == st["launches"] - 2 * ((nq + 4095) // 4096), "the bound pass did not run"
+        _assert_same(plain, want, f"lists {dtype} n={n} nq={nq} k={k}")
 
 
 def test_gemm_bound_pass_with_heavy_duplicates(coracle):
@@ -290,10 +299,25 @@ def test_gemm_bound_pass_with_heavy_duplicates(coracle):
     x[30000:30040] = q[5]            # 40 copies: K' = 32 of them fill the list, ties broken by row id
     x[512::1024] = q[7]              # one copy in every fourth tile
     idx = _index(x, "bf16")
+    want = coracle.cosine_topk(q, coracle.normalize_rows(x, "bf16"), 10)
     got = idx.search(q, 10)
-    assert idx.stats()["path"] == 1
-    _assert_same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, "bf16"), 10))
+    assert idx.stats()["path"] == 1 and idx.stats()["queries_rescanned"] == 0   # append mode needs no certificate
+    _assert_same(got, want)
     assert got[0][0].tolist() == list(range(100, 110))
+    idx.set_append_mode(False)
+    _assert_same(idx.search(q, 10), want)
+
+
+def test_gemm_append_overflow_goes_to_the_exact_tier(coracle):
+    """More duplicates of the best row than one query may rescore: the buffer overflows, tier 2 answers exactly."""
+    x = O.synth_rows(194, 0, 70000, 64)
+    q = O.synth_rows(195, 0, 6, 64)
+    x[1000:4000] = q[2] * 0.5
+    idx = _index(x, "f16")
+    got = idx.search(q, 10)
+    assert idx.stats()["path"] == 1 and idx.stats()["queries_rescanned"] == 1
+    _assert_same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, "f16"), 10))
+    assert got[0][2].tolist() == list(range(1000, 1010))
 
 
 def test_gemm_and_scan_paths_agree_and_knob_works(coracle):
