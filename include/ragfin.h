@@ -156,6 +156,11 @@ int ragfin_set_gemm_cluster(ragfin_t* h, int32_t cluster);
  * 0 = automatic.  Results are identical. */
 int ragfin_set_gemm_variant(ragfin_t* h, int32_t variant);
 
+/* Tuning knob: small-batch (1-2 query) scan kernel.  0 = automatic (default; currently 1), 1 = 128-bit register-path
+ * loads (scan_topk_kernel), 2 = shared-memory ring filled by cp.async.bulk (scan_tma_kernel; measured no faster).
+ * Results are identical. */
+int ragfin_set_scan_variant(ragfin_t* h, int32_t variant);
+
 /* Tuning knob: the tensor-core path first scores an evenly strided ~1 % sample of corpus tiles and seeds every
  * query's candidate threshold with the K'-th largest per-tile maximum (a valid lower bound of the global K'-th
  * score).  1 = on (default), 0 = off.  Results are identical; only the epilogue's bookkeeping cost changes. */

@@ -12,6 +12,7 @@
 #include "kernels.cuh"
 #include "gemm.cuh"
 #include "gemm_astat.cuh"
+#include "scan_tma.cuh"
 #include "bigk.cuh"
 
 using namespace rfk;
@@ -58,6 +59,7 @@ struct ragfin {
     int gemm_cluster = 0;     // 0 = choose by batch size; 1, 2 or 4 = force
     const uint32_t* cur_allow = nullptr;   // scalar filter of the search in flight (device bitmask), else null
     int64_t cur_allowed = 0;               // rows it allows
+    int scan_variant = 0;         // small-batch scan: 0 = automatic (= 1, measured faster), 1 = LDG kernel, 2 = TMA-fed ring
     bool use_append = true;       // tcgen05 path: append mode (threshold from the bound pass, no lists) when eligible
     bool use_bound_pass = true;   // tcgen05 path: sample pass that seeds the per-query thresholds (RAGFIN_NO_BOUND_PASS=1 disables)
     int gemm_variant = 1;     // 0 = automatic, 1 = streaming (A and B through shared memory), 2 = A-stationary (A in TMEM)
@@ -309,6 +311,28 @@ static scan_fn pick_scan(int dt, int nqt, int steps) {
         case 0: return pick_nq<0>(nqt, steps);
         case 1: return pick_nq<1>(nqt, steps);
         case 2: return pick_nq<2>(nqt, steps);
+    }
+    return nullptr;
+}
+// TMA-fed variant (scan_tma.cuh): 1 or 2 query register sets (larger batches take the tensor-core path)
+template <int DT, int NQ>
+static scan_fn pick_tma_steps(int steps) {
+    switch (steps) {
+        case 1: return scan_tma_kernel<DT, NQ, 1>;
+        case 2: return scan_tma_kernel<DT, NQ, 2>;
+        case 3: return scan_tma_kernel<DT, NQ, 3>;
+        case 4: return scan_tma_kernel<DT, NQ, 4>;
+        case 6: return scan_tma_kernel<DT, NQ, 6>;
+        case 8: return scan_tma_kernel<DT, NQ, 8>;
+    }
+    return nullptr;
+}
+static scan_fn pick_scan_tma(int dt, int nqt, int steps) {
+    if (nqt != 1 && nqt != 2) return nullptr;
+    switch (dt) {
+        case 0: return nqt == 1 ? pick_tma_steps<0, 1>(steps) : pick_tma_steps<0, 2>(steps);
+        case 1: return nqt == 1 ? pick_tma_steps<1, 1>(steps) : pick_tma_steps<1, 2>(steps);
+        case 2: return nqt == 1 ? pick_tma_steps<2, 1>(steps) : pick_tma_steps<2, 2>(steps);
     }
     return nullptr;
 }
@@ -783,6 +807,20 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
             scanned = n > 0 && steps > 0;
             eps = eps_fp32_accumulate(h->ld);
             G = 1;
+            // TMA-fed scan: whole batch of 1 or 2 queries, ring of 4 stages must fit in shared memory
+            const size_t row_bytes = (size_t)h->ld * esize(h->dtype);
+            const size_t tsm = scanned ? ts_smem_bytes(steps, row_bytes, nb, kp) : 0;
+            scan_fn tfn = (scanned && h->scan_variant == 2 && nb <= 2 && tsm <= (size_t)227 * 1024) ? pick_scan_tma(h->dtype, nb, steps) : nullptr;
+            if (tfn) {
+                G = h->num_sms;
+                if ((rc = ensure(h->cand, (size_t)nb4 * G * kp * sizeof(u64)))) return rc;
+                CU_TRY(cudaFuncSetAttribute(tfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+                prof_begin(h, st);
+                tfn<<<G, kTsThreads, tsm, st>>>(h->data, n, h->ld, qhat, nb, kp, (u64*)h->cand.p, (int64_t)G * kp, h->cur_allow);
+                prof_end(h, st);
+                CU_TRY(cudaGetLastError());
+                h->stats.launches++;
+            } else {
             if (scanned) {
                 int per_sm_min = kMaxScanCtasPerSm;
                 const int last = nb - (nb - 1) / 4 * 4;                      // queries in the last group: 1..4
@@ -816,6 +854,7 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
                     CU_TRY(cudaGetLastError());
                     h->stats.launches++;
                 }
+            }
             }
         }
         // 3. merge + exact rescore + certificate (an unscanned, non-empty corpus flags every query)
@@ -969,6 +1008,15 @@ extern "C" int ragfin_set_append_mode(ragfin_t* h, int32_t enable) {
     if (!h) return fail(RAGFIN_EINVAL, "NULL handle");
     std::lock_guard<std::mutex> lk(h->mu);
     h->use_append = enable != 0;
+    return RAGFIN_OK;
+}
+
+// Tuning knob: small-batch scan kernel.  0 = automatic, 1 = register-path loads (scan_topk_kernel), 2 = TMA-fed ring
+// (scan_tma_kernel; 1-2 queries).  Results are identical.
+extern "C" int ragfin_set_scan_variant(ragfin_t* h, int32_t variant) {
+    if (!h || variant < 0 || variant > 2) return fail(RAGFIN_EINVAL, "variant must be 0, 1 or 2");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->scan_variant = variant;
     return RAGFIN_OK;
 }
 

@@ -195,6 +195,10 @@ class Index:
         """tcgen05 path: threshold-seeding sample pass on/off (default on; results identical)."""
         _lib.check(self._L.ragfin_set_bound_pass(self._h, 1 if enable else 0))
 
+    def set_scan_variant(self, variant: int) -> None:
+        """Small-batch scan kernel: 0 automatic, 1 register-path loads, 2 TMA-fed shared-memory ring."""
+        _lib.check(self._L.ragfin_set_scan_variant(self._h, int(variant)))
+
     def set_append_mode(self, enable: bool) -> None:
         """tcgen05 path: append mode (no lists, threshold from the bound pass) on/off (default on; results identical)."""
         _lib.check(self._L.ragfin_set_append_mode(self._h, 1 if enable else 0))

@@ -30,6 +30,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma2(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst), "l"((uint64_t)m), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void bulk1(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void tma3(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst), "l"((uint64_t)m), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
@@ -37,7 +40,7 @@ __device__ __forceinline__ void tma4(uint32_t dst, const CUtensorMap* m, int c0,
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst), "l"((uint64_t)m), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
 
-struct Args { long long n_rows; int stages; int stage_bytes; };
+struct Args { long long n_rows; int stages; int stage_bytes; const char* base; int pieces; };
 
 template <int P>
 __global__ void __launch_bounds__(64, 1) probe(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmA, const Args a) {
@@ -52,9 +55,10 @@ __global__ void __launch_bounds__(64, 1) probe(const __grid_constant__ CUtensorM
     }
     __syncthreads();
     // rows per stage-group ("tile") and number of stage fills per tile
-    constexpr int TILE_ROWS = (P == 0 || P == 3 || P == 5) ? 256 : (P == 6 ? 64 : 32);
+    constexpr int TILE_ROWS = (P == 0 || P == 3 || P == 5) ? 256 : (P == 6 ? 64 : 32);   // P7: rows per stage = stage_bytes / 1536
+    const int tile_rows = P == 7 ? a.stage_bytes / 1536 : TILE_ROWS;
     constexpr int FILLS = (P == 0 || P == 3 || P == 5) ? 12 : 1;
-    const long long n_tiles = a.n_rows / TILE_ROWS;
+    const long long n_tiles = a.n_rows / tile_rows;
     const long long per = (n_tiles + gridDim.x - 1) / gridDim.x;
     const long long t0 = per * blockIdx.x;
     long long t1 = t0 + per;
@@ -62,7 +66,7 @@ __global__ void __launch_bounds__(64, 1) probe(const __grid_constant__ CUtensorM
     if (threadIdx.x == 0) {
         int stage = 0; uint32_t phase = 0;
         for (long long t = t0; t < t1; ++t) {
-            const int row0 = (int)(t * TILE_ROWS);
+            const int row0 = (int)(t * tile_rows);
             for (int f = 0; f < FILLS; ++f) {
                 mbar_wait(bar0 + 8 * (S + stage), phase ^ 1u);
                 const uint32_t full = bar0 + 8 * stage;
@@ -72,6 +76,7 @@ __global__ void __launch_bounds__(64, 1) probe(const __grid_constant__ CUtensorM
                 if (P == 5) { tma2(dst, &tm, f * 64, row0, full); tma2(dst + 32768, &tmA, f * 64, 0, full); }
                 if (P == 1) for (int kb = 0; kb < 12; ++kb) tma2(dst + kb * 4096, &tm, kb * 64, row0, full);
                 if (P == 2) tma3(dst, &tm, 0, 0, row0, full);
+                if (P == 7) { const int pb = a.stage_bytes / a.pieces; for (int i = 0; i < a.pieces; ++i) bulk1(dst + i * pb, a.base + (size_t)row0 * 1536 + (size_t)i * pb, pb, full); }
                 if (P == 3) tma4(dst, &tm, 0, 0, f, row0 / 8, full);
                 if (P == 4) tma4(dst, &tm, 0, 0, 0, row0 / 8, full);
                 if (P == 6) for (int kb = 0; kb < 12; ++kb) tma4(dst + kb * 8192, &tm, 0, 0, kb, row0 / 8, full);
@@ -99,9 +104,11 @@ static CUtensorMap mk(enc_fn enc, void* p, int rank, const cuuint64_t* dims, con
     return m;
 }
 
+static const char* g_base = nullptr;
+static int g_pieces = 1;
 template <int P>
 static void run(const char* name, const CUtensorMap& tm, const CUtensorMap& tmA, long long n, int stages, int stage_bytes, int grid) {
-    Args a{n, stages, stage_bytes};
+    Args a{n, stages, stage_bytes, g_base, g_pieces};
     const size_t smem = 1024 + (size_t)stages * stage_bytes + 256;
     CK(cudaFuncSetAttribute(probe<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0, e1;
@@ -122,6 +129,7 @@ static void run(const char* name, const CUtensorMap& tm, const CUtensorMap& tmA,
 int main(int argc, char** argv) {
     const long long n = argc > 1 ? atoll(argv[1]) : 10000000LL / 256 * 256;
     void* p; CK(cudaMalloc(&p, (size_t)n * 1536)); CK(cudaMemset(p, 0, (size_t)n * 1536));
+    g_base = (const char*)p;
     void* qa; CK(cudaMalloc(&qa, 128 * 1536)); CK(cudaMemset(qa, 0, 128 * 1536));
     void* fp = nullptr; cudaDriverEntryPointQueryResult qr;
     CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qr));
@@ -154,6 +162,13 @@ int main(int argc, char** argv) {
             run<3>("P3 8-row-interleaved k-blocked (1 KB pieces)", t3, tA, n, grid == 148 ? 4 : 3, 32768, grid);
             run<3>("P3 8-row-interleaved k-blocked (1 KB pieces)", t3, tA, n, st32, 32768, grid);
             run<4>("P4 8-row-interleaved contiguous 48 KB", t4, tA, n, st48, 49152, grid);
+            if (pi == 0) {
+                g_pieces = 1; run<7>("P7 1D cp.async.bulk, one 48 KB copy per stage", t0, tA, n, st48, 49152, grid);
+                g_pieces = 4; run<7>("P7 1D cp.async.bulk, 4 x 12 KB copies per stage", t0, tA, n, st48, 49152, grid);
+                g_pieces = 12; run<7>("P7 1D cp.async.bulk, 12 x 4 KB copies per stage", t0, tA, n, st48, 49152, grid);
+                g_pieces = 1; run<7>("P7 1D cp.async.bulk, 24 KB stages", t0, tA, n, grid == 148 ? 8 : 4, 24576, grid);
+                g_pieces = 1; run<7>("P7 1D cp.async.bulk, 12 KB stages", t0, tA, n, grid == 148 ? 16 : 8, 12288, grid);
+            }
             if (grid == 148) run<6>("P6 8-row-interleaved 64-row full-K stage (12 x 8 KB)", t6, tA, n, 2, 98304, grid);
         }
     }

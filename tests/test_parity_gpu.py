@@ -65,6 +65,31 @@ def test_search_matches_oracle(coracle, dtype, dim, nq, k):
 
 
 @pytest.mark.parametrize("dtype", O.DTYPES)
+@pytest.mark.parametrize("dim,n", [(768, 20001), (384, 5000), (100, 3000), (8, 257), (1024, 777), (2048, 1200), (768, 1)])
+@pytest.mark.parametrize("nq", [1, 2])
+def test_both_scan_kernels_match_the_oracle(coracle, dtype, dim, n, nq):
+    """Batches of 1-2 queries run the HBM-bound scan: TMA-fed ring (default) or register-path loads."""
+    x = O.synth_rows(45, 0, n, dim, dup_every=53, zero_every=509)
+    q = O.synth_rows(46, 0, nq, dim)
+    idx = _index(x, dtype)
+    want = coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), 10)
+    for variant in (2, 1, 0):
+        idx.set_scan_variant(variant)
+        got = idx.search(q, 10)
+        assert idx.stats()["path"] == 0
+        _assert_same(got, want, f"scan variant {variant} {dtype} dim={dim} n={n} nq={nq}")
+    keep = np.zeros(n, bool)
+    keep[::3] = True
+    stored = coracle.normalize_rows(x, dtype)
+    wi, ws = coracle.cosine_topk(q, stored[keep], 5)
+    rows = np.flatnonzero(keep)
+    wi = np.where(wi >= 0, rows[np.maximum(wi, 0)], -1)
+    for variant in (2, 1):
+        idx.set_scan_variant(variant)
+        _assert_same(idx.search(q, 5, allow=keep), (wi, ws), f"filtered scan variant {variant}")
+
+
+@pytest.mark.parametrize("dtype", O.DTYPES)
 @pytest.mark.parametrize("dim", [100, 33, 8, 2048, 1536])
 def test_search_odd_and_wide_dims(coracle, dtype, dim):
     x = O.synth_rows(50, 0, 3000, dim)
