@@ -24,6 +24,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "kernels.cuh"   // block_kth_largest
 
 namespace rfk {
 
@@ -463,28 +464,24 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
-// ---- bound pass, second half: the rank-th largest (1-based) of the query's nb block maxima, by rank counting ---
+// ---- bound pass, second half: the rank-th largest (1-based) of the query's nb <= 1024 block maxima ---
 // gtau != null (list mode): gtau[q] = that value as an ordered uint.
 // thr  != null (append mode): thr[q] = value - 2 * (eps_const + eps_q[q]) - 2^-22, cnt[q] = 0.  Every row whose
 //   exact score can be among the k best has an approximate score >= thr[q]:  exact_k >= approx_k - eps and
 //   approx >= exact - eps, and value <= approx_k (rank = k).
-__global__ void __launch_bounds__(1024) bound_select_kernel(const float* __restrict__ bmax, int nb, int rank,
-                                                            uint32_t* __restrict__ gtau, float* __restrict__ thr,
-                                                            uint32_t* __restrict__ cnt, float eps_const,
-                                                            const float* __restrict__ eps_q) {
+__global__ void __launch_bounds__(256) bound_select_kernel(const float* __restrict__ bmax, int nb, int rank,
+                                                           uint32_t* __restrict__ gtau, float* __restrict__ thr,
+                                                           uint32_t* __restrict__ cnt, float eps_const,
+                                                           const float* __restrict__ eps_q) {
     __shared__ uint32_t v[1024];
-    const int q = blockIdx.x, i = threadIdx.x;
-    v[i] = i < nb ? float_to_ordered(bmax[(size_t)q * nb + i] + 0.0f) : 0u;
-    if (i == 0 && cnt != nullptr) cnt[q] = 0u;
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s3[3];
+    const int q = blockIdx.x;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) v[i] = float_to_ordered(bmax[(size_t)q * nb + i] + 0.0f);
     __syncthreads();
-    if (i >= nb) return;
-    const uint32_t mine = v[i];
-    int r = 0;
-    for (int j = 0; j < nb; ++j) {
-        const uint32_t o = v[j];
-        r += (o > mine) || (o == mine && j < i);
-    }
-    if (r == rank - 1) {
+    const uint32_t mine = block_kth_largest([&](int i) { return v[i]; }, nb, (uint32_t)rank, hist, s3);
+    if (threadIdx.x == 0) {
+        if (cnt != nullptr) cnt[q] = 0u;
         if (gtau != nullptr) gtau[q] = mine;
         if (thr != nullptr) {
             const float e = eps_const + (eps_q ? eps_q[q] : 0.0f);

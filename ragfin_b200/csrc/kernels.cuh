@@ -387,73 +387,153 @@ finalize_kernel(const u64* __restrict__ cand, int G, int kp, const void* __restr
 }
 
 // ---------------------------------------------------------------------------------
-// K4 for the append mode of the tensor-core path: one CTA per query.
-//   buf[q][0..m)  keys (approximate score, row) of EVERY row whose approximate score reached thr[q]
+// Block-wide selection of the `want`-th largest (1-based) of m 32-bit values hi_of(0..m), by histogram narrowing:
+// 256 linear bins over [lo, hi], keep the bin that holds the wanted rank, repeat until the bin is one value wide
+// (<= 4 passes over the data for 32-bit values).  hist: 256 words, s3: 3 words of shared memory.  Every thread
+// of the block must call it (it synchronises); m >= want >= 1.
+// ---------------------------------------------------------------------------------
+template <typename F>
+__device__ __forceinline__ uint32_t block_kth_largest(F hi_of, int m, uint32_t want0, uint32_t* hist, uint32_t* s3) {
+    const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s3[0] = 0xFFFFFFFFu; s3[1] = 0u; s3[2] = want0; }
+    __syncthreads();
+    {
+        uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+        for (int i = tid; i < m; i += nthreads) {
+            const uint32_t h = hi_of(i);
+            lo = h < lo ? h : lo;
+            hi = h > hi ? h : hi;
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const uint32_t l2 = __shfl_xor_sync(kFull, lo, off), h2 = __shfl_xor_sync(kFull, hi, off);
+            lo = l2 < lo ? l2 : lo;
+            hi = h2 > hi ? h2 : hi;
+        }
+        if (lane == 0) { atomicMin(&s3[0], lo); atomicMax(&s3[1], hi); }
+    }
+    __syncthreads();
+    for (int pass = 0; pass < 6; ++pass) {
+        const uint32_t lo = s3[0], hi = s3[1], want = s3[2];
+        if (lo == hi) break;                                  // block-uniform: one value left
+        const uint32_t range = hi - lo;
+        const int bits = 32 - __clz(range);                   // range < 2^bits
+        const int sh = bits > 8 ? bits - 8 : 0;               // (range >> sh) <= 255
+        for (int i = tid; i < 256; i += nthreads) hist[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < m; i += nthreads) {
+            const uint32_t h = hi_of(i);
+            if (h >= lo && h <= hi) atomicAdd(&hist[(h - lo) >> sh], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {   // bin (from the top) in which the cumulative count reaches `want`; lane l owns bins 255-8l .. 248-8l
+            uint32_t c[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * lane - j]; sum += c[j]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t t = __shfl_up_sync(kFull, incl, off);
+                if (lane >= off) incl += t;
+            }
+            const uint32_t before = incl - sum;               // values in the bins above this lane's
+            if (before < want && incl >= want) {              // exactly one lane
+                uint32_t run = before;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (run < want && run + c[j] >= want) {
+                        const uint32_t bin = (uint32_t)(255 - 8 * lane - j);
+                        const uint32_t nlo = lo + (bin << sh);
+                        uint32_t nhi = nlo + ((1u << sh) - 1u);
+                        if (nhi > hi || nhi < nlo) nhi = hi;
+                        s3[0] = nlo; s3[1] = nhi; s3[2] = want - run;
+                    }
+                    run += c[j];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    return s3[0];
+}
+
+// ---------------------------------------------------------------------------------
+// K4 for the append mode of the tensor-core path: one CTA of 256 threads per query, O(m) work, ~18 KB of shared
+// memory (several CTAs per SM).
+//   buf[q][0..m)  keys (approximate score, row) of EVERY row whose approximate score reached thr[q], any order
 // With eps >= |approx - exact| for every row:  T = k-th largest approximate score (it is in the buffer, because
-// thr <= T - 2 eps), and every row of the exact top-k has approx >= T - 2 eps.  So: sort, cut at T - 2 eps,
-// recompute those rows canonically in fp64, order by the exact key, emit k.  Unconditionally exact - there is no
-// certificate to fail; only an overflowing buffer (m > cap, or more than kAppendRescore rows above the cut:
-// massive duplication) sends the query to tier 2.
+// thr <= T - 2 eps), and every row of the exact top-k has approx >= T - 2 eps.  So:
+//   1. select T: histogram narrowing over the ordered-uint scores (256 linear bins over [lo, hi], keep the bin that
+//      holds the k-th largest, repeat until the bin is one value wide: <= 4 passes over the buffer);
+//   2. gather the rows with approx >= T - 2 eps (~1.6 k of them) into shared memory;
+//   3. recompute those rows canonically in fp64, order by the exact key, emit k.
+// Unconditionally exact - there is no certificate to fail; only an overflowing buffer (m > cap, or more than
+// kAppendRescore rows above the cut: massive duplication) sends the query to tier 2.
 // ---------------------------------------------------------------------------------
 constexpr int kAppendRescore = 2048;   // most rows one query may rescore exactly
+constexpr int kFaThreads = 256;
+constexpr int kFaWarps = kFaThreads / kWarp;
 
-__global__ void __launch_bounds__(kFinThreads)
+__global__ void __launch_bounds__(kFaThreads)
 finalize_append_kernel(const u64* __restrict__ buf, const uint32_t* __restrict__ cnt, int cap,
                        const void* __restrict__ data, int dt, int64_t n_rows, int ld, const float* __restrict__ qhat,
                        float eps_const, const float* __restrict__ eps_q, int k, int64_t id_base,
                        int64_t* __restrict__ out_ids, float* __restrict__ out_scores, int* __restrict__ flags,
                        int* __restrict__ flag_count) {
-    extern __shared__ __align__(16) u64 fsm[];   // [P >= m keys][kAppendRescore exact keys]
+    __shared__ __align__(16) u64 sel[kAppendRescore];
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s3[3];
     __shared__ int s_c2;
-    const int q = blockIdx.x, tid = threadIdx.x;
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t m32 = cnt[q];
     const int keff = (int64_t)k < n_rows ? k : (int)n_rows;
-    bool bad = m32 > (uint32_t)cap;
-    const int m = bad ? 0 : (int)m32;
-    int P = 32;
-    while (P < m) P <<= 1;
-    u64* keys = fsm;
-    u64* ex = fsm + P;
+    const bool overflow = m32 > (uint32_t)cap || (int)m32 < keff;   // fewer than k rows cannot happen with a valid bound
+    const int m = overflow ? 0 : (int)m32;
     const u64* in = buf + (size_t)q * cap;
-    for (int i = tid; i < P; i += kFinThreads) keys[i] = i < m ? in[i] : 0ull;
     if (tid == 0) s_c2 = 0;
     __syncthreads();
-    if (!bad) block_bitonic_sort_desc(keys, P, tid, kFinThreads);
-    if (!bad && keff > 0 && (m < keff || keys[keff - 1] == 0ull)) bad = true;   // fewer than k rows collected: cannot happen with a valid bound
-    int c2 = 0;
-    if (!bad && keff > 0) {
-        const float eps = eps_const + (eps_q ? eps_q[q] : 0.0f);
-        const float cut = __fsub_rd(__fsub_rd(key_score(keys[keff - 1]), __fmul_ru(2.0f, eps)), 2.384185791015625e-07f);
-        for (int i = tid; i < m; i += kFinThreads) {   // sorted by score: the rows above the cut are a prefix
-            const bool in_i = keys[i] != 0ull && key_score(keys[i]) >= cut;
-            const bool in_n = i + 1 < m && keys[i + 1] != 0ull && key_score(keys[i + 1]) >= cut;
-            if (in_i && !in_n) s_c2 = i + 1;
-        }
-        __syncthreads();
-        c2 = s_c2;
-        if (c2 > kAppendRescore) bad = true;
+    if (overflow || keff == 0) {   // block-uniform
+        if (tid == 0) { flags[q] = overflow ? 1 : 0; if (overflow) atomicAdd(flag_count, 1); }
+        if (!overflow)
+            for (int i = tid; i < k; i += kFaThreads) { out_ids[(size_t)q * k + i] = -1; out_scores[(size_t)q * k + i] = -INFINITY; }
+        return;
     }
-    if (bad) {   // block-uniform
+    // ---- 1. T = keff-th largest approximate score, as an ordered uint ----
+    const uint32_t t_ord = block_kth_largest([&](int i) { return (uint32_t)(in[i] >> 32); }, m, (uint32_t)keff, hist, s3);
+    // ---- 2. gather the rows above the cut ----
+    const float eps = eps_const + (eps_q ? eps_q[q] : 0.0f);
+    const float cut = __fsub_rd(__fsub_rd(ordered_to_float(t_ord), __fmul_ru(2.0f, eps)), 2.384185791015625e-07f);
+    for (int i = tid; i < m; i += kFaThreads) {
+        const u64 key = in[i];
+        if (key_score(key) >= cut) {
+            const int pos = atomicAdd(&s_c2, 1);
+            if (pos < kAppendRescore) sel[pos] = key;
+        }
+    }
+    __syncthreads();
+    const int c2 = s_c2;
+    if (c2 > kAppendRescore) {   // block-uniform
         if (tid == 0) { flags[q] = 1; atomicAdd(flag_count, 1); }
         return;
     }
-    const int lane = tid & 31, warp = tid >> 5;
+    // ---- 3. exact rescore, order, emit ----
     const float* qv = qhat + (size_t)q * ld;
-    for (int c = warp; c < c2; c += kFinWarps) {
-        const uint32_t row = key_row(keys[c]);
+    for (int c = warp; c < c2; c += kFaWarps) {
+        const uint32_t row = key_row(sel[c]);
         double sc;
         if (dt == 0) sc = rescore_row<0>(data, row, ld, qv, lane);
         else if (dt == 1) sc = rescore_row<1>(data, row, ld, qv, lane);
         else sc = rescore_row<2>(data, row, ld, qv, lane);
-        if (lane == 0) ex[c] = make_key((float)sc + 0.0f, row);
+        __syncwarp();
+        if (lane == 0) sel[c] = make_key((float)sc + 0.0f, row);
     }
     int P2 = 32;
     while (P2 < c2) P2 <<= 1;
-    for (int i = c2 + tid; i < P2; i += kFinThreads) ex[i] = 0ull;
+    for (int i = c2 + tid; i < P2; i += kFaThreads) sel[i] = 0ull;
     __syncthreads();
-    block_bitonic_sort_desc(ex, P2, tid, kFinThreads);
-    for (int i = tid; i < k; i += kFinThreads) {
-        const u64 key = i < keff ? ex[i] : 0;
+    block_bitonic_sort_desc(sel, P2, tid, kFaThreads);
+    for (int i = tid; i < k; i += kFaThreads) {
+        const u64 key = i < keff ? sel[i] : 0;
         out_ids[(size_t)q * k + i] = key ? id_base + (int64_t)key_row(key) : -1;
         out_scores[(size_t)q * k + i] = key ? key_score(key) : -INFINITY;
     }

@@ -488,13 +488,21 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
         if (want_blk < 256) want_blk = 256;
         if (want_blk > 1024) want_blk = 1024;
         nblk = (int)(n_tiles / 2 < want_blk ? n_tiles / 2 : want_blk);
-        // sample enough rows that a query expects to collect well under kAppendCap rows: ~1.6 * k / fraction
+        // Sample fraction f.  A query collects ~1.6 * k / f rows; the bound pass costs f of a sweep.  HBM-bound
+        // batches (one query tile) have epilogue slack, so f only has to keep the buffer well under kAppendCap;
+        // tensor-bound batches pay ~2.6e-3 ms per unit of k / f in the epilogue's slow path (measured: 13 ms at
+        // k = 100, f = 2 %), which puts the optimum near 0.8 % * sqrt(k) (2.5 % for k = 10, 8 % for k = 100).
         double frac = append ? (double)k / 5000.0 : 0.0;
         if (frac < 1.0 / 96.0) frac = 1.0 / 96.0;
+        if (append && QT0 >= 2) {
+            const double opt = 0.008 * sqrt((double)k);
+            if (opt > frac) frac = opt;
+        }
         int64_t sample = (int64_t)(frac * (double)n_tiles);
         if (sample < nblk) sample = nblk;
         if (sample > n_tiles / 2) sample = n_tiles / 2;
-        g = (int)((sample + nblk - 1) / nblk);
+        g = (int)((sample + nblk / 2) / nblk);
+        if (g < 1) g = 1;
         while (g > 1 && (int64_t)nblk * g > n_tiles / 2) --g;
         bstride = (n_tiles - 1) / ((int64_t)nblk * g);   // the last (possibly partial) tile is never sampled
         if (bstride < 1) bstride = 1;
@@ -596,7 +604,7 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
         const int64_t items = (int64_t)groups * nblk;
         cfg.gridDim = dim3((unsigned)(items < clusters ? items : clusters) * C);
         CU_TRY(cudaLaunchKernelEx(&cfg, bfn, tmA, tmB, b));
-        bound_select_kernel<<<nb, 1024, 0, st>>>((const float*)h->bmax.p, nblk, rank, append ? nullptr : (uint32_t*)h->gtau.p,
+        bound_select_kernel<<<nb, 256, 0, st>>>((const float*)h->bmax.p, nblk, rank, append ? nullptr : (uint32_t*)h->gtau.p,
                                                  append ? (float*)h->athr.p : nullptr, append ? (uint32_t*)h->acnt.p : nullptr,
                                                  eps_gemm_const(h->dtype, h->ld), (const float*)h->eps_q.p);
         CU_TRY(cudaGetLastError());
@@ -859,9 +867,7 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
         }
         // 3. merge + exact rescore + certificate (an unscanned, non-empty corpus flags every query)
         if (appended) {
-            const size_t fsm = (size_t)(kAppendCap + kAppendRescore) * sizeof(u64);
-            CU_TRY(cudaFuncSetAttribute(finalize_append_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-            finalize_append_kernel<<<nb, kFinThreads, fsm, st>>>(
+            finalize_append_kernel<<<nb, kFaThreads, 0, st>>>(
                 (const u64*)h->cand.p, (const uint32_t*)h->acnt.p, kAppendCap, h->data, h->dtype, n_eff, h->ld, qhat, eps, eps_q, k,
                 h->id_base, out_ids + (size_t)q0 * k, out_scores + (size_t)q0 * k, flags, flag_count);
             CU_TRY(cudaGetLastError());

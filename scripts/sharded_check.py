@@ -18,7 +18,8 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
 for dtype, dim, n, nq, k in [("bf16", 768, 50001, 1, 10), ("f16", 768, 30000, 4, 100), ("f32", 384, 9000, 40, 5),
-                             ("bf16", 768, 7, 3, 10), ("bf16", 1024, 40000, 300, 10)]:
+                             ("bf16", 768, 7, 3, 10), ("bf16", 1024, 40000, 300, 10),
+                             ("bf16", 128, 600000, 40, 10), ("f16", 64, 900000, 5, 100)]:   # shards large enough for append mode
     row0, cnt = shard_bounds(n, world, rank)
     idx = ragfin_b200.Index(dim, dtype, capacity=max(cnt, 1), device=local)
     if cnt:
