@@ -245,6 +245,37 @@ def test_reference_call_sites_through_the_shim(coracle):
     mc.utility.drop_collection("fin_chunks")
 
 
+def test_chunk_ingest_pipeline_end_to_end(coracle):
+    """N2: statements -> chunker -> encoder -> insert / flush / load -> search, as "chunking_storing (1).py":335-417 runs
+    it (MiniLM replaced by the hashing stand-in: no weights offline).  Every chunk's own text must retrieve it first."""
+    from ragfin_b200 import chunker, milvus_compat as mc
+    from ragfin_b200.vector_rag import HashingEncoder, VectorRAG
+    F, D = mc.FieldSchema, mc.DataType
+    fields = [F("id", D.VARCHAR, max_length=100, is_primary=True), F("text", D.VARCHAR, max_length=4000),
+              F("embedding", D.FLOAT_VECTOR, dim=384), F("period", D.VARCHAR, max_length=20),
+              F("chunk_type", D.VARCHAR, max_length=30), F("statement_type", D.VARCHAR, max_length=30),
+              F("primary_value", D.DOUBLE)]
+    if mc.utility.has_collection("fin_chunks"):
+        mc.utility.drop_collection("fin_chunks")
+    col = mc.Collection("fin_chunks", mc.CollectionSchema(fields, "Financial complete context chunks"))
+    col.create_index("embedding", {"index_type": "IVF_FLAT", "metric_type": "COSINE", "params": {"nlist": 128}})
+    chunks = chunker.build_corpus(os.path.join(GOLDEN, "extract_data"))
+    enc = HashingEncoder(384)
+    chunker.ingest_chunks(col, chunks, enc.encode)
+    assert col.num_entities == 16
+    emb = enc.encode([c["text"] for c in chunks])
+    want_ids, want_sc = coracle.cosine_topk(emb, coracle.normalize_rows(emb, "f32"), 3)
+    res = col.search(emb, "embedding", {"metric_type": "COSINE"}, 3, output_fields=["text", "period", "chunk_type"])
+    for i, hits in enumerate(res):
+        assert hits[0].id == chunks[i]["id"] and hits[0].entity.get("text") == chunks[i]["text"]
+        assert [h.id for h in hits] == [chunks[j]["id"] for j in want_ids[i]]
+        assert [np.float32(h.score).view(np.uint32).item() for h in hits] == want_sc[i].view(np.uint32).tolist()
+    rag = VectorRAG(enc, collection=col)
+    top = rag.search("ICICI Bank Limited Q3_FY2024 Balance Sheet Analysis total assets advances", 1)[0]
+    assert top["period"] == "Q3_FY2024" and top["chunk_type"] == "balance_sheet_analysis"
+    mc.utility.drop_collection("fin_chunks")
+
+
 # ------------------------------------------------------------------------------------------------
 # tensor-core path (query batches >= 9 rows)
 # ------------------------------------------------------------------------------------------------
