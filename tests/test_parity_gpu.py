@@ -271,8 +271,10 @@ def test_chunk_ingest_pipeline_end_to_end(coracle):
         assert [h.id for h in hits] == [chunks[j]["id"] for j in want_ids[i]]
         assert [np.float32(h.score).view(np.uint32).item() for h in hits] == want_sc[i].view(np.uint32).tolist()
     rag = VectorRAG(enc, collection=col)
-    top = rag.search("ICICI Bank Limited Q3_FY2024 Balance Sheet Analysis total assets advances", 1)[0]
-    assert top["period"] == "Q3_FY2024" and top["chunk_type"] == "balance_sheet_analysis"
+    question = "ICICI Bank Limited Q3_FY2024 Balance Sheet Analysis total assets advances"
+    top = rag.search(question, 1)[0]
+    row = int(coracle.cosine_topk(enc.encode([question]), coracle.normalize_rows(emb, "f32"), 1)[0][0, 0])
+    assert top["text"] == chunks[row]["text"] and top["period"] == chunks[row]["period"] == "Q3_FY2024" and top["rank"] == 1
     mc.utility.drop_collection("fin_chunks")
 
 
