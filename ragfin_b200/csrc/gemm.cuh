@@ -490,6 +490,52 @@ __global__ void __launch_bounds__(256) bound_select_kernel(const float* __restri
     }
 }
 
+// ---- query preparation for the tensor-core path, one launch: normalise (bit-identical to ingest_kernel<0>), zero-pad
+// to whole query tiles, round to the storage type with the rounding error eps_q = |qhat - q16|_2, reset the per-batch
+// flag counter and the published thresholds.  DT = storage type of the corpus (0: fp32, no 16-bit copy). ------------
+template <int DT>
+__global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restrict__ q, int nq, int n_pad, int dim, int ld,
+                                                           float* __restrict__ qhat, typename Store<DT>::T* __restrict__ q16,
+                                                           float* __restrict__ eps_q, int* __restrict__ flag_count,
+                                                           uint32_t* __restrict__ gtau) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *flag_count = 0;
+    if (row >= n_pad) return;
+    float* out = qhat + (size_t)row * ld;
+    if (row >= nq) {   // padding row of the last query tile
+        for (int i = lane; i < ld; i += kWarp) {
+            out[i] = 0.0f;
+            if (DT != 0) q16[(size_t)row * ld + i] = Store<DT>::from_f32(0.0f);
+        }
+        return;
+    }
+    const float* x = q + (size_t)row * dim;
+    double acc = 0.0;
+    for (int i = lane; i < dim; i += kWarp) {
+        const double v = (double)x[i];
+        acc = acc + v * v;
+    }
+    const double n2 = warp_butterfly_f64(acc);
+    const double inv = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
+    double d2 = 0.0;
+    for (int i = lane; i < ld; i += kWarp) {
+        const float y = i < dim ? (float)((double)x[i] * inv) : 0.0f;
+        out[i] = y;
+        if (DT != 0) {
+            const typename Store<DT>::T r = Store<DT>::from_f32(y);
+            q16[(size_t)row * ld + i] = r;
+            const double d = (double)y - (double)Store<DT>::to_f32(r);
+            d2 += d * d;
+        }
+    }
+    d2 = warp_butterfly_f64(d2);
+    if (lane == 0) {
+        eps_q[row] = DT != 0 ? (float)(sqrt(d2) * 1.0078125) + 1e-9f : 0.0f;   // * max |stored row| (<= 1 + 2^-8), rounded up
+        gtau[row] = 0u;
+    }
+}
+
 // ---- query conversion for the f16-kind path: q16 = RNE(qhat), eps_q = |qhat - q16|_2 ------------------
 template <int DT>
 __global__ void __launch_bounds__(256) qconv_kernel(const float* __restrict__ qhat, int nq, int ld,

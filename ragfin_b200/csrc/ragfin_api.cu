@@ -55,7 +55,8 @@ struct ragfin {
     std::mutex mu;
     // workspace (grow-only)
     Buf qhat, q16, eps_q, gtau, bmax, acnt, athr, allow, bk_scores, bk_state, bk_keys, cand, cand_e, flags, stage_q, stage_ids, stage_scores, add_stage;
-    int gemm_min_nq = 3;      // query batches of at least this many rows take the tcgen05 path (1-2: HBM-bound scan)
+    int gemm_min_nq = 3;      // query batches of at least this many rows take the tcgen05 path (1-2: HBM-bound scan) ...
+    int gemm_min_nq_large = 1;   // ... except on corpora of >= kSweepBytes, where the TMA-fed sweep wins from 1 query
     int gemm_cluster = 0;     // 0 = choose by batch size; 1, 2 or 4 = force
     const uint32_t* cur_allow = nullptr;   // scalar filter of the search in flight (device bitmask), else null
     int64_t cur_allowed = 0;               // rows it allows
@@ -443,6 +444,11 @@ static bool gemm_supported(const ragfin* h, int kp) { return kp <= 128 && h->cou
 
 // Scores the nb normalised queries in h->qhat against the corpus on the tensor cores.  Fills
 // h->cand as [nb][S][kp] (unsorted lists) and h->eps_q; returns S through *G.  dump != null: write raw scores instead.
+// Corpus size from which even 1-2 queries take the tensor-core sweep: its TMA ring keeps 192 KB per SM in flight
+// (7.4 TB/s against the LDG scan's 6.9), worth ~90 us per 15 GB, but it carries ~50 us more fixed cost per call
+// (bound pass, query conversion).  Measured 10M x 768 bf16, batch 1: 2.218 ms vs 2.313 ms.
+static const size_t kSweepBytes = (size_t)4 << 30;
+
 static const int kAppendCap = 16384;   // append mode: keys one query may collect before it overflows to tier 2
 static const int kAppendMaxK = 256;    // largest k the append mode serves (tier 2, its overflow path, keeps 256 keys)
 
@@ -455,7 +461,7 @@ static bool append_eligible(const ragfin* h, int k) {
 // Scores the nb normalised queries in h->qhat against the corpus on the tensor cores and leaves per-query candidates
 // for the finalize step: list mode fills h->cand as [nb][S][kp] (unsorted lists, S returned through *G); append
 // mode (*appended = true) fills h->cand as [nb][kAppendCap] with h->acnt[q] keys each.  dump != null: raw scores.
-static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, float* dump, cudaStream_t st) {
+static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, float* dump, cudaStream_t st, bool prepped = false) {
     int rc;
     const int64_t n = h->count;
     *appended = false;
@@ -493,7 +499,8 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
         // tensor-bound batches pay ~2.6e-3 ms per unit of k / f in the epilogue's slow path (measured: 13 ms at
         // k = 100, f = 2 %), which puts the optimum near 0.8 % * sqrt(k) (2.5 % for k = 10, 8 % for k = 100).
         double frac = append ? (double)k / 5000.0 : 0.0;
-        if (frac < 1.0 / 96.0) frac = 1.0 / 96.0;
+        const double frac_min = (append && QT0 == 1) ? 1.0 / 256.0 : 1.0 / 96.0;   // one query tile: the pass is pure latency
+        if (frac < frac_min) frac = frac_min;
         if (append && QT0 >= 2) {
             const double opt = 0.008 * sqrt((double)k);
             if (opt > frac) frac = opt;
@@ -535,8 +542,11 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
     const int nb_pad = p.QT * kGM;
     const float* qhat = (const float*)h->qhat.p;
     const void* a_base = qhat;
-    if ((rc = ensure(h->eps_q, (size_t)nb * sizeof(float)))) return rc;
-    if (h->dtype != 0) {
+    if (prepped) {   // prep_queries_kernel already produced qhat, q16, eps_q and cleared gtau
+        if (h->dtype != 0) a_base = h->q16.p;
+    } else if ((rc = ensure(h->eps_q, (size_t)nb * sizeof(float)))) {
+        return rc;
+    } else if (h->dtype != 0) {
         if ((rc = ensure(h->q16, (size_t)nb_pad * h->ld * 2))) return rc;
         if (nb_pad > nb) CU_TRY(cudaMemsetAsync((char*)h->q16.p + (size_t)nb * h->ld * 2, 0, (size_t)(nb_pad - nb) * h->ld * 2, st));
         const int wpb = 8;
@@ -572,7 +582,7 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
     a.stages = p.stages;
     a.kp = kp_smem;
     if ((rc = ensure(h->gtau, (size_t)nb * sizeof(uint32_t)))) return rc;
-    if (!append) CU_TRY(cudaMemsetAsync(h->gtau.p, 0, (size_t)nb * sizeof(uint32_t), st));
+    if (!append && !prepped) CU_TRY(cudaMemsetAsync(h->gtau.p, 0, (size_t)nb * sizeof(uint32_t), st));
     a.cand = (u64*)h->cand.p;
     a.gtau = (uint32_t*)h->gtau.p;
     a.allow = h->cur_allow;
@@ -771,7 +781,8 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
     const int64_t n_eff = h->cur_allow ? h->cur_allowed : n;   // rows a hit may come from
     int kp = cand_per_query(k);
     if (kp == 0 && n <= 256) kp = 256;   // every row is a candidate: any k (graph_cons.py:279 asks limit=1000 of 16 rows)
-    const bool ap = append_eligible(h, k) && nq >= h->gemm_min_nq;   // tensor-core append mode: no K' lists needed
+    const int min_nq_all = (size_t)n * h->ld * esize(h->dtype) >= kSweepBytes ? h->gemm_min_nq_large : h->gemm_min_nq;
+    const bool ap = append_eligible(h, k) && nq >= min_nq_all;   // tensor-core append mode: no K' lists needed
     if (kp == 0 && !ap) return search_bigk(h, q_dev, nq, k, out_ids, out_scores, st);
     if (kp == 0) kp = 256;
     h->stats.cand_per_query = kp;
@@ -784,15 +795,32 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
     for (int q0 = 0; q0 < nq; q0 += kMaxQueryBatch) {
         const int nb = nq - q0 < kMaxQueryBatch ? nq - q0 : kMaxQueryBatch;
         const int nb4 = (nb + 3) / 4 * 4;
-        const bool via_gemm = nb >= h->gemm_min_nq && (gemm_supported(h, kp) || (ap && h->count > 0));
+        const size_t corpus_bytes = (size_t)h->count * h->ld * esize(h->dtype);
+        const int min_nq = corpus_bytes >= kSweepBytes ? h->gemm_min_nq_large : h->gemm_min_nq;
+        const bool via_gemm = nb >= min_nq && (gemm_supported(h, kp) || (ap && h->count > 0));
         const int nbq = via_gemm ? (nb + kGM - 1) / kGM * kGM : nb4;   // tensor-core path: whole 128-query tiles
         // 1. normalise the queries (same kernel as ingest, fp32 out, stride ld); pad with zero rows
         if ((rc = ensure(h->qhat, (size_t)nbq * h->ld * sizeof(float)))) return rc;
         float* qhat = (float*)h->qhat.p;
-        if (nbq > nb) CU_TRY(cudaMemsetAsync(qhat + (size_t)nb * h->ld, 0, (size_t)(nbq - nb) * h->ld * sizeof(float), st));
-        if ((rc = launch_ingest<false>(0, q_dev + (size_t)q0 * h->dim, 0, 0, 0, 0, nb, h->dim, h->ld, qhat, h->num_sms, st))) return rc;
-        h->stats.launches++;
-        CU_TRY(cudaMemsetAsync(flag_count, 0, sizeof(int), st));   // flags[q] itself is written by finalize for every q
+        const bool prepped = via_gemm && !(!ap && use_astat(h, kp));
+        if (prepped) {   // one launch: normalise + pad + 16-bit copy + eps_q + counters
+            if ((rc = ensure(h->eps_q, (size_t)nbq * sizeof(float))) || (rc = ensure(h->gtau, (size_t)nbq * sizeof(uint32_t)))) return rc;
+            if (h->dtype != 0 && (rc = ensure(h->q16, (size_t)nbq * h->ld * 2))) return rc;
+            const int wpb = 8, blocks = (nbq + wpb - 1) / wpb;
+            const float* qsrc = q_dev + (size_t)q0 * h->dim;
+            switch (h->dtype) {
+                case 0: prep_queries_kernel<0><<<blocks, wpb * 32, 0, st>>>(qsrc, nb, nbq, h->dim, h->ld, qhat, nullptr, (float*)h->eps_q.p, flag_count, (uint32_t*)h->gtau.p); break;
+                case 1: prep_queries_kernel<1><<<blocks, wpb * 32, 0, st>>>(qsrc, nb, nbq, h->dim, h->ld, qhat, (__nv_bfloat16*)h->q16.p, (float*)h->eps_q.p, flag_count, (uint32_t*)h->gtau.p); break;
+                default: prep_queries_kernel<2><<<blocks, wpb * 32, 0, st>>>(qsrc, nb, nbq, h->dim, h->ld, qhat, (__half*)h->q16.p, (float*)h->eps_q.p, flag_count, (uint32_t*)h->gtau.p); break;
+            }
+            CU_TRY(cudaGetLastError());
+            h->stats.launches++;
+        } else {
+            if (nbq > nb) CU_TRY(cudaMemsetAsync(qhat + (size_t)nb * h->ld, 0, (size_t)(nbq - nb) * h->ld * sizeof(float), st));
+            if ((rc = launch_ingest<false>(0, q_dev + (size_t)q0 * h->dim, 0, 0, 0, 0, nb, h->dim, h->ld, qhat, h->num_sms, st))) return rc;
+            h->stats.launches++;
+            CU_TRY(cudaMemsetAsync(flag_count, 0, sizeof(int), st));   // flags[q] itself is written by finalize for every q
+        }
 
         int G = 0, sorted_lists = 1;
         bool scanned = false, appended = false;
@@ -801,7 +829,7 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
         if (via_gemm) {
             // 2a. tensor-core path
             if (!ap && use_astat(h, kp)) { if ((rc = run_gemm_astat(h, nb, kp, &G, nullptr, st))) return rc; }
-            else if ((rc = run_gemm(h, nb, k, kp, &G, &appended, nullptr, st))) return rc;
+            else if ((rc = run_gemm(h, nb, k, kp, &G, &appended, nullptr, st, prepped))) return rc;
             h->stats.path = 1;
             sorted_lists = 0;
             scanned = true;
@@ -993,11 +1021,12 @@ extern "C" int ragfin_debug_gemm_scores(ragfin_t* h, const float* q_dev, int32_t
     return mark_done(h, st);
 }
 
-// Dispatch knob: query batches of at least `min_nq` rows use the tcgen05 path (default 3; INT32_MAX = never).
+// Dispatch knob: query batches of at least `min_nq` rows use the tcgen05 path (default 3, and 1 on corpora of >= 4 GiB; INT32_MAX = never).
 extern "C" int ragfin_set_gemm_min_batch(ragfin_t* h, int32_t min_nq) {
-    if (!h || min_nq < 1) return fail(RAGFIN_EINVAL, "bad argument");
+    if (!h || min_nq < 0) return fail(RAGFIN_EINVAL, "bad argument");
     std::lock_guard<std::mutex> lk(h->mu);
-    h->gemm_min_nq = min_nq;
+    h->gemm_min_nq = min_nq ? min_nq : 3;          // 0 restores the defaults
+    h->gemm_min_nq_large = min_nq ? min_nq : 1;
     return RAGFIN_OK;
 }
 

@@ -20,7 +20,7 @@ for r in range(0, a.rows, 1_000_000):
     idx.add_synthetic(1234, r, min(1_000_000, a.rows - r))
 out = []
 for path in a.paths.split(","):
-    idx.set_gemm_min_batch({"auto": 3, "scan": 1 << 30, "gemm": 2}.get(path, 9) if not path.isdigit() else int(path))
+    idx.set_gemm_min_batch({"auto": 0, "scan": 1 << 30, "gemm": 2}.get(path, 9) if not path.isdigit() else int(path))
     for cluster in [int(x) for x in a.cluster.split(",")]:
         idx.set_gemm_cluster(cluster)
         for k in [int(x) for x in a.k.split(",")]:

@@ -105,3 +105,21 @@ def test_full_size_k100_stays_on_the_fast_path(corpus, coracle):
     assert idx.stats()["path"] == 0
     idx.set_gemm_min_batch(3)
     assert np.array_equal(ids_s, ids_g[:4]) and np.array_equal(sc_s.view(np.uint32), sc_g[:4].view(np.uint32))
+
+
+def test_full_size_default_dispatch_sweeps_even_one_query(corpus):
+    """On a corpus of >= 4 GiB the default dispatch sends 1-2 queries through the TMA-fed tensor-core sweep
+    (faster than the LDG scan); forcing the scan must give the same bits."""
+    idx, q = corpus
+    idx.set_gemm_min_batch(0)                 # defaults
+    a = idx.search(q[:1], K)
+    assert idx.stats()["path"] == 1
+    b2 = idx.search(q[:2], 100)
+    assert idx.stats()["path"] == 1
+    idx.set_gemm_min_batch(1 << 30)
+    s1 = idx.search(q[:1], K)
+    assert idx.stats()["path"] == 0
+    s2 = idx.search(q[:2], 100)
+    idx.set_gemm_min_batch(0)
+    for x, y in ((a, s1), (b2, s2)):
+        assert np.array_equal(x[0], y[0]) and np.array_equal(x[1].view(np.uint32), y[1].view(np.uint32))
