@@ -440,7 +440,9 @@ static float eps_gemm_const(int dtype, int ld) {
     return (float)e;
 }
 
-static bool gemm_supported(const ragfin* h, int kp) { return kp <= 128 && h->count > 0; }
+// TMA coordinates are signed 32-bit: shards of 2^31 rows or more stay on the scan path (int64 row arithmetic)
+static bool gemm_rows_ok(const ragfin* h) { return h->count > 0 && h->count < ((int64_t)1 << 31) - kGN; }
+static bool gemm_supported(const ragfin* h, int kp) { return kp <= 128 && gemm_rows_ok(h); }
 
 // Scores the nb normalised queries in h->qhat against the corpus on the tensor cores.  Fills
 // h->cand as [nb][S][kp] (unsorted lists) and h->eps_q; returns S through *G.  dump != null: write raw scores instead.
@@ -455,7 +457,8 @@ static const int kAppendMaxK = 256;    // largest k the append mode serves (tier
 // Append mode needs the bound pass (no scalar filter) and at least 4 k corpus tiles to draw 2 k sample blocks from.
 static bool append_eligible(const ragfin* h, int k) {
     const int64_t n_tiles = (h->count + kGN - 1) / kGN;
-    return h->use_bound_pass && h->use_append && h->cur_allow == nullptr && k <= kAppendMaxK && n_tiles >= 4 * (int64_t)k;
+    return h->use_bound_pass && h->use_append && h->cur_allow == nullptr && k <= kAppendMaxK && n_tiles >= 4 * (int64_t)k &&
+           h->count < ((int64_t)1 << 31) - kGN;
 }
 
 // Scores the nb normalised queries in h->qhat against the corpus on the tensor cores and leaves per-query candidates
