@@ -113,6 +113,23 @@ int ragfin_merge_topk(const int64_t* ids, const float* scores, int32_t nq, int32
                       int64_t ids_part_stride, int64_t scores_part_stride, int64_t query_stride,
                       int64_t* out_ids, float* out_scores, int32_t device, void* stream);
 
+/* Cross-shard exchange over NVLink peer memory, one process per GPU on one box - the fused alternative to
+ * "NCCL all-gather + ragfin_merge_topk".  Every rank allocates a gather area, publishes its CUDA IPC handle, and
+ * opens its peers' (ragfin_exchange_connect takes the `world` handles, RAGFIN_IPC_HANDLE_BYTES each, in rank order;
+ * the caller moves them between processes, e.g. torch.distributed.all_gather_object, and runs a barrier after
+ * connect and before destroy).  ragfin_exchange_allgather_merge then STORES this rank's exact hits {ids [nq,k] |
+ * scores [nq,k]} into every peer's area, publishes a per-step flag (release, system scope) and reduces the `world`
+ * records that arrived in its own area as soon as their flags are up (acquire) - two small kernels, no collective
+ * library call.  All ranks must call it in the same order with the same (nq, k); nq*k*12 <= record_bytes_max. */
+typedef struct ragfin_exchange ragfin_exchange_t;
+#define RAGFIN_IPC_HANDLE_BYTES 64
+int ragfin_exchange_create(ragfin_exchange_t** out, int32_t rank, int32_t world, int64_t record_bytes_max, int32_t device);
+int ragfin_exchange_handle(ragfin_exchange_t* x, void* handle_out /* RAGFIN_IPC_HANDLE_BYTES */);
+int ragfin_exchange_connect(ragfin_exchange_t* x, const void* handles /* world * RAGFIN_IPC_HANDLE_BYTES */);
+int ragfin_exchange_allgather_merge(ragfin_exchange_t* x, const int64_t* ids_dev, const float* scores_dev, int32_t nq,
+                                    int32_t k, int64_t* out_ids_dev, float* out_scores_dev, void* stream);
+void ragfin_exchange_destroy(ragfin_exchange_t* x);
+
 /* Copy rows row0..row0+n of the STORED matrix, raw storage bytes [n, ld], to host memory
  * (test hook for ingest parity).  *ld_out receives the row stride in elements. */
 int ragfin_read_rows(ragfin_t* h, int64_t row0, int64_t n, void* out_host, int32_t* ld_out);

@@ -17,6 +17,7 @@ SYMBOLS = (
     "ragfin_abi_version", "ragfin_create", "ragfin_add", "ragfin_add_synthetic", "ragfin_count",
     "ragfin_set_id_base", "ragfin_search", "ragfin_search_host", "ragfin_search_filtered", "ragfin_search_filtered_host", "ragfin_merge_topk", "ragfin_read_rows",
     "ragfin_last_search_stats", "ragfin_profile", "ragfin_profile_read", "ragfin_save", "ragfin_load", "ragfin_set_gemm_min_batch", "ragfin_set_gemm_cluster", "ragfin_set_gemm_variant", "ragfin_set_bound_pass", "ragfin_set_scan_variant", "ragfin_set_append_mode", "ragfin_debug_gemm_scores", "ragfin_destroy", "ragfin_last_error",
+    "ragfin_exchange_create", "ragfin_exchange_handle", "ragfin_exchange_connect", "ragfin_exchange_allgather_merge", "ragfin_exchange_destroy",
 )
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
@@ -64,6 +65,12 @@ def load() -> ctypes.CDLL:
     L.ragfin_set_gemm_cluster.argtypes = [vp, i32]
     L.ragfin_set_gemm_variant.argtypes = [vp, i32]
     L.ragfin_set_bound_pass.argtypes = [vp, i32]
+    L.ragfin_exchange_create.argtypes = [ctypes.POINTER(vp), i32, i32, i64, i32]
+    L.ragfin_exchange_handle.argtypes = [vp, vp]
+    L.ragfin_exchange_connect.argtypes = [vp, vp]
+    L.ragfin_exchange_allgather_merge.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
+    L.ragfin_exchange_destroy.argtypes = [vp]
+    L.ragfin_exchange_destroy.restype = None
     L.ragfin_set_scan_variant.argtypes = [vp, i32]
     L.ragfin_set_append_mode.argtypes = [vp, i32]
     L.ragfin_debug_gemm_scores.argtypes = [vp, vp, i32, vp, vp]
@@ -71,7 +78,7 @@ def load() -> ctypes.CDLL:
     L.ragfin_read_rows.argtypes = [vp, i64, i64, vp, ctypes.POINTER(i32)]
     L.ragfin_last_search_stats.argtypes = [vp, ctypes.POINTER(SearchStats)]
     for name in SYMBOLS:
-        if name not in ("ragfin_destroy", "ragfin_last_error"):
+        if name not in ("ragfin_destroy", "ragfin_last_error", "ragfin_exchange_destroy"):
             getattr(L, name).restype = ctypes.c_int
     L.ragfin_destroy.argtypes, L.ragfin_destroy.restype = [vp], None
     L.ragfin_last_error.argtypes, L.ragfin_last_error.restype = [], ctypes.c_char_p

@@ -592,9 +592,9 @@ __device__ __forceinline__ int count_better(const int64_t* ids, const float* sc,
     }
     return lo;
 }
-__global__ void merge_topk_kernel(const int64_t* __restrict__ ids, const float* __restrict__ scores, int nq,
-                                  int parts, int k, int64_t ips, int64_t sps, int64_t query_stride,
-                                  int64_t* __restrict__ out_ids, float* __restrict__ out_scores) {
+__device__ __forceinline__ void merge_topk_body(const int64_t* __restrict__ ids, const float* __restrict__ scores, int nq,
+                                                int parts, int k, int64_t ips, int64_t sps, int64_t query_stride,
+                                                int64_t* __restrict__ out_ids, float* __restrict__ out_scores) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t per_q = (int64_t)parts * k;
     if (t >= (int64_t)nq * per_q) return;
@@ -616,6 +616,66 @@ __global__ void merge_topk_kernel(const int64_t* __restrict__ ids, const float* 
     for (int pp = 0; pp < parts && rank < k; ++pp)
         if (pp != p) rank += count_better(qi + (size_t)pp * ips, qs + (size_t)pp * sps, k, s, id);
     if (rank < k) { out_ids[(size_t)q * k + rank] = id; out_scores[(size_t)q * k + rank] = s; }
+}
+__global__ void merge_topk_kernel(const int64_t* __restrict__ ids, const float* __restrict__ scores, int nq,
+                                  int parts, int k, int64_t ips, int64_t sps, int64_t query_stride,
+                                  int64_t* __restrict__ out_ids, float* __restrict__ out_scores) {
+    merge_topk_body(ids, scores, nq, parts, k, ips, sps, query_stride, out_ids, out_scores);
+}
+
+// ---------------------------------------------------------------------------------
+// Cross-shard exchange over NVLink peer memory (one process per GPU, buffers opened through CUDA IPC): instead of an
+// NCCL all-gather, every rank STORES its packed hit record {ids[nq*k] | scores[nq*k]} straight into slot `rank` of
+// every peer's gather area and then publishes the step number in that peer's flag word (release, system scope); the
+// reduce kernel spins (acquire) until all `world` flags of its own area carry the step number, then merges.
+// Gather areas and flags are double-buffered by step parity: a rank can be at most one step ahead of a peer (its
+// step t+1 reduce needs the peer's step t+1 record, sent after the peer's step t reduce in stream order).
+//   peer_area[p]  base of rank p's gather area: [2][world][record_bytes]
+//   peer_flag[p]  base of rank p's flags:       [2][world] uint32
+// grid = (chunks, world); blockIdx.y = destination peer.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void __launch_bounds__(256)
+exchange_push_kernel(const int64_t* __restrict__ ids, const float* __restrict__ scores, int64_t n_hits /*nq*k*/,
+                     int rank, int world, size_t record_bytes, uint32_t step, char* const* __restrict__ peer_area,
+                     uint32_t* const* __restrict__ peer_flag, unsigned int* __restrict__ done /*[world]*/) {
+    const int p = blockIdx.y;
+    char* dst = peer_area[p] + ((size_t)(step & 1u) * world + rank) * record_bytes;
+    int64_t* dids = reinterpret_cast<int64_t*>(dst);
+    float* dsc = reinterpret_cast<float*>(dst + (size_t)n_hits * 8);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_hits; i += (int64_t)gridDim.x * blockDim.x) {
+        dids[i] = ids[i];
+        dsc[i] = scores[i];
+    }
+    __threadfence_system();      // this thread's peer stores are visible system-wide before the CTA is counted
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(&done[p], 1u) == gridDim.x - 1) {   // last CTA of this destination: publish
+            done[p] = 0u;
+            __threadfence_system();
+            st_release_sys(peer_flag[p] + (size_t)(step & 1u) * world + rank, step);
+        }
+    }
+}
+__global__ void exchange_merge_kernel(const char* __restrict__ area, const uint32_t* __restrict__ flags, int nq, int world,
+                                      int k, size_t record_bytes, uint32_t step, int64_t* __restrict__ out_ids,
+                                      float* __restrict__ out_scores) {
+    if (threadIdx.x < world) {
+        const uint32_t* f = flags + (size_t)(step & 1u) * world + threadIdx.x;
+        while (ld_acquire_sys(f) != step) __nanosleep(20);
+    }
+    __syncthreads();
+    (void)ld_acquire_sys(flags + (size_t)(step & 1u) * world + threadIdx.x % world);   // every thread acquires for its own loads
+    const char* base = area + (size_t)(step & 1u) * world * record_bytes;
+    merge_topk_body(reinterpret_cast<const int64_t*>(base), reinterpret_cast<const float*>(base + (size_t)nq * k * 8), nq, world, k,
+                    (int64_t)(record_bytes / 8), (int64_t)(record_bytes / 4), (int64_t)k, out_ids, out_scores);
 }
 
 }  // namespace rfk

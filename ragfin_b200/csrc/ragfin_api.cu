@@ -1225,3 +1225,134 @@ extern "C" int ragfin_merge_topk(const int64_t* ids, const float* scores, int32_
     CU_TRY(cudaGetLastError());
     return RAGFIN_OK;
 }
+
+// ------------------------------------------------------------------------------
+// Cross-shard exchange over peer memory (CUDA IPC + NVLink P2P stores), see exchange_push_kernel
+// ------------------------------------------------------------------------------
+struct ragfin_exchange {
+    int rank = 0, world = 0, device = 0;
+    size_t record_max = 0, bytes = 0;
+    char* local = nullptr;               // [2][world][record_max] gather area, then [2][world] uint32 flags
+    char* peer_base[64] = {};            // base of every rank's block in this process's address space
+    bool opened[64] = {};
+    char** d_peer_area = nullptr;
+    uint32_t** d_peer_flag = nullptr;
+    unsigned int* d_done = nullptr;
+    uint32_t step = 0;
+    bool connected = false;
+    std::mutex mu;
+};
+
+extern "C" int ragfin_exchange_create(ragfin_exchange_t** out, int32_t rank, int32_t world, int64_t record_bytes_max, int32_t device) {
+    if (!out) return fail(RAGFIN_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (world < 1 || world > 64 || rank < 0 || rank >= world) return fail(RAGFIN_EINVAL, "rank %d / world %d out of range (world <= 64)", rank, world);
+    if (record_bytes_max < 16) return fail(RAGFIN_EINVAL, "record_bytes_max must be >= 16");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(RAGFIN_ECUDA, "cudaSetDevice(%d) failed", device);
+    ragfin_exchange* x = new (std::nothrow) ragfin_exchange();
+    if (!x) return fail(RAGFIN_ENOMEM, "host allocation failed");
+    x->rank = rank; x->world = world; x->device = device;
+    x->record_max = ((size_t)record_bytes_max + 15) / 16 * 16;
+    const size_t area = 2 * (size_t)world * x->record_max;
+    x->bytes = area + 2 * (size_t)world * sizeof(uint32_t);
+    cudaError_t e = cudaMalloc((void**)&x->local, x->bytes);
+    if (e == cudaSuccess) e = cudaMemset(x->local, 0, x->bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&x->d_peer_area, world * sizeof(char*));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&x->d_peer_flag, world * sizeof(uint32_t*));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&x->d_done, world * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(x->d_done, 0, world * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (x->local) cudaFree(x->local);
+        if (x->d_peer_area) cudaFree(x->d_peer_area);
+        if (x->d_peer_flag) cudaFree(x->d_peer_flag);
+        if (x->d_done) cudaFree(x->d_done);
+        delete x;
+        return fail(RAGFIN_ENOMEM, "exchange allocation failed: %s", cudaGetErrorString(e));
+    }
+    *out = x;
+    return RAGFIN_OK;
+}
+
+extern "C" int ragfin_exchange_handle(ragfin_exchange_t* x, void* handle_out) {
+    if (!x || !handle_out) return fail(RAGFIN_EINVAL, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == RAGFIN_IPC_HANDLE_BYTES, "IPC handle size");
+    DeviceGuard g(x->device);
+    cudaIpcMemHandle_t hd;
+    CU_TRY(cudaIpcGetMemHandle(&hd, x->local));
+    memcpy(handle_out, &hd, sizeof(hd));
+    return RAGFIN_OK;
+}
+
+extern "C" int ragfin_exchange_connect(ragfin_exchange_t* x, const void* handles) {
+    if (!x || !handles) return fail(RAGFIN_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(x->mu);
+    if (x->connected) return fail(RAGFIN_EINVAL, "exchange is already connected");
+    DeviceGuard g(x->device);
+    const size_t area = 2 * (size_t)x->world * x->record_max;
+    char* areas[64];
+    uint32_t* flags[64];
+    for (int p = 0; p < x->world; ++p) {
+        if (p == x->rank) {
+            x->peer_base[p] = x->local;
+        } else {
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, (const char*)handles + (size_t)p * sizeof(hd), sizeof(hd));
+            void* ptr = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                (void)cudaGetLastError();
+                return fail(RAGFIN_ECUDA, "cudaIpcOpenMemHandle for rank %d failed: %s (no peer access between the GPUs?)", p, cudaGetErrorString(e));
+            }
+            x->peer_base[p] = (char*)ptr;
+            x->opened[p] = true;
+        }
+        areas[p] = x->peer_base[p];
+        flags[p] = reinterpret_cast<uint32_t*>(x->peer_base[p] + area);
+    }
+    CU_TRY(cudaMemcpy(x->d_peer_area, areas, x->world * sizeof(char*), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(x->d_peer_flag, flags, x->world * sizeof(uint32_t*), cudaMemcpyHostToDevice));
+    x->connected = true;
+    return RAGFIN_OK;
+}
+
+extern "C" int ragfin_exchange_allgather_merge(ragfin_exchange_t* x, const int64_t* ids_dev, const float* scores_dev, int32_t nq,
+                                               int32_t k, int64_t* out_ids, float* out_scores, void* stream) {
+    if (!x || !ids_dev || !scores_dev || !out_ids || !out_scores) return fail(RAGFIN_EINVAL, "NULL argument");
+    if (nq < 1 || k < 1) return fail(RAGFIN_EINVAL, "bad nq/k");
+    std::lock_guard<std::mutex> lk(x->mu);
+    if (!x->connected) return fail(RAGFIN_EINVAL, "exchange is not connected");
+    const int64_t n_hits = (int64_t)nq * k;
+    const size_t record = ((size_t)n_hits * 12 + 15) / 16 * 16;
+    if (record > x->record_max) return fail(RAGFIN_EINVAL, "record of %zu bytes exceeds the exchange's %zu", record, x->record_max);
+    DeviceGuard g(x->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t step = ++x->step;
+    int chunks = (int)((n_hits + 255) / 256);
+    if (chunks > 64) chunks = 64;
+    exchange_push_kernel<<<dim3(chunks, x->world), 256, 0, st>>>(ids_dev, scores_dev, n_hits, x->rank, x->world, x->record_max, step,
+                                                                 x->d_peer_area, x->d_peer_flag, x->d_done);
+    CU_TRY(cudaGetLastError());
+    const int64_t total = n_hits * x->world;
+    const uint32_t* flags = reinterpret_cast<const uint32_t*>(x->local + 2 * (size_t)x->world * x->record_max);
+    exchange_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x->local, flags, nq, x->world, k, x->record_max, step,
+                                                                           out_ids, out_scores);
+    CU_TRY(cudaGetLastError());
+    return RAGFIN_OK;
+}
+
+extern "C" void ragfin_exchange_destroy(ragfin_exchange_t* x) {
+    if (!x) return;
+    DeviceGuard g(x->device);
+    (void)cudaDeviceSynchronize();
+    for (int p = 0; p < x->world; ++p)
+        if (x->opened[p]) (void)cudaIpcCloseMemHandle(x->peer_base[p]);
+    if (x->local) cudaFree(x->local);
+    if (x->d_peer_area) cudaFree(x->d_peer_area);
+    if (x->d_peer_flag) cudaFree(x->d_peer_flag);
+    if (x->d_done) cudaFree(x->d_done);
+    (void)cudaGetLastError();
+    delete x;
+}

@@ -276,3 +276,63 @@ class PackedHits:
         base = self.gathered.data_ptr()
         return _merge_raw(base, base + self.nq * self.k * 8, self.nq, self.world, self.k, self.record // 8,
                           self.record // 4, self.k, self.gathered.device, stream)
+
+
+class PeerExchange:
+    """Cross-shard exchange over NVLink peer memory (include/ragfin.h, ragfin_exchange_*): each rank stores its hit record
+    into every peer's gather area through CUDA IPC mappings and reduces what arrived in its own - two small kernels
+    instead of an NCCL all-gather + reduce.  One process per GPU of ONE box; construction is collective over `group`
+    (handles travel through torch.distributed) and raises on every rank if any rank cannot map its peers."""
+
+    def __init__(self, device: int, max_record_bytes: int = 8 << 20, group=None):
+        import torch
+        import torch.distributed as dist
+        self._L = _lib.load()
+        self.device = int(device)
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.max_record_bytes = int(max_record_bytes)
+        self._x = ctypes.c_void_p()
+        ok, err = 1, ""
+        try:
+            _lib.check(self._L.ragfin_exchange_create(ctypes.byref(self._x), self.rank, self.world, self.max_record_bytes, self.device))
+            mine = ctypes.create_string_buffer(64)
+            _lib.check(self._L.ragfin_exchange_handle(self._x, mine))
+            payload = bytes(mine.raw)
+        except Exception as e:   # noqa: BLE001 - reported collectively below
+            ok, err, payload = 0, str(e), b""
+        handles = [None] * self.world
+        dist.all_gather_object(handles, payload, group=group)
+        if ok and all(len(h) == 64 for h in handles):
+            try:
+                _lib.check(self._L.ragfin_exchange_connect(self._x, b"".join(handles)))
+            except Exception as e:   # noqa: BLE001
+                ok, err = 0, str(e)
+        else:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=torch.device("cuda", self.device))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)   # also the barrier after connect
+        if int(flag.item()) != 1:
+            self.close()
+            raise RuntimeError(f"peer-memory exchange unavailable on at least one rank ({err or 'a peer failed'})")
+
+    def allgather_merge(self, ids, scores, stream=None):
+        """ids int64 [nq, k], scores fp32 [nq, k] (this rank's exact hits, CUDA) -> global (ids, scores) [nq, k]."""
+        import torch
+        nq, k = ids.shape
+        out_ids = torch.empty((nq, k), dtype=torch.int64, device=ids.device)
+        out_scores = torch.empty((nq, k), dtype=torch.float32, device=ids.device)
+        _lib.check(self._L.ragfin_exchange_allgather_merge(self._x, ids.data_ptr(), scores.data_ptr(), nq, k,
+                                                           out_ids.data_ptr(), out_scores.data_ptr(), _stream_ptr(stream)))
+        return out_ids, out_scores
+
+    def close(self):
+        if getattr(self, "_x", None) is not None and self._x:
+            self._L.ragfin_exchange_destroy(self._x)
+            self._x = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # noqa: BLE001
+            pass

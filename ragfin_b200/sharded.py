@@ -30,7 +30,8 @@ class ShardedSearcher:
     (GPU path) the local hits are written straight into one packed record per rank, so the exchange
     is a single NCCL all-gather of nq*k*12 bytes."""
 
-    def __init__(self, local_search: Callable, merge: Callable, group=None, packed_factory: Optional[Callable] = None):
+    def __init__(self, local_search: Callable, merge: Callable, group=None, packed_factory: Optional[Callable] = None,
+                 exchange=None):
         import torch.distributed as dist
         self._dist = dist
         self.group = group
@@ -39,20 +40,47 @@ class ShardedSearcher:
         self.local_search = local_search
         self.merge = merge
         self.packed_factory = packed_factory
+        self.exchange = exchange          # PeerExchange: stores over NVLink peer memory instead of the NCCL all-gather
+        self._local = {}
         self._packed = {}
         self._gather_ids = None
         self._gather_scores = None
 
     @classmethod
-    def for_index(cls, index, group=None) -> "ShardedSearcher":
-        from .engine import PackedHits, merge_topk
-        return cls(index.search_device, merge_topk, group, packed_factory=PackedHits)
+    def for_index(cls, index, group=None, p2p: Optional[bool] = None) -> "ShardedSearcher":
+        """GPU wiring.  p2p: True = peer-memory exchange (raises if unavailable), False = NCCL all-gather + reduce,
+        None = peer-memory when it can be set up (env RAGFIN_NO_P2P=1 disables), else NCCL."""
+        import os
+        import torch.distributed as dist
+        from .engine import PackedHits, PeerExchange, merge_topk
+        exchange = None
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if p2p is None:
+            p2p = os.environ.get("RAGFIN_NO_P2P", "0") != "1"
+            required = False
+        else:
+            required = bool(p2p)
+        if p2p and world > 1:
+            try:
+                exchange = PeerExchange(index.device, group=group)
+            except RuntimeError:
+                if required:
+                    raise
+        return cls(index.search_device, merge_topk, group, packed_factory=PackedHits, exchange=exchange)
 
     def search(self, queries, k: int):
         import torch
         if self.world == 1:
             return self.local_search(queries, k)
         nq = queries.shape[0]
+        if self.exchange is not None and nq * k * 12 <= self.exchange.max_record_bytes:
+            key = (nq, k)
+            buf = self._local.get(key)
+            if buf is None:
+                buf = self._local[key] = (torch.empty((nq, k), dtype=torch.int64, device=queries.device),
+                                          torch.empty((nq, k), dtype=torch.float32, device=queries.device))
+            self.local_search(queries, k, out_ids=buf[0], out_scores=buf[1])
+            return self.exchange.allgather_merge(buf[0], buf[1])
         if self.packed_factory is not None:
             key = (nq, k)
             ph = self._packed.get(key)

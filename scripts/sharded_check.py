@@ -25,15 +25,23 @@ for dtype, dim, n, nq, k in [("bf16", 768, 50001, 1, 10), ("f16", 768, 30000, 4,
     if cnt:
         idx.add_synthetic(500, row0, cnt, dup_every=53)
     idx.set_id_base(row0)
-    s = ShardedSearcher.for_index(idx)
     q = O.synth_rows(501, 0, nq, dim)
-    ids, sc = s.search(torch.from_numpy(q).cuda(), k)
-    torch.cuda.synchronize()
+    qd = torch.from_numpy(q).cuda()
     wi, ws = C.cosine_topk(q, C.normalize_rows(O.synth_rows(500, 0, n, dim, dup_every=53), dtype), k)
-    same = np.array_equal(ids.cpu().numpy(), wi) and np.array_equal(sc.cpu().numpy().view(np.uint32), ws.view(np.uint32))
-    ok &= same
-    if rank == 0:
-        print(f"sharded x{world} {dtype} dim={dim} n={n} nq={nq} k={k}: parity={same}", flush=True)
+    for p2p in (None, False):      # peer-memory exchange (when the box allows it), then NCCL all-gather + reduce
+        s = ShardedSearcher.for_index(idx, p2p=p2p)
+        same = True
+        for _ in range(3):         # several steps: the exchange double-buffers by step parity
+            ids, sc = s.search(qd, k)
+            torch.cuda.synchronize()
+            same &= np.array_equal(ids.cpu().numpy(), wi) and np.array_equal(sc.cpu().numpy().view(np.uint32), ws.view(np.uint32))
+        ok &= same
+        if rank == 0:
+            how = "peer-memory" if s.exchange is not None else "nccl"
+            print(f"sharded x{world} {dtype} dim={dim} n={n} nq={nq} k={k} [{how}]: parity={same}", flush=True)
+        dist.barrier()
+        if s.exchange is not None:
+            s.exchange.close()
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
