@@ -28,7 +28,7 @@ for dtype, dim, n, nq, k in [("bf16", 768, 50001, 1, 10), ("f16", 768, 30000, 4,
     q = O.synth_rows(501, 0, nq, dim)
     qd = torch.from_numpy(q).cuda()
     wi, ws = C.cosine_topk(q, C.normalize_rows(O.synth_rows(500, 0, n, dim, dup_every=53), dtype), k)
-    for p2p in (None, False):      # peer-memory exchange (when the box allows it), then NCCL all-gather + reduce
+    for p2p in (True, False):      # peer-memory exchange (CUDA IPC + NVLink stores), then NCCL all-gather + reduce
         s = ShardedSearcher.for_index(idx, p2p=p2p)
         same = True
         for _ in range(3):         # several steps: the exchange double-buffers by step parity
