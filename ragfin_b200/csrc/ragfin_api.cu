@@ -64,6 +64,8 @@ struct ragfin {
     bool use_append = true;       // tcgen05 path: append mode (threshold from the bound pass, no lists) when eligible
     bool use_bound_pass = true;   // tcgen05 path: sample pass that seeds the per-query thresholds (RAGFIN_NO_BOUND_PASS=1 disables)
     int gemm_variant = 1;     // 0 = automatic, 1 = streaming (A and B through shared memory), 2 = A-stationary (A in TMEM)
+    void* hstage = nullptr;   // pinned, device-mapped staging for small host calls: kernels read the queries and write the hits
+                              // straight through PCIe, no copy engine launches (ragfin_search_host)
     cudaEvent_t last_done = nullptr;
     ragfin_search_stats stats = {0, 0, 0, 0};
     // measurement hook (ragfin_profile): event pairs around the dominant kernel
@@ -170,6 +172,7 @@ extern "C" void ragfin_destroy(ragfin_t* h) {
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->data) cudaFree(h->data);
+    if (h->hstage) cudaFreeHost(h->hstage);
     if (h->last_done) cudaEventDestroy(h->last_done);
     for (cudaEvent_t e : h->prof_ev)
         if (e) cudaEventDestroy(e);
@@ -357,6 +360,7 @@ static int cand_per_query(int k) {
 // fp32 rounding of the exact score and one ulp so that a tie after rounding cannot hide a row.
 static float eps_fp32_accumulate(int ld) { return (float)((ld + 64) * 5.9604644775390625e-08 * 1.0625 + 4.76837158203125e-07); }
 
+static const size_t kHostStageQ = 64 << 10, kHostStageOut = 64 << 10;   // mapped staging of ragfin_search_host (small requests)
 static const int kMaxQueryBatch = 4096;  // queries per pass through the pipeline (bounds the workspace)
 
 // ------------------------------------------------------------------------------
@@ -592,7 +596,10 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
     a.dump = dump;
     a.bound_tps = 0; a.bound_tiles = 0; a.bound_stride = 0;
     a.thr = (const float*)h->athr.p; a.cnt = (uint32_t*)h->acnt.p; a.cap = kAppendCap;
+    a.dbg = 0;
+#ifdef RAGFIN_TIMING_EXPERIMENTS   // scripts/gemm_dbg_sweep.py: switch pipeline stages off (INVALID results, timing only)
     { const char* e = getenv("RAGFIN_GEMM_DEBUG"); a.dbg = e ? atoi(e) : 0; }
+#endif
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = smem;
@@ -805,24 +812,19 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
         // 1. normalise the queries (same kernel as ingest, fp32 out, stride ld); pad with zero rows
         if ((rc = ensure(h->qhat, (size_t)nbq * h->ld * sizeof(float)))) return rc;
         float* qhat = (float*)h->qhat.p;
-        const bool prepped = via_gemm && !(!ap && use_astat(h, kp));
-        if (prepped) {   // one launch: normalise + pad + 16-bit copy + eps_q + counters
+        const bool prepped = via_gemm && !(!ap && use_astat(h, kp));   // the 16-bit query copy is made here too
+        {   // one launch: normalise + pad + [16-bit copy + eps_q] + counters (flags[q] itself is written by finalize for every q)
             if ((rc = ensure(h->eps_q, (size_t)nbq * sizeof(float))) || (rc = ensure(h->gtau, (size_t)nbq * sizeof(uint32_t)))) return rc;
-            if (h->dtype != 0 && (rc = ensure(h->q16, (size_t)nbq * h->ld * 2))) return rc;
+            if (prepped && h->dtype != 0 && (rc = ensure(h->q16, (size_t)nbq * h->ld * 2))) return rc;
             const int wpb = 8, blocks = (nbq + wpb - 1) / wpb;
             const float* qsrc = q_dev + (size_t)q0 * h->dim;
-            switch (h->dtype) {
+            switch (prepped ? h->dtype : 0) {
                 case 0: prep_queries_kernel<0><<<blocks, wpb * 32, 0, st>>>(qsrc, nb, nbq, h->dim, h->ld, qhat, nullptr, (float*)h->eps_q.p, flag_count, (uint32_t*)h->gtau.p); break;
                 case 1: prep_queries_kernel<1><<<blocks, wpb * 32, 0, st>>>(qsrc, nb, nbq, h->dim, h->ld, qhat, (__nv_bfloat16*)h->q16.p, (float*)h->eps_q.p, flag_count, (uint32_t*)h->gtau.p); break;
                 default: prep_queries_kernel<2><<<blocks, wpb * 32, 0, st>>>(qsrc, nb, nbq, h->dim, h->ld, qhat, (__half*)h->q16.p, (float*)h->eps_q.p, flag_count, (uint32_t*)h->gtau.p); break;
             }
             CU_TRY(cudaGetLastError());
             h->stats.launches++;
-        } else {
-            if (nbq > nb) CU_TRY(cudaMemsetAsync(qhat + (size_t)nb * h->ld, 0, (size_t)(nbq - nb) * h->ld * sizeof(float), st));
-            if ((rc = launch_ingest<false>(0, q_dev + (size_t)q0 * h->dim, 0, 0, 0, 0, nb, h->dim, h->ld, qhat, h->num_sms, st))) return rc;
-            h->stats.launches++;
-            CU_TRY(cudaMemsetAsync(flag_count, 0, sizeof(int), st));   // flags[q] itself is written by finalize for every q
         }
 
         int G = 0, sorted_lists = 1;
@@ -1101,6 +1103,27 @@ extern "C" int ragfin_search_host(ragfin_t* h, const float* q_host, int32_t nq, 
     int rc;
     if ((rc = wait_prev(h, st))) return rc;
     const size_t qb = (size_t)nq * h->dim * sizeof(float), ib = (size_t)nq * k * sizeof(int64_t), sb = (size_t)nq * k * sizeof(float);
+    if (qb <= kHostStageQ && ib + sb <= kHostStageOut) {
+        // small request: three copy-engine launches (~20 us) would cost more than the bytes; the kernels read the queries
+        // from, and write the hits to, device-mapped pinned memory
+        if (!h->hstage) {
+            if (cudaHostAlloc(&h->hstage, kHostStageQ + kHostStageOut, cudaHostAllocMapped) != cudaSuccess) { (void)cudaGetLastError(); h->hstage = nullptr; }
+        }
+        void* dptr = nullptr;
+        if (h->hstage && cudaHostGetDevicePointer(&dptr, h->hstage, 0) == cudaSuccess) {
+            char* hq = (char*)h->hstage;
+            char* ho = hq + kHostStageQ;
+            memcpy(hq, q_host, qb);
+            char* dq = (char*)dptr;
+            char* dout = dq + kHostStageQ;
+            if ((rc = search_locked(h, (const float*)dq, nq, k, (int64_t*)dout, (float*)(dout + ib), st))) return rc;
+            CU_TRY(cudaStreamSynchronize(st));
+            memcpy(out_ids_host, ho, ib);
+            memcpy(out_scores_host, ho + ib, sb);
+            return mark_done(h, st);
+        }
+        (void)cudaGetLastError();
+    }
     if ((rc = ensure(h->stage_q, qb)) || (rc = ensure(h->stage_ids, ib)) || (rc = ensure(h->stage_scores, sb))) return rc;
     CU_TRY(cudaMemcpyAsync(h->stage_q.p, q_host, qb, cudaMemcpyHostToDevice, st));
     if ((rc = search_locked(h, (const float*)h->stage_q.p, nq, k, (int64_t*)h->stage_ids.p, (float*)h->stage_scores.p, st))) return rc;

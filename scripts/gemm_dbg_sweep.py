@@ -1,6 +1,8 @@
 """Timing experiments on the tcgen05 path: which stage of the pipeline bounds the mid-batch regime?
 RAGFIN_GEMM_DEBUG bits: 1 skip the epilogue filter, 2 skip the MMAs, 4 skip the A (query tile) loads, 8 skip the B loads.
-Results with any bit set are INVALID (timing only)."""
+Results with any bit set are INVALID (timing only).
+The library honours the variable only when built with -DRAGFIN_TIMING_EXPERIMENTS (make NVFLAGS+=...); the shipped
+build ignores it."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import argparse, statistics, json
