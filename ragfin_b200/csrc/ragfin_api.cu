@@ -12,6 +12,7 @@
 #include "kernels.cuh"
 #include "gemm.cuh"
 #include "gemm_astat.cuh"
+#include "gemm_rows.cuh"
 #include "scan_tma.cuh"
 #include "bigk.cuh"
 
@@ -63,7 +64,8 @@ struct ragfin {
     int scan_variant = 0;         // small-batch scan: 0 = automatic (= 1, measured faster), 1 = LDG kernel, 2 = TMA-fed ring
     bool use_append = true;       // tcgen05 path: append mode (threshold from the bound pass, no lists) when eligible
     bool use_bound_pass = true;   // tcgen05 path: sample pass that seeds the per-query thresholds (RAGFIN_NO_BOUND_PASS=1 disables)
-    int gemm_variant = 1;     // 0 = automatic, 1 = streaming (A and B through shared memory), 2 = A-stationary (A in TMEM)
+    int gemm_variant = 1;     // 0 = automatic, 1 = streaming (A and B through shared memory), 2 = A-stationary (A in TMEM),
+                              // 3 = streaming + swapped operand roles for <= 16 queries (gemm_rows.cuh)
     void* hstage = nullptr;   // pinned, device-mapped staging for small host calls: kernels read the queries and write the hits
                               // straight through PCIe, no copy engine launches (ragfin_search_host)
     cudaEvent_t last_done = nullptr;
@@ -630,10 +632,28 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
         CU_TRY(cudaGetLastError());
         h->stats.launches += 2;
     }
-    cfg.gridDim = dim3(p.grid);
-    prof_begin(h, st);
-    CU_TRY(cudaLaunchKernelEx(&cfg, fn, tmA, tmB, a));
-    prof_end(h, st);
+    if (append && h->gemm_variant == 3 && nb <= kRN && C == 1 && rows_stages(a.num_kblocks) >= 3) {
+        // <= 16 queries, operand roles swapped (gemm_rows.cuh): corpus rows are the MMA's M, the queries its N = 16
+        RowsArgs r;
+        r.idesc = make_idesc_n(h->dtype == 0 ? 2 : h->dtype == 1 ? 1 : 0, kRN);
+        r.num_kblocks = a.num_kblocks; r.k_elems = a.k_elems; r.nq = nb; r.n_rows = n;
+        r.S = p.S; r.rows_per_slice = p.rows_per_slice; r.stages = rows_stages(a.num_kblocks);
+        r.cand = a.cand; r.thr = a.thr; r.cnt = a.cnt; r.cap = a.cap;
+        CUtensorMap tmQ;
+        if ((rc = make_map(&tmQ, h->dtype, a_base, nb_pad, h->ld, kRN))) return rc;
+        typedef void (*rows_fn)(const CUtensorMap, const CUtensorMap, const RowsArgs);
+        rows_fn rfn = h->dtype == 0 ? gemm_rows_kernel<1> : gemm_rows_kernel<0>;
+        const size_t rsmem = rows_smem_bytes(r.num_kblocks, r.stages);
+        CU_TRY(cudaFuncSetAttribute(rfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+        prof_begin(h, st);
+        rfn<<<p.grid, kGemmThreads, rsmem, st>>>(tmQ, tmB, r);
+        prof_end(h, st);
+    } else {
+        cfg.gridDim = dim3(p.grid);
+        prof_begin(h, st);
+        CU_TRY(cudaLaunchKernelEx(&cfg, fn, tmA, tmB, a));
+        prof_end(h, st);
+    }
     CU_TRY(cudaGetLastError());
     h->stats.launches++;
     *G = p.S;
@@ -728,7 +748,7 @@ static int run_gemm_astat(ragfin* h, int nb, int kp, int* G, float* dump, cudaSt
 }
 
 static bool use_astat(const ragfin* h, int kp) {
-    if (h->gemm_variant == 1) return false;
+    if (h->gemm_variant == 1 || h->gemm_variant == 3) return false;
     return astat_supported(h, kp);   // variant 2 (forced) and 0 (automatic) both need eligibility
 }
 
@@ -1062,7 +1082,7 @@ extern "C" int ragfin_set_scan_variant(ragfin_t* h, int32_t variant) {
 
 // Tuning knob: which tcgen05 kernel serves large batches (0 automatic, 1 streaming, 2 A-stationary when eligible).
 extern "C" int ragfin_set_gemm_variant(ragfin_t* h, int32_t variant) {
-    if (!h || variant < 0 || variant > 2) return fail(RAGFIN_EINVAL, "variant must be 0, 1 or 2");
+    if (!h || variant < 0 || variant > 3) return fail(RAGFIN_EINVAL, "variant must be 0, 1, 2 or 3");
     std::lock_guard<std::mutex> lk(h->mu);
     h->gemm_variant = variant;
     return RAGFIN_OK;

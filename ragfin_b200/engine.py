@@ -188,7 +188,8 @@ class Index:
         _lib.check(self._L.ragfin_set_gemm_cluster(self._h, int(cluster)))
 
     def set_gemm_variant(self, variant: int) -> None:
-        """tcgen05 kernel variant: 0 automatic, 1 streaming, 2 A-stationary (query tile in tensor memory)."""
+        """tcgen05 kernel variant: 0 automatic, 1 streaming, 2 A-stationary (query tile in tensor memory),
+        3 streaming with swapped operand roles for batches of <= 16 queries."""
         _lib.check(self._L.ragfin_set_gemm_variant(self._h, int(variant)))
 
     def set_bound_pass(self, enable: bool) -> None:

@@ -350,6 +350,28 @@ def test_gemm_append_and_bound_modes_agree_with_the_oracle(coracle, dtype, n, di
         _assert_same(plain, want, f"lists {dtype} n={n} nq={nq} k={k}")
 
 
+@pytest.mark.parametrize("dtype", O.DTYPES)
+@pytest.mark.parametrize("n,dim,nq,k", [(70000, 128, 1, 10), (70000, 128, 2, 1), (70000, 128, 16, 10), (150000, 64, 5, 100),
+                                        (40000, 1024, 7, 10), (66000, 100, 3, 10), (35000, 768, 16, 5), (70000, 128, 17, 10)])
+def test_gemm_swapped_roles_for_small_batches(coracle, dtype, n, dim, nq, k):
+    """Variant 3: batches of <= 16 queries in append mode run gemm_rows_kernel (corpus rows are the MMA's M, the
+    queries its N = 16); 17 queries fall back to the standard orientation.  Same bits either way."""
+    x = O.synth_rows(196, 0, n, dim, dup_every=61, zero_every=1999)
+    q = O.synth_rows(197, 0, nq, dim)
+    if nq >= 3:
+        x[4000:4030] = q[2] * 2.0        # 30 exact duplicates of one query: ties resolved by row id
+    want = coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), k)
+    idx = _index(x, dtype)
+    idx.set_gemm_min_batch(1)
+    idx.set_gemm_variant(3)
+    got = idx.search(q, k)
+    st = idx.stats()
+    assert st["path"] == 1 and st["queries_rescanned"] == 0
+    _assert_same(got, want, f"swapped roles {dtype} n={n} dim={dim} nq={nq} k={k}")
+    idx.set_gemm_variant(1)
+    _assert_same(idx.search(q, k), want, "standard orientation")
+
+
 def test_gemm_bound_pass_with_heavy_duplicates(coracle):
     x = O.synth_rows(192, 0, 70000, 128)
     q = O.synth_rows(193, 0, 20, 128)
