@@ -220,6 +220,17 @@ def build_corpus(data_folder: str) -> List[dict]:
     return out
 
 
+def build_corpus_from_bundle(bundle: Dict[str, Dict[str, dict]]) -> List[dict]:
+    """Same as build_corpus for statements already in memory: {quarter directory: {file name: document}}
+    (the layout of tests/golden/fin_statements.json)."""
+    out: List[dict] = []
+    for quarter, period in QUARTERS:
+        docs = bundle.get(f"icici_{quarter}")
+        if docs:
+            out.extend(build_chunks([docs[name] for name in sorted(docs)], period))
+    return out
+
+
 FIELD_ORDER = ("id", "text", "embedding", "period", "chunk_type", "statement_type", "primary_value")
 
 

@@ -259,7 +259,8 @@ def test_chunk_ingest_pipeline_end_to_end(coracle):
         mc.utility.drop_collection("fin_chunks")
     col = mc.Collection("fin_chunks", mc.CollectionSchema(fields, "Financial complete context chunks"))
     col.create_index("embedding", {"index_type": "IVF_FLAT", "metric_type": "COSINE", "params": {"nlist": 128}})
-    chunks = chunker.build_corpus(os.path.join(GOLDEN, "extract_data"))
+    with open(os.path.join(GOLDEN, "fin_statements.json")) as f:
+        chunks = chunker.build_corpus_from_bundle(json.load(f))
     enc = HashingEncoder(384)
     chunker.ingest_chunks(col, chunks, enc.encode)
     assert col.num_entities == 16
