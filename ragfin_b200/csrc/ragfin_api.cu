@@ -5,8 +5,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
 #include <new>
+#include <utility>
 
 #include "../../include/ragfin.h"
 #include "kernels.cuh"
@@ -66,6 +68,9 @@ struct ragfin {
     bool use_bound_pass = true;   // tcgen05 path: sample pass that seeds the per-query thresholds (RAGFIN_NO_BOUND_PASS=1 disables)
     int gemm_variant = 1;     // 0 = automatic, 1 = streaming (A and B through shared memory), 2 = A-stationary (A in TMEM),
                               // 3 = streaming + swapped operand roles for <= 16 queries (gemm_rows.cuh)
+    struct MapSlot { const void* base = nullptr; int64_t rows = 0; int ld = 0, dtype = 0, box_rows = 0; CUtensorMap map; };
+    MapSlot map_cache[8];     // tensor maps are pure functions of (base, rows, ld, dtype, box): encode once
+    int map_next = 0;
     void* hstage = nullptr;   // pinned, device-mapped staging for small host calls: kernels read the queries and write the hits
                               // straight through PCIe, no copy engine launches (ragfin_search_host)
     cudaEvent_t last_done = nullptr;
@@ -402,6 +407,44 @@ static int make_map(CUtensorMap* map, int dtype, const void* base, int64_t rows,
     return 0;
 }
 
+// make_map through the handle's cache (caller holds h->mu)
+static int cached_map(ragfin* h, CUtensorMap* map, int dtype, const void* base, int64_t rows, int ld, int box_rows) {
+    for (ragfin::MapSlot& m : h->map_cache)
+        if (m.base == base && m.rows == rows && m.ld == ld && m.dtype == dtype && m.box_rows == box_rows) { *map = m.map; return 0; }
+    int rc = make_map(map, dtype, base, rows, ld, box_rows);
+    if (rc) return rc;
+    ragfin::MapSlot& m = h->map_cache[h->map_next];
+    h->map_next = (h->map_next + 1) % 8;
+    m.base = base; m.rows = rows; m.ld = ld; m.dtype = dtype; m.box_rows = box_rows; m.map = *map;
+    return 0;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the occupancy query are per (device, function) facts: doing
+// them once instead of on every call takes ~10 us of host time off each search (it shows in the host-path latency).
+static std::mutex g_fn_mu;
+static std::map<std::pair<int, const void*>, size_t> g_fn_smem;
+static std::map<std::pair<std::pair<int, const void*>, size_t>, int> g_fn_occ;
+static int set_dyn_smem(int device, const void* fn, size_t smem) {
+    std::lock_guard<std::mutex> lk(g_fn_mu);
+    auto key = std::make_pair(device, fn);
+    auto it = g_fn_smem.find(key);
+    if (it != g_fn_smem.end() && it->second >= smem) return 0;
+    CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    g_fn_smem[key] = smem;
+    return 0;
+}
+static int blocks_per_sm(int device, const void* fn, int threads, size_t smem, int* out) {
+    std::lock_guard<std::mutex> lk(g_fn_mu);
+    auto key = std::make_pair(std::make_pair(device, fn), smem);
+    auto it = g_fn_occ.find(key);
+    if (it != g_fn_occ.end()) { *out = it->second; return 0; }
+    int v = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, fn, threads, smem));
+    g_fn_occ[key] = v;
+    *out = v;
+    return 0;
+}
+
 struct GemmPlan {
     int QT, S, stages, grid, C;
     int64_t rows_per_slice;
@@ -528,7 +571,7 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
     const size_t smem = gemm_smem_bytes(stages0, kp_smem);
     const int mode = dump ? 1 : append ? 3 : 0;
     gemm_fn fn = pick(C, mode);
-    CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if ((rc = set_dyn_smem(h->device, (const void*)fn, smem))) return rc;
     int resident_clusters = h->num_sms;
     if (C > 1) {   // how many clusters of C CTAs the device can hold at once (GPC packing may strand SMs)
         cudaLaunchConfig_t qc = {};
@@ -541,7 +584,7 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
         qc.attrs = at; qc.numAttrs = 1;
         int nc = 0;
         CU_TRY(cudaOccupancyMaxActiveClusters(&nc, (const void*)fn, &qc));
-        if (nc < 1) { C = 1; fn = pick(1, mode); CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
+        if (nc < 1) { C = 1; fn = pick(1, mode); if ((rc = set_dyn_smem(h->device, (const void*)fn, smem))) return rc; }
         else resident_clusters = nc;
     }
     GemmPlan p = plan_gemm(nb, n, C > 1 ? resident_clusters * C : h->num_sms, kp, C);
@@ -570,8 +613,8 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
         CU_TRY(cudaMemsetAsync(h->eps_q.p, 0, (size_t)nb * sizeof(float), st));
     }
     CUtensorMap tmA, tmB;
-    if ((rc = make_map(&tmA, h->dtype, a_base, nb_pad, h->ld, kGM))) return rc;
-    if ((rc = make_map(&tmB, h->dtype, h->data, n, h->ld, kGN / C))) return rc;   // each CTA fetches 1/C of a tile
+    if ((rc = cached_map(h, &tmA, h->dtype, a_base, nb_pad, h->ld, kGM))) return rc;
+    if ((rc = cached_map(h, &tmB, h->dtype, h->data, n, h->ld, kGN / C))) return rc;   // each CTA fetches 1/C of a tile
     if (append) {
         if ((rc = ensure(h->cand, (size_t)nb * kAppendCap * sizeof(u64)))) return rc;
         if ((rc = ensure(h->acnt, (size_t)nb * sizeof(uint32_t)))) return rc;
@@ -622,7 +665,7 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
         if ((rc = ensure(h->bmax, (size_t)nb * nblk * sizeof(float)))) return rc;
         b.dump = (float*)h->bmax.p;
         gemm_fn bfn = pick(C, 2);
-        CU_TRY(cudaFuncSetAttribute(bfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if ((rc = set_dyn_smem(h->device, (const void*)bfn, smem))) return rc;
         const int64_t items = (int64_t)groups * nblk;
         cfg.gridDim = dim3((unsigned)(items < clusters ? items : clusters) * C);
         CU_TRY(cudaLaunchKernelEx(&cfg, bfn, tmA, tmB, b));
@@ -640,11 +683,11 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
         r.S = p.S; r.rows_per_slice = p.rows_per_slice; r.stages = rows_stages(a.num_kblocks);
         r.cand = a.cand; r.thr = a.thr; r.cnt = a.cnt; r.cap = a.cap;
         CUtensorMap tmQ;
-        if ((rc = make_map(&tmQ, h->dtype, a_base, nb_pad, h->ld, kRN))) return rc;
+        if ((rc = cached_map(h, &tmQ, h->dtype, a_base, nb_pad, h->ld, kRN))) return rc;
         typedef void (*rows_fn)(const CUtensorMap, const CUtensorMap, const RowsArgs);
         rows_fn rfn = h->dtype == 0 ? gemm_rows_kernel<1> : gemm_rows_kernel<0>;
         const size_t rsmem = rows_smem_bytes(r.num_kblocks, r.stages);
-        CU_TRY(cudaFuncSetAttribute(rfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+        if ((rc = set_dyn_smem(h->device, (const void*)rfn, rsmem))) return rc;
         prof_begin(h, st);
         rfn<<<p.grid, kGemmThreads, rsmem, st>>>(tmQ, tmB, r);
         prof_end(h, st);
@@ -679,7 +722,7 @@ static int run_gemm_astat(ragfin* h, int nb, int kp, int* G, float* dump, cudaSt
     if (dump) C = 1;
     const size_t smem = astat_smem_bytes(kp);
     astat_fn fn = pick(C);
-    CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if ((rc = set_dyn_smem(h->device, (const void*)fn, smem))) return rc;
     int resident_clusters = h->num_sms;
     if (C > 1) {
         cudaLaunchConfig_t qc = {};
@@ -692,7 +735,7 @@ static int run_gemm_astat(ragfin* h, int nb, int kp, int* G, float* dump, cudaSt
         qc.attrs = at; qc.numAttrs = 1;
         int nc = 0;
         CU_TRY(cudaOccupancyMaxActiveClusters(&nc, (const void*)fn, &qc));
-        if (nc < 1) { C = 1; fn = pick(1); CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
+        if (nc < 1) { C = 1; fn = pick(1); if ((rc = set_dyn_smem(h->device, (const void*)fn, smem))) return rc; }
         else resident_clusters = nc;
     }
     const GemmPlan p = plan_gemm(nb, n, C > 1 ? resident_clusters * C : h->num_sms, kp, C);
@@ -707,7 +750,7 @@ static int run_gemm_astat(ragfin* h, int nb, int kp, int* G, float* dump, cudaSt
     CU_TRY(cudaGetLastError());
     h->stats.launches++;
     CUtensorMap tmB;
-    if ((rc = make_map(&tmB, h->dtype, h->data, n, h->ld, kSN / C))) return rc;
+    if ((rc = cached_map(h, &tmB, h->dtype, h->data, n, h->ld, kSN / C))) return rc;
     if (!dump) {
         if ((rc = ensure(h->cand, (size_t)nb * p.S * kp * sizeof(u64)))) return rc;
     }
@@ -875,7 +918,7 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
             if (tfn) {
                 G = h->num_sms;
                 if ((rc = ensure(h->cand, (size_t)nb4 * G * kp * sizeof(u64)))) return rc;
-                CU_TRY(cudaFuncSetAttribute(tfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+                if ((rc = set_dyn_smem(h->device, (const void*)tfn, tsm))) return rc;
                 prof_begin(h, st);
                 tfn<<<G, kTsThreads, tsm, st>>>(h->data, n, h->ld, qhat, nb, kp, (u64*)h->cand.p, (int64_t)G * kp, h->cur_allow);
                 prof_end(h, st);
@@ -891,9 +934,9 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
                     scan_fn fn = pick_scan(h->dtype, nqt, steps);
                     if (!fn) return fail(RAGFIN_EUNSUPPORTED, "no scan kernel for dtype %d nq %d steps %d", h->dtype, nqt, steps);
                     const size_t smem = (size_t)nqt * kScanWarps * kp * sizeof(u64);
-                    CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    if ((rc = set_dyn_smem(h->device, (const void*)fn, smem))) return rc;
                     int per_sm = 0;
-                    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kScanThreads, smem));
+                    if ((rc = blocks_per_sm(h->device, (const void*)fn, kScanThreads, smem, &per_sm))) return rc;
                     if (per_sm < 1) return fail(RAGFIN_ECUDA, "scan kernel does not fit on an SM (smem %zu)", smem);
                     if (per_sm < per_sm_min) per_sm_min = per_sm;
                 }

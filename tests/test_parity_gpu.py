@@ -589,3 +589,32 @@ def test_filtered_search_through_the_shim():
     allhits = col.search(q, "embedding", {"metric_type": "COSINE"}, 2000, output_fields=["period"])[0]
     assert len(hits) == 7 and [h.id for h in hits] == [h.id for h in allhits if h.entity.period == "Q3_FY2024"][:7]
     mc.utility.drop_collection("filt")
+
+
+def test_concurrent_searches_on_one_handle(coracle):
+    """FastMCP runs sync tools on worker threads: concurrent search calls on one collection handle must
+    serialise inside the library and each return its own, correct hits."""
+    import threading
+    x = O.synth_rows(210, 0, 80000, 128, dup_every=71)
+    idx = _index(x, "bf16")
+    stored = coracle.normalize_rows(x, "bf16")
+    qs = [O.synth_rows(300 + t, 0, nq, 128) for t, nq in enumerate((1, 2, 7, 40))]
+    want = [coracle.cosine_topk(q, stored, 10) for q in qs]
+    errors = []
+
+    def worker(t):
+        try:
+            for _ in range(15):
+                got = idx.search(qs[t], 10)
+                if not (np.array_equal(got[0], want[t][0]) and np.array_equal(got[1].view(np.uint32), want[t][1].view(np.uint32))):
+                    errors.append(f"thread {t}: wrong hits")
+                    return
+        except Exception as e:   # noqa: BLE001
+            errors.append(f"thread {t}: {e!r}")
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
