@@ -170,10 +170,10 @@ int ragfin_set_gemm_min_batch(ragfin_t* h, int32_t min_nq);
 int ragfin_set_gemm_cluster(ragfin_t* h, int32_t cluster);
 
 /* Tuning knob: tcgen05 kernel variant. 1 = streaming (query and corpus tiles through shared memory, any
- * dtype / width); 2 = A-stationary (query tile resident in tensor memory; 16-bit storage, dim <= 768);
- * 3 = streaming, and batches of <= 16 queries in append mode run with the operand roles swapped (corpus rows are
- * the MMA's M dimension, the queries its N = 16: a sixteenth of the tensor work per byte); 0 = automatic.
- * Results are identical. */
+ * dtype / width); 2 = A-stationary (query tile resident in tensor memory; 16-bit storage, dim <= 768; measured
+ * slower); 3 = streaming, and batches of <= 16 queries in append mode run with the operand roles swapped (corpus
+ * rows are the MMA's M dimension, the queries its N = 16: a sixteenth of the tensor work per byte, full SM clock);
+ * 0 = automatic (default; currently 3).  Results are identical. */
 int ragfin_set_gemm_variant(ragfin_t* h, int32_t variant);
 
 /* Tuning knob: small-batch (1-2 query) scan kernel.  0 = automatic (default; currently 1), 1 = 128-bit register-path

@@ -1,4 +1,4 @@
-// K3r: tensor-core sweep for at most 16 queries with the operand roles SWAPPED (opt-in, append mode only).
+// K3r: tensor-core sweep for at most 16 queries with the operand roles SWAPPED (append mode only).
 //
 // gemm_topk_kernel makes the queries the MMA's M dimension, so one query still costs a full 128-row MMA per corpus
 // tile: at batch 1 the tensor pipe is 49 % busy multiplying zero padding and the GPU draws 370-440 W for an
@@ -7,16 +7,17 @@
 // bytes - and the epilogue thread (TMEM lane = corpus row) reads 16 scores per half tile instead of 256.
 //
 //   shared memory   query block [num_kblocks][16 rows x 128 B] resident for the whole sweep (one TMA burst)
-//                   + ring of `stages` (up to 6) corpus stages [256 rows x 128 B]: nothing but corpus bytes stream
-//   tensor memory   2 tiles x 2 halves x 16 fp32 columns (64 columns)
+//                   + ring of `stages` (up to 4) corpus stages [256 rows x 128 B]: nothing but corpus bytes stream
+//   tensor memory   2 tiles x 2 halves x 4 partial accumulators x 16 fp32 columns (256 columns)
 //   epilogue        v[j] >= thr[j]  ->  append (score, row) to query j's buffer (exactly MODE 3 of gemm.cuh)
 // Both operands are K-major SWIZZLE_128B tiles, so the corpus stages are the same TMA boxes as in gemm.cuh.
 //
-// MEASURED (10M x 768 bf16, k = 10, one B200): bit-exact, SM clock stays at 1.96 GHz (the standard orientation is
-// power-capped to ~1.1 GHz at batch 1), but SLOWER: 2.35 ms per call / sweep at 6 756 GB/s against 2.20 ms / 7 037 GB/s
-// at batches 1-16.  A tile now needs 96 MMA instructions (2 halves x 48 k-steps) instead of 48, and an N = 16 MMA
-// does not shrink with N: the single issuing thread becomes the bottleneck (~150 cycles per instruction against a
-// 15 k-cycle tile budget).  Kept as opt-in variant 3 (ragfin_set_gemm_variant); the standard orientation stays default.
+// MEASURED (10M x 768 bf16, k = 10, one B200, batch 1): 2.161 ms per call = 462.8 queries/s, sweep at 7 328 GB/s with
+// the SM clock at 1.965 GHz; the standard orientation on the same box: 2.19-2.26 ms, 7 050 GB/s, clock capped to
+// 1.1-1.2 GHz.  Two things had to be found first: (1) ring depth - 4 stages of 32 KB; with 5-6 stages (160-192 KB in
+// flight per SM) the sweep drops to 6.8 TB/s, with 2 to 6.46; (2) the four k-steps of a k-block accumulate into four
+// separate TMEM accumulators per half tile (summed in the epilogue) so that no MMA waits on the previous one's result.
+// Default for <= 16 queries in append mode (gemm variant 0 = automatic, 3 = forced; 1 = standard orientation).
 // The bound pass and finalize_append_kernel are shared with the main path; approximate scores need not be
 // bit-identical between the two orientations (DESIGN.md 2.4 only uses |approx - exact| <= eps).
 #pragma once
@@ -26,7 +27,10 @@ namespace rfk {
 
 constexpr int kRN = 16;                        // queries per sweep (UMMA N)
 constexpr int kRQBytes = kRN * kGKBytes;       // 2 KB: one k-block of the query block
-constexpr int kRMaxStages = 6;
+constexpr int kRMaxStages = 4;                 // measured: 3-4 stages 7.28-7.33 TB/s, 5-6 stages 6.8 TB/s, 2 stages 6.46 TB/s
+constexpr int kRSplit = 4;                     // partial accumulators per half tile = k-steps per k-block
+constexpr int kRAccCols = 2 * kRSplit * kRN;   // TMEM columns of one tile's accumulators (128)
+static_assert(kRSplit == kGKBytes / 32, "one partial accumulator per k-step of a k-block");
 
 __host__ __device__ constexpr int rows_stages(int num_kblocks) {
     const long avail = 227L * 1024 - 1024 - 256 - (long)num_kblocks * kRQBytes;
@@ -74,7 +78,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t smB = base + (uint32_t)nkb * kRQBytes;              // [stages][32 KB]  (2 KB multiples keep 1 KB alignment)
     uint64_t* bars = reinterpret_cast<uint64_t*>(rsm + (size_t)nkb * kRQBytes + (size_t)stages * kBBytes);
     const uint32_t bar0 = smem_u32(bars);
-    // barrier slots: full[0..6) empty[6..12) qfull[12] tmem_full[13..15) tmem_empty[15..17); tmem base at slot 17
+    // barrier slots: full[kRMaxStages] empty[kRMaxStages] qfull tmem_full[2] tmem_empty[2]; tmem base after them
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (kRMaxStages + s); };
     const uint32_t qfull_bar = bar0 + 8u * (2 * kRMaxStages);
@@ -89,8 +93,8 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {   // 2 tiles x 2 halves x 16 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    if (warp == 1) {   // 2 tiles x 2 halves x 4 partial accumulators x 16 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -140,12 +144,16 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                         tc_fence_after();
                         const uint64_t qd = make_smem_desc(smQ + (uint32_t)kb * kRQBytes);
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {   // corpus rows [128 h, 128 h + 128) of the tile are the M operand
-                            const uint64_t cd = make_smem_desc(smB + (uint32_t)stage * kBBytes + (uint32_t)h * (kBBytes / 2));
-                            const uint32_t d_tmem = tmem_base + (uint32_t)acc * 2 * kRN + (uint32_t)h * kRN;
+                        for (int k4 = 0; k4 < kGKBytes / 32; ++k4) {
+                            // An N = 16 MMA is ~8 tensor cycles but an accumulate into the SAME TMEM columns waits for the
+                            // previous one (~170 cycles measured): the four k-steps of a k-block go to four separate
+                            // accumulators per half (summed in the epilogue), giving eight independent chains.
 #pragma unroll
-                            for (int k4 = 0; k4 < kGKBytes / 32; ++k4)
-                                tc_mma<KIND>(d_tmem, cd + 2u * k4, qd + 2u * k4, a.idesc, (uint32_t)((kb | k4) != 0));
+                            for (int h = 0; h < 2; ++h) {   // corpus rows [128 h, 128 h + 128) of the tile are the M operand
+                                const uint64_t cd = make_smem_desc(smB + (uint32_t)stage * kBBytes + (uint32_t)h * (kBBytes / 2));
+                                const uint32_t d_tmem = tmem_base + (uint32_t)acc * kRAccCols + (uint32_t)h * (kRSplit * kRN) + (uint32_t)k4 * kRN;
+                                tc_mma<KIND>(d_tmem, cd + 2u * k4, qd + 2u * k4, a.idesc, (uint32_t)(kb != 0));
+                            }
                         }
                         tc_commit(empty_bar(stage));
                         if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -172,13 +180,15 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 const long long trow = r0 + (long long)t * kGN;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    uint32_t v[kRN];
-                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 2 * kRN + (uint32_t)h * kRN, v);
+                    uint32_t v[kRSplit][kRN];
+#pragma unroll
+                    for (int p = 0; p < kRSplit; ++p)
+                        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kRAccCols + (uint32_t)h * (kRSplit * kRN) + (uint32_t)p * kRN, v[p]);
                     const long long row = trow + h * 128 + m;
                     if (row < r1) {   // rows past the slice / corpus (zero-filled by TMA) never qualify
 #pragma unroll
                         for (int j = 0; j < kRN; ++j) {
-                            const float sc = __uint_as_float(v[j]);
+                            const float sc = (__uint_as_float(v[0][j]) + __uint_as_float(v[1][j])) + (__uint_as_float(v[2][j]) + __uint_as_float(v[3][j]));
                             if (sc >= thr[j]) {
                                 const uint32_t pos = atomicAdd(a.cnt + j, 1u);
                                 if (pos < (uint32_t)a.cap) a.cand[(size_t)j * a.cap + pos] = make_key(sc + 0.0f, (uint32_t)row);
@@ -196,7 +206,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem_base) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
     }
 }
 

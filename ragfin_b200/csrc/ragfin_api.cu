@@ -66,8 +66,8 @@ struct ragfin {
     int scan_variant = 0;         // small-batch scan: 0 = automatic (= 1, measured faster), 1 = LDG kernel, 2 = TMA-fed ring
     bool use_append = true;       // tcgen05 path: append mode (threshold from the bound pass, no lists) when eligible
     bool use_bound_pass = true;   // tcgen05 path: sample pass that seeds the per-query thresholds (RAGFIN_NO_BOUND_PASS=1 disables)
-    int gemm_variant = 1;     // 0 = automatic, 1 = streaming (A and B through shared memory), 2 = A-stationary (A in TMEM),
-                              // 3 = streaming + swapped operand roles for <= 16 queries (gemm_rows.cuh)
+    int gemm_variant = 0;     // 0 = automatic (= 3), 1 = streaming (A and B through shared memory), 2 = A-stationary (A in TMEM),
+                              // 3 = streaming + swapped operand roles for <= 16 queries in append mode (gemm_rows.cuh)
     struct MapSlot { const void* base = nullptr; int64_t rows = 0; int ld = 0, dtype = 0, box_rows = 0; CUtensorMap map; };
     MapSlot map_cache[8];     // tensor maps are pure functions of (base, rows, ld, dtype, box): encode once
     int map_next = 0;
@@ -675,7 +675,7 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
         CU_TRY(cudaGetLastError());
         h->stats.launches += 2;
     }
-    if (append && h->gemm_variant == 3 && nb <= kRN && C == 1 && rows_stages(a.num_kblocks) >= 3) {
+    if (append && (h->gemm_variant == 3 || h->gemm_variant == 0) && nb <= kRN && C == 1 && rows_stages(a.num_kblocks) >= 3) {
         // <= 16 queries, operand roles swapped (gemm_rows.cuh): corpus rows are the MMA's M, the queries its N = 16
         RowsArgs r;
         r.idesc = make_idesc_n(h->dtype == 0 ? 2 : h->dtype == 1 ? 1 : 0, kRN);
@@ -791,8 +791,8 @@ static int run_gemm_astat(ragfin* h, int nb, int kp, int* G, float* dump, cudaSt
 }
 
 static bool use_astat(const ragfin* h, int kp) {
-    if (h->gemm_variant == 1 || h->gemm_variant == 3) return false;
-    return astat_supported(h, kp);   // variant 2 (forced) and 0 (automatic) both need eligibility
+    if (h->gemm_variant != 2) return false;   // measured slower: only when asked for
+    return astat_supported(h, kp);
 }
 
 // ------------------------------------------------------------------------------
