@@ -161,8 +161,8 @@ int ragfin_save(ragfin_t* h, const char* path);
 int ragfin_load(ragfin_t** out, const char* path, int64_t capacity_rows, int32_t device);
 
 /* Dispatch knob: query batches of at least `min_nq` rows take the tcgen05 tensor-core path, smaller
- * ones the HBM-bound scan.  Default: 3, and 1 on corpora of >= 4 GiB (there the TMA-fed sweep is faster even for
- * one query: 2.22 vs 2.31 ms on 10M x 768 bf16).  Setting it overrides both; 0 restores the defaults.  Both paths return identical results. */
+ * ones the HBM-bound scan.  Default: 3, and 1 on corpora of >= 1 GiB (there the TMA-fed sweep is faster even for
+ * one query: 2.16 vs 2.31 ms on 10M x 768 bf16, 0.340 vs 0.355 ms on 1.25M rows).  Setting it overrides both; 0 restores the defaults.  Both paths return identical results. */
 int ragfin_set_gemm_min_batch(ragfin_t* h, int32_t min_nq);
 
 /* Tuning knob: thread-block cluster size of the tcgen05 path along the query-tile axis (corpus tiles

@@ -495,10 +495,11 @@ static bool gemm_supported(const ragfin* h, int kp) { return kp <= 128 && gemm_r
 
 // Scores the nb normalised queries in h->qhat against the corpus on the tensor cores.  Fills
 // h->cand as [nb][S][kp] (unsorted lists) and h->eps_q; returns S through *G.  dump != null: write raw scores instead.
-// Corpus size from which even 1-2 queries take the tensor-core sweep: its TMA ring keeps 192 KB per SM in flight
-// (7.4 TB/s against the LDG scan's 6.9), worth ~90 us per 15 GB, but it carries ~50 us more fixed cost per call
-// (bound pass, query conversion).  Measured 10M x 768 bf16, batch 1: 2.218 ms vs 2.313 ms.
-static const size_t kSweepBytes = (size_t)4 << 30;
+// Corpus size from which even 1-2 queries take the tensor-core sweep: its TMA ring streams at 7.3 TB/s against the
+// LDG scan's 6.9, but it carries ~35 us more fixed cost per call (bound pass, append finalize).  Measured (bf16,
+// 768-d, batch 1, whole call): 10M rows 2.16 vs 2.31 ms; 2.5M rows 0.606 vs 0.632 ms; 1.25M rows (1.9 GB, the shard
+// of the 8-GPU split) 0.340 vs 0.355 ms, batch 2: 0.339 vs 0.389 ms.
+static const size_t kSweepBytes = (size_t)1 << 30;
 
 static const int kAppendCap = 16384;   // append mode: keys one query may collect before it overflows to tier 2
 static const int kAppendMaxK = 256;    // largest k the append mode serves (tier 2, its overflow path, keeps 256 keys)
@@ -566,7 +567,10 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
         bstride = (n_tiles - 1) / ((int64_t)nblk * g);   // the last (possibly partial) tile is never sampled
         if (bstride < 1) bstride = 1;
     }
-    const int stages0 = append ? 4 : kp <= 32 ? 4 : kp <= 64 ? 3 : 2;
+    int stages0 = append ? 4 : kp <= 32 ? 4 : kp <= 64 ? 3 : 2;
+#ifdef RAGFIN_TIMING_EXPERIMENTS
+    { const char* e = getenv("RAGFIN_GEMM_STAGES"); if (e && atoi(e) >= 2 && atoi(e) <= stages0) stages0 = atoi(e); }
+#endif
     const int kp_smem = append ? 0 : kp;      // append mode keeps no lists in shared memory
     const size_t smem = gemm_smem_bytes(stages0, kp_smem);
     const int mode = dump ? 1 : append ? 3 : 0;
@@ -1089,7 +1093,7 @@ extern "C" int ragfin_debug_gemm_scores(ragfin_t* h, const float* q_dev, int32_t
     return mark_done(h, st);
 }
 
-// Dispatch knob: query batches of at least `min_nq` rows use the tcgen05 path (default 3, and 1 on corpora of >= 4 GiB; INT32_MAX = never).
+// Dispatch knob: query batches of at least `min_nq` rows use the tcgen05 path (default 3, and 1 on corpora of >= 1 GiB; INT32_MAX = never).
 extern "C" int ragfin_set_gemm_min_batch(ragfin_t* h, int32_t min_nq) {
     if (!h || min_nq < 0) return fail(RAGFIN_EINVAL, "bad argument");
     std::lock_guard<std::mutex> lk(h->mu);

@@ -108,7 +108,7 @@ def test_full_size_k100_stays_on_the_fast_path(corpus, coracle):
 
 
 def test_full_size_default_dispatch_sweeps_even_one_query(corpus):
-    """On a corpus of >= 4 GiB the default dispatch sends 1-2 queries through the TMA-fed tensor-core sweep
+    """On a corpus of >= 1 GiB the default dispatch sends 1-2 queries through the TMA-fed tensor-core sweep
     (faster than the LDG scan); forcing the scan must give the same bits."""
     idx, q = corpus
     idx.set_gemm_min_batch(0)                 # defaults
