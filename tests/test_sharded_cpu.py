@@ -66,3 +66,63 @@ def test_sharded_search_over_gloo(world, n, k):
     out = mp.get_context("spawn").Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), n, k, out), nprocs=world, join=True)
     assert dict(out) == {r: 1 for r in range(world)}
+
+
+class _GlooExchange:
+    """Stand-in for engine.PeerExchange (peer-memory stores need GPUs): same interface, the records travel through a
+    gloo all-gather.  Exercises ShardedSearcher's exchange branch: local hits written into per-(nq, k) buffers, one
+    collective call per step, fallback to the packed path when a record exceeds the exchange's capacity."""
+
+    def __init__(self, world, max_record_bytes):
+        self.world, self.max_record_bytes, self.steps = world, max_record_bytes, 0
+
+    def allgather_merge(self, ids, scores):
+        self.steps += 1
+        gi = [torch.empty_like(ids) for _ in range(self.world)]
+        gs = [torch.empty_like(scores) for _ in range(self.world)]
+        dist.all_gather(gi, ids)
+        dist.all_gather(gs, scores)
+        mi, ms = O.merge_topk([t.numpy() for t in gi], [t.numpy() for t in gs], ids.shape[1])
+        return torch.from_numpy(mi), torch.from_numpy(ms)
+
+
+def _worker_exchange(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n, dim = 300, 32
+        x = O.normalize_rows(O.synth_rows(31, 0, n, dim, dup_every=7), "f16")
+        row0, cnt = shard_bounds(n, world, rank)
+        calls = []
+
+        def local_search(queries, kk, out_ids=None, out_scores=None):
+            ids, sc = O.cosine_topk(queries.numpy(), x[row0:row0 + cnt], kk, id_base=row0)
+            calls.append((out_ids is not None, queries.shape[0], kk))
+            if out_ids is not None:                      # the exchange branch hands in its per-(nq, k) buffers
+                out_ids.copy_(torch.from_numpy(ids)); out_scores.copy_(torch.from_numpy(sc))
+                return out_ids, out_scores
+            return torch.from_numpy(ids), torch.from_numpy(sc)
+
+        def merge(ids, sc, parts, kk):
+            mi, ms = O.merge_topk([ids[p].numpy() for p in range(parts)], [sc[p].numpy() for p in range(parts)], kk)
+            return torch.from_numpy(mi), torch.from_numpy(ms)
+
+        ex = _GlooExchange(world, max_record_bytes=4 * 10 * 12)      # fits 4 queries x k = 10, not 9 x 10
+        s = ShardedSearcher(local_search, merge, exchange=ex)
+        ok = True
+        for nq in (4, 4, 9, 1):
+            q = O.synth_rows(40 + nq, 0, nq, dim)
+            ids, sc = s.search(torch.from_numpy(q), 10)
+            wi, ws = O.cosine_topk(q, x, 10)
+            ok &= np.array_equal(ids.numpy(), wi) and np.array_equal(sc.numpy().view(np.uint32), ws.view(np.uint32))
+        ok &= ex.steps == 3                                           # the 9-query batch took the all-gather path
+        ok &= [c[0] for c in calls] == [True, True, False, True]
+        out[rank] = int(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchange_branch_and_its_fallback_over_gloo():
+    out = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_worker_exchange, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert dict(out) == {0: 1, 1: 1}
