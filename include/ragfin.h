@@ -114,7 +114,8 @@ int ragfin_merge_topk(const int64_t* ids, const float* scores, int32_t nq, int32
                       int64_t* out_ids, float* out_scores, int32_t device, void* stream);
 
 /* Cross-shard exchange over NVLink peer memory, one process per GPU on one box - the fused alternative to
- * "NCCL all-gather + ragfin_merge_topk".  Every rank allocates a gather area, publishes its CUDA IPC handle, and
+ * "NCCL all-gather + ragfin_merge_topk" (like it, it stands in for the querynode -> proxy top-k reduce of a sharded
+ * Milvus deployment of the reference; that reduce is not in the reference repository).  Every rank allocates a gather area, publishes its CUDA IPC handle, and
  * opens its peers' (ragfin_exchange_connect takes the `world` handles, RAGFIN_IPC_HANDLE_BYTES each, in rank order;
  * the caller moves them between processes, e.g. torch.distributed.all_gather_object, and runs a barrier after
  * connect and before destroy).  ragfin_exchange_allgather_merge then STORES this rank's exact hits {ids [nq,k] |
