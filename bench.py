@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--also-batch", type=int, default=4096,
                     help="second regime measured in the same run and reported under 'regimes' (0 = off)")
     ap.add_argument("--gemm-cluster", type=int, default=0, help="tcgen05 path cluster size: 0 auto, 1, 2 or 4")
-    ap.add_argument("--gemm-variant", type=int, default=-1, help="tcgen05 kernel: 0 auto, 1 streaming, 2 A-stationary, 3 swapped roles for <= 16 queries (-1 = library default)")
+    ap.add_argument("--gemm-variant", type=int, default=-1, help="tcgen05 kernel: 0 auto, 1 streaming, 2 A-stationary, 3 swapped roles for <= 16 queries, 4 experimental 2-SM pairs (-1 = library default)")
     ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="rows of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -334,7 +334,7 @@ def run_ours(a):
         else:                 # tensor-bound GEMM: algorithmic flops = 2 * nq * shard rows * dim per launch
             alg = 2.0 * batch * shard_rows * a.dim
             achieved = alg / (kern_avg_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "gemm_topk_kernel", "achieved": achieved, "peak": peaks["bf16"],
+            roof = {"bound": "tensor", "kernel": "gemm_pair_kernel" if a.gemm_variant == 4 and batch > 128 else "gemm_topk_kernel", "achieved": achieved, "peak": peaks["bf16"],
                     "unit": "TFLOP/s", "frac": achieved / peaks["bf16"], "algorithmic_flops_per_launch": alg,
                     "frac_of_sustained_peak": achieved / peaks["bf16_sustained"] if peaks.get("bf16_sustained") else None}
         roof.update({"kernel_ms_avg": kern_avg_ms, "kernel_launches_timed": kern_n, "peak_source": peaks["source"],

@@ -174,7 +174,10 @@ int ragfin_set_gemm_cluster(ragfin_t* h, int32_t cluster);
  * dtype / width); 2 = A-stationary (query tile resident in tensor memory; 16-bit storage, dim <= 768; measured
  * slower); 3 = streaming, and batches of <= 16 queries in append mode run with the operand roles swapped (corpus
  * rows are the MMA's M dimension, the queries its N = 16: a sixteenth of the tensor work per byte, full SM clock);
- * 0 = automatic (default; currently 3).  Results are identical. */
+ * 4 = EXPERIMENTAL, never chosen automatically and not yet run on a GPU (written after the round's GPU budget was
+ * spent; scripts/pair_check.py is its first test): batches of >= 2 query tiles in append mode sweep with a 2-SM MMA
+ * (tcgen05 cta_group::2, M = 256: each CTA of a pair holds its own query tile and half of the corpus tile);
+ * 0 = automatic (default; currently 3).  Results are identical (variants 0-3: tested; 4: to be shown). */
 int ragfin_set_gemm_variant(ragfin_t* h, int32_t variant);
 
 /* Tuning knob: small-batch (1-2 query) scan kernel.  0 = automatic (default; currently 1), 1 = 128-bit register-path

@@ -15,6 +15,7 @@
 #include "gemm.cuh"
 #include "gemm_astat.cuh"
 #include "gemm_rows.cuh"
+#include "gemm_pair.cuh"
 #include "scan_tma.cuh"
 #include "bigk.cuh"
 
@@ -67,7 +68,8 @@ struct ragfin {
     bool use_append = true;       // tcgen05 path: append mode (threshold from the bound pass, no lists) when eligible
     bool use_bound_pass = true;   // tcgen05 path: sample pass that seeds the per-query thresholds (RAGFIN_NO_BOUND_PASS=1 disables)
     int gemm_variant = 0;     // 0 = automatic (= 3), 1 = streaming (A and B through shared memory), 2 = A-stationary (A in TMEM),
-                              // 3 = streaming + swapped operand roles for <= 16 queries in append mode (gemm_rows.cuh)
+                              // 3 = streaming + swapped operand roles for <= 16 queries in append mode (gemm_rows.cuh),
+                              // 4 = EXPERIMENTAL 2-SM MMA pairs for >= 2 query tiles in append mode (gemm_pair.cuh; not yet run on a GPU)
     struct MapSlot { const void* base = nullptr; int64_t rows = 0; int ld = 0, dtype = 0, box_rows = 0; CUtensorMap map; };
     MapSlot map_cache[8];     // tensor maps are pure functions of (base, rows, ld, dtype, box): encode once
     int map_next = 0;
@@ -523,6 +525,8 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
     // measured on 10M x 768 bf16 (profiles/r01): pairs use all 148 SMs and win from 1024 queries up (49.7 vs 53.1 ms
     // at 4096); quads strand 16 SMs but read each corpus tile once, which wins at 3-7 query tiles (6.35 vs 6.80 ms at 512)
     int C = h->gemm_cluster ? h->gemm_cluster : (QT0 >= 8 ? 2 : QT0 >= 3 ? 4 : QT0 >= 2 ? 2 : 1);
+    const bool want_pair = h->gemm_variant == 4 && QT0 >= 2;   // experimental 2-SM MMA sweep: pairs of query tiles
+    if (want_pair) C = 2;
     typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const GemmArgs);
 #define RF_PICK_MODE(KIND, CC) (mode == 0 ? gemm_topk_kernel<KIND, 0, CC> : mode == 1 ? gemm_topk_kernel<KIND, 1, CC> : mode == 2 ? gemm_topk_kernel<KIND, 2, CC> : gemm_topk_kernel<KIND, 3, CC>)
     auto pick = [&](int c, int mode) -> gemm_fn {
@@ -694,6 +698,20 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
         if ((rc = set_dyn_smem(h->device, (const void*)rfn, rsmem))) return rc;
         prof_begin(h, st);
         rfn<<<p.grid, kGemmThreads, rsmem, st>>>(tmQ, tmB, r);
+        prof_end(h, st);
+    } else if (want_pair && C == 2 && (append || dump)) {
+        // EXPERIMENTAL (gemm variant 4, gemm_pair.cuh): one M = 256 MMA per cluster, each CTA holds half of the corpus tile
+        GemmArgs pa = a;
+        pa.idesc = make_idesc_pair(h->dtype == 0 ? 2 : h->dtype == 1 ? 1 : 0);
+        pa.stages = kPMaxStages;
+        gemm_fn pfn = h->dtype == 0 ? (dump ? gemm_pair_kernel<1, 1> : gemm_pair_kernel<1, 3>)
+                                    : (dump ? gemm_pair_kernel<0, 1> : gemm_pair_kernel<0, 3>);
+        const size_t psmem = pair_smem_bytes(pa.stages);
+        if ((rc = set_dyn_smem(h->device, (const void*)pfn, psmem))) return rc;
+        cfg.dynamicSmemBytes = psmem;
+        cfg.gridDim = dim3(p.grid);
+        prof_begin(h, st);
+        CU_TRY(cudaLaunchKernelEx(&cfg, pfn, tmA, tmB, pa));
         prof_end(h, st);
     } else {
         cfg.gridDim = dim3(p.grid);
@@ -1127,9 +1145,10 @@ extern "C" int ragfin_set_scan_variant(ragfin_t* h, int32_t variant) {
     return RAGFIN_OK;
 }
 
-// Tuning knob: which tcgen05 kernel serves large batches (0 automatic, 1 streaming, 2 A-stationary when eligible).
+// Tuning knob: which tcgen05 kernel serves large batches (0 automatic, 1 streaming, 2 A-stationary when eligible,
+// 3 swapped roles for <= 16 queries, 4 EXPERIMENTAL 2-SM MMA pairs for >= 2 query tiles in append mode).
 extern "C" int ragfin_set_gemm_variant(ragfin_t* h, int32_t variant) {
-    if (!h || variant < 0 || variant > 3) return fail(RAGFIN_EINVAL, "variant must be 0, 1, 2 or 3");
+    if (!h || variant < 0 || variant > 4) return fail(RAGFIN_EINVAL, "variant must be 0, 1, 2, 3 or 4");
     std::lock_guard<std::mutex> lk(h->mu);
     h->gemm_variant = variant;
     return RAGFIN_OK;

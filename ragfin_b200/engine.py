@@ -93,8 +93,12 @@ class Index:
                     raise ValueError(f"rows live on cuda:{rows.device.index}, index on cuda:{self.device}")
                 rows = rows.to(torch.float32).contiguous()
                 with torch.cuda.device(self.device):
+                    if stream is None:
+                        stream = torch.cuda.current_stream()
+                    elif not hasattr(stream, "synchronize"):      # a raw cudaStream_t
+                        stream = torch.cuda.ExternalStream(int(stream))
                     _lib.check(self._L.ragfin_add(self._h, rows.data_ptr(), rows.shape[0], 1, _stream_ptr(stream)))
-                    torch.cuda.current_stream().synchronize()  # `rows` may be freed by the caller
+                    stream.synchronize()  # `rows` may be freed by the caller
                 return
         a = np.ascontiguousarray(rows, dtype=np.float32)
         if a.ndim == 1:
@@ -180,7 +184,8 @@ class Index:
         return out_ids, out_scores
 
     def set_gemm_min_batch(self, min_nq: int) -> None:
-        """Query batches of at least `min_nq` rows use the tcgen05 path (default 5)."""
+        """Query batches of at least `min_nq` rows use the tcgen05 path (0 restores the defaults: 3, and 1 on
+        corpora of >= 1 GiB)."""
         _lib.check(self._L.ragfin_set_gemm_min_batch(self._h, int(min_nq)))
 
     def set_gemm_cluster(self, cluster: int) -> None:
@@ -189,7 +194,8 @@ class Index:
 
     def set_gemm_variant(self, variant: int) -> None:
         """tcgen05 kernel variant: 0 automatic, 1 streaming, 2 A-stationary (query tile in tensor memory),
-        3 streaming with swapped operand roles for batches of <= 16 queries."""
+        3 streaming with swapped operand roles for batches of <= 16 queries, 4 EXPERIMENTAL 2-SM MMA pairs
+        (csrc/gemm_pair.cuh; not yet run on a GPU, never chosen automatically)."""
         _lib.check(self._L.ragfin_set_gemm_variant(self._h, int(variant)))
 
     def set_bound_pass(self, enable: bool) -> None:
