@@ -24,6 +24,25 @@ using namespace rfk;
 // ------------------------------------------------------------------------------
 // error plumbing: thread-local message, negative codes, no exceptions across the ABI
 // ------------------------------------------------------------------------------
+// Launch helper for the kernels of a search call that begin with pdl_wait() (common.cuh).  Default build: a plain
+// <<<>>> launch.  -DRAGFIN_PDL (experimental, not yet measured): programmatic stream serialization, so the kernel's
+// CTAs may be scheduled while its predecessor drains.
+#ifdef RAGFIN_PDL
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#define RF_LAUNCH(kern, grid, block, smem, st, ...) launch_pdl(kern, dim3(grid), dim3(block), smem, st, __VA_ARGS__)
+#else
+#define RF_LAUNCH(kern, grid, block, smem, st, ...) kern<<<grid, block, smem, st>>>(__VA_ARGS__)
+#endif
+
 static thread_local char g_err[512] = "";
 
 static int fail(int code, const char* fmt, ...) {
@@ -657,10 +676,15 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+#ifdef RAGFIN_PDL   // gemm_topk_kernel / gemm_pair_kernel call pdl_wait() after their setup
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+#endif
 
     if (bound) {
         const int groups = (p.QT + C - 1) / C;
@@ -677,7 +701,7 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
         const int64_t items = (int64_t)groups * nblk;
         cfg.gridDim = dim3((unsigned)(items < clusters ? items : clusters) * C);
         CU_TRY(cudaLaunchKernelEx(&cfg, bfn, tmA, tmB, b));
-        bound_select_kernel<<<nb, 256, 0, st>>>((const float*)h->bmax.p, nblk, rank, append ? nullptr : (uint32_t*)h->gtau.p,
+        RF_LAUNCH(bound_select_kernel, nb, 256, 0, st, (const float*)h->bmax.p, nblk, rank, append ? nullptr : (uint32_t*)h->gtau.p,
                                                  append ? (float*)h->athr.p : nullptr, append ? (uint32_t*)h->acnt.p : nullptr,
                                                  eps_gemm_const(h->dtype, h->ld), (const float*)h->eps_q.p);
         CU_TRY(cudaGetLastError());
@@ -697,7 +721,7 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
         const size_t rsmem = rows_smem_bytes(r.num_kblocks, r.stages);
         if ((rc = set_dyn_smem(h->device, (const void*)rfn, rsmem))) return rc;
         prof_begin(h, st);
-        rfn<<<p.grid, kGemmThreads, rsmem, st>>>(tmQ, tmB, r);
+        RF_LAUNCH(rfn, p.grid, kGemmThreads, rsmem, st, tmQ, tmB, r);
         prof_end(h, st);
     } else if (want_pair && C == 2 && (append || dump)) {
         // EXPERIMENTAL (gemm variant 4, gemm_pair.cuh): one M = 256 MMA per cluster, each CTA holds half of the corpus tile
@@ -904,9 +928,9 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
             const int wpb = 8, blocks = (nbq + wpb - 1) / wpb;
             const float* qsrc = q_dev + (size_t)q0 * h->dim;
             switch (prepped ? h->dtype : 0) {
-                case 0: prep_queries_kernel<0><<<blocks, wpb * 32, 0, st>>>(qsrc, nb, nbq, h->dim, h->ld, qhat, nullptr, (float*)h->eps_q.p, flag_count, (uint32_t*)h->gtau.p); break;
-                case 1: prep_queries_kernel<1><<<blocks, wpb * 32, 0, st>>>(qsrc, nb, nbq, h->dim, h->ld, qhat, (__nv_bfloat16*)h->q16.p, (float*)h->eps_q.p, flag_count, (uint32_t*)h->gtau.p); break;
-                default: prep_queries_kernel<2><<<blocks, wpb * 32, 0, st>>>(qsrc, nb, nbq, h->dim, h->ld, qhat, (__half*)h->q16.p, (float*)h->eps_q.p, flag_count, (uint32_t*)h->gtau.p); break;
+                case 0: RF_LAUNCH(prep_queries_kernel<0>, blocks, wpb * 32, 0, st, qsrc, nb, nbq, h->dim, h->ld, qhat, nullptr, (float*)h->eps_q.p, flag_count, (uint32_t*)h->gtau.p); break;
+                case 1: RF_LAUNCH(prep_queries_kernel<1>, blocks, wpb * 32, 0, st, qsrc, nb, nbq, h->dim, h->ld, qhat, (__nv_bfloat16*)h->q16.p, (float*)h->eps_q.p, flag_count, (uint32_t*)h->gtau.p); break;
+                default: RF_LAUNCH(prep_queries_kernel<2>, blocks, wpb * 32, 0, st, qsrc, nb, nbq, h->dim, h->ld, qhat, (__half*)h->q16.p, (float*)h->eps_q.p, flag_count, (uint32_t*)h->gtau.p); break;
             }
             CU_TRY(cudaGetLastError());
             h->stats.launches++;
@@ -973,7 +997,7 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
                     scan_fn fn = pick_scan(h->dtype, nqt, steps);
                     const size_t smem = (size_t)nqt * kScanWarps * kp * sizeof(u64);
                     prof_begin(h, st);
-                    fn<<<G, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat + (size_t)g0 * h->ld, left < nqt ? left : nqt, kp,
+                    RF_LAUNCH(fn, G, kScanThreads, smem, st, h->data, n, h->ld, qhat + (size_t)g0 * h->ld, left < nqt ? left : nqt, kp,
                                                        (u64*)h->cand.p + (size_t)g0 * G * kp,
                                                        (int64_t)G * kp, h->cur_allow);
                     prof_end(h, st);
@@ -985,13 +1009,13 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
         }
         // 3. merge + exact rescore + certificate (an unscanned, non-empty corpus flags every query)
         if (appended) {
-            finalize_append_kernel<<<nb, kFaThreads, 0, st>>>(
+            RF_LAUNCH(finalize_append_kernel, nb, kFaThreads, 0, st,
                 (const u64*)h->cand.p, (const uint32_t*)h->acnt.p, kAppendCap, h->data, h->dtype, n_eff, h->ld, qhat, eps, eps_q, k,
                 h->id_base, out_ids + (size_t)q0 * k, out_scores + (size_t)q0 * k, flags, flag_count);
             CU_TRY(cudaGetLastError());
             h->stats.launches++;
         } else {
-            finalize_kernel<false><<<nb, kFinThreads, 0, st>>>(
+            RF_LAUNCH(finalize_kernel<false>, nb, kFinThreads, 0, st,
                 (const u64*)h->cand.p, G, kp, h->data, h->dtype, n_eff, (scanned || n == 0) ? 1 : 0, sorted_lists,
                 sorted_lists ? nullptr : (const uint32_t*)h->gtau.p, h->ld, qhat, eps, eps_q, k, h->id_base, out_ids + (size_t)q0 * k, out_scores + (size_t)q0 * k, flags, flag_count);
             CU_TRY(cudaGetLastError());
@@ -1003,12 +1027,12 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
             if ((rc = ensure(h->cand_e, (size_t)nb * Ge * kpe * sizeof(u64)))) return rc;
             const size_t smem = (size_t)kScanWarps * kpe * sizeof(u64);
             switch (h->dtype) {
-                case 0: exact_scan_kernel<0><<<Ge, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat, nb, flags, flag_count, kpe, (u64*)h->cand_e.p, h->cur_allow); break;
-                case 1: exact_scan_kernel<1><<<Ge, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat, nb, flags, flag_count, kpe, (u64*)h->cand_e.p, h->cur_allow); break;
-                default: exact_scan_kernel<2><<<Ge, kScanThreads, smem, st>>>(h->data, n, h->ld, qhat, nb, flags, flag_count, kpe, (u64*)h->cand_e.p, h->cur_allow); break;
+                case 0: RF_LAUNCH(exact_scan_kernel<0>, Ge, kScanThreads, smem, st, h->data, n, h->ld, qhat, nb, flags, flag_count, kpe, (u64*)h->cand_e.p, h->cur_allow); break;
+                case 1: RF_LAUNCH(exact_scan_kernel<1>, Ge, kScanThreads, smem, st, h->data, n, h->ld, qhat, nb, flags, flag_count, kpe, (u64*)h->cand_e.p, h->cur_allow); break;
+                default: RF_LAUNCH(exact_scan_kernel<2>, Ge, kScanThreads, smem, st, h->data, n, h->ld, qhat, nb, flags, flag_count, kpe, (u64*)h->cand_e.p, h->cur_allow); break;
             }
             CU_TRY(cudaGetLastError());
-            finalize_kernel<true><<<nb, kFinThreads, 0, st>>>((const u64*)h->cand_e.p, Ge, kpe, h->data, h->dtype, n_eff, 1, 1, nullptr,
+            RF_LAUNCH(finalize_kernel<true>, nb, kFinThreads, 0, st, (const u64*)h->cand_e.p, Ge, kpe, h->data, h->dtype, n_eff, 1, 1, nullptr,
                                                               h->ld, qhat, 0.0f, nullptr, k, h->id_base,
                                                                 out_ids + (size_t)q0 * k, out_scores + (size_t)q0 * k,
                                                                 flags, flag_count);
