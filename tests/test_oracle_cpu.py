@@ -159,3 +159,26 @@ def test_fast_cpu_port_within_1e5_of_canonical(coracle):
         gi, gs = fast_cpu.fast_topk(torch.from_numpy(st), q, 10)
         assert np.array_equal(np.sort(gi, axis=1), np.sort(wi, axis=1))
         assert np.allclose(gs, ws, rtol=1e-5, atol=1e-7)
+
+
+def test_oracle_agrees_with_third_party_brute_force_cosine():
+    """Independent check of the restated semantics (the oracle is otherwise pinned only to itself): scikit-learn's
+    brute-force cosine k-NN and scipy's cosine distance - third-party implementations of "cosine similarity, larger
+    is better, k best in descending order" on RAW (un-normalised) fp32 rows, the way a COSINE collection is fed
+    (reference "chunking_storing (1).py":29,383-396 and retrieve.py:28-34).  Same index lists on tie-free data,
+    similarity = 1 - distance within fp32 accuracy."""
+    from scipy.spatial.distance import cdist
+    from sklearn.neighbors import NearestNeighbors
+    rng = np.random.default_rng(7)
+    x = (O.synth_rows(41, 0, 5000, 384) * rng.uniform(0.1, 30.0, size=(5000, 1))).astype(np.float32)   # norms all over the place
+    q = (O.synth_rows(42, 0, 9, 384) * rng.uniform(0.5, 4.0, size=(9, 1))).astype(np.float32)
+    k = 10
+    wi, ws = O.cosine_topk(q, O.normalize_rows(x, "f32"), k)
+    nn = NearestNeighbors(n_neighbors=k, metric="cosine", algorithm="brute").fit(x.astype(np.float64))
+    dist, ind = nn.kneighbors(q.astype(np.float64))
+    assert np.array_equal(ind, wi)
+    assert np.allclose(1.0 - dist, ws, rtol=1e-5, atol=1e-6)
+    d = cdist(q.astype(np.float64), x.astype(np.float64), metric="cosine")
+    order = np.argsort(d, axis=1, kind="stable")[:, :k]
+    assert np.array_equal(order, wi)
+    assert np.allclose(1.0 - np.take_along_axis(d, order, axis=1), ws, rtol=1e-5, atol=1e-6)
