@@ -1,0 +1,62 @@
+"""GPU parity of the opt-in variants that have NOT yet run on a GPU (written after round 1's GPU budget was spent).
+
+Skipped unless RAGFIN_EXPERIMENTAL=1: a kernel nobody has executed must not be able to hang or fail the round-end
+`pytest -m gpu` run.  Once scripts/pair_check.py / scripts/pdl_check.py have passed on a B200, drop the gate.
+    RAGFIN_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_experimental_gpu.py -m gpu -x -q
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ragfin_oracle as O
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("RAGFIN_EXPERIMENTAL") != "1", reason="unverified variants: set RAGFIN_EXPERIMENTAL=1"),
+              pytest.mark.timeout(120)]
+
+
+def _assert_same(got, want, what=""):
+    gi, gs = got
+    wi, ws = want
+    assert np.array_equal(gi, wi), f"{what}: ids differ\n{gi}\n{wi}"
+    assert np.array_equal(gs.view(np.uint32), ws.view(np.uint32)), f"{what}: score bits differ\n{gs}\n{ws}"
+
+
+@pytest.mark.parametrize("dtype", O.DTYPES)
+@pytest.mark.parametrize("n,dim,nq,k", [(30000, 768, 256, 10), (20011, 384, 130, 5), (50000, 128, 1000, 10), (120000, 768, 513, 100),
+                                        (66000, 100, 257, 10), (40000, 1024, 384, 1)])
+def test_two_sm_mma_sweep_matches_oracle(coracle, dtype, n, dim, nq, k):
+    """Variant 4 (csrc/gemm_pair.cuh): >= 2 query tiles in append mode sweep with tcgen05 cta_group::2 pairs; odd tile
+    counts leave the second CTA of the last pair on zero padding.  Same bits as the oracle and as variant 1."""
+    import ragfin_b200
+    x = O.synth_rows(296, 0, n, dim, dup_every=61, zero_every=1999)
+    q = O.synth_rows(297, 0, nq, dim)
+    x[4000:4030] = q[2] * 2.0        # 30 exact duplicates of one query: ties resolved by row id
+    want = coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), k)
+    idx = ragfin_b200.Index(dim, dtype, capacity=n, device=0)
+    idx.add(x)
+    idx.set_gemm_min_batch(1)
+    idx.set_gemm_variant(4)
+    got = idx.search(q, k)
+    st = idx.stats()
+    assert st["path"] == 1 and st["queries_rescanned"] == 0
+    _assert_same(got, want, f"2-SM pairs {dtype} n={n} dim={dim} nq={nq} k={k}")
+    idx.set_gemm_variant(1)
+    _assert_same(idx.search(q, k), want, "single-CTA MMA")
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+def test_two_sm_mma_raw_scores_equal_single_cta(dtype):
+    import torch
+    import ragfin_b200
+    x = O.synth_rows(5, 0, 5000, 768)
+    q = torch.from_numpy(O.synth_rows(6, 0, 300, 768)).cuda()
+    idx = ragfin_b200.Index(768, dtype, capacity=5000, device=0)
+    idx.add(x)
+    idx.set_gemm_variant(1)
+    idx.set_gemm_cluster(2)
+    base = idx.debug_gemm_scores(q).cpu()
+    idx.set_gemm_variant(4)
+    got = idx.debug_gemm_scores(q).cpu()
+    assert torch.equal(got, base)     # same k-order per output element
