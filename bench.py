@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--also-batch", type=int, default=4096,
                     help="second regime measured in the same run and reported under 'regimes' (0 = off)")
     ap.add_argument("--gemm-cluster", type=int, default=0, help="tcgen05 path cluster size: 0 auto, 1, 2 or 4")
-    ap.add_argument("--gemm-variant", type=int, default=-1, help="tcgen05 kernel: 0 auto, 1 streaming, 2 A-stationary, 3 swapped roles for <= 16 queries, 4 experimental 2-SM pairs (-1 = library default)")
+    ap.add_argument("--gemm-variant", type=int, default=-1, help="tcgen05 kernel: 0 auto, 1 streaming, 2 A-stationary, 3 swapped roles for <= 16 queries, 4 experimental 2-SM pairs, 5 experimental self-seeded sweep (-1 = library default)")
     ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="rows of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -327,7 +327,8 @@ def run_ours(a):
             alg = shard_rows * ld * esize
             achieved = alg / (kern_avg_ms * 1e-3) / 1e9
             # <= 16 queries run the swapped-role kernel unless a variant is forced (csrc/gemm_rows.cuh)
-            kname = "scan_topk_kernel" if st["path"] == 0 else ("gemm_rows_kernel" if batch <= 16 and a.gemm_variant in (-1, 0, 3) else "gemm_topk_kernel")
+            kname = ("scan_topk_kernel" if st["path"] == 0 else "gemm_rows_kernel" if batch <= 16 and a.gemm_variant in (-1, 0, 3)
+                     else "gemm_rows_seeded_kernel" if batch <= 16 and a.k <= 16 and a.gemm_variant == 5 else "gemm_topk_kernel")
             roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": achieved / peaks["hbm"], "algorithmic_bytes_per_launch": alg,
                     "frac_of_nominal_8TBps": achieved / 8000.0}

@@ -177,7 +177,10 @@ int ragfin_set_gemm_cluster(ragfin_t* h, int32_t cluster);
  * 4 = EXPERIMENTAL, never chosen automatically and not yet run on a GPU (written after the round's GPU budget was
  * spent; scripts/pair_check.py is its first test): batches of >= 2 query tiles in append mode sweep with a 2-SM MMA
  * (tcgen05 cta_group::2, M = 256: each CTA of a pair holds its own query tile and half of the corpus tile);
- * 0 = automatic (default; currently 3).  Results are identical (variants 0-3: tested; 4: to be shown). */
+ * 5 = EXPERIMENTAL, same status as 4: variant 3 with the bound pass inside the sweep for k <= 16 (every CTA samples the
+ * head of its first slice, a grid-wide barrier under a cooperative launch, thresholds computed in the kernel: two
+ * launches fewer per call; scripts/seeded_check.py);
+ * 0 = automatic (default; currently 3).  Results are identical (variants 0-3: tested; 4, 5: to be shown). */
 int ragfin_set_gemm_variant(ragfin_t* h, int32_t variant);
 
 /* Tuning knob: small-batch (1-2 query) scan kernel.  0 = automatic (default; currently 1), 1 = 128-bit register-path

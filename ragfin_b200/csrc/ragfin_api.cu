@@ -16,6 +16,7 @@
 #include "gemm_astat.cuh"
 #include "gemm_rows.cuh"
 #include "gemm_pair.cuh"
+#include "gemm_rows_seeded.cuh"
 #include "scan_tma.cuh"
 #include "bigk.cuh"
 
@@ -89,6 +90,9 @@ struct ragfin {
     int gemm_variant = 0;     // 0 = automatic (= 3), 1 = streaming (A and B through shared memory), 2 = A-stationary (A in TMEM),
                               // 3 = streaming + swapped operand roles for <= 16 queries in append mode (gemm_rows.cuh),
                               // 4 = EXPERIMENTAL 2-SM MMA pairs for >= 2 query tiles in append mode (gemm_pair.cuh; not yet run on a GPU)
+                              // 5 = EXPERIMENTAL self-seeded sweep for <= 16 queries, k <= 16 (gemm_rows_seeded.cuh; not yet run on a GPU)
+    Buf gbar;                 // variant 5: grid-wide arrival counter (monotonic) ...
+    uint32_t gbar_target = 0; // ... and the value it reaches once the last launch's CTAs have all arrived
     struct MapSlot { const void* base = nullptr; int64_t rows = 0; int ld = 0, dtype = 0, box_rows = 0; CUtensorMap map; };
     MapSlot map_cache[8];     // tensor maps are pure functions of (base, rows, ld, dtype, box): encode once
     int map_next = 0;
@@ -196,7 +200,7 @@ extern "C" void ragfin_destroy(ragfin_t* h) {
     if (!h) return;
     DeviceGuard g(h->device);
     (void)cudaDeviceSynchronize();
-    Buf* bufs[] = {&h->qhat, &h->q16, &h->eps_q, &h->gtau, &h->bmax, &h->acnt, &h->athr, &h->allow, &h->bk_scores, &h->bk_state, &h->bk_keys, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage};
+    Buf* bufs[] = {&h->qhat, &h->q16, &h->eps_q, &h->gtau, &h->bmax, &h->acnt, &h->athr, &h->allow, &h->bk_scores, &h->bk_state, &h->bk_keys, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage, &h->gbar};
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->data) cudaFree(h->data);
@@ -686,7 +690,19 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
     cfg.numAttrs = 2;
 #endif
 
-    if (bound) {
+    // EXPERIMENTAL (gemm variant 5, gemm_rows_seeded.cuh): the <= 16-query sweep computes its own thresholds from the head
+    // tiles of every CTA's first slice, behind a grid-wide barrier (cooperative launch) - no bound-pass launches
+    int seed_tiles = 0;
+    if (append && h->gemm_variant == 5 && nb <= kRN && C == 1 && k <= kSeedMaxK && p.grid <= p.S) {
+        const int64_t want_tiles = (n_tiles + 255) / 256;                      // >= 1/256 of the corpus, like the bound pass
+        seed_tiles = (int)((want_tiles + p.grid - 1) / p.grid);
+        if (seed_tiles < 1) seed_tiles = 1;
+        if (seed_tiles > kSeedMaxSampleTiles) seed_tiles = kSeedMaxSampleTiles;
+        const long avail = 227L * 1024 - 1024 - 256 - (long)a.num_kblocks * kRQBytes - (long)seeded_extra_smem(p.grid, seed_tiles);
+        if (avail / kBBytes < 3 || (int64_t)p.grid * 2 * seed_tiles < 2 * (int64_t)k) seed_tiles = 0;   // not eligible
+    }
+    const bool seeded = seed_tiles > 0;
+    if (bound && !seeded) {
         const int groups = (p.QT + C - 1) / C;
         const int clusters = C > 1 ? resident_clusters : h->num_sms;
         GemmArgs b = a;
@@ -707,7 +723,45 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
         CU_TRY(cudaGetLastError());
         h->stats.launches += 2;
     }
-    if (append && (h->gemm_variant == 3 || h->gemm_variant == 0) && nb <= kRN && C == 1 && rows_stages(a.num_kblocks) >= 3) {
+    if (seeded) {
+        SeededArgs sa;
+        RowsArgs& r = sa.r;
+        r.idesc = make_idesc_n(h->dtype == 0 ? 2 : h->dtype == 1 ? 1 : 0, kRN);
+        r.num_kblocks = a.num_kblocks; r.k_elems = a.k_elems; r.nq = nb; r.n_rows = n;
+        r.S = p.S; r.rows_per_slice = p.rows_per_slice;
+        const size_t extra = seeded_extra_smem(p.grid, seed_tiles);
+        const long avail = 227L * 1024 - 1024 - 256 - (long)r.num_kblocks * kRQBytes - (long)extra;
+        r.stages = (int)(avail / kBBytes) > kRMaxStages ? kRMaxStages : (int)(avail / kBBytes);
+        r.cand = a.cand; r.thr = nullptr; r.cnt = a.cnt; r.cap = a.cap;
+        const int nblk_s = p.grid * 2 * seed_tiles;
+        if ((rc = ensure(h->bmax, (size_t)nb * nblk_s * sizeof(float)))) return rc;
+        if (!h->gbar.p) {
+            if ((rc = ensure(h->gbar, sizeof(uint32_t)))) return rc;
+            CU_TRY(cudaMemsetAsync(h->gbar.p, 0, sizeof(uint32_t), st));
+            h->gbar_target = 0;
+        }
+        sa.sample_tiles = seed_tiles; sa.rank = k;
+        sa.eps_const = eps_gemm_const(h->dtype, h->ld); sa.eps_q = (const float*)h->eps_q.p;
+        sa.bmax = (float*)h->bmax.p; sa.gbar = (uint32_t*)h->gbar.p;
+        sa.gbar_target = h->gbar_target + (uint32_t)p.grid;
+        CU_TRY(cudaMemsetAsync(h->acnt.p, 0, (size_t)nb * sizeof(uint32_t), st));   // bound_select_kernel's other job
+        CUtensorMap tmQ;
+        if ((rc = cached_map(h, &tmQ, h->dtype, a_base, nb_pad, h->ld, kRN))) return rc;
+        typedef void (*seeded_fn)(const CUtensorMap, const CUtensorMap, const SeededArgs);
+        seeded_fn sfn = h->dtype == 0 ? gemm_rows_seeded_kernel<1> : gemm_rows_seeded_kernel<0>;
+        const size_t ssmem = rows_smem_bytes(r.num_kblocks, r.stages) + extra;
+        if ((rc = set_dyn_smem(h->device, (const void*)sfn, ssmem))) return rc;
+        cudaLaunchConfig_t sc = {};
+        sc.gridDim = dim3(p.grid); sc.blockDim = dim3(kGemmThreads); sc.dynamicSmemBytes = ssmem; sc.stream = st;
+        cudaLaunchAttribute sat[1];
+        sat[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: the kernel holds a grid-wide barrier
+        sat[0].val.cooperative = 1;
+        sc.attrs = sat; sc.numAttrs = 1;
+        prof_begin(h, st);
+        CU_TRY(cudaLaunchKernelEx(&sc, sfn, tmQ, tmB, sa));
+        prof_end(h, st);
+        h->gbar_target = sa.gbar_target;                 // only a launch that went out moves the counter
+    } else if (append && (h->gemm_variant == 3 || h->gemm_variant == 0) && nb <= kRN && C == 1 && rows_stages(a.num_kblocks) >= 3) {
         // <= 16 queries, operand roles swapped (gemm_rows.cuh): corpus rows are the MMA's M, the queries its N = 16
         RowsArgs r;
         r.idesc = make_idesc_n(h->dtype == 0 ? 2 : h->dtype == 1 ? 1 : 0, kRN);
@@ -1170,9 +1224,10 @@ extern "C" int ragfin_set_scan_variant(ragfin_t* h, int32_t variant) {
 }
 
 // Tuning knob: which tcgen05 kernel serves large batches (0 automatic, 1 streaming, 2 A-stationary when eligible,
-// 3 swapped roles for <= 16 queries, 4 EXPERIMENTAL 2-SM MMA pairs for >= 2 query tiles in append mode).
+// 3 swapped roles for <= 16 queries, 4 EXPERIMENTAL 2-SM MMA pairs for >= 2 query tiles in append mode,
+// 5 EXPERIMENTAL variant 3 with the bound pass inside the sweep for k <= 16).
 extern "C" int ragfin_set_gemm_variant(ragfin_t* h, int32_t variant) {
-    if (!h || variant < 0 || variant > 4) return fail(RAGFIN_EINVAL, "variant must be 0, 1, 2, 3 or 4");
+    if (!h || variant < 0 || variant > 5) return fail(RAGFIN_EINVAL, "variant must be 0 ... 5");
     std::lock_guard<std::mutex> lk(h->mu);
     h->gemm_variant = variant;
     return RAGFIN_OK;

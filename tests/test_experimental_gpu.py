@@ -60,3 +60,29 @@ def test_two_sm_mma_raw_scores_equal_single_cta(dtype):
     idx.set_gemm_variant(4)
     got = idx.debug_gemm_scores(q).cpu()
     assert torch.equal(got, base)     # same k-order per output element
+
+
+@pytest.mark.parametrize("dtype", O.DTYPES)
+@pytest.mark.parametrize("n,dim,nq,k", [(70000, 128, 1, 10), (70000, 128, 2, 1), (70000, 128, 16, 10), (150000, 64, 5, 16),
+                                        (40000, 1024, 7, 10), (66000, 100, 3, 10), (35000, 768, 16, 5), (300000, 768, 1, 10)])
+def test_self_seeded_sweep_matches_oracle(coracle, dtype, n, dim, nq, k):
+    """Variant 5 (csrc/gemm_rows_seeded.cuh): the <= 16-query sweep samples, synchronises grid-wide and computes its own
+    thresholds - two launches fewer than variant 3, same bits as the oracle; repeated calls reuse the monotonic counter."""
+    import ragfin_b200
+    x = O.synth_rows(196, 0, n, dim, dup_every=61, zero_every=1999)
+    q = O.synth_rows(197, 0, nq, dim)
+    if nq >= 3:
+        x[4000:4030] = q[2] * 2.0
+    want = coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), k)
+    idx = ragfin_b200.Index(dim, dtype, capacity=n, device=0)
+    idx.add(x)
+    idx.set_gemm_min_batch(1)
+    idx.set_gemm_variant(3)
+    _assert_same(idx.search(q, k), want, "variant 3")
+    base = idx.stats()["launches"]
+    idx.set_gemm_variant(5)
+    for _rep in range(3):
+        got = idx.search(q, k)
+        st = idx.stats()
+        assert st["path"] == 1 and st["queries_rescanned"] == 0 and st["launches"] == base - 2
+        _assert_same(got, want, f"self-seeded {dtype} n={n} dim={dim} nq={nq} k={k}")
