@@ -182,3 +182,15 @@ def test_oracle_agrees_with_third_party_brute_force_cosine():
     order = np.argsort(d, axis=1, kind="stable")[:, :k]
     assert np.array_equal(order, wi)
     assert np.allclose(1.0 - np.take_along_axis(d, order, axis=1), ws, rtol=1e-5, atol=1e-6)
+
+
+def test_c_oracle_under_address_and_ub_sanitizers():
+    """The checker itself is checked: oracle/ragfin_oracle.c + oracle/selftest.c built with -fsanitize=address,undefined
+    and run over ragged dims, zero rows, duplicates, k > n, n = 0 and the threaded paths."""
+    import subprocess
+    odir = os.path.join(os.path.dirname(GOLDEN), os.pardir, "oracle")
+    b = subprocess.run(["make", "-C", odir, "selftest"], capture_output=True, text=True)
+    if b.returncode != 0:
+        pytest.skip("no sanitizer runtime for this compiler: " + b.stderr.strip().splitlines()[-1][:200])
+    r = subprocess.run([os.path.join(odir, "_san", "selftest")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ORACLE SELFTEST OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
