@@ -204,6 +204,13 @@ int ragfin_set_append_mode(ragfin_t* h, int32_t enable);
  * stored row, out_scores_dev [nq, count] device memory.  Validates the TMA / tcgen05 plumbing. */
 int ragfin_debug_gemm_scores(ragfin_t* h, const float* q_dev, int32_t nq, float* out_scores_dev, void* stream);
 
+/* Test hook, pure host arithmetic (needs no device): how the tcgen05 path would split a search of nq queries over
+ * n_rows rows on a device with num_sms SMs - cluster size, query tiles, corpus slices, grid - and the geometry of its
+ * sample ("bound") pass.  out[10] = {C, QT, S, rows_per_slice, grid, append_by_size, bound, nblk, g, bstride}.
+ * The CPU suite checks the invariants exactness rests on: slices cover every row once, sample tiles are distinct and
+ * never the last (partial) tile, at least 2 x rank sample blocks. */
+int ragfin_debug_plan(int32_t nq, int64_t n_rows, int32_t num_sms, int32_t k, int32_t cluster, int64_t* out);
+
 void ragfin_destroy(ragfin_t* h);
 
 const char* ragfin_last_error(void);

@@ -536,6 +536,40 @@ static bool append_eligible(const ragfin* h, int k) {
            h->count < ((int64_t)1 << 31) - kGN;
 }
 
+// Cluster size by the number of query tiles.  Measured on 10M x 768 bf16 (profiles/r01): pairs use all 148 SMs and win from
+// 1024 queries up; quads strand 16 SMs but read each corpus tile once, which wins at 3-7 query tiles.
+static int auto_cluster(int QT0) { return QT0 >= 8 ? 2 : QT0 >= 3 ? 4 : QT0 >= 2 ? 2 : 1; }
+
+// Sample ("bound") pass geometry: nblk blocks of g sample tiles each; sample tile j is corpus tile j * bstride, so the
+// tiles are distinct and the last (possibly partial) tile is never sampled.  Callers guarantee n_tiles >= 4 * rank.
+static void bound_geometry(int64_t n_tiles, int rank, bool append, int QT0, int k, int* nblk_out, int* g_out, int64_t* bstride_out) {
+    // blocks: 16 x rank keeps the rank best sample rows in distinct blocks (expected collisions rank / 32)
+    int64_t want_blk = 16 * (int64_t)rank;
+    if (want_blk < 256) want_blk = 256;
+    if (want_blk > 1024) want_blk = 1024;
+    int nblk = (int)(n_tiles / 2 < want_blk ? n_tiles / 2 : want_blk);
+    // Sample fraction f.  A query collects ~1.6 * k / f rows; the bound pass costs f of a sweep.  HBM-bound
+    // batches (one query tile) have epilogue slack, so f only has to keep the buffer well under kAppendCap;
+    // tensor-bound batches pay ~2.6e-3 ms per unit of k / f in the epilogue's slow path (measured: 13 ms at
+    // k = 100, f = 2 %), which puts the optimum near 0.8 % * sqrt(k) (2.5 % for k = 10, 8 % for k = 100).
+    double frac = append ? (double)k / 5000.0 : 0.0;
+    const double frac_min = (append && QT0 == 1) ? 1.0 / 256.0 : 1.0 / 96.0;   // one query tile: the pass is pure latency
+    if (frac < frac_min) frac = frac_min;
+    if (append && QT0 >= 2) {
+        const double opt = 0.008 * sqrt((double)k);
+        if (opt > frac) frac = opt;
+    }
+    int64_t sample = (int64_t)(frac * (double)n_tiles);
+    if (sample < nblk) sample = nblk;
+    if (sample > n_tiles / 2) sample = n_tiles / 2;
+    int g = (int)((sample + nblk / 2) / nblk);
+    if (g < 1) g = 1;
+    while (g > 1 && (int64_t)nblk * g > n_tiles / 2) --g;
+    int64_t bstride = (n_tiles - 1) / ((int64_t)nblk * g);   // the last (possibly partial) tile is never sampled
+    if (bstride < 1) bstride = 1;
+    *nblk_out = nblk; *g_out = g; *bstride_out = bstride;
+}
+
 // Scores the nb normalised queries in h->qhat against the corpus on the tensor cores and leaves per-query candidates
 // for the finalize step: list mode fills h->cand as [nb][S][kp] (unsorted lists, S returned through *G); append
 // mode (*appended = true) fills h->cand as [nb][kAppendCap] with h->acnt[q] keys each.  dump != null: raw scores.
@@ -547,7 +581,7 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
     const int QT0 = (nb + kGM - 1) / kGM;
     // measured on 10M x 768 bf16 (profiles/r01): pairs use all 148 SMs and win from 1024 queries up (49.7 vs 53.1 ms
     // at 4096); quads strand 16 SMs but read each corpus tile once, which wins at 3-7 query tiles (6.35 vs 6.80 ms at 512)
-    int C = h->gemm_cluster ? h->gemm_cluster : (QT0 >= 8 ? 2 : QT0 >= 3 ? 4 : QT0 >= 2 ? 2 : 1);
+    int C = h->gemm_cluster ? h->gemm_cluster : auto_cluster(QT0);
     const bool want_pair = h->gemm_variant == 4 && QT0 >= 2;   // experimental 2-SM MMA sweep: pairs of query tiles
     if (want_pair) C = 2;
     typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const GemmArgs);
@@ -568,32 +602,7 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
     const int rank = append ? k : kp;
     int nblk = 0, g = 1;
     int64_t bstride = 1;
-    if (bound) {
-        // blocks: 16 x rank keeps the rank best sample rows in distinct blocks (expected collisions rank / 32)
-        int64_t want_blk = 16 * (int64_t)rank;
-        if (want_blk < 256) want_blk = 256;
-        if (want_blk > 1024) want_blk = 1024;
-        nblk = (int)(n_tiles / 2 < want_blk ? n_tiles / 2 : want_blk);
-        // Sample fraction f.  A query collects ~1.6 * k / f rows; the bound pass costs f of a sweep.  HBM-bound
-        // batches (one query tile) have epilogue slack, so f only has to keep the buffer well under kAppendCap;
-        // tensor-bound batches pay ~2.6e-3 ms per unit of k / f in the epilogue's slow path (measured: 13 ms at
-        // k = 100, f = 2 %), which puts the optimum near 0.8 % * sqrt(k) (2.5 % for k = 10, 8 % for k = 100).
-        double frac = append ? (double)k / 5000.0 : 0.0;
-        const double frac_min = (append && QT0 == 1) ? 1.0 / 256.0 : 1.0 / 96.0;   // one query tile: the pass is pure latency
-        if (frac < frac_min) frac = frac_min;
-        if (append && QT0 >= 2) {
-            const double opt = 0.008 * sqrt((double)k);
-            if (opt > frac) frac = opt;
-        }
-        int64_t sample = (int64_t)(frac * (double)n_tiles);
-        if (sample < nblk) sample = nblk;
-        if (sample > n_tiles / 2) sample = n_tiles / 2;
-        g = (int)((sample + nblk / 2) / nblk);
-        if (g < 1) g = 1;
-        while (g > 1 && (int64_t)nblk * g > n_tiles / 2) --g;
-        bstride = (n_tiles - 1) / ((int64_t)nblk * g);   // the last (possibly partial) tile is never sampled
-        if (bstride < 1) bstride = 1;
-    }
+    if (bound) bound_geometry(n_tiles, rank, append, QT0, k, &nblk, &g, &bstride);
     int stages0 = append ? 4 : kp <= 32 ? 4 : kp <= 64 ? 3 : 2;
 #ifdef RAGFIN_TIMING_EXPERIMENTS
     { const char* e = getenv("RAGFIN_GEMM_STAGES"); if (e && atoi(e) >= 2 && atoi(e) <= stages0) stages0 = atoi(e); }
@@ -1187,6 +1196,27 @@ extern "C" int ragfin_debug_gemm_scores(ragfin_t* h, const float* q_dev, int32_t
     if (use_astat(h, 32)) { if ((rc = run_gemm_astat(h, nq, 32, &G, out_scores_dev, st))) return rc; }
     else { bool ap = false; if ((rc = run_gemm(h, nq, 10, 32, &G, &ap, out_scores_dev, st))) return rc; }
     return mark_done(h, st);
+}
+
+// Test hook, pure host arithmetic (no device needed): the tcgen05 path's work plan and bound-pass geometry for a shape
+// on a device of `num_sms` SMs.  out[10] = {C, QT, S, rows_per_slice, grid, append (by size), bound, nblk, g, bstride}.
+extern "C" int ragfin_debug_plan(int32_t nq, int64_t n_rows, int32_t num_sms, int32_t k, int32_t cluster, int64_t* out) {
+    if (!out || nq < 1 || n_rows < 1 || num_sms < 4 || k < 1 || k > 16384 || !(cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4))
+        return fail(RAGFIN_EINVAL, "bad argument");
+    int kp = cand_per_query(k);
+    if (kp == 0) kp = 256;
+    const int QT0 = (nq + kGM - 1) / kGM;
+    const int C = cluster ? cluster : auto_cluster(QT0);
+    const int64_t n_tiles = (n_rows + kGN - 1) / kGN;
+    const bool append = k <= kAppendMaxK && n_tiles >= 4 * (int64_t)k && n_rows < ((int64_t)1 << 31) - kGN;   // append_eligible, size part
+    const bool bound = append || n_tiles >= 4 * (int64_t)kp;
+    const GemmPlan p = plan_gemm(nq, n_rows, num_sms / C * C, kp, C);
+    int nblk = 0, g = 1;
+    int64_t bstride = 1;
+    if (bound) bound_geometry(n_tiles, append ? k : kp, append, QT0, k, &nblk, &g, &bstride);
+    const int64_t v[10] = {C, p.QT, p.S, p.rows_per_slice, p.grid, append, bound, nblk, g, bstride};
+    for (int i = 0; i < 10; ++i) out[i] = v[i];
+    return RAGFIN_OK;
 }
 
 // Dispatch knob: query batches of at least `min_nq` rows use the tcgen05 path (default 3, and 1 on corpora of >= 1 GiB; INT32_MAX = never).
