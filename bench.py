@@ -184,6 +184,10 @@ def cpu_baseline(a, budget_s: float, steps: int | None = None):
     import torch
     from oracle import c_oracle, fast_cpu
     c_oracle.build()
+    # all host threads: torchrun exports OMP_NUM_THREADS=1 to its workers, which would make the N > 1 reference arm scalar
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if torch.get_num_threads() < ncpu:
+        torch.set_num_threads(ncpu)
     rows = min(a.cpu_rows, a.rows)
     nq = a.batch if a.batch <= 64 else 64           # bounded sample of the query batch
     x = c_oracle.synth_rows(SEED_CORPUS, 0, rows, a.dim)
