@@ -537,7 +537,8 @@ static bool append_eligible(const ragfin* h, int k) {
 }
 
 // Cluster size by the number of query tiles.  Measured on 10M x 768 bf16 (profiles/r01): pairs use all 148 SMs and win from
-// 1024 queries up; quads strand 16 SMs but read each corpus tile once, which wins at 3-7 query tiles.
+// 1024 queries up (49.7 vs 53.1 ms at 4096); quads strand 16 SMs but read each corpus tile once, which wins at 3-7 query
+// tiles (6.35 vs 6.80 ms at 512).
 static int auto_cluster(int QT0) { return QT0 >= 8 ? 2 : QT0 >= 3 ? 4 : QT0 >= 2 ? 2 : 1; }
 
 // Sample ("bound") pass geometry: nblk blocks of g sample tiles each; sample tile j is corpus tile j * bstride, so the
@@ -579,8 +580,6 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
     *appended = false;
     // cluster size along the query-tile axis: multicast pays once several query tiles share a slice
     const int QT0 = (nb + kGM - 1) / kGM;
-    // measured on 10M x 768 bf16 (profiles/r01): pairs use all 148 SMs and win from 1024 queries up (49.7 vs 53.1 ms
-    // at 4096); quads strand 16 SMs but read each corpus tile once, which wins at 3-7 query tiles (6.35 vs 6.80 ms at 512)
     int C = h->gemm_cluster ? h->gemm_cluster : auto_cluster(QT0);
     const bool want_pair = h->gemm_variant == 4 && QT0 >= 2;   // experimental 2-SM MMA sweep: pairs of query tiles
     if (want_pair) C = 2;
