@@ -211,6 +211,14 @@ int ragfin_debug_gemm_scores(ragfin_t* h, const float* q_dev, int32_t nq, float*
  * never the last (partial) tile, at least 2 x rank sample blocks. */
 int ragfin_debug_plan(int32_t nq, int64_t n_rows, int32_t num_sms, int32_t k, int32_t cluster, int64_t* out);
 
+/* A second handle over the SAME device matrix (no copy) with its own workspace: searches through the parent and the
+ * view (or two views) may be in flight at once on different streams, so the latency-bound head and tail of one call
+ * (query preparation, bound pass, finalize, exchange) overlap the neighbour's sweep.  Replaces nothing in the reference
+ * (a Milvus querynode serves concurrent searches from one loaded segment the same way).  The view sees the rows present
+ * when it is made, inherits the parent's tuning knobs, is read-only (ragfin_add returns RAGFIN_EUNSUPPORTED) and must
+ * be destroyed before its parent.  NOT yet exercised on a GPU (scripts/pipeline_check.py). */
+int ragfin_create_view(ragfin_t* parent, ragfin_t** out);
+
 void ragfin_destroy(ragfin_t* h);
 
 const char* ragfin_last_error(void);

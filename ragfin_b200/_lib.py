@@ -16,7 +16,7 @@ SO_PATH = os.environ.get("RAGFIN_LIB") or os.path.join(CSRC, "libragfin.so")
 
 # every symbol include/ragfin.h declares
 SYMBOLS = (
-    "ragfin_abi_version", "ragfin_create", "ragfin_add", "ragfin_add_synthetic", "ragfin_count",
+    "ragfin_abi_version", "ragfin_create", "ragfin_create_view", "ragfin_add", "ragfin_add_synthetic", "ragfin_count",
     "ragfin_set_id_base", "ragfin_search", "ragfin_search_host", "ragfin_search_filtered", "ragfin_search_filtered_host", "ragfin_merge_topk", "ragfin_read_rows",
     "ragfin_last_search_stats", "ragfin_profile", "ragfin_profile_read", "ragfin_save", "ragfin_load", "ragfin_set_gemm_min_batch", "ragfin_set_gemm_cluster", "ragfin_set_gemm_variant", "ragfin_set_bound_pass", "ragfin_set_scan_variant", "ragfin_set_append_mode", "ragfin_debug_gemm_scores", "ragfin_debug_plan", "ragfin_destroy", "ragfin_last_error",
     "ragfin_exchange_create", "ragfin_exchange_handle", "ragfin_exchange_connect", "ragfin_exchange_allgather_merge", "ragfin_exchange_destroy",
@@ -51,6 +51,7 @@ def load() -> ctypes.CDLL:
     vp, i32, i64, u64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64
     L.ragfin_abi_version.argtypes, L.ragfin_abi_version.restype = [], ctypes.c_int
     L.ragfin_create.argtypes = [ctypes.POINTER(vp), i32, i32, i64, i32]
+    L.ragfin_create_view.argtypes = [vp, ctypes.POINTER(vp)]
     L.ragfin_add.argtypes = [vp, vp, i64, i32, vp]
     L.ragfin_add_synthetic.argtypes = [vp, u64, i64, i64, i32, i32, vp]
     L.ragfin_count.argtypes = [vp, ctypes.POINTER(i64)]

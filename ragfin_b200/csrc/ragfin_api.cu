@@ -76,6 +76,7 @@ struct ragfin {
     int dim = 0, ld = 0, dtype = 0, device = 0, num_sms = 0;
     int64_t capacity = 0, count = 0, id_base = 0;
     void* data = nullptr;  // [capacity, ld] storage, row-major, L2-normalised
+    bool is_view = false;  // ragfin_create_view: `data` belongs to another handle (read-only here, never freed here)
     std::mutex mu;
     // workspace (grow-only)
     Buf qhat, q16, eps_q, gtau, bmax, acnt, athr, allow, bk_scores, bk_state, bk_keys, cand, cand_e, flags, stage_q, stage_ids, stage_scores, add_stage;
@@ -196,6 +197,34 @@ extern "C" int ragfin_create(ragfin_t** out, int32_t dim, int32_t dtype, int64_t
     return RAGFIN_OK;
 }
 
+// A second handle over the SAME device matrix (no copy) with its own workspace, so that searches through the two handles
+// can be in flight at once on different streams (the latency-bound head and tail of one call overlap the other's sweep).
+// The view sees the rows present now, is read-only (ragfin_add fails) and must be destroyed before its parent.
+extern "C" int ragfin_create_view(ragfin_t* parent, ragfin_t** out) {
+    if (!parent || !out) return fail(RAGFIN_EINVAL, "NULL argument");
+    *out = nullptr;
+    std::lock_guard<std::mutex> lk(parent->mu);
+    DeviceGuard g(parent->device);
+    if (!g.ok) return fail(RAGFIN_ECUDA, "cudaSetDevice(%d) failed", parent->device);
+    CU_TRY(cudaDeviceSynchronize());   // every row the parent has accepted is in the matrix
+    ragfin* h = new (std::nothrow) ragfin();
+    if (!h) return fail(RAGFIN_ENOMEM, "host allocation failed");
+    h->dim = parent->dim; h->ld = parent->ld; h->dtype = parent->dtype; h->device = parent->device; h->num_sms = parent->num_sms;
+    h->capacity = parent->count > 0 ? parent->count : 1; h->count = parent->count; h->id_base = parent->id_base;
+    h->data = parent->data;
+    h->is_view = true;
+    h->gemm_min_nq = parent->gemm_min_nq; h->gemm_min_nq_large = parent->gemm_min_nq_large; h->gemm_cluster = parent->gemm_cluster;
+    h->scan_variant = parent->scan_variant; h->use_append = parent->use_append; h->use_bound_pass = parent->use_bound_pass;
+    h->gemm_variant = parent->gemm_variant;
+    cudaError_t e = cudaEventCreateWithFlags(&h->last_done, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(RAGFIN_ECUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return RAGFIN_OK;
+}
+
 extern "C" void ragfin_destroy(ragfin_t* h) {
     if (!h) return;
     DeviceGuard g(h->device);
@@ -203,7 +232,7 @@ extern "C" void ragfin_destroy(ragfin_t* h) {
     Buf* bufs[] = {&h->qhat, &h->q16, &h->eps_q, &h->gtau, &h->bmax, &h->acnt, &h->athr, &h->allow, &h->bk_scores, &h->bk_state, &h->bk_keys, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage, &h->gbar};
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
-    if (h->data) cudaFree(h->data);
+    if (h->data && !h->is_view) cudaFree(h->data);
     if (h->hstage) cudaFreeHost(h->hstage);
     if (h->last_done) cudaEventDestroy(h->last_done);
     for (cudaEvent_t e : h->prof_ev)
@@ -253,6 +282,7 @@ extern "C" int ragfin_add(ragfin_t* h, const float* rows, int64_t n, int32_t src
     if (n < 0 || (n > 0 && !rows)) return fail(RAGFIN_EINVAL, "bad rows/n");
     if (n == 0) return RAGFIN_OK;
     std::lock_guard<std::mutex> lk(h->mu);
+    if (h->is_view) return fail(RAGFIN_EUNSUPPORTED, "a view is read-only: add rows through the handle that owns the matrix");
     if (h->count + n > h->capacity)
         return fail(RAGFIN_ENOMEM, "add of %lld rows exceeds capacity (%lld of %lld used)", (long long)n,
                     (long long)h->count, (long long)h->capacity);
@@ -287,6 +317,7 @@ extern "C" int ragfin_add_synthetic(ragfin_t* h, uint64_t seed, int64_t row0, in
     if (n < 0 || row0 < 0) return fail(RAGFIN_EINVAL, "bad row0/n");
     if (n == 0) return RAGFIN_OK;
     std::lock_guard<std::mutex> lk(h->mu);
+    if (h->is_view) return fail(RAGFIN_EUNSUPPORTED, "a view is read-only: add rows through the handle that owns the matrix");
     if (h->count + n > h->capacity)
         return fail(RAGFIN_ENOMEM, "add of %lld rows exceeds capacity (%lld of %lld used)", (long long)n,
                     (long long)h->count, (long long)h->capacity);

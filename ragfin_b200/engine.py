@@ -57,11 +57,22 @@ class Index:
         self.capacity = max(int(capacity), int.from_bytes(hd[24:32], "little", signed=True), 1)
         return self
 
+    def view(self) -> "Index":
+        """A second handle over the same device matrix (no copy) with its own workspace: searches through `self` and the
+        view may be in flight at once on different CUDA streams.  Read-only; sees the rows present now; keeps `self` alive."""
+        h = ctypes.c_void_p()
+        _lib.check(self._L.ragfin_create_view(self._h, ctypes.byref(h)))
+        v = Index.__new__(Index)
+        v._L, v._h, v._parent = self._L, h, self
+        v.dim, v.dtype, v.device, v.capacity = self.dim, self.dtype, self.device, max(len(self), 1)
+        return v
+
     # -- lifecycle -------------------------------------------------------------------
     def close(self) -> None:
         if getattr(self, "_h", None):
             self._L.ragfin_destroy(self._h)
             self._h = None
+            self._parent = None
 
     def __del__(self):
         try:

@@ -56,3 +56,9 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dp, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
                 assert "ragfin_oracle" not in src.replace("oracle/ragfin_oracle", ""), fn
+
+
+def test_view_argument_validation_without_device(lib):
+    out = ctypes.c_void_p()
+    assert lib.ragfin_create_view(None, ctypes.byref(out)) == -1       # EINVAL: no parent
+    assert out.value is None

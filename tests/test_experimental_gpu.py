@@ -86,3 +86,32 @@ def test_self_seeded_sweep_matches_oracle(coracle, dtype, n, dim, nq, k):
         st = idx.stats()
         assert st["path"] == 1 and st["queries_rescanned"] == 0 and st["launches"] == base - 2
         _assert_same(got, want, f"self-seeded {dtype} n={n} dim={dim} nq={nq} k={k}")
+
+
+def test_view_shares_the_matrix_and_is_read_only(coracle):
+    """ragfin_create_view: a second handle over the same device matrix with its own workspace; searches through parent
+    and view on two streams at once return what each returns alone."""
+    import torch
+    import ragfin_b200
+    x = O.synth_rows(7, 0, 70000, 128, dup_every=61)
+    q = O.synth_rows(8, 0, 5, 128)
+    want = coracle.cosine_topk(q, coracle.normalize_rows(x, "bf16"), 10)
+    idx = ragfin_b200.Index(128, "bf16", capacity=80000, device=0)
+    idx.add(x)
+    v = idx.view()
+    assert len(v) == 70000
+    _assert_same(v.search(q, 10), want, "view")
+    with pytest.raises(ragfin_b200.RagfinError):
+        v.add(x[:1])
+    qd = torch.from_numpy(q).cuda()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for i in range(20):
+        h, s = (idx, s1) if i % 2 == 0 else (v, s2)
+        with torch.cuda.stream(s):
+            outs.append(h.search_device(qd, 10, stream=s))
+    torch.cuda.synchronize()
+    for ids, sc in outs:
+        _assert_same((ids.cpu().numpy(), sc.cpu().numpy()), want, "interleaved")
+    v.close()
+    idx.close()
