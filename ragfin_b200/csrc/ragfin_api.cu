@@ -242,6 +242,7 @@ extern "C" void ragfin_destroy(ragfin_t* h) {
 
 extern "C" int ragfin_count(const ragfin_t* h, int64_t* n) {
     if (!h || !n) return fail(RAGFIN_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(const_cast<ragfin*>(h)->mu);   // count is written under the lock by ragfin_add
     *n = h->count;
     return RAGFIN_OK;
 }
