@@ -116,13 +116,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    cluster_sync_all();   // both CTAs are running and their barriers exist before the paired allocation
     if (warp == 1) {   // both CTAs: all 512 columns of each SM's tensor memory (two 256-column accumulators)
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();   // the peer's barriers must be initialised before any remote arrive / complete_tx / commit
+    cluster_sync_all();   // the peer's tensor memory is allocated before the leader's MMAs write into it
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();
