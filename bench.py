@@ -52,7 +52,8 @@ def parse_args():
                     help="second regime measured in the same run and reported under 'regimes' (0 = off)")
     ap.add_argument("--gemm-cluster", type=int, default=0, help="tcgen05 path cluster size: 0 auto, 1, 2 or 4")
     ap.add_argument("--gemm-variant", type=int, default=-1, help="tcgen05 kernel: 0 auto, 1 streaming, 2 A-stationary, 3 swapped roles for <= 16 queries, 4 experimental 2-SM pairs, 5 experimental self-seeded sweep (-1 = library default)")
-    ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="rows of the CPU baseline sample")
+    ap.add_argument("--cpu-rows", type=int, default=0,
+                    help="rows of the CPU baseline sample (0 = the whole corpus when MemAvailable >= 1.3 x rows*dim*4, else 2M rows, extrapolated)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -179,6 +180,32 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CPU baseline (oracle port; the only place bench.py executes oracle/)
 # ----------------------------------------------------------------------------------------------
+def mem_available_bytes():
+    try:
+        with open("/proc/meminfo") as f:
+            for ln in f:
+                if ln.startswith("MemAvailable:"):
+                    return int(ln.split()[1]) * 1024
+    except OSError:
+        pass
+    return 0
+
+
+def cpu_corpus(a, rows):
+    """fp32 normalised rows [rows, dim] of the synthetic corpus as a torch CPU tensor, generated block by block with the C
+    oracle (what a CPU Milvus would hold: bf16 / fp16 corpora are up-cast)."""
+    import numpy as np
+    import torch
+    from oracle import c_oracle
+    out = torch.empty((rows, a.dim), dtype=torch.float32)
+    o = out.numpy()
+    blk = 500_000
+    for r0 in range(0, rows, blk):
+        m = min(blk, rows - r0)
+        o[r0:r0 + m] = c_oracle.normalize_rows(c_oracle.synth_rows(SEED_CORPUS, r0, m, a.dim), "f32")
+    return out
+
+
 def cpu_baseline(a, budget_s: float, steps: int | None = None):
     import numpy as np
     import torch
@@ -188,11 +215,14 @@ def cpu_baseline(a, budget_s: float, steps: int | None = None):
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if torch.get_num_threads() < ncpu:
         torch.set_num_threads(ncpu)
-    rows = min(a.cpu_rows, a.rows)
+    # the whole corpus when the host can hold it in fp32 (30.7 GB at 10M x 768), else a slice, scaled linearly
+    full_bytes = a.rows * a.dim * 4
+    rows = a.rows if (a.cpu_rows <= 0 and mem_available_bytes() >= 1.3 * full_bytes) else min(a.cpu_rows if a.cpu_rows > 0 else 2_000_000, a.rows)
+    extrapolated = rows < a.rows
     nq = a.batch if a.batch <= 64 else 64           # bounded sample of the query batch
-    x = c_oracle.synth_rows(SEED_CORPUS, 0, rows, a.dim)
-    stored = torch.from_numpy(c_oracle.normalize_rows(x, "f32"))
-    del x
+    t_gen = time.perf_counter()
+    stored = cpu_corpus(a, rows)
+    t_gen = time.perf_counter() - t_gen
     q = c_oracle.synth_rows(SEED_QUERY, 0, nq * 4, a.dim)
     fast_cpu.fast_topk(stored, q[:nq], a.k)          # warm-up
     times, t_end, i = [], time.perf_counter() + budget_s, 0
@@ -204,10 +234,13 @@ def cpu_baseline(a, budget_s: float, steps: int | None = None):
         if steps is None and i >= 400:
             break
     per_call = statistics.median(times)
-    qps = nq / per_call * (rows / a.rows)            # linear in corpus rows (brute force)
-    sample = (f"{nq} of {a.batch} queries per call over a {rows}-row fp32 slice of the {a.rows}-row corpus, "
-              f"{len(times)} calls, median; throughput scaled by {rows}/{a.rows} (extrapolated, linear in rows)")
+    qps = nq / per_call * (rows / a.rows)            # linear in corpus rows (brute force); factor 1 when not extrapolated
+    sample = (f"{nq} of {a.batch} queries per call over " +
+              (f"the whole {a.rows}-row corpus held as fp32 ({full_bytes / 1e9:.1f} GB)" if not extrapolated else
+               f"a {rows}-row fp32 slice of the {a.rows}-row corpus; throughput scaled by {rows}/{a.rows} (linear in rows)") +
+              f", {len(times)} calls, median")
     return {"value": qps, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
+            "extrapolated": extrapolated, "rows_timed": rows, "corpus_build_s": round(t_gen, 1),
             "ms_per_call_on_sample": per_call * 1e3}, len(times), per_call
 
 
@@ -215,7 +248,8 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, n, per_call = cpu_baseline(a, budget_s=0.0, steps=a.steps + a.warmup)
+    # every step is one search of the batch over the corpus; at most 60 calls are timed so that the run ends within minutes
+    base, n, per_call = cpu_baseline(a, budget_s=0.0, steps=min(a.steps + a.warmup, 60))
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "queries/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": a.batch / base["value"] * 1e3,
@@ -347,7 +381,10 @@ def run_ours(a):
                     "frac_of_sustained_peak": achieved / peaks["bf16_sustained"] if peaks.get("bf16_sustained") else None}
         roof.update({"kernel_ms_avg": kern_avg_ms, "kernel_launches_timed": kern_n, "peak_source": peaks["source"],
                      "kernel_share_of_step": kern_avg_ms * launches_of_kernel_per_step / (ms / steps),
-                     "traffic": load_traffic(a, batch)})
+                     # DRAM bytes of the same kernel from the committed ncu --set full capture of this workload on ONE GPU
+                     # (profiles/traffic.json): a profile figure, not a measurement of this run; null for shards
+                     "traffic": load_traffic(a, batch) if world == 1 else None,
+                     "traffic_source": "profiles/traffic.json (ncu --set full capture of this workload, not this run)" if world == 1 else None})
         return {
             "value": batch * steps / (ms * 1e-3), "unit": "queries/s", "batch": batch, "steps": steps,
             "ms_per_step": ms / steps, "clocks": clocks,
@@ -374,10 +411,101 @@ def run_ours(a):
             m["remeasured_after"] = rejected
         return m
 
+    def parity_check(batch):
+        """Correctness of the path that was just timed, OUTSIDE the timed region, on the (sharded) result as every rank sees
+        it: the timed query batches re-run through the same call plus one needle batch; rank 0 verifies with the oracle
+          order      score descending, ties to the lower id
+          scores     every returned score bit-equal to the oracle's canonical score of that row (row regenerated on the host)
+          needles    queries that are copies of corpus rows planted in EVERY shard come back first with their global id
+          sample     a random 200k-row sample (oracle-scored) holds no row that beats the k-th hit of the checked queries
+          agree      every rank holds the same merged result (hash compared over the ranks)."""
+        from oracle import c_oracle
+        nbatches = 4
+        q_all = synth_rows(SEED_QUERY, 0, nbatches * batch, a.dim).reshape(nbatches, batch, a.dim)
+        # positions checked inside a batch: everything for small batches, else 2 per 128-query tile (every tile of the batch)
+        if batch <= 16:
+            pos = list(range(batch))
+        else:
+            pos = sorted({min(batch - 1, t * 128 + (37 * t + 5) % 128) for t in range((batch + 127) // 128)} |
+                         {min(batch - 1, t * 128 + (91 * t + 64) % 128) for t in range((batch + 127) // 128)})
+        # needle rows: one in every shard (none on a shard boundary), as queries at the checked positions of one extra batch
+        needle_rows = []
+        for w in range(world):
+            r0, cnt = shard_bounds(a.rows, world, w)
+            if cnt > 0:
+                needle_rows += [r0 + cnt // 3, r0 + (2 * cnt) // 3]
+        needle_batches = []
+        for c0 in range(0, len(needle_rows), len(pos)):
+            qb = q_all[1 % nbatches].copy()
+            chunk = needle_rows[c0:c0 + len(pos)]
+            for p_, r in zip(pos, chunk):
+                qb[p_] = c_oracle.synth_rows(SEED_CORPUS, r, 1, a.dim)[0]
+            needle_batches.append((qb, dict(zip(pos, chunk))))
+        runs = [(q_all[i], {}) for i in range(nbatches if batch <= 16 else 1)] + needle_batches
+        results = []
+        agree = True
+        for qb, needles in runs:
+            ids, sc = searcher.search(torch.from_numpy(qb).to(dev), a.k)
+            torch.cuda.synchronize()
+            ids, sc = ids.cpu().numpy(), sc.cpu().numpy()
+            if world > 1:   # every rank must hold the same merged result
+                import hashlib
+                hsh = int.from_bytes(hashlib.blake2b(ids.tobytes() + sc.tobytes(), digest_size=8).digest(), "little") >> 1
+                t = torch.tensor([hsh, -hsh], dtype=torch.int64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                agree &= int(t[0].item()) == -int(t[1].item())
+            results.append((qb, needles, ids, sc))
+        if rank != 0:
+            return None
+        t0 = time.perf_counter()
+        fails, checked, n_needles = [], 0, 0
+        rng = np.random.default_rng(7)
+        nblk, blk_rows = 100, 2000
+        starts = rng.integers(0, max(1, a.rows - blk_rows), size=nblk)
+        sample = [(int(s0), c_oracle.normalize_rows(c_oracle.synth_rows(SEED_CORPUS, int(s0), min(blk_rows, a.rows - int(s0)), a.dim), a.dtype)) for s0 in starts]
+        sample_queries = 0
+        for qb, needles, ids, sc in results:
+            qhat = c_oracle.normalize_rows(qb[pos], "f32")
+            for j, p_ in enumerate(pos):
+                i_, s_ = ids[p_], sc[p_]
+                checked += 1
+                keff = min(a.k, a.rows)
+                if (i_[:keff] < 0).any() or (i_[:keff] >= a.rows).any():
+                    fails.append(f"q{p_}: id out of range"); continue
+                for x in range(keff - 1):
+                    if not (s_[x] > s_[x + 1] or (s_[x] == s_[x + 1] and i_[x] < i_[x + 1])):
+                        fails.append(f"q{p_}: order at {x}"); break
+                rows_ = np.concatenate([c_oracle.synth_rows(SEED_CORPUS, int(r), 1, a.dim) for r in i_[:keff]])
+                want = c_oracle.exact_scores(c_oracle.normalize_rows(rows_, a.dtype), qhat[j])
+                if not np.array_equal(want.view(np.uint32), s_[:keff].view(np.uint32)):
+                    fails.append(f"q{p_}: score bits differ from the oracle's")
+                if p_ in needles:
+                    n_needles += 1
+                    if int(i_[0]) != needles[p_] or abs(float(s_[0]) - 1.0) > 1e-2:
+                        fails.append(f"needle row {needles[p_]} came back as {int(i_[0])} ({float(s_[0]):.6f})")
+                if sample_queries < 12 and (j % max(1, len(pos) // 4) == 0):   # sample property on a few queries of every run
+                    sample_queries += 1
+                    kth_s, kth_i, have = s_[keff - 1], i_[keff - 1], set(i_[:keff].tolist())
+                    for s0, blk in sample:
+                        ssc = c_oracle.exact_scores(blk, qhat[j])
+                        rws = np.arange(s0, s0 + blk.shape[0])
+                        better = (ssc > kth_s) | ((ssc == kth_s) & (rws < kth_i))
+                        if not set(rws[better].tolist()) <= have:
+                            fails.append(f"q{p_}: a sampled row near {s0} beats the k-th hit"); break
+        return {"ok": not fails and agree, "queries": checked, "needles": n_needles, "needle_shards": world,
+                "sample_rows": nblk * blk_rows, "sample_queries": sample_queries, "ranks_agree": agree,
+                "failures": fails[:5], "check_s": round(time.perf_counter() - t0, 1),
+                "how": "timed batches + needle batch re-run through the timed call after the timed region; rank 0 checks order, "
+                       "score bits == oracle canonical score of the regenerated rows, needles (copies of corpus rows in every "
+                       "shard) first with their global id, no row of a 200k-row oracle-scored sample beats the k-th hit; "
+                       "result hash equal on every rank"}
+
     main = measure_checked(a.batch, a.steps, a.warmup)
+    main["parity_check"] = parity_check(a.batch)
     other = None
     if a.also_batch and a.also_batch != a.batch:
         other = measure_checked(a.also_batch, max(5, a.steps // 10), a.warmup)
+        other["parity_check"] = parity_check(a.also_batch)
 
     if rank == 0:
         line = {
@@ -390,6 +518,7 @@ def run_ours(a):
                        "ingest_s": round(ingest_s, 2), "queries_rescanned_last_step": main["queries_rescanned_last_step"]},
             "clocks": dict(main["clocks"] or {}, **({"remeasured_after": main["remeasured_after"]} if "remeasured_after" in main else {})),
             "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "roofline": main["roofline"],
+            "parity_check": main["parity_check"],
         }
         if other is not None:
             line["regimes"] = {f"batch_{other['batch']}": other}

@@ -159,6 +159,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int ab_format) {
            ((uint32_t)(kGM >> 4) << 24);
 }
 
+// Stage switches of scripts/gemm_dbg_sweep.py (timing only, results invalid): compiled in only with
+// -DRAGFIN_TIMING_EXPERIMENTS; in the default build RF_DBG(...) is the constant 0 and the branches vanish.
+#ifdef RAGFIN_TIMING_EXPERIMENTS
+#define RF_DBG(a, bit) ((a).dbg & (bit))
+#else
+#define RF_DBG(a, bit) 0
+#endif
+
 // ---- the kernel ------------------------------------------------------------------------------------
 struct GemmArgs {
     uint32_t idesc;
@@ -308,11 +316,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int t = 0; t < ntiles; ++t) {
                     for (int kb = 0; kb < nkb; ++kb) {
                         mbar_wait(empty_bar(stage), phase ^ 1u);
-                        mbar_expect_tx(full_bar(stage), ((a.dbg & 4) ? 0 : kABytes) + ((a.dbg & 8) ? 0 : kBBytes));   // own A tile + the whole B tile (C parts)
-                        if (!(a.dbg & 4)) tma_load_2d(smA + (uint32_t)stage * kABytes, &tmA, kb * a.k_elems, qt * kGM, full_bar(stage));
+                        mbar_expect_tx(full_bar(stage), (RF_DBG(a, 4) ? 0 : kABytes) + (RF_DBG(a, 8) ? 0 : kBBytes));   // own A tile + the whole B tile (C parts)
+                        if (!RF_DBG(a, 4)) tma_load_2d(smA + (uint32_t)stage * kABytes, &tmA, kb * a.k_elems, qt * kGM, full_bar(stage));
                         const uint32_t bdst = smB + (uint32_t)stage * kBBytes + crank * (uint32_t)(kSubRows * kGKBytes);
                         const int brow = (int)(r0 + (long long)t * step) + (int)crank * kSubRows;
-                        if (a.dbg & 8) {}
+                        if (RF_DBG(a, 8)) {}
                         else if (C > 1) tma_load_2d_mc(bdst, &tmB, kb * a.k_elems, brow, full_bar(stage), cmask);
                         else tma_load_2d(bdst, &tmB, kb * a.k_elems, brow, full_bar(stage));
                         if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -339,7 +347,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const uint64_t bd = make_smem_desc(smB + (uint32_t)stage * kBBytes);
 #pragma unroll
                         for (int k4 = 0; k4 < kGKBytes / 32; ++k4)   // 32 B of K per instruction: +2 in 16-byte units
-                            if (!(a.dbg & 2)) tc_mma<KIND>(d_tmem, ad + 2u * k4, bd + 2u * k4, a.idesc, (uint32_t)((kb | k4) != 0));
+                            if (!RF_DBG(a, 2)) tc_mma<KIND>(d_tmem, ad + 2u * k4, bd + 2u * k4, a.idesc, (uint32_t)((kb | k4) != 0));
                         if (C > 1) tc_commit_mc(empty_bar(stage), cmask);
                         else tc_commit(empty_bar(stage));
                         if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -384,7 +392,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kGN;
                 const int valid = r1 - trow < kGN ? (int)(r1 - trow) : kGN;   // rows of this tile inside the corpus
                 uint32_t vb[2][32];
-                if (a.dbg & 1) { tc_fence_before(); mbar_arrive(tempty_bar(acc)); if (++acc == 2) { acc = 0; acc_phase ^= 1u; } continue; }
+                if (RF_DBG(a, 1)) { tc_fence_before(); mbar_arrive(tempty_bar(acc)); if (++acc == 2) { acc = 0; acc_phase ^= 1u; } continue; }
                 tmem_ld32_async(taddr, vb[0]);
 #pragma unroll 2   // two chunks per iteration keep vb[c & 1] in fixed registers; a full unroll is 138 KB of code
                 for (int c = 0; c < kGN / 32; ++c) {

@@ -591,16 +591,24 @@ exact_scan_kernel(const void* __restrict__ data, int64_t n_rows, int ld, const f
 __device__ __forceinline__ bool hit_better(float sa, int64_t ia, float sb, int64_t ib) {
     return sa > sb || (sa == sb && ia < ib);
 }
+// PEER = true: the lists are written by other GPUs DURING this kernel (exchange_merge_kernel); they must be read with
+// coherent loads (ld.global.cg, never the non-coherent .nc path, which PTX only allows for memory that is read-only for
+// the kernel's lifetime and which the acquire on the flag does not order).
+template <bool PEER> __device__ __forceinline__ int64_t ld_hit_id(const int64_t* p) { return PEER ? __ldcg(p) : *p; }
+template <bool PEER> __device__ __forceinline__ float ld_hit_score(const float* p) { return PEER ? __ldcg(p) : *p; }
+template <bool PEER>
 __device__ __forceinline__ int count_better(const int64_t* ids, const float* sc, int k, float s, int64_t id) {
     int lo = 0, hi = k;  // first index whose element does NOT beat (s, id); padding never beats
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const bool b = ids[mid] >= 0 && hit_better(sc[mid], ids[mid], s, id);
+        const int64_t im = ld_hit_id<PEER>(ids + mid);
+        const bool b = im >= 0 && hit_better(ld_hit_score<PEER>(sc + mid), im, s, id);
         if (b) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
-__device__ __forceinline__ void merge_topk_body(const int64_t* __restrict__ ids, const float* __restrict__ scores, int nq,
+template <bool PEER>
+__device__ __forceinline__ void merge_topk_body(const int64_t* ids, const float* scores, int nq,
                                                 int parts, int k, int64_t ips, int64_t sps, int64_t query_stride,
                                                 int64_t* __restrict__ out_ids, float* __restrict__ out_scores) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -614,21 +622,21 @@ __device__ __forceinline__ void merge_topk_body(const int64_t* __restrict__ ids,
     if (p == 0) {  // slot i of the output: pad it if fewer than i+1 valid hits exist in total
         int valid = 0;
         for (int pp = 0; pp < parts; ++pp)
-            valid += count_better(qi + (size_t)pp * ips, qs + (size_t)pp * sps, k, -INFINITY, INT64_MAX);
+            valid += count_better<PEER>(qi + (size_t)pp * ips, qs + (size_t)pp * sps, k, -INFINITY, INT64_MAX);
         if (i >= valid) { out_ids[(size_t)q * k + i] = -1; out_scores[(size_t)q * k + i] = -INFINITY; }
     }
-    const int64_t id = qi[(size_t)p * ips + i];
+    const int64_t id = ld_hit_id<PEER>(qi + (size_t)p * ips + i);
     if (id < 0) return;
-    const float s = qs[(size_t)p * sps + i];
+    const float s = ld_hit_score<PEER>(qs + (size_t)p * sps + i);
     int rank = i;
     for (int pp = 0; pp < parts && rank < k; ++pp)
-        if (pp != p) rank += count_better(qi + (size_t)pp * ips, qs + (size_t)pp * sps, k, s, id);
+        if (pp != p) rank += count_better<PEER>(qi + (size_t)pp * ips, qs + (size_t)pp * sps, k, s, id);
     if (rank < k) { out_ids[(size_t)q * k + rank] = id; out_scores[(size_t)q * k + rank] = s; }
 }
 __global__ void merge_topk_kernel(const int64_t* __restrict__ ids, const float* __restrict__ scores, int nq,
                                   int parts, int k, int64_t ips, int64_t sps, int64_t query_stride,
                                   int64_t* __restrict__ out_ids, float* __restrict__ out_scores) {
-    merge_topk_body(ids, scores, nq, parts, k, ips, sps, query_stride, out_ids, out_scores);
+    merge_topk_body<false>(ids, scores, nq, parts, k, ips, sps, query_stride, out_ids, out_scores);
 }
 
 // ---------------------------------------------------------------------------------
@@ -672,7 +680,7 @@ exchange_push_kernel(const int64_t* __restrict__ ids, const float* __restrict__ 
         }
     }
 }
-__global__ void exchange_merge_kernel(const char* __restrict__ area, const uint32_t* __restrict__ flags, int nq, int world,
+__global__ void exchange_merge_kernel(const char* area, const uint32_t* flags, int nq, int world,
                                       int k, size_t record_bytes, uint32_t step, int64_t* __restrict__ out_ids,
                                       float* __restrict__ out_scores) {
     if (threadIdx.x < world) {
@@ -682,7 +690,7 @@ __global__ void exchange_merge_kernel(const char* __restrict__ area, const uint3
     __syncthreads();
     (void)ld_acquire_sys(flags + (size_t)(step & 1u) * world + threadIdx.x % world);   // every thread acquires for its own loads
     const char* base = area + (size_t)(step & 1u) * world * record_bytes;
-    merge_topk_body(reinterpret_cast<const int64_t*>(base), reinterpret_cast<const float*>(base + (size_t)nq * k * 8), nq, world, k,
+    merge_topk_body<true>(reinterpret_cast<const int64_t*>(base), reinterpret_cast<const float*>(base + (size_t)nq * k * 8), nq, world, k,
                     (int64_t)(record_bytes / 8), (int64_t)(record_bytes / 4), (int64_t)k, out_ids, out_scores);
 }
 

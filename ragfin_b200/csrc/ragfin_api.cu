@@ -62,6 +62,10 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 extern "C" const char* ragfin_last_error(void) { return g_err; }
+
+// Code paths that no GPU test covers in the default suite stay behind RAGFIN_EXPERIMENTAL=1 (they are reachable through
+// the public ABI otherwise): a protocol bug there is a device hang on a shared pool, not a wrong answer.
+static bool experimental_enabled() { const char* e = getenv("RAGFIN_EXPERIMENTAL"); return e && atoi(e) != 0; }
 extern "C" int ragfin_abi_version(void) { return RAGFIN_ABI_VERSION; }
 
 // ------------------------------------------------------------------------------
@@ -203,6 +207,7 @@ extern "C" int ragfin_create(ragfin_t** out, int32_t dim, int32_t dtype, int64_t
 extern "C" int ragfin_create_view(ragfin_t* parent, ragfin_t** out) {
     if (!parent || !out) return fail(RAGFIN_EINVAL, "NULL argument");
     *out = nullptr;
+    if (!experimental_enabled()) return fail(RAGFIN_EUNSUPPORTED, "ragfin_create_view is experimental: set RAGFIN_EXPERIMENTAL=1");
     std::lock_guard<std::mutex> lk(parent->mu);
     DeviceGuard g(parent->device);
     if (!g.ok) return fail(RAGFIN_ECUDA, "cudaSetDevice(%d) failed", parent->device);
@@ -1289,6 +1294,8 @@ extern "C" int ragfin_set_scan_variant(ragfin_t* h, int32_t variant) {
 // 5 EXPERIMENTAL variant 3 with the bound pass inside the sweep for k <= 16).
 extern "C" int ragfin_set_gemm_variant(ragfin_t* h, int32_t variant) {
     if (!h || variant < 0 || variant > 5) return fail(RAGFIN_EINVAL, "variant must be 0 ... 5");
+    if (variant >= 4 && !experimental_enabled())
+        return fail(RAGFIN_EUNSUPPORTED, "gemm variant %d is experimental: set RAGFIN_EXPERIMENTAL=1", variant);
     std::lock_guard<std::mutex> lk(h->mu);
     h->gemm_variant = variant;
     return RAGFIN_OK;
@@ -1489,6 +1496,8 @@ struct ragfin_exchange {
     unsigned int* d_done = nullptr;
     uint32_t step = 0;
     bool connected = false;
+    bool have_stream = false;            // the double-buffer argument (a rank is at most one step ahead of a peer) holds only
+    cudaStream_t stream = nullptr;       // if every step of this rank is issued on ONE stream: recorded at step 1, checked after
     std::mutex mu;
 };
 
@@ -1578,6 +1587,9 @@ extern "C" int ragfin_exchange_allgather_merge(ragfin_exchange_t* x, const int64
     if (record > x->record_max) return fail(RAGFIN_EINVAL, "record of %zu bytes exceeds the exchange's %zu", record, x->record_max);
     DeviceGuard g(x->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (x->have_stream && x->stream != st)
+        return fail(RAGFIN_EINVAL, "every step of an exchange must be issued on the same CUDA stream (its double buffering relies on stream order)");
+    x->have_stream = true; x->stream = st;
     const uint32_t step = ++x->step;
     int chunks = (int)((n_hits + 255) / 256);
     if (chunks > 64) chunks = 64;
