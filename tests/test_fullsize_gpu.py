@@ -123,3 +123,80 @@ def test_full_size_default_dispatch_sweeps_even_one_query(corpus):
     idx.set_gemm_min_batch(0)
     for x, y in ((a, s1), (b2, s2)):
         assert np.array_equal(x[0], y[0]) and np.array_equal(x[1].view(np.uint32), y[1].view(np.uint32))
+
+
+def test_full_size_batch_4096_cluster_pairs(corpus, coracle):
+    """BASELINE config 3b at its own shape: 4096 queries over the 10M-row corpus - 32 query tiles, thread-block cluster
+    pairs (the path bench.py times under regimes.batch_4096).  Checked on two queries of EVERY query tile: bits equal to
+    the 64-query search of the same queries (one query tile, no cluster), scores equal to the oracle's canonical score
+    of the regenerated rows, order, needles, and the sampled-rows property."""
+    idx, q64 = corpus
+    q = O.synth_rows(SEED + 1, 0, 4096, DIM)
+    assert np.array_equal(q[:64], q64)
+    idx.set_gemm_min_batch(3)
+    idx.set_gemm_cluster(2)
+    ids_b, sc_b = idx.search(q, K)
+    st = idx.stats()
+    idx.set_gemm_cluster(0)
+    assert st["path"] == 1 and st["queries_rescanned"] == 0
+    ids_a, sc_a = idx.search(q, K)                     # automatic cluster policy (pairs at 32 tiles) must agree too
+    assert np.array_equal(ids_a, ids_b) and np.array_equal(sc_a.view(np.uint32), sc_b.view(np.uint32))
+    ids_g, sc_g = idx.search(q64, K)
+    assert np.array_equal(ids_b[:64], ids_g) and np.array_equal(sc_b[:64].view(np.uint32), sc_g.view(np.uint32))
+    qhat = O.normalize_rows(q, "f32")
+    picks = sorted({t * 128 + (37 * t + 5) % 128 for t in range(32)} | {t * 128 + (91 * t + 64) % 128 for t in range(32)} | {0, 1, 2, 3})
+    for qi in picks:
+        ids, sc = ids_b[qi], sc_b[qi]
+        for j in range(K - 1):
+            assert sc[j] > sc[j + 1] or (sc[j] == sc[j + 1] and ids[j] < ids[j + 1])
+        if qi < 4:
+            assert ids[0] == N + qi and abs(float(sc[0]) - 1.0) < 1e-2
+        syn = ids < N
+        want = O.exact_scores(_host_rows(ids[syn]), qhat[qi])
+        assert np.array_equal(sc[syn].view(np.uint32), want.view(np.uint32)), qi
+    rng = np.random.default_rng(11)
+    for s0 in rng.integers(0, N - 2000, size=60):
+        blk = coracle.normalize_rows(coracle.synth_rows(SEED, int(s0), 2000, DIM, 5000, 0), "bf16")
+        rows = np.arange(s0, s0 + 2000)
+        for qi in picks[::8]:
+            s = coracle.exact_scores(blk, qhat[qi])
+            kth_s, kth_i = sc_b[qi, K - 1], ids_b[qi, K - 1]
+            better = (s > kth_s) | ((s == kth_s) & (rows < kth_i))
+            assert set(rows[better].tolist()) <= set(ids_b[qi].tolist()), (qi, s0)
+
+
+def test_config2_1m_f32_1024_queries(coracle):
+    """BASELINE config 2 at its own shape: synthetic 1M x 768 fp32 corpus, 1024 queries, k = 10 (kind::tf32 path).
+    The C oracle's full top-k for 32 of the queries (bit-exact ids and scores), properties for all 1024."""
+    import ragfin_b200
+    n, nq = 1_000_000, 1024
+    idx = ragfin_b200.Index(DIM, "f32", capacity=n, device=0)
+    idx.add_synthetic(SEED + 7, 0, n, dup_every=997)
+    q = O.synth_rows(SEED + 8, 0, nq, DIM)
+    ids, sc = idx.search(q, K)
+    st = idx.stats()
+    assert st["path"] == 1 and len(idx) == n
+    stored = coracle.normalize_rows(coracle.synth_rows(SEED + 7, 0, n, DIM, 997, 0), "f32")
+    # the device matrix holds the oracle's bits (spot rows) ...
+    for r0 in (0, 499_990, n - 10):
+        assert np.array_equal(idx.read_rows(r0, 10).view(np.uint32), stored[r0:r0 + 10].view(np.uint32))
+    # ... full top-k of 32 queries spread over all 8 query tiles
+    picks = [t * 128 + (53 * t + 9) % 128 for t in range(8)] + list(range(24))
+    wi, ws = coracle.cosine_topk(q[picks], stored, K)
+    assert np.array_equal(ids[picks], wi)
+    assert np.array_equal(sc[picks].view(np.uint32), ws.view(np.uint32))
+    # ... and for all 1024: order, and scores == canonical scores of the returned rows
+    qhat = coracle.normalize_rows(q, "f32")
+    for qi in range(nq):
+        i_, s_ = ids[qi], sc[qi]
+        assert (i_ >= 0).all() and (i_ < n).all()
+        for j in range(K - 1):
+            assert s_[j] > s_[j + 1] or (s_[j] == s_[j + 1] and i_[j] < i_[j + 1])
+        want = coracle.exact_scores(stored[i_], qhat[qi])
+        assert np.array_equal(want.view(np.uint32), s_.view(np.uint32)), qi
+    # the small-batch path answers the same bits
+    idx.set_gemm_min_batch(1 << 30)
+    ids_s, sc_s = idx.search(q[:4], K)
+    assert idx.stats()["path"] == 0
+    assert np.array_equal(ids_s, ids[:4]) and np.array_equal(sc_s.view(np.uint32), sc[:4].view(np.uint32))
+    idx.close()

@@ -194,3 +194,19 @@ def test_c_oracle_under_address_and_ub_sanitizers():
         pytest.skip("no sanitizer runtime for this compiler: " + b.stderr.strip().splitlines()[-1][:200])
     r = subprocess.run([os.path.join(odir, "_san", "selftest")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ORACLE SELFTEST OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+import _thirdparty as TP   # noqa: E402
+
+
+@pytest.mark.parametrize("case", TP.cases(), ids=lambda c: c["name"])
+def test_oracle_pinned_by_committed_thirdparty_fixtures(coracle, case):
+    """tests/golden/thirdparty_topk.json was written by scikit-learn (+ scipy) from the raw rows, without the oracle
+    (scripts/make_thirdparty_golden.py): both oracle implementations must reproduce its id lists and similarities."""
+    x, q = TP.raw_inputs(case["seed"], case["n"], case["dim"], case["nq"], case["scale_seed"])
+    q = q[case["queries"]]
+    ids_c, sc_c = coracle.cosine_topk(q, coracle.normalize_rows(x, "f32"), case["k"])
+    TP.check(case, ids_c, sc_c)
+    if case["n"] <= 5000:                                          # the numpy restatement is slow: small cases only
+        ids_p, sc_p = O.cosine_topk(q, O.normalize_rows(x, "f32"), case["k"])
+        assert np.array_equal(ids_p, ids_c) and np.array_equal(sc_p.view(np.uint32), sc_c.view(np.uint32))

@@ -618,3 +618,32 @@ def test_concurrent_searches_on_one_handle(coracle):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+import _thirdparty as TP   # noqa: E402
+
+
+@pytest.mark.parametrize("case", TP.cases(), ids=lambda c: c["name"])
+def test_engine_reproduces_committed_thirdparty_fixtures(case):
+    """tests/golden/thirdparty_topk.json (written by scikit-learn + scipy from the raw rows, scripts/make_thirdparty_golden.py;
+    the oracle takes no part): the engine with fp32 storage returns the same id lists, similarities within 1e-5 relative
+    (north_star's fp32 tolerance); with bf16 / fp16 storage the fp32 answer is recalled completely once the candidates are
+    rescored in fp32 (recall@k = 1.0 against an fp32 rescore: the 16-bit top-(k + margin) contains the fp32 top-k)."""
+    x, q = TP.raw_inputs(case["seed"], case["n"], case["dim"], case["nq"], case["scale_seed"])
+    q = q[case["queries"]]
+    k = case["k"]
+    idx = _index(x, "f32")
+    ids, sc = idx.search(q, k)
+    TP.check(case, ids, sc)
+    idx.close()
+    if case["strict"] and case["n"] >= 2000:
+        want = np.asarray(case["ids"])
+        for dtype, tol in (("bf16", 4e-3), ("f16", 5e-4)):         # stated tolerance of a 16-bit stored score vs fp32
+            idx = _index(x, dtype)
+            wide_ids, wide_sc = idx.search(q, min(4 * k, case["n"]))
+            for r in range(len(q)):
+                assert set(want[r].tolist()) <= set(wide_ids[r].tolist()), (case["name"], dtype, r)
+                pos = {int(i): j for j, i in enumerate(wide_ids[r])}
+                got = np.array([wide_sc[r][pos[int(i)]] for i in want[r]])
+                assert np.allclose(got, np.asarray(case["sims"])[r], rtol=0, atol=tol), (case["name"], dtype)
+            idx.close()
