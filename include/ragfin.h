@@ -46,7 +46,7 @@ enum {
 };
 
 /* ABI version of this header; bumped on any signature change. */
-#define RAGFIN_ABI_VERSION 2
+#define RAGFIN_ABI_VERSION 3
 int ragfin_abi_version(void);
 
 /* Create an empty collection of `dim`-wide embeddings stored as `dtype` on CUDA device
@@ -71,6 +71,11 @@ int ragfin_add_synthetic(ragfin_t* h, uint64_t seed, int64_t row0, int64_t n, in
 
 /* Number of rows held.  Replaces: Collection.num_entities - vector_rag_mcp/main.py:164. */
 int ragfin_count(const ragfin_t* h, int64_t* n);
+
+/* Grow the matrix to at least capacity_rows rows: a new device allocation and a device-to-device copy of the stored rows
+ * (bits unchanged, nothing re-normalised, no host copy of the embeddings).  No-op when the capacity is already there.
+ * Replaces: Milvus growing a collection's segments under repeated insert() - "chunking_storing (1).py":383-396. */
+int ragfin_reserve(ragfin_t* h, int64_t capacity_rows);
 
 /* Global id of local row 0 (row-sharded corpora: shard r sets its base). Default 0. */
 int ragfin_set_id_base(ragfin_t* h, int64_t id_base);

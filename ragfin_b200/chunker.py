@@ -236,14 +236,16 @@ FIELD_ORDER = ("id", "text", "embedding", "period", "chunk_type", "statement_typ
 
 def ingest_chunks(collection, chunks: Sequence[dict], encode: Callable[[List[str]], "object"]):
     """`texts -> encode -> insert -> flush -> load` (`chunking_storing (1).py:379-396`).  `encode` returns one embedding
-    per text (anything `numpy.asarray` accepts: list of lists, numpy, a CPU torch tensor); the collection normalises and
-    casts on the device (K1).  Returns the insert result."""
+    per text: list of lists / numpy / a CPU torch tensor (host feed, as the reference's `model.encode(texts).tolist()`), or
+    a CUDA torch tensor - embeddings produced on the GPU stay there and reach K1 through `ragfin_add(src_is_device=1)`
+    without a host round trip.  The collection normalises and casts on the device (K1).  Returns the insert result."""
     import numpy as np
     texts = [c["text"] for c in chunks]
     emb = encode(texts)
-    if hasattr(emb, "detach"):
-        emb = emb.detach().cpu().numpy()
-    emb = np.asarray(emb, dtype=np.float32)
+    if not (hasattr(emb, "is_cuda") and emb.is_cuda):
+        if hasattr(emb, "detach"):
+            emb = emb.detach().numpy()
+        emb = np.asarray(emb, dtype=np.float32)
     columns: Dict[str, list] = {name: [c[name] for c in chunks] for name in FIELD_ORDER if name != "embedding"}
     data = [emb if name == "embedding" else columns[name] for name in FIELD_ORDER]
     res = collection.insert(data)

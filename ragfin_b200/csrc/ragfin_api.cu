@@ -252,6 +252,35 @@ extern "C" int ragfin_count(const ragfin_t* h, int64_t* n) {
     return RAGFIN_OK;
 }
 
+// Grow the device matrix to at least `capacity_rows` rows: new allocation + device-to-device copy of the stored rows (they
+// are already normalised and rounded, so nothing is recomputed and no host copy of the embeddings is needed).
+extern "C" int ragfin_reserve(ragfin_t* h, int64_t capacity_rows) {
+    if (!h) return fail(RAGFIN_EINVAL, "NULL handle");
+    if (capacity_rows < 1 || capacity_rows >= (int64_t)0xFFFFFFFF)
+        return fail(RAGFIN_EINVAL, "capacity_rows %lld out of range [1, 2^32-1)", (long long)capacity_rows);
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->is_view) return fail(RAGFIN_EUNSUPPORTED, "a view is read-only");
+    if (capacity_rows <= h->capacity) return RAGFIN_OK;
+    DeviceGuard g(h->device);
+    CU_TRY(cudaDeviceSynchronize());                 // no search may still be reading the old matrix
+    const size_t rb = (size_t)h->ld * esize(h->dtype);
+    void* nd = nullptr;
+    cudaError_t e = cudaMalloc(&nd, (size_t)capacity_rows * rb);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(RAGFIN_ENOMEM, "cudaMalloc of %zu bytes for the grown corpus failed: %s", (size_t)capacity_rows * rb, cudaGetErrorString(e));
+    }
+    if (h->count > 0) {
+        e = cudaMemcpy(nd, h->data, (size_t)h->count * rb, cudaMemcpyDeviceToDevice);
+        if (e != cudaSuccess) { cudaFree(nd); (void)cudaGetLastError(); return fail(RAGFIN_ECUDA, "device copy failed: %s", cudaGetErrorString(e)); }
+    }
+    CU_TRY(cudaFree(h->data));
+    h->data = nd;
+    h->capacity = capacity_rows;
+    for (ragfin::MapSlot& m : h->map_cache) m = ragfin::MapSlot();   // tensor maps of the old matrix are stale
+    return RAGFIN_OK;
+}
+
 extern "C" int ragfin_set_id_base(ragfin_t* h, int64_t id_base) {
     if (!h) return fail(RAGFIN_EINVAL, "NULL handle");
     if (id_base < 0) return fail(RAGFIN_EINVAL, "id_base must be >= 0");

@@ -87,6 +87,11 @@ class Index:
 
     num_entities = property(__len__)
 
+    def reserve(self, capacity: int) -> None:
+        """Grow the device matrix to at least `capacity` rows (device-to-device copy of the stored rows, bits unchanged)."""
+        _lib.check(self._L.ragfin_reserve(self._h, int(capacity)))
+        self.capacity = max(self.capacity, int(capacity))
+
     def set_id_base(self, base: int) -> None:
         _lib.check(self._L.ragfin_set_id_base(self._h, int(base)))
 

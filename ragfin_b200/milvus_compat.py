@@ -141,8 +141,7 @@ class _Store:
         self.storage_dtype, self.capacity, self.device = storage_dtype, capacity, device
         self.index_factory = index_factory
         self.columns: Dict[str, list] = {f.name: [] for f in schema.fields if f.dtype != DataType.FLOAT_VECTOR}
-        self.raw: List[np.ndarray] = []       # fp32 embedding blocks as inserted (host copy)
-        self.pending: List[np.ndarray] = []   # inserted, not yet flushed to the device
+        self.pending: list = []               # embedding blocks inserted but not yet flushed: numpy fp32 or CUDA tensors
         self.n_inserted = 0
         self.index = None
         self.metric: Optional[str] = None
@@ -150,22 +149,22 @@ class _Store:
         self.lock = threading.RLock()
 
     def flush(self):
+        """Upload the pending blocks through K1.  The collection keeps NO host copy of the embeddings: when the rows
+        outgrow the device matrix it is grown on the device (`Index.reserve`: new allocation + device-to-device copy of
+        the stored, already normalised rows), so nothing is re-normalised and host memory stays flat."""
         with self.lock:
             if not self.pending:
                 return
             need = self.n_inserted
-            if self.raw is None and need > self.capacity:
-                raise MilvusException(message="collection was loaded from disk with a fixed capacity; reload with a larger one")
-            if self.index is None or need > self.capacity:
+            if self.index is None:
                 while self.capacity < need:
                     self.capacity *= 2
-                if self.index is not None:
-                    self.index.close()
                 self.index = self.index_factory(self.schema.vector_field.dim, self.storage_dtype, self.capacity, self.device)
-                blocks = self.raw            # re-ingest everything from the host copy
-            else:
-                blocks = self.pending
-            for b in blocks:
+            elif need > self.capacity:
+                while self.capacity < need:
+                    self.capacity *= 2
+                self.index.reserve(self.capacity)
+            for b in self.pending:
                 self.index.add(b)
             self.pending = []
 
@@ -204,7 +203,6 @@ def load_collection(name: str, directory: str, device: int = 0, using: str = "de
     if st.n_inserted and os.path.exists(mpath):
         st.index = Index.load(mpath, capacity=max(st.capacity, st.n_inserted), device=device)
         st.capacity = st.index.capacity
-        st.raw = None          # the original fp32 rows are gone: growth past capacity is refused after a reload
     return col
 
 
@@ -284,8 +282,12 @@ class MutationResult:
         self.insert_count = len(self.primary_keys)
 
 
-_EXPR_IN = re.compile(r"^\s*(\w+)\s+in\s+\[(.*)\]\s*$", re.S)
-_EXPR_EQ = re.compile(r"^\s*(\w+)\s*==\s*(.+?)\s*$", re.S)
+_STR = r"\"[^\"]*\"|'[^']*'"
+_NUM = r"[-+]?(?:\d+\.?\d*(?:[eE][-+]?\d+)?|\.\d+(?:[eE][-+]?\d+)?)"
+_LIT = rf"(?:{_STR}|{_NUM})"
+_EXPR_IN = re.compile(rf"^\s*(\w+)\s+in\s+\[\s*((?:{_LIT}\s*(?:,\s*{_LIT}\s*)*)?)\]\s*$", re.S)
+_EXPR_EQ = re.compile(rf"^\s*(\w+)\s*==\s*({_LIT})\s*$", re.S)
+_LIT_RE = re.compile(_LIT, re.S)
 
 
 def _parse_literal(tok: str):
@@ -295,7 +297,10 @@ def _parse_literal(tok: str):
     try:
         return int(tok)
     except ValueError:
-        return float(tok)
+        try:
+            return float(tok)
+        except ValueError:
+            raise MilvusException(message=f"cannot parse expression: invalid literal {tok!r}") from None
 
 
 class Collection:
@@ -351,28 +356,45 @@ class Collection:
         if any(len(c) != n for c in cols):
             raise ParamError(message="all columns must have the same number of rows")
         vi = fields.index(st.schema.vector_field)
-        emb = np.ascontiguousarray(cols[vi], dtype=np.float32)
-        if n and (emb.ndim != 2 or emb.shape != (n, st.schema.vector_field.dim)):
-            raise ParamError(message=f"embedding column must be [{n}, {st.schema.vector_field.dim}], got {emb.shape}")
+        dim = st.schema.vector_field.dim
+        emb = cols[vi]
+        if hasattr(emb, "is_cuda") and emb.is_cuda:
+            # embeddings produced on the GPU (a torch encoder) stay there: K1 reads them through ragfin_add(src_is_device=1)
+            import torch
+            if emb.dim() != 2 or tuple(emb.shape) != (n, dim):
+                raise ParamError(message=f"embedding column must be [{n}, {dim}], got {tuple(emb.shape)}")
+            emb = emb.detach().to(torch.float32).contiguous().clone()      # the caller may reuse its buffer after insert()
+        else:
+            if hasattr(emb, "detach"):
+                emb = emb.detach().numpy()
+            emb = np.array(emb, dtype=np.float32, order="C")               # a private copy: pending until flush()
+            if n and (emb.ndim != 2 or emb.shape != (n, dim)):
+                raise ParamError(message=f"embedding column must be [{n}, {dim}], got {emb.shape}")
         pk_name = st.schema.primary_field.name
         pks = list(cols[fields.index(st.schema.primary_field)])
         with st.lock:
+            # ---- validate every column before anything is touched: a Milvus insert is all-or-nothing
+            if len(set(pks)) != len(pks):
+                raise MilvusException(message="duplicate primary keys inside one insert")
             for pk in pks:
                 if pk in st.pk_to_row:
                     raise MilvusException(message=f"duplicate primary key {pk!r}")
+            staged = {}
             for f, c in zip(fields, cols):
                 if f.dtype == DataType.FLOAT_VECTOR:
                     continue
+                c = list(c)
                 if f.dtype == DataType.VARCHAR and f.max_length:
                     for v in c:
                         if len(str(v)) > f.max_length:
                             raise MilvusException(message=f"length of varchar field {f.name} exceeds max length {f.max_length}")
-                st.columns[f.name].extend(c)
+                staged[f.name] = c
+            # ---- commit
+            for name, c in staged.items():
+                st.columns[name].extend(c)
             for j, pk in enumerate(pks):
                 st.pk_to_row[pk] = st.n_inserted + j
             if n:
-                if st.raw is not None:
-                    st.raw.append(emb)
                 st.pending.append(emb)
             st.n_inserted += n
         assert pk_name in st.columns
@@ -448,15 +470,17 @@ class Collection:
         """Rows (ascending) among the first n that satisfy `field in [...]` or `field == literal`."""
         st = self._st
         pk_name = st.schema.primary_field.name
+        # The two forms the reference uses (graph_cons.py:306-311 `id in [...]`, plus `field == literal`), matched in FULL:
+        # anything else - and / or / not, comparisons, unquoted strings, trailing text - is rejected instead of being
+        # swallowed into a literal (which would silently select no rows).
         m_in, m_eq = _EXPR_IN.match(expr), _EXPR_EQ.match(expr)
         if m_in:
             field = m_in.group(1)
-            body = m_in.group(2).strip()
-            wanted = [_parse_literal(t) for t in re.findall(r"\"[^\"]*\"|'[^']*'|[^,\s]+", body)] if body else []
+            wanted = [_parse_literal(t) for t in _LIT_RE.findall(m_in.group(2))]
         elif m_eq:
             field, wanted = m_eq.group(1), [_parse_literal(m_eq.group(2))]
         else:
-            raise MilvusException(message=f"cannot parse expression: {expr}")
+            raise MilvusException(message=f"cannot parse expression: {expr} (supported: `field in [literals]`, `field == literal`)")
         if field not in st.columns:
             raise MilvusException(message=f"field {field} not exist")
         if field == pk_name:

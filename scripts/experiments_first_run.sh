@@ -5,6 +5,7 @@
 #   gpurun --timeout 2400 -- 'bash scripts/experiments_first_run.sh'
 # Logs land in gpurun_out/{pair,seeded,pdl,pipeline}_check.log and gpurun_out/experimental_tests.log.
 mkdir -p gpurun_out
+export RAGFIN_EXPERIMENTAL=1   # the library refuses variants 4 / 5 and views without it
 timeout 900 python scripts/pair_check.py   > gpurun_out/pair_check.log   2>&1; echo "pair_check rc=$?"
 timeout 800 python scripts/seeded_check.py > gpurun_out/seeded_check.log 2>&1; echo "seeded_check rc=$?"
 if [ -f ragfin_b200/csrc/libragfin_pdl.so ]; then

@@ -99,7 +99,7 @@ def stage_time():
     return True
 
 
-STAGES = {"raw": (stage_raw, 180), "search": (stage_search, 240), "time": (stage_time, 420)}
+STAGES = {"raw": (stage_raw, 120), "search": (stage_search, 150), "time": (stage_time, 300)}
 
 if __name__ == "__main__":
     if len(sys.argv) > 1:

@@ -79,7 +79,7 @@ def stage_time():
     return True
 
 
-STAGES = {"search": (stage_search, 300), "time": (stage_time, 400)}
+STAGES = {"search": (stage_search, 150), "time": (stage_time, 300)}
 
 if __name__ == "__main__":
     if len(sys.argv) > 1:

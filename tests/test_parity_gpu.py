@@ -647,3 +647,70 @@ def test_engine_reproduces_committed_thirdparty_fixtures(case):
                 got = np.array([wide_sc[r][pos[int(i)]] for i in want[r]])
                 assert np.allclose(got, np.asarray(case["sims"])[r], rtol=0, atol=tol), (case["name"], dtype)
             idx.close()
+
+
+def test_reserve_grows_on_the_device_bit_identically(coracle):
+    """ragfin_reserve: new allocation + device-to-device copy; stored bits, ids and later searches unchanged."""
+    x = O.synth_rows(61, 0, 3000, 384, dup_every=13)
+    q = O.synth_rows(62, 0, 5, 384)
+    for dtype in O.DTYPES:
+        idx = _index(x[:1000], dtype, capacity=1000)
+        before = idx.search(q, 10)
+        with pytest.raises(Exception):
+            idx.add(x[1000:1001])                       # full
+        idx.reserve(3000)
+        assert len(idx) == 1000
+        _assert_same(idx.search(q, 10), before, "after reserve")
+        idx.add(x[1000:])
+        want_rows = coracle.normalize_rows(x, dtype)
+        assert np.array_equal(idx.read_rows(0, 3000).view(np.uint32), want_rows.view(np.uint32))
+        _assert_same(idx.search(q, 10), coracle.cosine_topk(q, want_rows, 10), f"{dtype} grown")
+        idx.close()
+
+
+def test_device_feed_through_the_shim_and_the_chunk_pipeline(coracle):
+    """N2 without the host round trip ("chunking_storing (1).py":379-396 with an encoder that lives on the GPU):
+    Collection.insert and ingest_chunks accept CUDA tensors, which reach K1 through ragfin_add(src_is_device=1); the
+    collection grows on the device.  Same bits as the host feed."""
+    import torch
+    from ragfin_b200 import milvus_compat as mc
+    from ragfin_b200.chunker import FIELD_ORDER, ingest_chunks
+    F, D = mc.FieldSchema, mc.DataType
+    fields = [F("id", D.VARCHAR, max_length=100, is_primary=True), F("text", D.VARCHAR, max_length=4000),
+              F("embedding", D.FLOAT_VECTOR, dim=384), F("period", D.VARCHAR, max_length=20),
+              F("chunk_type", D.VARCHAR, max_length=30), F("statement_type", D.VARCHAR, max_length=30),
+              F("primary_value", D.DOUBLE)]
+    x = O.synth_rows(71, 0, 300, 384)
+    chunks = [dict(id=f"c{i}", text=f"text {i}", period="Q1_FY2024", chunk_type="t", statement_type="s", primary_value=float(i))
+              for i in range(300)]
+
+    cols = {}
+    for feed in ("host", "device"):
+        name = f"feed_{feed}"
+        mc.utility.drop_collection(name)
+        col = mc.Collection(name, mc.CollectionSchema(fields, "x"), storage_dtype="bf16", initial_capacity=64)
+        col.create_index("embedding", {"index_type": "IVF_FLAT", "metric_type": "COSINE", "params": {"nlist": 128}})
+        seen = []
+
+        def encode(texts, feed=feed, seen=seen):
+            rows = x[[int(t.split()[1]) for t in texts]]
+            seen.append(len(texts))
+            return torch.from_numpy(rows).cuda() if feed == "device" else rows.tolist()
+
+        for r0 in range(0, 300, 100):                    # three ingests: the collection grows 64 -> 128 -> 256 -> 512
+            ingest_chunks(col, chunks[r0:r0 + 100], encode)
+        assert col.num_entities == 300 and seen == [100, 100, 100]
+        cols[feed] = col
+    a, b = cols["host"]._st.index, cols["device"]._st.index
+    want = coracle.normalize_rows(x, "bf16")
+    assert np.array_equal(a.read_rows(0, 300).view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(b.read_rows(0, 300).view(np.uint32), want.view(np.uint32))
+    q = O.synth_rows(72, 0, 3, 384)
+    ra = cols["host"].search(q, "embedding", {"metric_type": "COSINE"}, 5, output_fields=["text"])
+    rb = cols["device"].search(q, "embedding", {"metric_type": "COSINE"}, 5, output_fields=["text"])
+    wi, ws = coracle.cosine_topk(q, want, 5)
+    for qi in range(3):
+        assert [h.id for h in ra[qi]] == [h.id for h in rb[qi]] == [f"c{i}" for i in wi[qi]]
+        assert [h.score for h in ra[qi]] == [h.score for h in rb[qi]] == [float(v) for v in ws[qi]]
+    for n in ("feed_host", "feed_device"):
+        mc.utility.drop_collection(n)

@@ -26,6 +26,9 @@ class OracleIndex:
         assert len(self.rows) + len(rows) <= self.capacity
         self.rows = np.concatenate([self.rows, O.normalize_rows(rows, self.dtype)])
 
+    def reserve(self, capacity):
+        self.capacity = max(self.capacity, capacity)
+
     def search(self, q, k, allow=None):
         if allow is None:
             return O.cosine_topk(q, self.rows, k)
@@ -139,7 +142,7 @@ def test_open_existing_and_missing_collection():
     assert not mc.utility.has_collection("fin_chunks")
 
 
-def test_growth_reingests_from_host_copy_and_duplicate_pk():
+def test_growth_on_the_device_and_duplicate_pk():
     made = []
 
     def factory(*a):
@@ -153,8 +156,8 @@ def test_growth_reingests_from_host_copy_and_duplicate_pk():
         col.insert([[f"c{i}" for i in range(a, b)], ["t"] * (b - a), x[a:b], ["p"] * (b - a), ["k"] * (b - a),
                     ["s"] * (b - a), [0.0] * (b - a)])
         col.flush()
-    assert len(made) == 2 and made[0].closed and made[1].capacity == 16
-    assert np.array_equal(made[1].rows, O.normalize_rows(x, "f32"))
+    assert len(made) == 1 and not made[0].closed and made[0].capacity == 16      # grown in place (Index.reserve), never rebuilt
+    assert np.array_equal(made[0].rows, O.normalize_rows(x, "f32"))
     with pytest.raises(mc.MilvusException):
         col.insert([["c3"], ["t"], x[:1], ["p"], ["k"], ["s"], [0.0]])
     res = col.search(x[7:8] * 3.0, "embedding", {"metric_type": "COSINE"}, 1)
@@ -201,3 +204,71 @@ def test_filtered_search_expr():
     assert col.search(q, "embedding", {"metric_type": "COSINE"}, 5, expr='period == "none"')[0] == []
     with pytest.raises(mc.MilvusException):
         col.search(q, "embedding", {"metric_type": "COSINE"}, 5, expr="period like 'Q%'")
+
+
+def test_failed_insert_leaves_the_collection_unchanged():
+    """A Milvus insert is all-or-nothing: an over-long VARCHAR in a LATER column, a duplicate primary key or a wrong
+    embedding shape must not leave earlier columns one row longer (every later hit would carry the wrong fields)."""
+    col, g = build_collection("atomic_ins")
+    st = col._st
+    before = {k: list(v) for k, v in st.columns.items()}
+    n0, pk0 = st.n_inserted, dict(st.pk_to_row)
+    e = O.synth_rows(5, 0, 1, 384)
+    bad = [
+        [["a"], ["hello"], e.tolist(), ["p" * 21], ["t"], ["s"], [1.0]],                 # period exceeds max_length 20
+        [[g["chunks"][0]["id"]], ["hello"], e.tolist(), ["ok"], ["t"], ["s"], [1.0]],    # duplicate primary key
+        [["a", "a"], ["x", "y"], np.concatenate([e, e]).tolist(), ["ok", "ok"], ["t", "t"], ["s", "s"], [1.0, 2.0]],   # duplicate inside the insert
+        [["a"], ["hello"], e[:, :100].tolist(), ["ok"], ["t"], ["s"], [1.0]],            # wrong embedding width
+    ]
+    for data in bad:
+        with pytest.raises(mc.MilvusException):
+            col.insert(data)
+        assert st.columns == before and st.n_inserted == n0 and st.pk_to_row == pk0 and not st.pending
+    mr = col.insert([["a"], ["hello"], e.tolist(), ["ok"], ["t"], ["s"], [1.0]])
+    col.flush()
+    assert mr.primary_keys == ["a"] and col.num_entities == 17
+    assert col.query('id in ["a"]', output_fields=["text", "period"]) == [{"id": "a", "text": "hello", "period": "ok"}]
+
+
+def test_unsupported_expressions_are_rejected_not_swallowed():
+    col, g = build_collection("expr_strict")
+    for expr in ['chunk_type == "x" and period == "Q1"', "period == Q1", 'id in ["a" "b"]', "primary_value > 3",
+                 'not period == "x"', 'id in ["a",]', 'period == "x" or period == "y"']:
+        with pytest.raises(mc.MilvusException):
+            col.query(expr)
+        with pytest.raises(mc.MilvusException):
+            col.search(O.synth_rows(1, 0, 1, 384), "embedding", {"metric_type": "COSINE"}, 3, expr=expr)
+    pid = g["chunks"][3]["period"]
+    rows = col.query(f'period == "{pid}"', output_fields=["period"])
+    assert rows and all(r["period"] == pid for r in rows)
+    assert col.query("primary_value == 2.0", output_fields=["primary_value"])[0]["primary_value"] == 2.0
+    assert col.query("id in []") == []
+
+
+def test_collection_grows_without_a_host_copy_of_the_embeddings():
+    """Capacity doubling goes through Index.reserve (device-side growth): the shim holds no second copy of the rows and
+    nothing is re-ingested; results equal one big insert."""
+    calls = []
+
+    class Counting(OracleIndex):
+        def add(self, rows):
+            calls.append(len(rows))
+            super().add(rows)
+
+        def reserve(self, capacity):
+            calls.append(("reserve", capacity))
+            super().reserve(capacity)
+
+    name = "grow"
+    if mc.utility.has_collection(name):
+        mc.utility.drop_collection(name)
+    col = mc.Collection(name, mc.CollectionSchema(reference_fields(64), "g"), index_factory=Counting, initial_capacity=8)
+    x = O.synth_rows(9, 0, 40, 64)
+    for r0 in range(0, 40, 10):
+        col.insert([[f"k{r0 + i}" for i in range(10)], ["t"] * 10, x[r0:r0 + 10], ["p"] * 10, ["c"] * 10, ["s"] * 10, [0.0] * 10])
+        col.flush()
+    assert not hasattr(col._st, "raw")
+    assert [c for c in calls if not isinstance(c, tuple)] == [10, 10, 10, 10]        # every row ingested exactly once
+    assert [c for c in calls if isinstance(c, tuple)] == [("reserve", 32), ("reserve", 64)]
+    res = col.search(x[17:18], "embedding", {"metric_type": "COSINE"}, 3)
+    assert res[0][0].id == "k17"
