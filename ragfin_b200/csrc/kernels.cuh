@@ -67,6 +67,67 @@ __global__ void __launch_bounds__(256) ingest_kernel(const float* __restrict__ s
 }
 
 // ---------------------------------------------------------------------------------
+// K1, vectorised (the default for host / device fp32 sources with dim % 4 == 0 and dim <= 128 * NV): one warp per row,
+// the row is read ONCE with 128-bit loads (lane l, vector j holds elements [(32 j + l) * 4, +4)) and kept in registers.
+// The canonical sum of squares wants lane p to add the elements i = p, p + 32, ... in increasing i, which
+// is not the vector layout, so the warp transposes the row through its 128 NV * 16 bytes of shared memory (STS.128
+// in, conflict-free LDS.32 out); every lane then scales the elements it holds in registers and stores them with one
+// 64-bit (16-bit storage) or 128-bit (fp32 storage) store per vector.  Same bits as ingest_kernel.
+// Algorithmic HBM bytes per row: 4 * dim read + ld * sizeof(T) written.
+// ---------------------------------------------------------------------------------
+constexpr int kIngestThreads = 256;
+constexpr int kIngestWarps = kIngestThreads / kWarp;
+
+template <int DT, int NV>
+__global__ void __launch_bounds__(kIngestThreads) ingest_vec_kernel(const float* __restrict__ src, int64_t n, int dim, int ld,
+                                                                      typename Store<DT>::T* __restrict__ dst) {
+    typedef typename Store<DT>::T T;
+    __shared__ __align__(16) float stage[kIngestWarps][NV * 128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t gw = (int64_t)blockIdx.x * kIngestWarps + warp;
+    const int64_t nw = (int64_t)gridDim.x * kIngestWarps;
+    const int nvec = dim >> 2;                      // 16-byte vectors of the source row
+    const int nvec_out = ld >> 2;                   // groups of 4 output elements (ld % 8 == 0)
+    float* mine = stage[warp];
+    for (int64_t r = gw; r < n; r += nw) {
+        const float4* x = reinterpret_cast<const float4*>(src + r * (int64_t)dim);
+        float4 v[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int vi = j * kWarp + lane;
+            v[j] = vi < nvec ? __ldcs(x + vi) : make_float4(0.f, 0.f, 0.f, 0.f);   // streaming: read once
+        }
+#pragma unroll
+        for (int j = 0; j < NV; ++j) *reinterpret_cast<float4*>(mine + (j * kWarp + lane) * 4) = v[j];
+        __syncwarp();
+        double acc = 0.0;
+#pragma unroll 8
+        for (int i = lane; i < dim; i += kWarp) {
+            const double t = (double)mine[i];
+            acc = acc + t * t;
+        }
+        __syncwarp();                               // the staging row is free for the next iteration
+        const double n2 = warp_butterfly_f64(acc);
+        const double inv = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
+        T* out = dst + r * (int64_t)ld;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int vi = j * kWarp + lane;
+            if (vi < nvec_out) {                    // vectors in [nvec, nvec_out) are the zero padding of the stored row
+                const float y0 = (float)((double)v[j].x * inv), y1 = (float)((double)v[j].y * inv);
+                const float y2 = (float)((double)v[j].z * inv), y3 = (float)((double)v[j].w * inv);
+                if (DT == 0) {
+                    __stcs(reinterpret_cast<float4*>(out) + vi, make_float4(y0, y1, y2, y3));
+                } else {
+                    T pr[4] = {Store<DT>::from_f32(y0), Store<DT>::from_f32(y1), Store<DT>::from_f32(y2), Store<DT>::from_f32(y3)};
+                    __stcs(reinterpret_cast<uint2*>(out) + vi, *reinterpret_cast<uint2*>(pr));
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // Transposed warp reduction: every lane holds M partial sums (M a power of two <= 32);
 // afterwards lane l holds the warp-wide total of value index (l >> (5 - log2 M)).
 // log2(M) exchange rounds halve the live values, the remaining rounds are a plain butterfly:

@@ -101,6 +101,9 @@ struct ragfin {
     struct MapSlot { const void* base = nullptr; int64_t rows = 0; int ld = 0, dtype = 0, box_rows = 0; CUtensorMap map; };
     MapSlot map_cache[8];     // tensor maps are pure functions of (base, rows, ld, dtype, box): encode once
     int map_next = 0;
+    Buf add_stage2[2];        // ragfin_add from host memory: two staging slices ...
+    cudaStream_t copy_stream = nullptr;                       // ... filled on this stream while K1 runs on the caller's
+    cudaEvent_t stage_ready[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
     void* hstage = nullptr;   // pinned, device-mapped staging for small host calls: kernels read the queries and write the hits
                               // straight through PCIe, no copy engine launches (ragfin_search_host)
     cudaEvent_t last_done = nullptr;
@@ -238,6 +241,12 @@ extern "C" void ragfin_destroy(ragfin_t* h) {
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->data && !h->is_view) cudaFree(h->data);
+    for (int b = 0; b < 2; ++b) {
+        if (h->add_stage2[b].p) cudaFree(h->add_stage2[b].p);
+        if (h->stage_ready[b]) cudaEventDestroy(h->stage_ready[b]);
+        if (h->stage_free[b]) cudaEventDestroy(h->stage_free[b]);
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->hstage) cudaFreeHost(h->hstage);
     if (h->last_done) cudaEventDestroy(h->last_done);
     for (cudaEvent_t e : h->prof_ev)
@@ -298,6 +307,23 @@ static int launch_ingest(int dtype, const float* src, uint64_t key, int64_t row0
     if (n == 0) return 0;
     const int threads = 256, wpb = threads / 32;
     int64_t blocks = (n + wpb - 1) / wpb;
+    if (!SYNTH && dim % 4 == 0 && ld <= 1024 && ((uintptr_t)src & 15u) == 0) {
+        // vectorised single-pass kernel (kernels.cuh ingest_vec_kernel): NV 16-byte vectors per lane cover the stored row
+        const int nv = ld <= 256 ? 2 : ld <= 512 ? 4 : ld <= 768 ? 6 : 8;
+        const int64_t capv = (int64_t)num_sms * 8;
+        if (blocks > capv) blocks = capv;
+#define RF_INGEST_VEC(DT, TT) \
+        switch (nv) { \
+            case 2: ingest_vec_kernel<DT, 2><<<(int)blocks, kIngestThreads, 0, st>>>(src, n, dim, ld, (TT*)dst); break; \
+            case 4: ingest_vec_kernel<DT, 4><<<(int)blocks, kIngestThreads, 0, st>>>(src, n, dim, ld, (TT*)dst); break; \
+            case 6: ingest_vec_kernel<DT, 6><<<(int)blocks, kIngestThreads, 0, st>>>(src, n, dim, ld, (TT*)dst); break; \
+            default: ingest_vec_kernel<DT, 8><<<(int)blocks, kIngestThreads, 0, st>>>(src, n, dim, ld, (TT*)dst); break; \
+        }
+        if (dtype == 0) { RF_INGEST_VEC(0, float) } else if (dtype == 1) { RF_INGEST_VEC(1, __nv_bfloat16) } else { RF_INGEST_VEC(2, __half) }
+#undef RF_INGEST_VEC
+        CU_TRY(cudaGetLastError());
+        return 0;
+    }
     const int64_t cap = (int64_t)num_sms * 16;
     if (blocks > cap) blocks = cap;
     switch (dtype) {
@@ -327,20 +353,44 @@ extern "C" int ragfin_add(ragfin_t* h, const float* rows, int64_t n, int32_t src
     if ((rc = wait_prev(h, st))) return rc;
     char* dst = (char*)h->data + (size_t)h->count * h->ld * esize(h->dtype);
     if (src_is_device) {
+        prof_begin(h, st);
         if ((rc = launch_ingest<false>(h->dtype, rows, 0, 0, 0, 0, n, h->dim, h->ld, dst, h->num_sms, st))) return rc;
+        prof_end(h, st);
     } else {
-        // staged in slices so that a huge host matrix never needs a device copy of itself
-        const int64_t slice = (int64_t)((256u << 20) / ((size_t)h->dim * 4)) + 1;
-        for (int64_t r0 = 0; r0 < n; r0 += slice) {
+        // Staged in slices through TWO device buffers so that a huge host matrix never needs a device copy of itself and
+        // the copy of slice i + 1 (on the handle's copy stream) overlaps K1 on slice i (on `st`):
+        //   copy stream:  wait free[b] -> H2D into stage[b] -> record ready[b]
+        //   st:           wait ready[b] -> K1 -> record free[b]
+        const size_t row_b = (size_t)h->dim * 4;
+        const int64_t slice = (int64_t)((64u << 20) / row_b) + 1;
+        if (!h->copy_stream) {
+            CU_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; ++b) {
+                CU_TRY(cudaEventCreateWithFlags(&h->stage_ready[b], cudaEventDisableTiming));
+                CU_TRY(cudaEventCreateWithFlags(&h->stage_free[b], cudaEventDisableTiming));
+            }
+        }
+        const int64_t m_max = n < slice ? n : slice;
+        for (int b = 0; b < 2; ++b)
+            if ((rc = ensure(h->add_stage2[b], (size_t)m_max * row_b))) return rc;
+        CU_TRY(cudaEventRecord(h->stage_free[0], st));   // both buffers are free once the work queued on st so far is done
+        CU_TRY(cudaEventRecord(h->stage_free[1], st));
+        int b = 0;
+        for (int64_t r0 = 0; r0 < n; r0 += slice, b ^= 1) {
             const int64_t m = n - r0 < slice ? n - r0 : slice;
-            if ((rc = ensure(h->add_stage, (size_t)m * h->dim * 4))) return rc;
-            CU_TRY(cudaMemcpyAsync(h->add_stage.p, rows + (size_t)r0 * h->dim, (size_t)m * h->dim * 4,
-                                   cudaMemcpyHostToDevice, st));
-            if ((rc = launch_ingest<false>(h->dtype, (const float*)h->add_stage.p, 0, 0, 0, 0, m, h->dim, h->ld,
+            CU_TRY(cudaStreamWaitEvent(h->copy_stream, h->stage_free[b], 0));
+            CU_TRY(cudaMemcpyAsync(h->add_stage2[b].p, rows + (size_t)r0 * h->dim, (size_t)m * row_b, cudaMemcpyHostToDevice, h->copy_stream));
+            CU_TRY(cudaEventRecord(h->stage_ready[b], h->copy_stream));
+            CU_TRY(cudaStreamWaitEvent(st, h->stage_ready[b], 0));
+            prof_begin(h, st);
+            if ((rc = launch_ingest<false>(h->dtype, (const float*)h->add_stage2[b].p, 0, 0, 0, 0, m, h->dim, h->ld,
                                            dst + (size_t)r0 * h->ld * esize(h->dtype), h->num_sms, st)))
                 return rc;
-            CU_TRY(cudaStreamSynchronize(st));  // host buffer and staging slice are reusable on return
+            prof_end(h, st);
+            CU_TRY(cudaEventRecord(h->stage_free[b], st));
         }
+        CU_TRY(cudaStreamSynchronize(h->copy_stream));   // the host buffer is reusable on return
+        CU_TRY(cudaStreamSynchronize(st));
     }
     h->count += n;
     return mark_done(h, st);
