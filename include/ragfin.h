@@ -205,6 +205,13 @@ int ragfin_set_bound_pass(ragfin_t* h, int32_t enable);
  * 0 = per-query K' lists in shared memory + certificate.  Results are identical. */
 int ragfin_set_append_mode(ragfin_t* h, int32_t enable);
 
+/* Tuning knob: batches of <= 64 queries with k <= 128 over corpora of >= min_rows rows (default 8192) are answered by ONE
+ * kernel (csrc/sweep_fused.cuh): query preparation, tensor-core sweep with self-tightening thresholds, exact finalize and
+ * the exact fallback all inside it - no bound pass, no separate finalize, no gated launches.  1 = on (default), 0 = the
+ * multi-kernel paths.  min_rows = 0 leaves the row limit unchanged.  Results are identical.
+ * Replaces: the same Collection.search call sites; this is the batch-1 path of vector_rag_mcp/main.py:51-57. */
+int ragfin_set_fused(ragfin_t* h, int32_t enable, int64_t min_rows);
+
 /* Test hook: raw (approximate, fp32-accumulated) tensor-core scores of nq queries against every
  * stored row, out_scores_dev [nq, count] device memory.  Validates the TMA / tcgen05 plumbing. */
 int ragfin_debug_gemm_scores(ragfin_t* h, const float* q_dev, int32_t nq, float* out_scores_dev, void* stream);

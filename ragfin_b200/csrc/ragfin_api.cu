@@ -17,6 +17,7 @@
 #include "gemm_rows.cuh"
 #include "gemm_pair.cuh"
 #include "gemm_rows_seeded.cuh"
+#include "sweep_fused.cuh"
 #include "scan_tma.cuh"
 #include "bigk.cuh"
 
@@ -96,6 +97,10 @@ struct ragfin {
                               // 3 = streaming + swapped operand roles for <= 16 queries in append mode (gemm_rows.cuh),
                               // 4 = EXPERIMENTAL 2-SM MMA pairs for >= 2 query tiles in append mode (gemm_pair.cuh; not yet run on a GPU)
                               // 5 = EXPERIMENTAL self-seeded sweep for <= 16 queries, k <= 16 (gemm_rows_seeded.cuh; not yet run on a GPU)
+    Buf fctl;                 // fused sweep: control block (FusedCtl), zero between searches
+    bool fctl_dirty = true;   // set when a launch may have left it non-zero (first use, failed call): re-zeroed before the next launch
+    bool use_fused = true;    // <= 64 queries, k <= 128: the one-kernel search (sweep_fused.cuh); RAGFIN_NO_FUSED=1 disables
+    int fused_min_rows = 8192;
     Buf gbar;                 // variant 5: grid-wide arrival counter (monotonic) ...
     uint32_t gbar_target = 0; // ... and the value it reaches once the last launch's CTAs have all arrived
     struct MapSlot { const void* base = nullptr; int64_t rows = 0; int ld = 0, dtype = 0, box_rows = 0; CUtensorMap map; };
@@ -186,6 +191,7 @@ extern "C" int ragfin_create(ragfin_t** out, int32_t dim, int32_t dtype, int64_t
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
     { const char* e = getenv("RAGFIN_NO_BOUND_PASS"); if (e && atoi(e)) h->use_bound_pass = false; }
+    { const char* e = getenv("RAGFIN_NO_FUSED"); if (e && atoi(e)) h->use_fused = false; }
     h->capacity = capacity_rows;
     const size_t bytes = (size_t)capacity_rows * h->ld * esize(dtype);
     e = cudaMalloc(&h->data, bytes);
@@ -237,7 +243,7 @@ extern "C" void ragfin_destroy(ragfin_t* h) {
     if (!h) return;
     DeviceGuard g(h->device);
     (void)cudaDeviceSynchronize();
-    Buf* bufs[] = {&h->qhat, &h->q16, &h->eps_q, &h->gtau, &h->bmax, &h->acnt, &h->athr, &h->allow, &h->bk_scores, &h->bk_state, &h->bk_keys, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage, &h->gbar};
+    Buf* bufs[] = {&h->qhat, &h->q16, &h->eps_q, &h->gtau, &h->bmax, &h->acnt, &h->athr, &h->allow, &h->bk_scores, &h->bk_state, &h->bk_keys, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage, &h->gbar, &h->fctl};
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->data && !h->is_view) cudaFree(h->data);
@@ -1020,6 +1026,108 @@ static bool use_astat(const ragfin* h, int kp) {
 }
 
 // ------------------------------------------------------------------------------
+// K3f: the one-kernel search for <= 64 queries and k <= 128 (sweep_fused.cuh)
+// ------------------------------------------------------------------------------
+struct FusedPlan {
+    int ncol = 0, stages = 0, pend = 0, cap = 0;
+    bool split = false;
+    size_t smem = 0;
+};
+
+// Column count / split / ring depth for nb queries, or ncol = 0 when the shape does not fit one CTA's shared memory.
+static FusedPlan plan_fused(const ragfin* h, int nb, int k) {
+    FusedPlan best;
+    if (nb < 1 || nb > kFMaxQ || k > kFMaxK) return best;
+    const int es = (int)esize(h->dtype);
+    const int k_elems = kGKBytes / es;
+    const int nkb = (h->ld + k_elems - 1) / k_elems;
+    const int pend = nb <= 16 ? 64 : 32;
+    const bool can_split = h->dtype != 0;
+    // candidates in order of preference: split (tight error bound) first, then plain
+    const int cols_split[3] = {16, 32, 64}, cols_plain[3] = {16, 32, 64};
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool split = pass == 0;
+        if (split && !can_split) continue;
+        for (int ci = 0; ci < 3; ++ci) {
+            const int ncol = split ? cols_split[ci] : cols_plain[ci];
+            if ((split ? ncol / 2 : ncol) < nb) continue;
+            for (int stages = kRMaxStages; stages >= 3; --stages) {
+                const size_t smem = fused_smem_bytes(nkb, ncol, stages, nb, k, pend);
+                if (smem > (size_t)227 * 1024) continue;
+                const size_t region = (size_t)nkb * ncol * kGKBytes + (size_t)stages * kBBytes;
+                const size_t hdr = (((size_t)((h->ld + 3) / 4 * 4) * 4 + 256 * 4 + 16 + 15) / 16) * 16;
+                if (region < hdr + 4096 * sizeof(u64)) continue;
+                int cap = (int)((region - hdr) / sizeof(u64));
+                int p2 = 4096;                                  // the finalize pads its sort to a power of two inside the scratch
+                while (p2 * 2 <= cap) p2 *= 2;
+                cap = p2 < kAppendCap ? p2 : kAppendCap;
+                FusedPlan f;
+                f.ncol = ncol; f.split = split; f.stages = stages; f.pend = pend; f.cap = cap; f.smem = smem;
+                return f;
+            }
+        }
+    }
+    return best;
+}
+
+static bool fused_eligible(const ragfin* h, int nb, int k) {
+    return h->use_fused && h->count >= h->fused_min_rows && gemm_rows_ok(h) && plan_fused(h, nb, k).ncol != 0;
+}
+
+typedef void (*fused_fn)(const CUtensorMap, const FusedArgs);
+static fused_fn pick_fused(int dtype, int ncol, bool split) {
+    if (dtype == 0) return ncol == 16 ? sweep_fused_kernel<1, 16, false> : ncol == 32 ? sweep_fused_kernel<1, 32, false> : sweep_fused_kernel<1, 64, false>;
+    if (split) return ncol == 16 ? sweep_fused_kernel<0, 16, true> : ncol == 32 ? sweep_fused_kernel<0, 32, true> : sweep_fused_kernel<0, 64, true>;
+    return ncol == 16 ? sweep_fused_kernel<0, 16, false> : ncol == 32 ? sweep_fused_kernel<0, 32, false> : sweep_fused_kernel<0, 64, false>;
+}
+
+static int run_fused(ragfin* h, const float* q_dev, int nb, int k, int64_t n_eff, int64_t* out_ids, float* out_scores,
+                     int* flags, int* flag_count, cudaStream_t st) {
+    int rc;
+    const FusedPlan f = plan_fused(h, nb, k);
+    if (f.ncol == 0) return fail(RAGFIN_EUNSUPPORTED, "no fused sweep for %d queries, k = %d", nb, k);
+    const int64_t n = h->count;
+    if ((rc = ensure(h->cand, (size_t)nb * f.cap * sizeof(u64)))) return rc;
+    if (!h->fctl.p) { if ((rc = ensure(h->fctl, sizeof(FusedCtl)))) return rc; h->fctl_dirty = true; }
+    if (h->fctl_dirty) { CU_TRY(cudaMemsetAsync(h->fctl.p, 0, sizeof(FusedCtl), st)); h->fctl_dirty = false; }
+    const GemmPlan p = plan_gemm(nb, n, h->num_sms, 32, 1);
+    CUtensorMap tmB;
+    if ((rc = cached_map(h, &tmB, h->dtype, h->data, n, h->ld, kGN))) return rc;
+    FusedArgs a;
+    a.idesc = make_idesc_n(h->dtype == 0 ? 2 : h->dtype == 1 ? 1 : 0, f.ncol);
+    a.k_elems = kGKBytes / (int)esize(h->dtype);
+    a.num_kblocks = (h->ld + a.k_elems - 1) / a.k_elems;
+    a.dt = h->dtype;
+    a.nq = nb; a.dim = h->dim; a.ld = h->ld;
+    a.n_rows = n;
+    a.S = p.S; a.rows_per_slice = p.rows_per_slice;
+    a.stages = f.stages;
+    a.k = k; a.keff = (int)((int64_t)k < n_eff ? k : n_eff);
+    a.pend = f.pend;
+    a.q = q_dev;
+    a.data = h->data;
+    a.allow = h->cur_allow;
+    a.cand = (u64*)h->cand.p; a.cap = f.cap;
+    a.ctl = (FusedCtl*)h->fctl.p;
+    a.eps_const = eps_gemm_const(h->dtype, h->ld);
+    a.id_base = h->id_base;
+    a.out_ids = (long long*)out_ids; a.out_scores = out_scores;
+    a.flags = flags; a.flag_count = flag_count;
+    fused_fn fn = pick_fused(h->dtype, f.ncol, f.split);
+    if ((rc = set_dyn_smem(h->device, (const void*)fn, f.smem))) return rc;
+    h->fctl_dirty = true;          // until the launch is known to have been accepted
+    prof_begin(h, st);
+    fn<<<p.grid, kFThreads, f.smem, st>>>(tmB, a);
+    prof_end(h, st);
+    CU_TRY(cudaGetLastError());
+    h->fctl_dirty = false;
+    h->stats.launches++;
+    h->stats.path = 3;
+    h->stats.cand_per_query = f.cap;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------
 // Large-k path: exact scores of every row, radix select of the k-th key, rank sort.  One query at a time.
 // ------------------------------------------------------------------------------
 static int search_bigk(ragfin* h, const float* q_dev, int nq, int k, int64_t* out_ids, float* out_scores, cudaStream_t st) {
@@ -1076,6 +1184,11 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
     const int nvec = h->ld / V;
     const int steps = round_steps((nvec + 31) / 32);
     const int64_t n_eff = h->cur_allow ? h->cur_allowed : n;   // rows a hit may come from
+    if ((rc = ensure(h->flags, (size_t)(kMaxQueryBatch + 1) * sizeof(int)))) return rc;
+    if (nq <= kFMaxQ && fused_eligible(h, nq, k)) {   // the one-kernel search (sweep_fused.cuh): prep, sweep, finalize, exact fallback
+        int* fl = (int*)h->flags.p;
+        return run_fused(h, q_dev, nq, k, n_eff, out_ids, out_scores, fl, fl + kMaxQueryBatch, st);
+    }
     int kp = cand_per_query(k);
     if (kp == 0 && n <= 256) kp = 256;   // every row is a candidate: any k (graph_cons.py:279 asks limit=1000 of 16 rows)
     const int min_nq_all = (size_t)n * h->ld * esize(h->dtype) >= kSweepBytes ? h->gemm_min_nq_large : h->gemm_min_nq;
@@ -1359,6 +1472,16 @@ extern "C" int ragfin_set_append_mode(ragfin_t* h, int32_t enable) {
     return RAGFIN_OK;
 }
 
+// Tuning knob: the one-kernel search for <= 64 queries and k <= 128 (sweep_fused.cuh; default on; results are identical).
+// min_rows: corpora below this many rows keep the multi-kernel paths (0 = leave unchanged).
+extern "C" int ragfin_set_fused(ragfin_t* h, int32_t enable, int64_t min_rows) {
+    if (!h || min_rows < 0) return fail(RAGFIN_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->use_fused = enable != 0;
+    if (min_rows > 0) h->fused_min_rows = (int)(min_rows > 0x7FFFFFFF ? 0x7FFFFFFF : min_rows);
+    return RAGFIN_OK;
+}
+
 // Tuning knob: small-batch scan kernel.  0 = automatic, 1 = register-path loads (scan_topk_kernel), 2 = TMA-fed ring
 // (scan_tma_kernel; 1-2 queries).  Results are identical.
 extern "C" int ragfin_set_scan_variant(ragfin_t* h, int32_t variant) {
@@ -1428,7 +1551,15 @@ extern "C" int ragfin_search_host(ragfin_t* h, const float* q_host, int32_t nq, 
             memcpy(hq, q_host, qb);
             char* dq = (char*)dptr;
             char* dout = dq + kHostStageQ;
-            if ((rc = search_locked(h, (const float*)dq, nq, k, (int64_t*)dout, (float*)(dout + ib), st))) return rc;
+            const float* qsrc = (const float*)dq;
+            if (nq <= kFMaxQ && fused_eligible(h, nq, k)) {
+                // the one-kernel search reads the queries from every CTA: one small copy-engine transfer into HBM instead
+                // of ~150 reads of the same bytes over PCIe; the hits are still written straight into the mapped staging
+                if ((rc = ensure(h->stage_q, qb))) return rc;
+                CU_TRY(cudaMemcpyAsync(h->stage_q.p, hq, qb, cudaMemcpyHostToDevice, st));
+                qsrc = (const float*)h->stage_q.p;
+            }
+            if ((rc = search_locked(h, qsrc, nq, k, (int64_t*)dout, (float*)(dout + ib), st))) return rc;
             CU_TRY(cudaStreamSynchronize(st));
             memcpy(out_ids_host, ho, ib);
             memcpy(out_scores_host, ho + ib, sb);

@@ -1,0 +1,503 @@
+// K3f: the whole small-batch search in ONE kernel (<= 64 queries, k <= 128) - query preparation, tensor-core sweep with
+// self-tightening thresholds, exact finalize.  sm_100a only.
+//
+// Round 1 served these batches with six launches (query prep, bound pass, bound select, sweep, append finalize, two gated
+// tier-2 launches): ~65-90 us of latency-bound head and tail around a 0.27-2.1 ms sweep, which is what held the 8-GPU
+// strong-scaling efficiency at 0.74.  Here:
+//
+//   prologue   every CTA normalises the <= 64 queries itself (canonical fp64 arithmetic, bit-identical to ingest) and
+//              writes them straight into its shared memory in the tensor core's K-major SWIZZLE_128B layout, while the
+//              TMA producer already streams corpus tiles.  16-bit storage: every query is split into hi = round(q) and
+//              lo = round(q - hi), two MMA columns summed in the epilogue, so the query rounding error that dominated the
+//              rigorous error bound drops from ~1.6e-3 to ~8e-6 (SPLIT).
+//   sweep      as gemm_rows.cuh: corpus rows are the MMA's M (two 128-row halves per 256-row tile), the query block its
+//              N = 16 / 32 / 64, P partial accumulators per half so that no MMA waits on its predecessor.
+//   threshold  NO bound pass.  A row is appended to its query's buffer when approx >= thr[q]; thr[q] starts at -inf
+//              and only rises: every CTA keeps, per query, the sorted k best approximate scores among the rows IT has
+//              appended (k distinct rows, so the k-th is a lower bound of T, the k-th best approximate score of the
+//              corpus) and sets thr = kth - 2 eps; the best threshold any CTA has found is shared through one atomicMax
+//              word per query, re-read every tile.  Every row of the exact top-k satisfies approx >= T - 2 eps >= thr at
+//              any time, so it is in the buffer (DESIGN.md 2.4 with a moving threshold).  Tiles of a slice are visited in
+//              a strided permutation, so a corpus sorted by similarity cannot make every row beat the running bound.
+//   finalize   the last nq CTAs to finish wait for the grid-wide arrival counter and finalize one query each in place:
+//              histogram-narrowing select of T over the buffer, gather above T - 2 eps, canonical fp64 rescore, sort,
+//              emit; an overflowing buffer (> cap rows within reach of the top k: massive duplication) is answered by
+//              the same CTA with a canonical scan of the whole corpus - slow, exact, and no extra launch.
+// The control block (counters, published thresholds) is left zeroed by every search.
+#pragma once
+#include "gemm_rows.cuh"
+
+namespace rfk {
+
+constexpr int kFMaxQ = 64;        // queries per launch
+constexpr int kFThreads = 192;    // warp 0 producer, warp 1 MMA issuer, warps 2-5 epilogue; all six in prologue and finalize
+constexpr int kFMaxK = 128;       // sorted per-CTA lists live in shared memory
+
+struct FusedCtl {
+    uint32_t cnt[kFMaxQ];     // rows appended per query (may exceed cap: overflow)
+    uint32_t gthr[kFMaxQ];    // best published threshold, float_to_ordered (0 = none yet)
+    uint32_t done;            // CTAs that have finished their sweep
+    uint32_t fin_done;        // finalizing CTAs that have finished
+};
+
+struct FusedArgs {
+    uint32_t idesc;             // M = 128, N = NCOL
+    int num_kblocks, k_elems;   // k-blocks of 128 bytes; elements per k-block (64 for 16-bit storage, 32 for fp32)
+    int dt;                     // storage type of the corpus: 0 fp32, 1 bf16, 2 fp16
+    int nq, dim, ld;
+    long long n_rows;
+    int S;                      // corpus slices
+    long long rows_per_slice;   // multiple of kGN
+    int stages;
+    int k, keff;                // keff = min(k, rows a hit may come from)
+    int pend;                   // pending-score slots per query and tile
+    const float* q;             // [nq][dim] raw fp32 queries
+    const void* data;           // corpus [n_rows][ld]
+    const uint32_t* allow;      // scalar filter bitmask or null
+    u64* cand;                  // [nq][cap] append buffers
+    int cap;
+    FusedCtl* ctl;
+    float eps_const;            // accumulation allowance (+ tf32 truncation), see eps_gemm_const
+    long long id_base;
+    long long* out_ids;         // [nq][k]
+    float* out_scores;          // [nq][k]
+    int* flags;                 // [nq] 1 = the query took the in-kernel exact scan
+    int* flag_count;
+};
+
+__host__ __device__ constexpr size_t fused_state_bytes(int nq, int k, int pend) {
+    return (size_t)4 * kFMaxQ * 4 + (size_t)nq * (k + pend) * 4 + 64;
+}
+__host__ __device__ constexpr size_t fused_smem_bytes(int num_kblocks, int ncol, int stages, int nq, int k, int pend) {
+    return 1024 + (size_t)num_kblocks * ncol * kGKBytes + (size_t)stages * kBBytes + 256 + fused_state_bytes(nq, k, pend);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acq_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// thr = value - 2 eps - 2^-22, every step rounded down (never above the real bound)
+__device__ __forceinline__ float thr_below(float value, float eps) {
+    return __fsub_rd(__fsub_rd(value, __fmul_ru(2.0f, eps)), 2.384185791015625e-07f);
+}
+
+// multiplier of the tile permutation t -> (t * mult) % n: odd, near 0.618 n, coprime with n
+__device__ __forceinline__ int perm_mult(int n) {
+    if (n <= 2) return 1;
+    int m = (int)(0.6180339887 * n) | 1;
+    for (;; m += 2) {
+        int x = m % n, y = n;
+        if (x == 0) continue;
+        while (x) { const int t = y % x; y = x; x = t; }
+        if (y == 1) return m % n;
+    }
+}
+
+template <int KIND, int NCOL, bool SPLIT>
+__global__ void __launch_bounds__(kFThreads, 1)
+sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
+    constexpr int P = NCOL <= 32 ? 4 : 2;                      // partial accumulators per half tile
+    constexpr int kAcc = 2 * P * NCOL;                         // TMEM columns of one tile buffer
+    constexpr int kTmemCols = 2 * kAcc <= 256 ? 256 : 512;
+    constexpr int QPC = SPLIT ? 8 : 16;                        // queries per 16-column chunk
+    constexpr int QTILE = NCOL * kGKBytes;                     // bytes of one k-block of the query block
+    static_assert(2 * kAcc <= 512, "accumulators exceed tensor memory");
+    static_assert(!(SPLIT && KIND == 1), "the hi/lo split is for 16-bit storage");
+
+    extern __shared__ uint8_t fsm_raw[];
+    const uint32_t raw = smem_u32(fsm_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* fsm = fsm_raw + (base - raw);
+    const int stages = a.stages, nkb = a.num_kblocks, nq = a.nq, k = a.k;
+    const uint32_t smQ = base;                                             // [nkb][NCOL x 128 B]
+    const uint32_t smB = base + (uint32_t)nkb * QTILE;                     // [stages][32 KB]
+    const size_t region_bytes = (size_t)nkb * QTILE + (size_t)stages * kBBytes;   // reused as scratch by the finalize
+    uint64_t* bars = reinterpret_cast<uint64_t*>(fsm + region_bytes);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (kRMaxStages + s); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kRMaxStages + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kRMaxStages + 2 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRMaxStages + 4);
+    uint32_t* s_ticket = tmem_slot + 1;
+    // per-query threshold state
+    float* thr_s = reinterpret_cast<float*>(fsm + region_bytes + 256);     // [kFMaxQ]
+    float* eps_s = thr_s + kFMaxQ;                                          // [kFMaxQ]
+    int* scnt = reinterpret_cast<int*>(eps_s + kFMaxQ);                     // [kFMaxQ] entries of sorted[q]
+    int* pcnt = scnt + kFMaxQ;                                              // [kFMaxQ] entries appended to pend[q] this tile
+    uint32_t* sorted = reinterpret_cast<uint32_t*>(pcnt + kFMaxQ);          // [nq][k] descending ordered-uint scores
+    uint32_t* pend = sorted + (size_t)nq * k;                               // [nq][pend]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < kFMaxQ; i += kFThreads) { thr_s[i] = i < nq ? -INFINITY : INFINITY; eps_s[i] = 0.f; scnt[i] = 0; pcnt[i] = 0; }
+    if (blockIdx.x == 0 && tid == 0) *a.flag_count = 0;   // ordered before every finalizer's atomicAdd by the arrival counter
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto slice_tiles = [&](int sl, long long& r0, long long& r1) -> int {
+        r0 = (long long)sl * a.rows_per_slice;
+        r1 = r0 + a.rows_per_slice;
+        if (r1 > a.n_rows) r1 = a.n_rows;
+        return r1 > r0 ? (int)((r1 - r0 + kGN - 1) / kGN) : 0;
+    };
+
+    // ---- the producer gets the first ring-full of corpus bytes moving before anybody touches a query ----
+    int pre_issued = 0;
+    if (tid == 0) {
+        long long r0, r1;
+        const int ntiles = slice_tiles(blockIdx.x, r0, r1);
+        const int mult = perm_mult(ntiles);
+        for (int it = 0; it < stages && it < ntiles * nkb; ++it) {
+            const int t = it / nkb, kb = it % nkb;
+            const int tp = (int)(((long long)t * mult) % ntiles);
+            mbar_expect_tx(full_bar(it), kBBytes);
+            tma_load_2d(smB + (uint32_t)it * kBBytes, &tmB, kb * a.k_elems, (int)(r0 + (long long)tp * kGN), full_bar(it));
+            ++pre_issued;
+        }
+    }
+
+    // ---- prologue: the query block, written in place in the K-major SWIZZLE_128B layout ----
+    {
+        uint4* qz = reinterpret_cast<uint4*>(fsm);
+        for (int i = tid; i < nkb * QTILE / 16; i += kFThreads) qz[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        const int esz = KIND == 1 ? 4 : 2;
+        auto q_addr = [&](int row, int i) -> uint8_t* {   // element i of the padded embedding, MMA column `row`
+            const int kb = i / a.k_elems, c = (i % a.k_elems) * esz;
+            return fsm + (size_t)kb * QTILE + (size_t)(row >> 3) * 1024 + (size_t)(row & 7) * 128 + ((((c >> 4) ^ (row & 7)) << 4) | (c & 15));
+        };
+        for (int j = warp; j < nq; j += kFThreads / 32) {
+            const float* x = a.q + (size_t)j * a.dim;
+            double acc = 0.0;
+            for (int i = lane; i < a.dim; i += kWarp) {
+                const double v = (double)x[i];
+                acc = acc + v * v;
+            }
+            const double n2 = warp_butterfly_f64(acc);
+            const double inv = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
+            const int row_hi = SPLIT ? (j >> 3) * 16 + (j & 7) : j;
+            double d2 = 0.0;
+            for (int i = lane; i < a.dim; i += kWarp) {
+                const float y = (float)((double)x[i] * inv);
+                if (KIND == 1) {
+                    *reinterpret_cast<float*>(q_addr(row_hi, i)) = y;
+                } else if (a.dt == 1) {
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(y);
+                    const float rest = y - __bfloat162float(hi);            // exact: both are fp32 values within a binade or two
+                    const __nv_bfloat16 lo = SPLIT ? __float2bfloat16_rn(rest) : __float2bfloat16_rn(0.f);
+                    *reinterpret_cast<__nv_bfloat16*>(q_addr(row_hi, i)) = hi;
+                    if (SPLIT) *reinterpret_cast<__nv_bfloat16*>(q_addr(row_hi + 8, i)) = lo;
+                    const double d = (double)y - (double)__bfloat162float(hi) - (double)__bfloat162float(lo);
+                    d2 += d * d;
+                } else {
+                    const __half hi = __float2half_rn(y);
+                    const float rest = y - __half2float(hi);
+                    const __half lo = SPLIT ? __float2half_rn(rest) : __float2half_rn(0.f);
+                    *reinterpret_cast<__half*>(q_addr(row_hi, i)) = hi;
+                    if (SPLIT) *reinterpret_cast<__half*>(q_addr(row_hi + 8, i)) = lo;
+                    const double d = (double)y - (double)__half2float(hi) - (double)__half2float(lo);
+                    d2 += d * d;
+                }
+            }
+            d2 = warp_butterfly_f64(d2);
+            // |approx - exact| <= |q - hi - lo|_2 * max |stored row|_2 (<= 1 + 2^-8) + the accumulation allowance
+            if (lane == 0) eps_s[j] = a.eps_const + (KIND == 1 ? 0.0f : (float)(sqrt(d2) * 1.0078125) + 1e-9f);
+        }
+        fence_proxy_async_smem();   // generic-proxy writes above -> visible to the tensor core's async-proxy reads
+        __syncthreads();
+    }
+
+    if (warp == 0) {
+        if (lane == 0) {   // ===== TMA producer =====
+            int stage = 0, skip = pre_issued;
+            uint32_t phase = 0;
+            for (int sl = blockIdx.x; sl < a.S; sl += gridDim.x) {
+                long long r0, r1;
+                const int ntiles = slice_tiles(sl, r0, r1);
+                const int mult = perm_mult(ntiles);
+                for (int t = 0; t < ntiles; ++t) {
+                    const int tp = (int)(((long long)t * mult) % ntiles);
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        if (skip > 0) {
+                            --skip;                        // issued before the prologue (first round of the ring: slots were free)
+                        } else {
+                            mbar_wait(empty_bar(stage), phase ^ 1u);
+                            mbar_expect_tx(full_bar(stage), kBBytes);
+                            tma_load_2d(smB + (uint32_t)stage * kBBytes, &tmB, kb * a.k_elems, (int)(r0 + (long long)tp * kGN), full_bar(stage));
+                        }
+                        if (++stage == stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // ===== MMA issuer =====
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int sl = blockIdx.x; sl < a.S; sl += gridDim.x) {
+                long long r0, r1;
+                const int ntiles = slice_tiles(sl, r0, r1);
+                for (int t = 0; t < ntiles; ++t) {
+                    mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                    tc_fence_after();
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        const uint64_t qd = make_smem_desc(smQ + (uint32_t)kb * QTILE);
+#pragma unroll
+                        for (int k4 = 0; k4 < kGKBytes / 32; ++k4) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint64_t cd = make_smem_desc(smB + (uint32_t)stage * kBBytes + (uint32_t)h * (kBBytes / 2));
+                                const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAcc + (uint32_t)h * (P * NCOL) + (uint32_t)(k4 % P) * NCOL;
+                                tc_mma<KIND>(d_tmem, cd + 2u * k4, qd + 2u * k4, a.idesc, (uint32_t)(kb != 0 || k4 >= P));
+                            }
+                        }
+                        tc_commit(empty_bar(stage));
+                        if (++stage == stages) { stage = 0; phase ^= 1u; }
+                    }
+                    tc_commit(tfull_bar(acc));
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                }
+            }
+        }
+    } else {   // ===== epilogue: thread <-> TMEM lane <-> corpus row of a half tile =====
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;          // row of the half tile
+        const int et = tid - 64;                    // 0..127 among the epilogue threads; thread et < nq maintains query et
+        const float my_eps = et < nq ? eps_s[et] : 0.f;
+        const int npend = a.pend;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int sl = blockIdx.x; sl < a.S; sl += gridDim.x) {
+            long long r0, r1;
+            const int ntiles = slice_tiles(sl, r0, r1);
+            const int mult = perm_mult(ntiles);
+            for (int t = 0; t < ntiles; ++t) {
+                const int tp = (int)(((long long)t * mult) % ntiles);
+                const long long trow = r0 + (long long)tp * kGN;
+                uint32_t g_pub = 0u;
+                if (et < nq) g_pub = __ldcg(a.ctl->gthr + et);       // what the other CTAs have published; used after the tile
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    const long long row = trow + h * 128 + m;
+                    const bool row_ok = row < r1;                     // rows past the slice / corpus (zero-filled by TMA) never qualify
+#pragma unroll 1
+                    for (int c = 0; c < NCOL / 16; ++c) {
+                        uint32_t v[P][16];
+#pragma unroll
+                        for (int p = 0; p < P; ++p)
+                            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kAcc + (uint32_t)h * (P * NCOL) + (uint32_t)p * NCOL + (uint32_t)c * 16, v[p]);
+                        float s16[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float s = __uint_as_float(v[0][j]) + __uint_as_float(v[1][j]);
+                            if (P == 4) s += __uint_as_float(v[2][j]) + __uint_as_float(v[3][j]);
+                            s16[j] = s;
+                        }
+                        if (row_ok) {
+#pragma unroll
+                            for (int j = 0; j < QPC; ++j) {
+                                const int qi = c * QPC + j;
+                                const float sc = SPLIT ? s16[j] + s16[j + 8] : s16[j];
+                                if (sc >= thr_s[qi]) {                 // shared-memory broadcast; padding queries hold +inf
+                                    if (a.allow != nullptr && !row_allowed(a.allow, row)) continue;
+                                    const uint32_t pos = atomicAdd(a.ctl->cnt + qi, 1u);
+                                    if (pos < (uint32_t)a.cap) a.cand[(size_t)qi * a.cap + pos] = make_key(sc + 0.0f, (uint32_t)row);
+                                    const int lp = atomicAdd(pcnt + qi, 1);
+                                    if (lp < npend) pend[(size_t)qi * npend + lp] = float_to_ordered(sc + 0.0f);
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(tempty_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                // ---- threshold maintenance: the tile's appended scores enter the query's sorted list ----
+                named_bar_sync(1, 128);
+                if (et < nq) {
+                    uint32_t* sl_ = sorted + (size_t)et * k;
+                    int sc_n = scnt[et];
+                    int pc = pcnt[et];
+                    if (pc > 0) {
+                        if (pc > npend) pc = npend;                    // the surplus was dropped: only tightening information is lost
+                        for (int i = 0; i < pc; ++i) {
+                            const uint32_t val = pend[(size_t)et * npend + i];
+                            int j;
+                            if (sc_n < k) j = sc_n++;
+                            else if (val > sl_[k - 1]) j = k - 1;
+                            else continue;
+                            while (j > 0 && sl_[j - 1] < val) { sl_[j] = sl_[j - 1]; --j; }
+                            sl_[j] = val;
+                        }
+                        scnt[et] = sc_n;
+                        pcnt[et] = 0;
+                    }
+                    float nt = thr_s[et];
+                    if (sc_n >= a.keff && a.keff > 0) nt = fmaxf(nt, thr_below(ordered_to_float(sl_[a.keff - 1]), my_eps));
+                    const float gf = g_pub ? ordered_to_float(g_pub) : -INFINITY;
+                    if (nt > gf) atomicMax(a.ctl->gthr + et, float_to_ordered(nt));
+                    else nt = gf;
+                    thr_s[et] = nt;
+                }
+                named_bar_sync(2, 128);
+            }
+        }
+        __threadfence();   // this thread's appended keys are visible device-wide before the CTA is counted as done
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+
+    // ---- tail: the last n_fin CTAs to arrive finalize one query each ----
+    const int n_fin = nq < (int)gridDim.x ? nq : (int)gridDim.x;
+    if (tid == 0) {
+        __threadfence();
+        *s_ticket = atomicAdd(&a.ctl->done, 1u);
+    }
+    __syncthreads();
+    const int ticket = (int)*s_ticket;
+    const int first_fin = (int)gridDim.x - n_fin;
+    if (ticket < first_fin) return;
+    if (tid == 0) {
+        while (ld_acq_gpu(&a.ctl->done) < gridDim.x) __nanosleep(64);
+        __threadfence();
+    }
+    fence_proxy_async_smem();   // the ring was written by TMA and read by the tensor core; from here on plain stores reuse it
+    __syncthreads();
+
+    // scratch over the query block + ring: qv [ld] fp32 | hist [256] | s3 [3] + c2 | sel [..] u64
+    float* qv = reinterpret_cast<float*>(fsm);
+    const int ld_al = (a.ld + 3) / 4 * 4;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(qv + ld_al);
+    uint32_t* s3 = hist + 256;
+    int* s_c2 = reinterpret_cast<int*>(s3 + 3);
+    u64* sel = reinterpret_cast<u64*>(fsm + (((size_t)ld_al * 4 + 256 * 4 + 16 + 15) / 16) * 16);
+    const int sel_cap = (int)((region_bytes - (size_t)(reinterpret_cast<uint8_t*>(sel) - fsm)) / sizeof(u64));
+
+    for (int qi = ticket - first_fin; qi < nq; qi += n_fin) {
+        // normalised fp32 query (the rescore operand), recomputed: bit-identical to the prologue and to ingest
+        {
+            const float* x = a.q + (size_t)qi * a.dim;
+            if (warp == 0) {
+                double acc = 0.0;
+                for (int i = lane; i < a.dim; i += kWarp) {
+                    const double v = (double)x[i];
+                    acc = acc + v * v;
+                }
+                const double n2 = warp_butterfly_f64(acc);
+                const double inv = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
+                for (int i = lane; i < a.ld; i += kWarp) qv[i] = i < a.dim ? (float)((double)x[i] * inv) : 0.0f;
+            }
+            if (tid == 0) *s_c2 = 0;
+        }
+        __syncthreads();
+        const uint32_t m32 = __ldcg(a.ctl->cnt + qi);
+        const int keff = a.keff;
+        long long* oid = a.out_ids + (size_t)qi * k;
+        float* osc = a.out_scores + (size_t)qi * k;
+        const u64* in = a.cand + (size_t)qi * a.cap;
+        bool exact_scan = m32 > (uint32_t)a.cap || (int)m32 > sel_cap || (int)m32 < keff;   // block-uniform
+        if (!exact_scan && keff > 0) {
+            const int m = (int)m32;
+            const uint32_t t_ord = block_kth_largest([&](int i) { return (uint32_t)(__ldcg(in + i) >> 32); }, m, (uint32_t)keff, hist, s3);
+            const float cut = thr_below(ordered_to_float(t_ord), eps_s[qi]);
+            for (int i = tid; i < m; i += kFThreads) {
+                const u64 key = __ldcg(in + i);
+                if (key_score(key) >= cut) sel[atomicAdd(s_c2, 1)] = key;      // <= m <= sel_cap
+            }
+            __syncthreads();
+            const int c2 = *s_c2;
+            for (int c = warp; c < c2; c += kFThreads / 32) {
+                const uint32_t row = key_row(sel[c]);
+                double sc;
+                if (a.dt == 0) sc = rescore_row<0>(a.data, row, a.ld, qv, lane);
+                else if (a.dt == 1) sc = rescore_row<1>(a.data, row, a.ld, qv, lane);
+                else sc = rescore_row<2>(a.data, row, a.ld, qv, lane);
+                __syncwarp();
+                if (lane == 0) sel[c] = make_key((float)sc + 0.0f, row);
+            }
+            int P2 = 32;
+            while (P2 < c2) P2 <<= 1;
+            if (P2 > sel_cap) {
+                exact_scan = true;       // cannot pad to a power of two: leave it to the scan (never with the host's sizing)
+            } else {
+                for (int i = c2 + tid; i < P2; i += kFThreads) sel[i] = 0ull;
+                __syncthreads();
+                block_bitonic_sort_desc(sel, P2, tid, kFThreads);
+                for (int i = tid; i < k; i += kFThreads) {
+                    const u64 key = i < keff ? sel[i] : 0ull;
+                    oid[i] = key ? a.id_base + (long long)key_row(key) : -1;
+                    osc[i] = key ? key_score(key) : -INFINITY;
+                }
+                if (tid == 0) a.flags[qi] = 0;
+            }
+        } else if (!exact_scan) {   // keff == 0: nothing to return
+            for (int i = tid; i < k; i += kFThreads) { oid[i] = -1; osc[i] = -INFINITY; }
+            if (tid == 0) a.flags[qi] = 0;
+        }
+        if (exact_scan) {
+            // The buffer overflowed (more than cap rows within reach of the k-th score).  Answer exactly, here: canonical
+            // score of every row, per-warp sorted lists of kpe keys, one merge.  ~0.1 s on a 15 GB corpus, no extra launch.
+            __syncthreads();
+            int kpe = 32;
+            while (kpe < k) kpe <<= 1;
+            u64* lists = sel;                                  // [6][kpe], then padded to a power of two for the sort
+            const int total = (kFThreads / 32) * kpe;
+            int P2 = 32;
+            while (P2 < total) P2 <<= 1;
+            for (int i = tid; i < P2; i += kFThreads) lists[i] = 0ull;
+            __syncthreads();
+            u64* mine = lists + (size_t)warp * kpe;
+            for (long long r = warp; r < a.n_rows; r += kFThreads / 32) {
+                if (a.allow != nullptr && !row_allowed(a.allow, r)) continue;
+                double sc;
+                if (a.dt == 0) sc = rescore_row<0>(a.data, r, a.ld, qv, lane);
+                else if (a.dt == 1) sc = rescore_row<1>(a.data, r, a.ld, qv, lane);
+                else sc = rescore_row<2>(a.data, r, a.ld, qv, lane);
+                const u64 key = make_key((float)sc + 0.0f, (uint32_t)r);
+                if (key > mine[kpe - 1]) warp_list_insert(mine, kpe, key, lane);
+            }
+            __syncthreads();
+            block_bitonic_sort_desc(lists, P2, tid, kFThreads);
+            for (int i = tid; i < k; i += kFThreads) {
+                const u64 key = i < keff ? lists[i] : 0ull;
+                oid[i] = key ? a.id_base + (long long)key_row(key) : -1;
+                osc[i] = key ? key_score(key) : -INFINITY;
+            }
+            if (tid == 0) { a.flags[qi] = 1; atomicAdd(a.flag_count, 1); }
+        }
+        __syncthreads();
+        if (tid == 0) { a.ctl->cnt[qi] = 0u; a.ctl->gthr[qi] = 0u; }   // leave the control block clean for the next search
+    }
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(&a.ctl->fin_done, 1u) == (uint32_t)n_fin - 1u) {   // last finalizer: counters back to zero
+            a.ctl->done = 0u;
+            a.ctl->fin_done = 0u;
+        }
+    }
+}
+
+}  // namespace rfk

@@ -223,6 +223,11 @@ class Index:
         """Small-batch scan kernel: 0 automatic, 1 register-path loads, 2 TMA-fed shared-memory ring."""
         _lib.check(self._L.ragfin_set_scan_variant(self._h, int(variant)))
 
+    def set_fused(self, enable: bool, min_rows: int = 0) -> None:
+        """One-kernel search for <= 64 queries, k <= 128 (csrc/sweep_fused.cuh) on/off (default on; results identical);
+        min_rows > 0 also sets the smallest corpus it serves."""
+        _lib.check(self._L.ragfin_set_fused(self._h, 1 if enable else 0, int(min_rows)))
+
     def set_append_mode(self, enable: bool) -> None:
         """tcgen05 path: append mode (no lists, threshold from the bound pass) on/off (default on; results identical)."""
         _lib.check(self._L.ragfin_set_append_mode(self._h, 1 if enable else 0))

@@ -1,0 +1,121 @@
+"""GPU parity of the one-kernel search (csrc/sweep_fused.cuh, stats path 3) against the C oracle: every storage type, every
+column configuration (hi/lo split and plain, N = 16 / 32 / 64), ragged shapes, duplicates, zero rows, scalar filters, corpora
+sorted by similarity (the adversarial order for a self-tightening threshold), buffer overflow (in-kernel exact scan), and
+the control block left clean between searches.  Ids and fp32 score bits must be equal."""
+import numpy as np
+import pytest
+
+from oracle import ragfin_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _index(x, dtype, min_rows=1):
+    import ragfin_b200
+    idx = ragfin_b200.Index(x.shape[1], dtype, capacity=max(len(x), 1), device=0)
+    idx.add(x)
+    idx.set_fused(True, min_rows)
+    return idx
+
+
+def _same(got, want, what=""):
+    assert np.array_equal(got[0], want[0]), f"{what}: ids differ\n{got[0]}\n{want[0]}"
+    assert np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32)), f"{what}: score bits differ"
+
+
+@pytest.mark.parametrize("dtype", O.DTYPES)
+@pytest.mark.parametrize("nq,k", [(1, 10), (2, 1), (8, 10), (9, 5), (16, 100), (17, 10), (32, 10), (33, 3), (64, 10), (5, 128)])
+def test_fused_matches_oracle(coracle, dtype, nq, k):
+    n, dim = 70000, 128
+    x = O.synth_rows(300, 0, n, dim, dup_every=211, zero_every=4099)
+    q = O.synth_rows(301, 0, nq, dim)
+    idx = _index(x, dtype)
+    got = idx.search(q, k)
+    st = idx.stats()
+    assert st["path"] == 3 and st["launches"] == 1 and st["queries_rescanned"] == 0, st
+    _same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), k), f"{dtype} nq={nq} k={k}")
+    again = idx.search(q, k)                       # the control block was left clean
+    _same(again, got, "second search")
+    idx.close()
+
+
+@pytest.mark.parametrize("dtype,dim,n,nq,k", [("bf16", 768, 40000, 1, 10), ("bf16", 768, 40000, 16, 10), ("f16", 384, 30001, 7, 5),
+                                               ("f32", 768, 20000, 3, 10), ("f32", 384, 25000, 20, 10), ("bf16", 1024, 20000, 12, 10),
+                                               ("bf16", 100, 33333, 4, 10), ("f16", 33, 50000, 2, 20), ("f32", 8, 9000, 5, 3),
+                                               ("bf16", 2048, 9000, 3, 10), ("bf16", 768, 257, 2, 10), ("bf16", 768, 9000, 40, 10)])
+def test_fused_shapes(coracle, dtype, dim, n, nq, k):
+    x = O.synth_rows(310 + dim, 0, n, dim, dup_every=97)
+    q = O.synth_rows(311 + dim, 0, nq, dim)
+    idx = _index(x, dtype)
+    got = idx.search(q, k)
+    want = coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), k)
+    _same(got, want, f"{dtype} dim={dim} n={n} nq={nq} k={k}")
+    idx.set_fused(False)
+    _same(idx.search(q, k), want, "multi-kernel path")
+    idx.close()
+
+
+def test_fused_corpus_sorted_by_similarity(coracle):
+    """Rows in ascending order of their similarity to the query: with a sequential sweep every row would beat the running
+    k-th score and be appended; the permuted tile order and the shared threshold keep the buffers small."""
+    n, dim, k = 200000, 64, 10
+    x = O.synth_rows(320, 0, n, dim)
+    q = O.synth_rows(321, 0, 2, dim)
+    s = coracle.exact_scores(coracle.normalize_rows(x, "f32"), coracle.normalize_rows(q[:1], "f32")[0])
+    x = np.ascontiguousarray(x[np.argsort(s, kind="stable")])
+    for dtype in ("bf16", "f32"):
+        idx = _index(x, dtype)
+        got = idx.search(q, k)
+        st = idx.stats()
+        assert st["path"] == 3 and st["queries_rescanned"] == 0, st
+        _same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), k), f"sorted {dtype}")
+        idx.close()
+
+
+def test_fused_overflow_takes_the_in_kernel_exact_scan(coracle):
+    """Every row identical: all scores tie, every row stays within reach of the k-th score, the buffer overflows and the
+    finalizing CTA answers with a canonical scan (ties to the lowest ids).  A normal query in the same batch is unaffected."""
+    n, dim, k = 60000, 64, 10
+    x = np.tile(O.synth_rows(330, 0, 1, dim), (n, 1))
+    x[40000:] = O.synth_rows(331, 0, n - 40000, dim)
+    q = np.concatenate([O.synth_rows(330, 0, 1, dim), O.synth_rows(332, 0, 1, dim)])
+    for dtype in ("bf16", "f32"):
+        idx = _index(x, dtype)
+        got = idx.search(q, k)
+        st = idx.stats()
+        assert st["path"] == 3 and st["queries_rescanned"] >= 1, st
+        _same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), k), f"overflow {dtype}")
+        assert list(got[0][0]) == list(range(k))
+        _same(idx.search(q[1:], k), coracle.cosine_topk(q[1:], coracle.normalize_rows(x, dtype), k), "after overflow")
+        idx.close()
+
+
+@pytest.mark.parametrize("keep", [0.5, 0.01, 0.0001, 0.0])
+def test_fused_filtered_search(coracle, keep):
+    n, dim, nq, k = 80000, 128, 6, 10
+    x = O.synth_rows(340, 0, n, dim, dup_every=53)
+    q = O.synth_rows(341, 0, nq, dim)
+    rng = np.random.default_rng(3)
+    allow = rng.random(n) < keep
+    idx = _index(x, "bf16")
+    ids, sc = idx.search(q, k, allow=allow)
+    assert idx.stats()["path"] == 3
+    rows = np.flatnonzero(allow)
+    wi, ws = coracle.cosine_topk(q, coracle.normalize_rows(x, "bf16")[rows], k)
+    wi = np.where(wi >= 0, rows[np.clip(wi, 0, max(len(rows) - 1, 0))] if len(rows) else -1, -1)
+    assert np.array_equal(ids, wi) and np.array_equal(sc.view(np.uint32), ws.view(np.uint32))
+    idx.close()
+
+
+def test_fused_device_api_and_id_base(coracle):
+    import torch
+    n, dim, nq, k = 50000, 768, 3, 10
+    x = O.synth_rows(350, 0, n, dim)
+    q = O.synth_rows(351, 0, nq, dim)
+    idx = _index(x, "bf16")
+    idx.set_id_base(1_000_000)
+    ids, sc = idx.search_device(torch.from_numpy(q).cuda(), k)
+    torch.cuda.synchronize()
+    wi, ws = coracle.cosine_topk(q, coracle.normalize_rows(x, "bf16"), k, id_base=1_000_000)
+    assert np.array_equal(ids.cpu().numpy(), wi) and np.array_equal(sc.cpu().numpy().view(np.uint32), ws.view(np.uint32))
+    idx.close()
