@@ -179,13 +179,11 @@ int ragfin_set_gemm_cluster(ragfin_t* h, int32_t cluster);
  * dtype / width); 2 = A-stationary (query tile resident in tensor memory; 16-bit storage, dim <= 768; measured
  * slower); 3 = streaming, and batches of <= 16 queries in append mode run with the operand roles swapped (corpus
  * rows are the MMA's M dimension, the queries its N = 16: a sixteenth of the tensor work per byte, full SM clock);
- * 4 = EXPERIMENTAL, never chosen automatically and not yet run on a GPU (written after the round's GPU budget was
- * spent; scripts/pair_check.py is its first test): batches of >= 2 query tiles in append mode sweep with a 2-SM MMA
- * (tcgen05 cta_group::2, M = 256: each CTA of a pair holds its own query tile and half of the corpus tile);
- * 5 = EXPERIMENTAL, same status as 4: variant 3 with the bound pass inside the sweep for k <= 16 (every CTA samples the
- * head of its first slice, a grid-wide barrier under a cooperative launch, thresholds computed in the kernel: two
- * launches fewer per call; scripts/seeded_check.py);
- * 0 = automatic (default; currently 3).  Results are identical (variants 0-3: tested; 4, 5: to be shown). */
+ * 4 = batches of >= 2 query tiles in append mode sweep with a 2-SM MMA (tcgen05 cta_group::2, M = 256: each CTA of a
+ * pair holds its own query tile and half of the corpus tile; csrc/gemm_pair.cuh).  Bit-exact on the GPU
+ * (tests/test_parity_gpu.py); measured faster at 256 / 512 / 2048 queries and slower at 1024 / 4096 under the power cap
+ * (profiles/r02), so it is not chosen automatically.
+ * 0 = automatic (default; currently 3).  Results are identical. */
 int ragfin_set_gemm_variant(ragfin_t* h, int32_t variant);
 
 /* Tuning knob: small-batch (1-2 query) scan kernel.  0 = automatic (default; currently 1), 1 = 128-bit register-path
@@ -228,7 +226,8 @@ int ragfin_debug_plan(int32_t nq, int64_t n_rows, int32_t num_sms, int32_t k, in
  * (query preparation, bound pass, finalize, exchange) overlap the neighbour's sweep.  Replaces nothing in the reference
  * (a Milvus querynode serves concurrent searches from one loaded segment the same way).  The view sees the rows present
  * when it is made, inherits the parent's tuning knobs, is read-only (ragfin_add returns RAGFIN_EUNSUPPORTED) and must
- * be destroyed before its parent.  NOT yet exercised on a GPU (scripts/pipeline_check.py). */
+ * be destroyed before its parent.  Measured (scripts/pipeline_check.py, profiles/r02): 1.25M-row shard, batch 1, three
+ * handles on three streams: 0.284 ms per query against 0.327 ms on one handle. */
 int ragfin_create_view(ragfin_t* parent, ragfin_t** out);
 
 void ragfin_destroy(ragfin_t* h);

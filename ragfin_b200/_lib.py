@@ -10,8 +10,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-# RAGFIN_LIB selects another build of the SAME library (e.g. csrc/libragfin_pdl.so, the experimental
-# programmatic-dependent-launch flavour); it is not a fallback: a missing file raises like the default does.
+# RAGFIN_LIB selects another build of the SAME library (e.g. one made with EXTRA=-DRAGFIN_TIMING_EXPERIMENTS);
+# it is not a fallback: a missing file raises like the default does.
 SO_PATH = os.environ.get("RAGFIN_LIB") or os.path.join(CSRC, "libragfin.so")
 
 # every symbol include/ragfin.h declares

@@ -14,25 +14,6 @@ constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 // ---------------------------------------------------------------------------------
-// Programmatic dependent launch (build flag -DRAGFIN_PDL, OFF by default: written after the round's GPU budget was
-// spent, to be measured next).  With the flag, the kernels of one search call are launched with
-// cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel's CTAs may become resident - and run their setup:
-// barrier init, tensor-memory allocation - while its predecessor drains; pdl_wait() blocks until the predecessor grid
-// has completed and its writes are visible, and MUST precede the kernel's first global-memory access; pdl_trigger()
-// lets the successor be scheduled.  Without the flag both are empty and the launches are plain.
-// ---------------------------------------------------------------------------------
-__device__ __forceinline__ void pdl_wait() {
-#ifdef RAGFIN_PDL
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-#endif
-}
-__device__ __forceinline__ void pdl_trigger() {
-#ifdef RAGFIN_PDL
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
-}
-
-// ---------------------------------------------------------------------------------
 // Candidate key: (score, row) packed so that ONE unsigned 64-bit compare orders by
 // (score descending, row ascending) when "larger key = better".  0 is "empty".
 // ---------------------------------------------------------------------------------

@@ -282,8 +282,6 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (C > 1) cluster_sync_all();   // peers' barriers must be initialised before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();      // everything above is setup; from here on the kernel reads what its predecessors wrote
-    pdl_trigger();
 
     const int n_items = n_groups * a.S;
     const int nkb = a.num_kblocks;
@@ -487,8 +485,6 @@ __global__ void __launch_bounds__(256) bound_select_kernel(const float* __restri
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s3[3];
     const int q = blockIdx.x;
-    pdl_wait();
-    pdl_trigger();
     for (int i = threadIdx.x; i < nb; i += blockDim.x) v[i] = float_to_ordered(bmax[(size_t)q * nb + i] + 0.0f);
     __syncthreads();
     const uint32_t mine = block_kth_largest([&](int i) { return v[i]; }, nb, (uint32_t)rank, hist, s3);
@@ -512,8 +508,6 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
                                                            uint32_t* __restrict__ gtau) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    pdl_wait();      // the previous search's kernels may still be reading the workspace this kernel rewrites
-    pdl_trigger();
     if (blockIdx.x == 0 && threadIdx.x == 0) *flag_count = 0;
     if (row >= n_pad) return;
     float* out = qhat + (size_t)row * ld;

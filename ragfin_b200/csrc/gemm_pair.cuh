@@ -126,8 +126,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     cluster_sync_all();   // the peer's tensor memory is allocated before the leader's MMAs write into it
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();
-    pdl_trigger();
 
     const int n_items = n_groups * a.S;
     const int nkb = a.num_kblocks;

@@ -101,8 +101,6 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();
-    pdl_trigger();
 
     auto slice_tiles = [&](int sl, long long& r0, long long& r1) -> int {
         r0 = (long long)sl * a.rows_per_slice;

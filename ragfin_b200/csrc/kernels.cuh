@@ -183,8 +183,6 @@ scan_topk_kernel(const void* __restrict__ data, int64_t n_rows, int ld, const fl
     constexpr int SH = 5 - ilog2(M);
     static_assert(M <= 32, "too many partial sums per lane");
     extern __shared__ __align__(16) u64 lists[];  // [NQ][kScanWarps][kp]
-    pdl_wait();
-    pdl_trigger();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < NQ * kScanWarps * kp; i += kScanThreads) lists[i] = 0;
@@ -404,8 +402,6 @@ finalize_kernel(const u64* __restrict__ cand, int G, int kp, const void* __restr
     __shared__ int s_cnt;
     __shared__ u64 s_tau;
     const int q = blockIdx.x;
-    pdl_wait();
-    pdl_trigger();
     if (EXACT_IN && flags[q] == 0) return;
     u64 bound = 0;
     if (!sorted_lists && gtau != nullptr) bound = (u64)gtau[q] << 32;   // key >= bound  <=>  score >= published bound
@@ -550,8 +546,6 @@ finalize_append_kernel(const u64* __restrict__ buf, const uint32_t* __restrict__
     __shared__ uint32_t s3[3];
     __shared__ int s_c2;
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    pdl_wait();
-    pdl_trigger();
     const uint32_t m32 = cnt[q];
     const int keff = (int64_t)k < n_rows ? k : (int)n_rows;
     const bool overflow = m32 > (uint32_t)cap || (int)m32 < keff;   // fewer than k rows cannot happen with a valid bound
@@ -617,8 +611,6 @@ __global__ void __launch_bounds__(kScanThreads)
 exact_scan_kernel(const void* __restrict__ data, int64_t n_rows, int ld, const float* __restrict__ qhat,
                   int nq, const int* __restrict__ flags, const int* __restrict__ flag_count, int kpe,
                   u64* __restrict__ cand_e, const uint32_t* __restrict__ allow) {
-    pdl_wait();
-    pdl_trigger();
     if (*flag_count == 0) return;
     extern __shared__ __align__(16) u64 lists[];  // [kScanWarps][kpe]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

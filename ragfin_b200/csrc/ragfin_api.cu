@@ -16,7 +16,6 @@
 #include "gemm_astat.cuh"
 #include "gemm_rows.cuh"
 #include "gemm_pair.cuh"
-#include "gemm_rows_seeded.cuh"
 #include "sweep_fused.cuh"
 #include "scan_tma.cuh"
 #include "bigk.cuh"
@@ -26,24 +25,7 @@ using namespace rfk;
 // ------------------------------------------------------------------------------
 // error plumbing: thread-local message, negative codes, no exceptions across the ABI
 // ------------------------------------------------------------------------------
-// Launch helper for the kernels of a search call that begin with pdl_wait() (common.cuh).  Default build: a plain
-// <<<>>> launch.  -DRAGFIN_PDL (experimental, not yet measured): programmatic stream serialization, so the kernel's
-// CTAs may be scheduled while its predecessor drains.
-#ifdef RAGFIN_PDL
-template <typename... KArgs, typename... Args>
-static void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
-}
-#define RF_LAUNCH(kern, grid, block, smem, st, ...) launch_pdl(kern, dim3(grid), dim3(block), smem, st, __VA_ARGS__)
-#else
 #define RF_LAUNCH(kern, grid, block, smem, st, ...) kern<<<grid, block, smem, st>>>(__VA_ARGS__)
-#endif
 
 static thread_local char g_err[512] = "";
 
@@ -63,10 +45,6 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 extern "C" const char* ragfin_last_error(void) { return g_err; }
-
-// Code paths that no GPU test covers in the default suite stay behind RAGFIN_EXPERIMENTAL=1 (they are reachable through
-// the public ABI otherwise): a protocol bug there is a device hang on a shared pool, not a wrong answer.
-static bool experimental_enabled() { const char* e = getenv("RAGFIN_EXPERIMENTAL"); return e && atoi(e) != 0; }
 extern "C" int ragfin_abi_version(void) { return RAGFIN_ABI_VERSION; }
 
 // ------------------------------------------------------------------------------
@@ -95,14 +73,11 @@ struct ragfin {
     bool use_bound_pass = true;   // tcgen05 path: sample pass that seeds the per-query thresholds (RAGFIN_NO_BOUND_PASS=1 disables)
     int gemm_variant = 0;     // 0 = automatic (= 3), 1 = streaming (A and B through shared memory), 2 = A-stationary (A in TMEM),
                               // 3 = streaming + swapped operand roles for <= 16 queries in append mode (gemm_rows.cuh),
-                              // 4 = EXPERIMENTAL 2-SM MMA pairs for >= 2 query tiles in append mode (gemm_pair.cuh; not yet run on a GPU)
-                              // 5 = EXPERIMENTAL self-seeded sweep for <= 16 queries, k <= 16 (gemm_rows_seeded.cuh; not yet run on a GPU)
+                              // 4 = 2-SM MMA pairs (cta_group::2) for >= 2 query tiles in append mode (gemm_pair.cuh)
     Buf fctl;                 // fused sweep: control block (FusedCtl), zero between searches
     bool fctl_dirty = true;   // set when a launch may have left it non-zero (first use, failed call): re-zeroed before the next launch
     bool use_fused = true;    // <= 64 queries, k <= 128: the one-kernel search (sweep_fused.cuh); RAGFIN_NO_FUSED=1 disables
     int fused_min_rows = 8192;
-    Buf gbar;                 // variant 5: grid-wide arrival counter (monotonic) ...
-    uint32_t gbar_target = 0; // ... and the value it reaches once the last launch's CTAs have all arrived
     struct MapSlot { const void* base = nullptr; int64_t rows = 0; int ld = 0, dtype = 0, box_rows = 0; CUtensorMap map; };
     MapSlot map_cache[8];     // tensor maps are pure functions of (base, rows, ld, dtype, box): encode once
     int map_next = 0;
@@ -216,7 +191,6 @@ extern "C" int ragfin_create(ragfin_t** out, int32_t dim, int32_t dtype, int64_t
 extern "C" int ragfin_create_view(ragfin_t* parent, ragfin_t** out) {
     if (!parent || !out) return fail(RAGFIN_EINVAL, "NULL argument");
     *out = nullptr;
-    if (!experimental_enabled()) return fail(RAGFIN_EUNSUPPORTED, "ragfin_create_view is experimental: set RAGFIN_EXPERIMENTAL=1");
     std::lock_guard<std::mutex> lk(parent->mu);
     DeviceGuard g(parent->device);
     if (!g.ok) return fail(RAGFIN_ECUDA, "cudaSetDevice(%d) failed", parent->device);
@@ -243,7 +217,7 @@ extern "C" void ragfin_destroy(ragfin_t* h) {
     if (!h) return;
     DeviceGuard g(h->device);
     (void)cudaDeviceSynchronize();
-    Buf* bufs[] = {&h->qhat, &h->q16, &h->eps_q, &h->gtau, &h->bmax, &h->acnt, &h->athr, &h->allow, &h->bk_scores, &h->bk_state, &h->bk_keys, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage, &h->gbar, &h->fctl};
+    Buf* bufs[] = {&h->qhat, &h->q16, &h->eps_q, &h->gtau, &h->bmax, &h->acnt, &h->athr, &h->allow, &h->bk_scores, &h->bk_state, &h->bk_keys, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage, &h->fctl};
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->data && !h->is_view) cudaFree(h->data);
@@ -703,7 +677,7 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
     // cluster size along the query-tile axis: multicast pays once several query tiles share a slice
     const int QT0 = (nb + kGM - 1) / kGM;
     int C = h->gemm_cluster ? h->gemm_cluster : auto_cluster(QT0);
-    const bool want_pair = h->gemm_variant == 4 && QT0 >= 2;   // experimental 2-SM MMA sweep: pairs of query tiles
+    const bool want_pair = h->gemm_variant == 4 && QT0 >= 2;   // 2-SM MMA sweep: pairs of query tiles
     if (want_pair) C = 2;
     typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const GemmArgs);
 #define RF_PICK_MODE(KIND, CC) (mode == 0 ? gemm_topk_kernel<KIND, 0, CC> : mode == 1 ? gemm_topk_kernel<KIND, 1, CC> : mode == 2 ? gemm_topk_kernel<KIND, 2, CC> : gemm_topk_kernel<KIND, 3, CC>)
@@ -814,25 +788,8 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-#ifdef RAGFIN_PDL   // gemm_topk_kernel / gemm_pair_kernel call pdl_wait() after their setup
-    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.numAttrs = 2;
-#endif
 
-    // EXPERIMENTAL (gemm variant 5, gemm_rows_seeded.cuh): the <= 16-query sweep computes its own thresholds from the head
-    // tiles of every CTA's first slice, behind a grid-wide barrier (cooperative launch) - no bound-pass launches
-    int seed_tiles = 0;
-    if (append && h->gemm_variant == 5 && nb <= kRN && C == 1 && k <= kSeedMaxK && p.grid <= p.S) {
-        const int64_t want_tiles = (n_tiles + 255) / 256;                      // >= 1/256 of the corpus, like the bound pass
-        seed_tiles = (int)((want_tiles + p.grid - 1) / p.grid);
-        if (seed_tiles < 1) seed_tiles = 1;
-        if (seed_tiles > kSeedMaxSampleTiles) seed_tiles = kSeedMaxSampleTiles;
-        const long avail = 227L * 1024 - 1024 - 256 - (long)a.num_kblocks * kRQBytes - (long)seeded_extra_smem(p.grid, seed_tiles);
-        if (avail / kBBytes < 3 || (int64_t)p.grid * 2 * seed_tiles < 2 * (int64_t)k) seed_tiles = 0;   // not eligible
-    }
-    const bool seeded = seed_tiles > 0;
-    if (bound && !seeded) {
+    if (bound) {
         const int groups = (p.QT + C - 1) / C;
         const int clusters = C > 1 ? resident_clusters : h->num_sms;
         GemmArgs b = a;
@@ -853,45 +810,7 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
         CU_TRY(cudaGetLastError());
         h->stats.launches += 2;
     }
-    if (seeded) {
-        SeededArgs sa;
-        RowsArgs& r = sa.r;
-        r.idesc = make_idesc_n(h->dtype == 0 ? 2 : h->dtype == 1 ? 1 : 0, kRN);
-        r.num_kblocks = a.num_kblocks; r.k_elems = a.k_elems; r.nq = nb; r.n_rows = n;
-        r.S = p.S; r.rows_per_slice = p.rows_per_slice;
-        const size_t extra = seeded_extra_smem(p.grid, seed_tiles);
-        const long avail = 227L * 1024 - 1024 - 256 - (long)r.num_kblocks * kRQBytes - (long)extra;
-        r.stages = (int)(avail / kBBytes) > kRMaxStages ? kRMaxStages : (int)(avail / kBBytes);
-        r.cand = a.cand; r.thr = nullptr; r.cnt = a.cnt; r.cap = a.cap;
-        const int nblk_s = p.grid * 2 * seed_tiles;
-        if ((rc = ensure(h->bmax, (size_t)nb * nblk_s * sizeof(float)))) return rc;
-        if (!h->gbar.p) {
-            if ((rc = ensure(h->gbar, sizeof(uint32_t)))) return rc;
-            CU_TRY(cudaMemsetAsync(h->gbar.p, 0, sizeof(uint32_t), st));
-            h->gbar_target = 0;
-        }
-        sa.sample_tiles = seed_tiles; sa.rank = k;
-        sa.eps_const = eps_gemm_const(h->dtype, h->ld); sa.eps_q = (const float*)h->eps_q.p;
-        sa.bmax = (float*)h->bmax.p; sa.gbar = (uint32_t*)h->gbar.p;
-        sa.gbar_target = h->gbar_target + (uint32_t)p.grid;
-        CU_TRY(cudaMemsetAsync(h->acnt.p, 0, (size_t)nb * sizeof(uint32_t), st));   // bound_select_kernel's other job
-        CUtensorMap tmQ;
-        if ((rc = cached_map(h, &tmQ, h->dtype, a_base, nb_pad, h->ld, kRN))) return rc;
-        typedef void (*seeded_fn)(const CUtensorMap, const CUtensorMap, const SeededArgs);
-        seeded_fn sfn = h->dtype == 0 ? gemm_rows_seeded_kernel<1> : gemm_rows_seeded_kernel<0>;
-        const size_t ssmem = rows_smem_bytes(r.num_kblocks, r.stages) + extra;
-        if ((rc = set_dyn_smem(h->device, (const void*)sfn, ssmem))) return rc;
-        cudaLaunchConfig_t sc = {};
-        sc.gridDim = dim3(p.grid); sc.blockDim = dim3(kGemmThreads); sc.dynamicSmemBytes = ssmem; sc.stream = st;
-        cudaLaunchAttribute sat[1];
-        sat[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: the kernel holds a grid-wide barrier
-        sat[0].val.cooperative = 1;
-        sc.attrs = sat; sc.numAttrs = 1;
-        prof_begin(h, st);
-        CU_TRY(cudaLaunchKernelEx(&sc, sfn, tmQ, tmB, sa));
-        prof_end(h, st);
-        h->gbar_target = sa.gbar_target;                 // only a launch that went out moves the counter
-    } else if (append && (h->gemm_variant == 3 || h->gemm_variant == 0) && nb <= kRN && C == 1 && rows_stages(a.num_kblocks) >= 3) {
+    if (append && (h->gemm_variant == 3 || h->gemm_variant == 0) && nb <= kRN && C == 1 && rows_stages(a.num_kblocks) >= 3) {
         // <= 16 queries, operand roles swapped (gemm_rows.cuh): corpus rows are the MMA's M, the queries its N = 16
         RowsArgs r;
         r.idesc = make_idesc_n(h->dtype == 0 ? 2 : h->dtype == 1 ? 1 : 0, kRN);
@@ -908,7 +827,7 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
         RF_LAUNCH(rfn, p.grid, kGemmThreads, rsmem, st, tmQ, tmB, r);
         prof_end(h, st);
     } else if (want_pair && C == 2 && (append || dump)) {
-        // EXPERIMENTAL (gemm variant 4, gemm_pair.cuh): one M = 256 MMA per cluster, each CTA holds half of the corpus tile
+        // gemm variant 4 (gemm_pair.cuh): one M = 256 MMA per cluster, each CTA holds half of the corpus tile
         GemmArgs pa = a;
         pa.idesc = make_idesc_pair(h->dtype == 0 ? 2 : h->dtype == 1 ? 1 : 0);
         pa.stages = kPMaxStages;
@@ -1056,11 +975,9 @@ static FusedPlan plan_fused(const ragfin* h, int nb, int k) {
                 if (smem > (size_t)227 * 1024) continue;
                 const size_t region = (size_t)nkb * ncol * kGKBytes + (size_t)stages * kBBytes;
                 const size_t hdr = (((size_t)((h->ld + 3) / 4 * 4) * 4 + 256 * 4 + 16 + 15) / 16) * 16;
-                if (region < hdr + 4096 * sizeof(u64)) continue;
-                int cap = (int)((region - hdr) / sizeof(u64));
-                int p2 = 4096;                                  // the finalize pads its sort to a power of two inside the scratch
-                while (p2 * 2 <= cap) p2 *= 2;
-                cap = p2 < kAppendCap ? p2 : kAppendCap;
+                if (region < hdr + 4096 * sizeof(u64)) continue;      // the finalize's scratch (rows within 2 eps of the k-th score)
+                // every CTA appends ~k rows of its first tile, so the buffer scales with k (148 CTAs x 128 = 19 k rows)
+                const int cap = k <= 16 ? kAppendCap : 4 * kAppendCap;
                 FusedPlan f;
                 f.ncol = ncol; f.split = split; f.stages = stages; f.pend = pend; f.cap = cap; f.smem = smem;
                 return f;
@@ -1492,12 +1409,9 @@ extern "C" int ragfin_set_scan_variant(ragfin_t* h, int32_t variant) {
 }
 
 // Tuning knob: which tcgen05 kernel serves large batches (0 automatic, 1 streaming, 2 A-stationary when eligible,
-// 3 swapped roles for <= 16 queries, 4 EXPERIMENTAL 2-SM MMA pairs for >= 2 query tiles in append mode,
-// 5 EXPERIMENTAL variant 3 with the bound pass inside the sweep for k <= 16).
+// 3 swapped roles for <= 16 queries, 4 2-SM MMA pairs for >= 2 query tiles in append mode).
 extern "C" int ragfin_set_gemm_variant(ragfin_t* h, int32_t variant) {
-    if (!h || variant < 0 || variant > 5) return fail(RAGFIN_EINVAL, "variant must be 0 ... 5");
-    if (variant >= 4 && !experimental_enabled())
-        return fail(RAGFIN_EUNSUPPORTED, "gemm variant %d is experimental: set RAGFIN_EXPERIMENTAL=1", variant);
+    if (!h || variant < 0 || variant > 4) return fail(RAGFIN_EINVAL, "variant must be 0 ... 4");
     std::lock_guard<std::mutex> lk(h->mu);
     h->gemm_variant = variant;
     return RAGFIN_OK;

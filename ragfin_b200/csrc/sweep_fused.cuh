@@ -32,6 +32,8 @@ namespace rfk {
 constexpr int kFMaxQ = 64;        // queries per launch
 constexpr int kFThreads = 192;    // warp 0 producer, warp 1 MMA issuer, warps 2-5 epilogue; all six in prologue and finalize
 constexpr int kFMaxK = 128;       // sorted per-CTA lists live in shared memory
+constexpr int kObsQ = 16;         // queries observed at a time in a CTA's first tile ...
+constexpr int kObsStride = kGN + 1;   // ... [kObsQ][256 (+1: bank spread)] ordered scores in the pending area
 
 struct FusedCtl {
     uint32_t cnt[kFMaxQ];     // rows appended per query (may exceed cap: overflow)
@@ -65,8 +67,12 @@ struct FusedArgs {
     int* flag_count;
 };
 
+// pending area: [nq][pend] appended scores per tile in steady state, [kObsQ][kObsStride] observed scores in the first tile
+__host__ __device__ constexpr size_t fused_pend_words(int nq, int pend) {
+    return (size_t)nq * pend > (size_t)kObsQ * kObsStride ? (size_t)nq * pend : (size_t)kObsQ * kObsStride;
+}
 __host__ __device__ constexpr size_t fused_state_bytes(int nq, int k, int pend) {
-    return (size_t)4 * kFMaxQ * 4 + (size_t)nq * (k + pend) * 4 + 64;
+    return (size_t)4 * kFMaxQ * 4 + ((size_t)nq * k + fused_pend_words(nq, pend)) * 4 + 64;
 }
 __host__ __device__ constexpr size_t fused_smem_bytes(int num_kblocks, int ncol, int stages, int nq, int k, int pend) {
     return 1024 + (size_t)num_kblocks * ncol * kGKBytes + (size_t)stages * kBBytes + 256 + fused_state_bytes(nq, k, pend);
@@ -85,7 +91,11 @@ __device__ __forceinline__ float thr_below(float value, float eps) {
     return __fsub_rd(__fsub_rd(value, __fmul_ru(2.0f, eps)), 2.384185791015625e-07f);
 }
 
-// multiplier of the tile permutation t -> (t * mult) % n: odd, near 0.618 n, coprime with n
+// Tiles of a slice are visited in the order perm_tile(t) = (n / 2 + t * mult) % n: a stride near 0.618 n (coprime with n, so
+// every tile is visited once) starting in the middle, so that the first few tiles sample the whole slice - on a corpus sorted
+// by similarity a sequential sweep would see every row beat the running k-th score.
+__device__ __forceinline__ int perm_tile(int t, int mult, int n) { return (int)(((long long)t * mult + n / 2) % n); }
+// multiplier of the tile permutation: odd, near 0.618 n, coprime with n
 __device__ __forceinline__ int perm_mult(int n) {
     if (n <= 2) return 1;
     int m = (int)(0.6180339887 * n) | 1;
@@ -164,7 +174,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
         const int mult = perm_mult(ntiles);
         for (int it = 0; it < stages && it < ntiles * nkb; ++it) {
             const int t = it / nkb, kb = it % nkb;
-            const int tp = (int)(((long long)t * mult) % ntiles);
+            const int tp = perm_tile(t, mult, ntiles);
             mbar_expect_tx(full_bar(it), kBBytes);
             tma_load_2d(smB + (uint32_t)it * kBBytes, &tmB, kb * a.k_elems, (int)(r0 + (long long)tp * kGN), full_bar(it));
             ++pre_issued;
@@ -231,7 +241,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                 const int ntiles = slice_tiles(sl, r0, r1);
                 const int mult = perm_mult(ntiles);
                 for (int t = 0; t < ntiles; ++t) {
-                    const int tp = (int)(((long long)t * mult) % ntiles);
+                    const int tp = perm_tile(t, mult, ntiles);
                     for (int kb = 0; kb < nkb; ++kb) {
                         if (skip > 0) {
                             --skip;                        // issued before the prologue (first round of the ring: slots were free)
@@ -284,45 +294,102 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
         const int npend = a.pend;
         int acc = 0;
         uint32_t acc_phase = 0;
+        bool warm = true;                           // the CTA's first tile is observed before anything is appended
+        // scores of the 16-column chunk c of half h of the current accumulator: QPC queries per chunk
+        auto chunk_scores = [&](int h, int c, float (&out)[QPC]) {
+            uint32_t v[P][16];
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kAcc + (uint32_t)h * (P * NCOL) + (uint32_t)p * NCOL + (uint32_t)c * 16, v[p]);
+            float s16[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float s = __uint_as_float(v[0][j]) + __uint_as_float(v[1][j]);
+                if (P == 4) s += __uint_as_float(v[2][j]) + __uint_as_float(v[3][j]);
+                s16[j] = s;
+            }
+#pragma unroll
+            for (int j = 0; j < QPC; ++j) out[j] = SPLIT ? s16[j] + s16[j + 8] : s16[j];
+        };
+        // sorted-list insert of one ordered score for the query whose list is sl_ (entries so far: sc_n)
+        auto list_insert = [&](uint32_t* sl_, int& sc_n, uint32_t val) {
+            int j;
+            if (sc_n < k) j = sc_n++;
+            else if (val > sl_[k - 1]) j = k - 1;
+            else return;
+            while (j > 0 && sl_[j - 1] < val) { sl_[j] = sl_[j - 1]; --j; }
+            sl_[j] = val;
+        };
         for (int sl = blockIdx.x; sl < a.S; sl += gridDim.x) {
             long long r0, r1;
             const int ntiles = slice_tiles(sl, r0, r1);
             const int mult = perm_mult(ntiles);
             for (int t = 0; t < ntiles; ++t) {
-                const int tp = (int)(((long long)t * mult) % ntiles);
+                const int tp = perm_tile(t, mult, ntiles);
                 const long long trow = r0 + (long long)tp * kGN;
-                uint32_t g_pub = 0u;
-                if (et < nq) g_pub = __ldcg(a.ctl->gthr + et);       // what the other CTAs have published; used after the tile
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
+                // rows past the slice / corpus (zero-filled by TMA) and filtered rows never qualify
+                const long long row_h0 = trow + m, row_h1 = trow + 128 + m;
+                const bool ok0 = row_h0 < r1 && (a.allow == nullptr || row_allowed(a.allow, row_h0));
+                const bool ok1 = row_h1 < r1 && (a.allow == nullptr || row_allowed(a.allow, row_h1));
+                if (warm) {
+                    // ---- the CTA's first tile, pass 1 of 2: OBSERVE.  With thr = -inf every CTA would append its whole first
+                    // tile (148 x 256 rows per query, all on one counter).  Instead the tile's scores go to shared memory in
+                    // groups of kObsQ queries, the query's thread builds the sorted k best of the 256, and the tile is then
+                    // read a second time from tensor memory (pass 2, below) against thr = kth - 2 eps.
+                    for (int q0 = 0; q0 < nq; q0 += kObsQ) {
+#pragma unroll 1
+                        for (int h = 0; h < 2; ++h) {
+#pragma unroll 1
+                            for (int c = q0 / QPC; c < (q0 + kObsQ) / QPC && c < NCOL / 16; ++c) {
+                                float sc[QPC];
+                                chunk_scores(h, c, sc);
+#pragma unroll
+                                for (int j = 0; j < QPC; ++j)
+                                    pend[(size_t)(c * QPC + j - q0) * kObsStride + h * 128 + m] = (h ? ok1 : ok0) ? float_to_ordered(sc[j] + 0.0f) : 0u;
+                            }
+                        }
+                        named_bar_sync(1, 128);
+                        if (et >= q0 && et < q0 + kObsQ && et < nq) {
+                            const uint32_t g_pub = __ldcg(a.ctl->gthr + et);   // what the other CTAs have published so far
+                            uint32_t* sl_ = sorted + (size_t)et * k;
+                            int sc_n = 0;
+                            const uint32_t* ob = pend + (size_t)(et - q0) * kObsStride;
+                            for (int i = 0; i < kGN; ++i) {
+                                const uint32_t val = ob[i];
+                                if (val != 0u) list_insert(sl_, sc_n, val);
+                            }
+                            scnt[et] = sc_n;
+                            float nt = -INFINITY;
+                            if (sc_n >= a.keff && a.keff > 0) nt = thr_below(ordered_to_float(sl_[a.keff - 1]), my_eps);
+                            const float gf = g_pub ? ordered_to_float(g_pub) : -INFINITY;
+                            if (nt > gf) atomicMax(a.ctl->gthr + et, float_to_ordered(nt));
+                            else nt = gf;
+                            thr_s[et] = nt;
+                        }
+                        named_bar_sync(2, 128);
+                    }
+                }
+                // ---- append pass: every row whose approximate score reaches the query's current threshold ----
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
                     const long long row = trow + h * 128 + m;
-                    const bool row_ok = row < r1;                     // rows past the slice / corpus (zero-filled by TMA) never qualify
 #pragma unroll 1
                     for (int c = 0; c < NCOL / 16; ++c) {
-                        uint32_t v[P][16];
-#pragma unroll
-                        for (int p = 0; p < P; ++p)
-                            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kAcc + (uint32_t)h * (P * NCOL) + (uint32_t)p * NCOL + (uint32_t)c * 16, v[p]);
-                        float s16[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float s = __uint_as_float(v[0][j]) + __uint_as_float(v[1][j]);
-                            if (P == 4) s += __uint_as_float(v[2][j]) + __uint_as_float(v[3][j]);
-                            s16[j] = s;
-                        }
-                        if (row_ok) {
+                        float sc[QPC];
+                        chunk_scores(h, c, sc);
+                        if (h ? ok1 : ok0) {
 #pragma unroll
                             for (int j = 0; j < QPC; ++j) {
                                 const int qi = c * QPC + j;
-                                const float sc = SPLIT ? s16[j] + s16[j + 8] : s16[j];
-                                if (sc >= thr_s[qi]) {                 // shared-memory broadcast; padding queries hold +inf
-                                    if (a.allow != nullptr && !row_allowed(a.allow, row)) continue;
+                                if (sc[j] >= thr_s[qi]) {              // shared-memory broadcast; padding queries hold +inf
                                     const uint32_t pos = atomicAdd(a.ctl->cnt + qi, 1u);
-                                    if (pos < (uint32_t)a.cap) a.cand[(size_t)qi * a.cap + pos] = make_key(sc + 0.0f, (uint32_t)row);
-                                    const int lp = atomicAdd(pcnt + qi, 1);
-                                    if (lp < npend) pend[(size_t)qi * npend + lp] = float_to_ordered(sc + 0.0f);
+                                    if (pos < (uint32_t)a.cap) a.cand[(size_t)qi * a.cap + pos] = make_key(sc[j] + 0.0f, (uint32_t)row);
+                                    if (!warm) {                       // the first tile's scores are already in the sorted list
+                                        const int lp = atomicAdd(pcnt + qi, 1);
+                                        if (lp < npend) pend[(size_t)qi * npend + lp] = float_to_ordered(sc[j] + 0.0f);
+                                    }
                                 }
                             }
                         }
@@ -333,21 +400,16 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
                 // ---- threshold maintenance: the tile's appended scores enter the query's sorted list ----
                 named_bar_sync(1, 128);
-                if (et < nq) {
+                if (et < nq && !warm) {
+                    // read NOW (not a tile ago): the next tile is filtered with the best bound any CTA has found; the L2 round
+                    // trip overlaps the list update below
+                    const uint32_t g_pub = __ldcg(a.ctl->gthr + et);
                     uint32_t* sl_ = sorted + (size_t)et * k;
                     int sc_n = scnt[et];
                     int pc = pcnt[et];
                     if (pc > 0) {
                         if (pc > npend) pc = npend;                    // the surplus was dropped: only tightening information is lost
-                        for (int i = 0; i < pc; ++i) {
-                            const uint32_t val = pend[(size_t)et * npend + i];
-                            int j;
-                            if (sc_n < k) j = sc_n++;
-                            else if (val > sl_[k - 1]) j = k - 1;
-                            else continue;
-                            while (j > 0 && sl_[j - 1] < val) { sl_[j] = sl_[j - 1]; --j; }
-                            sl_[j] = val;
-                        }
+                        for (int i = 0; i < pc; ++i) list_insert(sl_, sc_n, pend[(size_t)et * npend + i]);
                         scnt[et] = sc_n;
                         pcnt[et] = 0;
                     }
@@ -358,6 +420,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                     else nt = gf;
                     thr_s[et] = nt;
                 }
+                warm = false;
                 named_bar_sync(2, 128);
             }
         }
@@ -418,17 +481,24 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
         long long* oid = a.out_ids + (size_t)qi * k;
         float* osc = a.out_scores + (size_t)qi * k;
         const u64* in = a.cand + (size_t)qi * a.cap;
-        bool exact_scan = m32 > (uint32_t)a.cap || (int)m32 > sel_cap || (int)m32 < keff;   // block-uniform
+        bool exact_scan = m32 > (uint32_t)a.cap || (int)m32 < keff;   // block-uniform
         if (!exact_scan && keff > 0) {
             const int m = (int)m32;
             const uint32_t t_ord = block_kth_largest([&](int i) { return (uint32_t)(__ldcg(in + i) >> 32); }, m, (uint32_t)keff, hist, s3);
             const float cut = thr_below(ordered_to_float(t_ord), eps_s[qi]);
             for (int i = tid; i < m; i += kFThreads) {
                 const u64 key = __ldcg(in + i);
-                if (key_score(key) >= cut) sel[atomicAdd(s_c2, 1)] = key;      // <= m <= sel_cap
+                if (key_score(key) >= cut) {
+                    const int pos = atomicAdd(s_c2, 1);
+                    if (pos < sel_cap) sel[pos] = key;
+                }
             }
             __syncthreads();
             const int c2 = *s_c2;
+            int P2 = 32;
+            while (P2 < c2) P2 <<= 1;
+            if (P2 > sel_cap) exact_scan = true;   // more rows within 2 eps of the k-th score than the scratch holds: massive duplication
+            else {
             for (int c = warp; c < c2; c += kFThreads / 32) {
                 const uint32_t row = key_row(sel[c]);
                 double sc;
@@ -438,11 +508,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                 __syncwarp();
                 if (lane == 0) sel[c] = make_key((float)sc + 0.0f, row);
             }
-            int P2 = 32;
-            while (P2 < c2) P2 <<= 1;
-            if (P2 > sel_cap) {
-                exact_scan = true;       // cannot pad to a power of two: leave it to the scan (never with the host's sizing)
-            } else {
+            {
                 for (int i = c2 + tid; i < P2; i += kFThreads) sel[i] = 0ull;
                 __syncthreads();
                 block_bitonic_sort_desc(sel, P2, tid, kFThreads);
@@ -452,6 +518,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                     osc[i] = key ? key_score(key) : -INFINITY;
                 }
                 if (tid == 0) a.flags[qi] = 0;
+            }
             }
         } else if (!exact_scan) {   // keff == 0: nothing to return
             for (int i = tid; i < k; i += kFThreads) { oid[i] = -1; osc[i] = -INFINITY; }

@@ -210,9 +210,8 @@ class Index:
 
     def set_gemm_variant(self, variant: int) -> None:
         """tcgen05 kernel variant: 0 automatic, 1 streaming, 2 A-stationary (query tile in tensor memory),
-        3 streaming with swapped operand roles for batches of <= 16 queries, 4 EXPERIMENTAL 2-SM MMA pairs
-        (csrc/gemm_pair.cuh), 5 EXPERIMENTAL self-seeded sweep for <= 16 queries and k <= 16 (csrc/gemm_rows_seeded.cuh);
-        4 and 5 have not yet run on a GPU and are never chosen automatically."""
+        3 streaming with swapped operand roles for batches of <= 16 queries, 4 2-SM MMA pairs (csrc/gemm_pair.cuh,
+        tcgen05 cta_group::2; never chosen automatically)."""
         _lib.check(self._L.ragfin_set_gemm_variant(self._h, int(variant)))
 
     def set_bound_pass(self, enable: bool) -> None:

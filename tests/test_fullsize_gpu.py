@@ -19,6 +19,7 @@ N, DIM, K, SEED = 10_000_000, 768, 10, 1234
 def corpus():
     import ragfin_b200
     idx = ragfin_b200.Index(DIM, "bf16", capacity=N + 16, device=0)
+    idx.set_fused(False)              # the tests below pin the multi-kernel paths; the one-kernel search has its own at the end
     for r in range(0, N, 1_000_000):
         idx.add_synthetic(SEED, r, 1_000_000, dup_every=5000)
     q = O.synth_rows(SEED + 1, 0, 64, DIM)
@@ -78,6 +79,7 @@ def test_full_size_properties(corpus, coracle):
     outs = []
     for a, b in ((0, half), (half, N)):
         sh = ragfin_b200.Index(DIM, "bf16", capacity=b - a + 4, device=0)
+        sh.set_fused(False)
         for r in range(a, b, 1_000_000):
             sh.add_synthetic(SEED, r, min(1_000_000, b - r), dup_every=5000)
         if b == N:
@@ -171,6 +173,7 @@ def test_config2_1m_f32_1024_queries(coracle):
     import ragfin_b200
     n, nq = 1_000_000, 1024
     idx = ragfin_b200.Index(DIM, "f32", capacity=n, device=0)
+    idx.set_fused(False)
     idx.add_synthetic(SEED + 7, 0, n, dup_every=997)
     q = O.synth_rows(SEED + 8, 0, nq, DIM)
     ids, sc = idx.search(q, K)
@@ -194,9 +197,41 @@ def test_config2_1m_f32_1024_queries(coracle):
             assert s_[j] > s_[j + 1] or (s_[j] == s_[j + 1] and i_[j] < i_[j + 1])
         want = coracle.exact_scores(stored[i_], qhat[qi])
         assert np.array_equal(want.view(np.uint32), s_.view(np.uint32)), qi
+    # the one-kernel search (<= 64 queries, kind::tf32 with 32 / 64 query columns) answers the same bits
+    idx.set_fused(True)
+    for a, b in ((0, 1), (100, 116), (200, 264)):
+        ids_f, sc_f = idx.search(q[a:b], K)
+        assert idx.stats()["path"] == 3 and idx.stats()["queries_rescanned"] == 0
+        assert np.array_equal(ids_f, ids[a:b]) and np.array_equal(sc_f.view(np.uint32), sc[a:b].view(np.uint32))
+    idx.set_fused(False)
     # the small-batch path answers the same bits
     idx.set_gemm_min_batch(1 << 30)
     ids_s, sc_s = idx.search(q[:4], K)
     assert idx.stats()["path"] == 0
     assert np.array_equal(ids_s, ids[:4]) and np.array_equal(sc_s.view(np.uint32), sc[:4].view(np.uint32))
     idx.close()
+
+
+def test_full_size_one_kernel_search(corpus, coracle):
+    """The default path for <= 64 queries (csrc/sweep_fused.cuh) at BASELINE's full size: batches of 1, 8, 16, 33 and 64
+    queries, k = 10 and 100, bit-identical to the multi-kernel tensor-core path (itself pinned above), no in-kernel
+    exact scan, needles first."""
+    idx, q = corpus
+    idx.set_gemm_min_batch(3)
+    ref10 = idx.search(q, K)
+    ref100 = idx.search(q[:16], 100)
+    idx.set_fused(True)
+    try:
+        for nq in (1, 8, 16, 33, 64):
+            ids, sc = idx.search(q[:nq], K)
+            st = idx.stats()
+            assert st["path"] == 3 and st["launches"] == 1 and st["queries_rescanned"] == 0, (nq, st)
+            assert np.array_equal(ids, ref10[0][:nq]) and np.array_equal(sc.view(np.uint32), ref10[1][:nq].view(np.uint32)), nq
+            assert ids[0][0] == N
+        for nq in (1, 16):
+            ids, sc = idx.search(q[:nq], 100)
+            st = idx.stats()
+            assert st["path"] == 3 and st["queries_rescanned"] == 0, (nq, st)
+            assert np.array_equal(ids, ref100[0][:nq]) and np.array_equal(sc.view(np.uint32), ref100[1][:nq].view(np.uint32)), nq
+    finally:
+        idx.set_fused(False)

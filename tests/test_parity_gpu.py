@@ -12,6 +12,13 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
+@pytest.fixture(autouse=True)
+def _multi_kernel_paths(monkeypatch):
+    """This module pins the multi-kernel paths (K2 scan, K3 / K3r sweeps, large k): handles created here do not take the
+    one-kernel search, which has its own parity suite (tests/test_fused_gpu.py) and serves <= 64 queries by default."""
+    monkeypatch.setenv("RAGFIN_NO_FUSED", "1")
+
+
 def _index(x, dtype, capacity=None):
     import ragfin_b200
     idx = ragfin_b200.Index(x.shape[1], dtype, capacity=capacity or max(len(x), 1), device=0)
@@ -714,3 +721,72 @@ def test_device_feed_through_the_shim_and_the_chunk_pipeline(coracle):
         assert [h.score for h in ra[qi]] == [h.score for h in rb[qi]] == [float(v) for v in ws[qi]]
     for n in ("feed_host", "feed_device"):
         mc.utility.drop_collection(n)
+
+
+# ---- variants first run on a GPU at the start of round 2 (profiles/r02): 2-SM MMA pairs, views -------------------------
+@pytest.mark.parametrize("dtype", O.DTYPES)
+@pytest.mark.parametrize("n,dim,nq,k", [(30000, 768, 256, 10), (20011, 384, 130, 5), (50000, 128, 1000, 10), (120000, 768, 513, 100),
+                                        (66000, 100, 257, 10), (40000, 1024, 384, 1)])
+def test_two_sm_mma_sweep_matches_oracle(coracle, dtype, n, dim, nq, k):
+    """Variant 4 (csrc/gemm_pair.cuh): >= 2 query tiles in append mode sweep with tcgen05 cta_group::2 pairs; odd tile
+    counts leave the second CTA of the last pair on zero padding.  Same bits as the oracle and as variant 1."""
+    import ragfin_b200
+    x = O.synth_rows(296, 0, n, dim, dup_every=61, zero_every=1999)
+    q = O.synth_rows(297, 0, nq, dim)
+    x[4000:4030] = q[2] * 2.0        # 30 exact duplicates of one query: ties resolved by row id
+    want = coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), k)
+    idx = ragfin_b200.Index(dim, dtype, capacity=n, device=0)
+    idx.add(x)
+    idx.set_gemm_min_batch(1)
+    idx.set_gemm_variant(4)
+    got = idx.search(q, k)
+    st = idx.stats()
+    assert st["path"] == 1 and st["queries_rescanned"] == 0
+    _assert_same(got, want, f"2-SM pairs {dtype} n={n} dim={dim} nq={nq} k={k}")
+    idx.set_gemm_variant(1)
+    _assert_same(idx.search(q, k), want, "single-CTA MMA")
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+def test_two_sm_mma_raw_scores_equal_single_cta(dtype):
+    import torch
+    import ragfin_b200
+    x = O.synth_rows(5, 0, 5000, 768)
+    q = torch.from_numpy(O.synth_rows(6, 0, 300, 768)).cuda()
+    idx = ragfin_b200.Index(768, dtype, capacity=5000, device=0)
+    idx.add(x)
+    idx.set_gemm_variant(1)
+    idx.set_gemm_cluster(2)
+    base = idx.debug_gemm_scores(q).cpu()
+    idx.set_gemm_variant(4)
+    got = idx.debug_gemm_scores(q).cpu()
+    assert torch.equal(got, base)     # same k-order per output element
+
+
+def test_view_shares_the_matrix_and_is_read_only(coracle):
+    """ragfin_create_view: a second handle over the same device matrix with its own workspace; searches through parent
+    and view on two streams at once return what each returns alone."""
+    import torch
+    import ragfin_b200
+    x = O.synth_rows(7, 0, 70000, 128, dup_every=61)
+    q = O.synth_rows(8, 0, 5, 128)
+    want = coracle.cosine_topk(q, coracle.normalize_rows(x, "bf16"), 10)
+    idx = ragfin_b200.Index(128, "bf16", capacity=80000, device=0)
+    idx.add(x)
+    v = idx.view()
+    assert len(v) == 70000
+    _assert_same(v.search(q, 10), want, "view")
+    with pytest.raises(ragfin_b200.RagfinError):
+        v.add(x[:1])
+    qd = torch.from_numpy(q).cuda()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for i in range(20):
+        h, s = (idx, s1) if i % 2 == 0 else (v, s2)
+        with torch.cuda.stream(s):
+            outs.append(h.search_device(qd, 10, stream=s))
+    torch.cuda.synchronize()
+    for ids, sc in outs:
+        _assert_same((ids.cpu().numpy(), sc.cpu().numpy()), want, "interleaved")
+    v.close()
+    idx.close()

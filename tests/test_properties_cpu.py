@@ -61,34 +61,3 @@ def test_exact_duplicates_come_back_in_row_order(seed, n, copies):
     x[rows] = q[0] * 3.0                                                                  # identical best rows
     ids, sc = O.cosine_topk(q, O.normalize_rows(x, "f16"), len(rows))
     assert ids[0].tolist() == rows.tolist() and len(set(sc[0].view(np.uint32).tolist())) == 1
-
-
-def _warp_kth_largest(values, want):
-    """Line-by-line Python restatement of warp_kth_largest (csrc/gemm_rows_seeded.cuh): 32 lanes stride over the
-    ordered-uint values; each round takes the largest value below the previous one and counts its multiplicity."""
-    n, prev, first, remaining = len(values), 0, True, want
-    for _ in range(want):
-        best = 0
-        for lane in range(32):                      # per-lane scan + __reduce_max_sync
-            for i in range(lane, n, 32):
-                x = values[i]
-                if (first or x < prev) and x > best:
-                    best = x
-        if best == 0:
-            break
-        c = sum(1 for x in values if x == best)     # per-lane counts + __reduce_add_sync
-        if c >= remaining:
-            return best
-        remaining -= c
-        prev, first = best, False
-    return 0x007FFFFF                               # -inf: collect everything
-
-
-@settings(max_examples=200, deadline=None)
-@given(vals=st.lists(st.integers(1, 50), min_size=1, max_size=300), want=st.integers(1, 16))
-def test_warp_select_restatement_is_the_kth_largest_with_multiplicity(vals, want):
-    got = _warp_kth_largest(vals, want)
-    if want <= len(vals):
-        assert got == sorted(vals, reverse=True)[want - 1]
-    else:
-        assert got == 0x007FFFFF
