@@ -210,6 +210,11 @@ int ragfin_set_append_mode(ragfin_t* h, int32_t enable);
  * Replaces: the same Collection.search call sites; this is the batch-1 path of vector_rag_mcp/main.py:51-57. */
 int ragfin_set_fused(ragfin_t* h, int32_t enable, int64_t min_rows);
 
+/* Test / bench hook: per-query diagnostics of the last one-kernel search on this handle - rows appended to the query's
+ * buffer during the sweep and rows rescored exactly by the finalize (-1: the buffer overflowed and the query was answered
+ * by the in-kernel exact scan).  Synchronises. */
+int ragfin_debug_fused_counts(ragfin_t* h, int32_t nq, int64_t* out_appended, int64_t* out_rescored);
+
 /* Test hook: raw (approximate, fp32-accumulated) tensor-core scores of nq queries against every
  * stored row, out_scores_dev [nq, count] device memory.  Validates the TMA / tcgen05 plumbing. */
 int ragfin_debug_gemm_scores(ragfin_t* h, const float* q_dev, int32_t nq, float* out_scores_dev, void* stream);

@@ -1021,6 +1021,10 @@ static int run_fused(ragfin* h, const float* q_dev, int nb, int k, int64_t n_eff
     a.stages = f.stages;
     a.k = k; a.keff = (int)((int64_t)k < n_eff ? k : n_eff);
     a.pend = f.pend;
+    a.groups = p.grid < kFGroups ? p.grid : kFGroups;
+    if (a.keff > 0 && a.groups > a.keff) a.groups = a.keff;
+    if (a.groups < 1) a.groups = 1;
+    a.grank = a.keff > 0 ? (a.keff + a.groups - 1) / a.groups : 0;
     a.q = q_dev;
     a.data = h->data;
     a.allow = h->cur_allow;
@@ -1386,6 +1390,23 @@ extern "C" int ragfin_set_append_mode(ragfin_t* h, int32_t enable) {
     if (!h) return fail(RAGFIN_EINVAL, "NULL handle");
     std::lock_guard<std::mutex> lk(h->mu);
     h->use_append = enable != 0;
+    return RAGFIN_OK;
+}
+
+// Diagnostics of the last one-kernel search: rows appended per query (out_appended[nq]) and rows rescored exactly
+// (out_rescored[nq]; -1 = the query took the in-kernel exact scan).  Synchronises the device.
+extern "C" int ragfin_debug_fused_counts(ragfin_t* h, int32_t nq, int64_t* out_appended, int64_t* out_rescored) {
+    if (!h || !out_appended || !out_rescored || nq < 1 || nq > kFMaxQ) return fail(RAGFIN_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    if (!h->fctl.p) return fail(RAGFIN_EINVAL, "no one-kernel search has run on this handle");
+    CU_TRY(cudaDeviceSynchronize());
+    FusedCtl c;
+    CU_TRY(cudaMemcpy(&c, h->fctl.p, sizeof(c), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < nq; ++i) {
+        out_appended[i] = c.last_cnt[i];
+        out_rescored[i] = c.last_resc[i] == 0xFFFFFFFFu ? -1 : (int64_t)c.last_resc[i];
+    }
     return RAGFIN_OK;
 }
 

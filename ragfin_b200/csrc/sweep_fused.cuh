@@ -15,8 +15,10 @@
 //   threshold  NO bound pass.  A row is appended to its query's buffer when approx >= thr[q]; thr[q] starts at -inf
 //              and only rises: every CTA keeps, per query, the sorted k best approximate scores among the rows IT has
 //              appended (k distinct rows, so the k-th is a lower bound of T, the k-th best approximate score of the
-//              corpus) and sets thr = kth - 2 eps; the best threshold any CTA has found is shared through one atomicMax
-//              word per query, re-read every tile.  Every row of the exact top-k satisfies approx >= T - 2 eps >= thr at
+//              corpus) and sets thr = kth - 2 eps.  CTAs cooperate through G = 16 words per query: CTA c publishes its
+//              ceil(k / G)-th best score (minus 2 eps) into word c % G by atomicMax; the MINIMUM of the G words is a valid
+//              bound too (G different CTAs each hold ceil(k / G) distinct rows at or above their word) and a much tighter
+//              one for large k - a CTA only has to find k / 16 good rows, not k.  Re-read every tile.  Every row of the exact top-k satisfies approx >= T - 2 eps >= thr at
 //              any time, so it is in the buffer (DESIGN.md 2.4 with a moving threshold).  Tiles of a slice are visited in
 //              a strided permutation, so a corpus sorted by similarity cannot make every row beat the running bound.
 //   finalize   the last nq CTAs to finish wait for the grid-wide arrival counter and finalize one query each in place:
@@ -32,14 +34,18 @@ namespace rfk {
 constexpr int kFMaxQ = 64;        // queries per launch
 constexpr int kFThreads = 192;    // warp 0 producer, warp 1 MMA issuer, warps 2-5 epilogue; all six in prologue and finalize
 constexpr int kFMaxK = 128;       // sorted per-CTA lists live in shared memory
+constexpr int kFGroups = 16;      // CTA groups of the shared bound (see "threshold" above)
 constexpr int kObsQ = 16;         // queries observed at a time in a CTA's first tile ...
 constexpr int kObsStride = kGN + 1;   // ... [kObsQ][256 (+1: bank spread)] ordered scores in the pending area
 
 struct FusedCtl {
     uint32_t cnt[kFMaxQ];     // rows appended per query (may exceed cap: overflow)
-    uint32_t gthr[kFMaxQ];    // best published threshold, float_to_ordered (0 = none yet)
+    uint32_t gthr[kFMaxQ][kFGroups];   // published bounds per (query, CTA group), float_to_ordered (0 = none yet)
     uint32_t done;            // CTAs that have finished their sweep
+    uint32_t obs_done;        // CTAs that have observed their first tile and published its bound
     uint32_t fin_done;        // finalizing CTAs that have finished
+    uint32_t last_cnt[kFMaxQ];   // diagnostics of the last search: rows appended per query ...
+    uint32_t last_resc[kFMaxQ];  // ... and rows rescored exactly (0xFFFFFFFF: the query took the exact scan)
 };
 
 struct FusedArgs {
@@ -53,6 +59,7 @@ struct FusedArgs {
     int stages;
     int k, keff;                // keff = min(k, rows a hit may come from)
     int pend;                   // pending-score slots per query and tile
+    int groups, grank;          // CTA groups of the shared bound and the rank each CTA publishes: ceil(keff / groups)
     const float* q;             // [nq][dim] raw fp32 queries
     const void* data;           // corpus [n_rows][ld]
     const uint32_t* allow;      // scalar filter bitmask or null
@@ -320,6 +327,29 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
             while (j > 0 && sl_[j - 1] < val) { sl_[j] = sl_[j - 1]; --j; }
             sl_[j] = val;
         };
+        // min over the CTA groups of the bound each group has published for query qi (-inf until every group has one): read
+        // NOW, so that the next tile is filtered with the best bound the grid has found
+        const int my_group = (int)(blockIdx.x % (unsigned)a.groups);
+        uint32_t my_pub = 0u;                          // what this CTA last published for its query (thread et)
+        auto group_bound = [&](int qi) -> float {
+            uint32_t mn = 0xFFFFFFFFu;
+            for (int g = 0; g < a.groups; ++g) {
+                const uint32_t v = __ldcg(&a.ctl->gthr[qi][g]);
+                mn = v < mn ? v : mn;
+            }
+            return mn ? ordered_to_float(mn) : -INFINITY;
+        };
+        // new threshold of query qi from its sorted list (own k-th best), the published group bounds, and the old value;
+        // publishes this CTA's grank-th best for its group when that improved
+        auto refresh = [&](int qi, const uint32_t* sl_, int sc_n, float old_thr) -> float {
+            float nt = old_thr;
+            if (sc_n >= a.keff && a.keff > 0) nt = fmaxf(nt, thr_below(ordered_to_float(sl_[a.keff - 1]), my_eps));
+            if (sc_n >= a.grank && a.grank > 0) {
+                const uint32_t pv = float_to_ordered(thr_below(ordered_to_float(sl_[a.grank - 1]), my_eps));
+                if (pv > my_pub) { my_pub = pv; atomicMax(&a.ctl->gthr[qi][my_group], pv); __threadfence(); }
+            }
+            return fmaxf(nt, group_bound(qi));
+        };
         for (int sl = blockIdx.x; sl < a.S; sl += gridDim.x) {
             long long r0, r1;
             const int ntiles = slice_tiles(sl, r0, r1);
@@ -352,7 +382,6 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                         }
                         named_bar_sync(1, 128);
                         if (et >= q0 && et < q0 + kObsQ && et < nq) {
-                            const uint32_t g_pub = __ldcg(a.ctl->gthr + et);   // what the other CTAs have published so far
                             uint32_t* sl_ = sorted + (size_t)et * k;
                             int sc_n = 0;
                             const uint32_t* ob = pend + (size_t)(et - q0) * kObsStride;
@@ -361,15 +390,23 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                                 if (val != 0u) list_insert(sl_, sc_n, val);
                             }
                             scnt[et] = sc_n;
-                            float nt = -INFINITY;
-                            if (sc_n >= a.keff && a.keff > 0) nt = thr_below(ordered_to_float(sl_[a.keff - 1]), my_eps);
-                            const float gf = g_pub ? ordered_to_float(g_pub) : -INFINITY;
-                            if (nt > gf) atomicMax(a.ctl->gthr + et, float_to_ordered(nt));
-                            else nt = gf;
-                            thr_s[et] = nt;
+                            thr_s[et] = refresh(et, sl_, sc_n, -INFINITY);
                         }
                         named_bar_sync(2, 128);
                     }
+                    // Best-effort rendezvous: all CTAs observe their first tile at the same time, so a few microseconds later
+                    // every bound is published and the first tile can be filtered with the best of them (on a corpus sorted
+                    // by similarity - or with the coarse tf32 error bound - the LOCAL bound admits every row of the tile).
+                    // The wait is bounded: a CTA that is not resident yet (another kernel on the device) only costs tightness.
+                    // TMA and the tensor core keep running ahead meanwhile (second accumulator, ring).
+                    if (et == 0) {
+                        __threadfence();
+                        atomicAdd(&a.ctl->obs_done, 1u);
+                        for (int spins = 0; spins < 256 && ld_acq_gpu(&a.ctl->obs_done) < gridDim.x; ++spins) __nanosleep(40);
+                    }
+                    named_bar_sync(1, 128);
+                    if (et < nq) thr_s[et] = fmaxf(thr_s[et], group_bound(et));
+                    named_bar_sync(2, 128);
                 }
                 // ---- append pass: every row whose approximate score reaches the query's current threshold ----
 #pragma unroll 1
@@ -401,9 +438,6 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                 // ---- threshold maintenance: the tile's appended scores enter the query's sorted list ----
                 named_bar_sync(1, 128);
                 if (et < nq && !warm) {
-                    // read NOW (not a tile ago): the next tile is filtered with the best bound any CTA has found; the L2 round
-                    // trip overlaps the list update below
-                    const uint32_t g_pub = __ldcg(a.ctl->gthr + et);
                     uint32_t* sl_ = sorted + (size_t)et * k;
                     int sc_n = scnt[et];
                     int pc = pcnt[et];
@@ -413,12 +447,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                         scnt[et] = sc_n;
                         pcnt[et] = 0;
                     }
-                    float nt = thr_s[et];
-                    if (sc_n >= a.keff && a.keff > 0) nt = fmaxf(nt, thr_below(ordered_to_float(sl_[a.keff - 1]), my_eps));
-                    const float gf = g_pub ? ordered_to_float(g_pub) : -INFINITY;
-                    if (nt > gf) atomicMax(a.ctl->gthr + et, float_to_ordered(nt));
-                    else nt = gf;
-                    thr_s[et] = nt;
+                    thr_s[et] = refresh(et, sl_, sc_n, thr_s[et]);
                 }
                 warm = false;
                 named_bar_sync(2, 128);
@@ -477,6 +506,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
         }
         __syncthreads();
         const uint32_t m32 = __ldcg(a.ctl->cnt + qi);
+        if (tid == 0) { a.ctl->last_cnt[qi] = m32; a.ctl->last_resc[qi] = 0xFFFFFFFFu; }
         const int keff = a.keff;
         long long* oid = a.out_ids + (size_t)qi * k;
         float* osc = a.out_scores + (size_t)qi * k;
@@ -517,7 +547,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                     oid[i] = key ? a.id_base + (long long)key_row(key) : -1;
                     osc[i] = key ? key_score(key) : -INFINITY;
                 }
-                if (tid == 0) a.flags[qi] = 0;
+                if (tid == 0) { a.flags[qi] = 0; a.ctl->last_resc[qi] = (uint32_t)c2; }
             }
             }
         } else if (!exact_scan) {   // keff == 0: nothing to return
@@ -556,12 +586,14 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
             if (tid == 0) { a.flags[qi] = 1; atomicAdd(a.flag_count, 1); }
         }
         __syncthreads();
-        if (tid == 0) { a.ctl->cnt[qi] = 0u; a.ctl->gthr[qi] = 0u; }   // leave the control block clean for the next search
+        if (tid == 0) a.ctl->cnt[qi] = 0u;                             // leave the control block clean for the next search
+        if (tid < kFGroups) a.ctl->gthr[qi][tid] = 0u;
     }
     if (tid == 0) {
         __threadfence();
         if (atomicAdd(&a.ctl->fin_done, 1u) == (uint32_t)n_fin - 1u) {   // last finalizer: counters back to zero
             a.ctl->done = 0u;
+            a.ctl->obs_done = 0u;
             a.ctl->fin_done = 0u;
         }
     }

@@ -227,6 +227,12 @@ class Index:
         min_rows > 0 also sets the smallest corpus it serves."""
         _lib.check(self._L.ragfin_set_fused(self._h, 1 if enable else 0, int(min_rows)))
 
+    def fused_counts(self, nq: int):
+        """Diagnostics of the last one-kernel search: (rows appended per query, rows rescored per query; -1 = exact scan)."""
+        a, r = np.zeros(nq, np.int64), np.zeros(nq, np.int64)
+        _lib.check(self._L.ragfin_debug_fused_counts(self._h, int(nq), a.ctypes.data, r.ctypes.data))
+        return a, r
+
     def set_append_mode(self, enable: bool) -> None:
         """tcgen05 path: append mode (no lists, threshold from the bound pass) on/off (default on; results identical)."""
         _lib.check(self._L.ragfin_set_append_mode(self._h, 1 if enable else 0))

@@ -1,11 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
+python scripts/fused_debug.py > gpurun_out/r02_2_fused_debug.log 2>&1; tail -n 14 gpurun_out/r02_2_fused_debug.log
 timeout 420 python -m pytest tests/test_fused_gpu.py -m gpu -x -q > gpurun_out/r02_2_fused_tests.log 2>&1; rc=$?; echo "fused tests rc=$rc"; tail -n 15 gpurun_out/r02_2_fused_tests.log
 if [ $rc -ne 0 ]; then
   # narrow down: the smallest configuration alone
   timeout 120 python -m pytest tests/test_fused_gpu.py -m gpu -x -q -k "test_fused_matches_oracle and bf16 and 1-10" > gpurun_out/r02_2_fused_min.log 2>&1; echo "fused minimal rc=$?"; tail -n 30 gpurun_out/r02_2_fused_min.log
 fi
-timeout 600 python -m pytest tests/test_parity_gpu.py -m gpu -x -q > gpurun_out/r02_2_parity.log 2>&1; echo "parity tests rc=$?"; tail -n 8 gpurun_out/r02_2_parity.log
+echo "(parity suite: passed in the previous call, skipped here)"
 if [ $rc -eq 0 ]; then
   timeout 600 python scripts/fused_check.py > gpurun_out/r02_2_fused_check.log 2>&1; echo "fused_check rc=$?"; cat gpurun_out/r02_2_fused_check.log
   timeout 600 python -m pytest tests/test_fullsize_gpu.py -m gpu -x -q > gpurun_out/r02_2_fullsize.log 2>&1; echo "fullsize rc=$?"; tail -n 5 gpurun_out/r02_2_fullsize.log
