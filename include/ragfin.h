@@ -134,6 +134,25 @@ int ragfin_exchange_handle(ragfin_exchange_t* x, void* handle_out /* RAGFIN_IPC_
 int ragfin_exchange_connect(ragfin_exchange_t* x, const void* handles /* world * RAGFIN_IPC_HANDLE_BYTES */);
 int ragfin_exchange_allgather_merge(ragfin_exchange_t* x, const int64_t* ids_dev, const float* scores_dev, int32_t nq,
                                     int32_t k, int64_t* out_ids_dev, float* out_scores_dev, void* stream);
+/* Whether a search of nq queries with limit k on this handle takes the one-kernel search (csrc/sweep_fused.cuh).  The
+ * ranks of a sharded search must agree before they call ragfin_search_sharded (shard sizes differ by a row), so the host
+ * layer reduces *out over the ranks once per (nq, k). */
+int ragfin_fused_eligible(ragfin_t* h, int32_t nq, int32_t k, int32_t* out);
+
+/* Row-sharded search in ONE kernel per GPU: this rank's shard is swept by the one-kernel search, whose finalizing CTAs store
+ * the shard's exact hits into every rank's gather area over NVLink (the exchange's CUDA IPC mappings), wait for the other
+ * ranks' hits and write the GLOBAL top-k into out_ids / out_scores on every rank - no collective call, no separate reduce
+ * kernel.  Collective: every rank calls it once per step with the same (nq <= 64, k <= 128) and the same queries, always
+ * on the same stream; fails with RAGFIN_EUNSUPPORTED when the shape does not take the one-kernel search on this shard.
+ * _host: host buffers, queries staged through pinned memory, hits written by the kernel into device-mapped pinned memory,
+ * one stream synchronisation.
+ * Replaces: the querynode -> proxy reduce behind Collection.search on a sharded Milvus deployment
+ * (vector_rag_mcp/main.py:51-57), i.e. local search + NCCL all-gather + ragfin_merge_topk. */
+int ragfin_search_sharded(ragfin_t* h, ragfin_exchange_t* x, const float* q, int32_t nq, int32_t k, int64_t* out_ids,
+                          float* out_scores, void* stream);
+int ragfin_search_sharded_host(ragfin_t* h, ragfin_exchange_t* x, const float* q_host, int32_t nq, int32_t k,
+                               int64_t* out_ids_host, float* out_scores_host);
+
 void ragfin_exchange_destroy(ragfin_exchange_t* x);
 
 /* Copy rows row0..row0+n of the STORED matrix, raw storage bytes [n, ld], to host memory

@@ -19,7 +19,7 @@ SYMBOLS = (
     "ragfin_abi_version", "ragfin_create", "ragfin_create_view", "ragfin_add", "ragfin_add_synthetic", "ragfin_count", "ragfin_reserve",
     "ragfin_set_id_base", "ragfin_search", "ragfin_search_host", "ragfin_search_filtered", "ragfin_search_filtered_host", "ragfin_merge_topk", "ragfin_read_rows",
     "ragfin_last_search_stats", "ragfin_profile", "ragfin_profile_read", "ragfin_save", "ragfin_load", "ragfin_set_gemm_min_batch", "ragfin_set_gemm_cluster", "ragfin_set_gemm_variant", "ragfin_set_bound_pass", "ragfin_set_scan_variant", "ragfin_set_append_mode", "ragfin_set_fused", "ragfin_debug_fused_counts", "ragfin_debug_gemm_scores", "ragfin_debug_plan", "ragfin_destroy", "ragfin_last_error",
-    "ragfin_exchange_create", "ragfin_exchange_handle", "ragfin_exchange_connect", "ragfin_exchange_allgather_merge", "ragfin_exchange_destroy",
+    "ragfin_exchange_create", "ragfin_exchange_handle", "ragfin_exchange_connect", "ragfin_exchange_allgather_merge", "ragfin_fused_eligible", "ragfin_search_sharded", "ragfin_search_sharded_host", "ragfin_exchange_destroy",
 )
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
@@ -74,6 +74,9 @@ def load() -> ctypes.CDLL:
     L.ragfin_exchange_connect.argtypes = [vp, vp]
     L.ragfin_exchange_allgather_merge.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
     L.ragfin_exchange_destroy.argtypes = [vp]
+    L.ragfin_fused_eligible.argtypes = [vp, i32, i32, ctypes.POINTER(i32)]
+    L.ragfin_search_sharded.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
+    L.ragfin_search_sharded_host.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.ragfin_exchange_destroy.restype = None
     L.ragfin_set_scan_variant.argtypes = [vp, i32]
     L.ragfin_set_append_mode.argtypes = [vp, i32]

@@ -945,6 +945,27 @@ static bool use_astat(const ragfin* h, int kp) {
 }
 
 // ------------------------------------------------------------------------------
+// Cross-shard exchange state (CUDA IPC gather areas over NVLink peer memory), used by the one-kernel search's finalize
+// and by the stand-alone exchange kernels further down
+// ------------------------------------------------------------------------------
+struct ragfin_exchange {
+    int rank = 0, world = 0, device = 0;
+    size_t record_max = 0, bytes = 0;
+    char* local = nullptr;               // [2][world][record_max] gather area | [2][world] u32 flags | [2][world][kFMaxQ] u32 per-query flags
+    char* peer_base[64] = {};            // base of every rank's block in this process's address space
+    bool opened[64] = {};
+    char** d_peer_area = nullptr;
+    uint32_t** d_peer_flag = nullptr;
+    uint32_t** d_peer_qflag = nullptr;
+    unsigned int* d_done = nullptr;
+    uint32_t step = 0;
+    bool connected = false;
+    bool have_stream = false;            // the double-buffer argument (a rank is at most one step ahead of a peer) holds only
+    cudaStream_t stream = nullptr;       // if every step of this rank is issued on ONE stream: recorded at step 1, checked after
+    std::mutex mu;
+};
+
+// ------------------------------------------------------------------------------
 // K3f: the one-kernel search for <= 64 queries and k <= 128 (sweep_fused.cuh)
 // ------------------------------------------------------------------------------
 struct FusedPlan {
@@ -999,7 +1020,7 @@ static fused_fn pick_fused(int dtype, int ncol, bool split) {
 }
 
 static int run_fused(ragfin* h, const float* q_dev, int nb, int k, int64_t n_eff, int64_t* out_ids, float* out_scores,
-                     int* flags, int* flag_count, cudaStream_t st) {
+                     int* flags, int* flag_count, cudaStream_t st, ragfin_exchange* x = nullptr, uint32_t xstep = 0) {
     int rc;
     const FusedPlan f = plan_fused(h, nb, k);
     if (f.ncol == 0) return fail(RAGFIN_EUNSUPPORTED, "no fused sweep for %d queries, k = %d", nb, k);
@@ -1034,6 +1055,11 @@ static int run_fused(ragfin* h, const float* q_dev, int nb, int k, int64_t n_eff
     a.id_base = h->id_base;
     a.out_ids = (long long*)out_ids; a.out_scores = out_scores;
     a.flags = flags; a.flag_count = flag_count;
+    a.xworld = 0; a.xrank = 0; a.xstep = 0; a.xrec_max = 0; a.xpeer_area = nullptr; a.xpeer_qflag = nullptr;
+    if (x != nullptr && x->world > 1) {
+        a.xworld = x->world; a.xrank = x->rank; a.xstep = xstep; a.xrec_max = x->record_max;
+        a.xpeer_area = x->d_peer_area; a.xpeer_qflag = x->d_peer_qflag;
+    }
     fused_fn fn = pick_fused(h->dtype, f.ncol, f.split);
     if ((rc = set_dyn_smem(h->device, (const void*)fn, f.smem))) return rc;
     h->fctl_dirty = true;          // until the launch is known to have been accepted
@@ -1630,22 +1656,6 @@ extern "C" int ragfin_merge_topk(const int64_t* ids, const float* scores, int32_
 // ------------------------------------------------------------------------------
 // Cross-shard exchange over peer memory (CUDA IPC + NVLink P2P stores), see exchange_push_kernel
 // ------------------------------------------------------------------------------
-struct ragfin_exchange {
-    int rank = 0, world = 0, device = 0;
-    size_t record_max = 0, bytes = 0;
-    char* local = nullptr;               // [2][world][record_max] gather area, then [2][world] uint32 flags
-    char* peer_base[64] = {};            // base of every rank's block in this process's address space
-    bool opened[64] = {};
-    char** d_peer_area = nullptr;
-    uint32_t** d_peer_flag = nullptr;
-    unsigned int* d_done = nullptr;
-    uint32_t step = 0;
-    bool connected = false;
-    bool have_stream = false;            // the double-buffer argument (a rank is at most one step ahead of a peer) holds only
-    cudaStream_t stream = nullptr;       // if every step of this rank is issued on ONE stream: recorded at step 1, checked after
-    std::mutex mu;
-};
-
 extern "C" int ragfin_exchange_create(ragfin_exchange_t** out, int32_t rank, int32_t world, int64_t record_bytes_max, int32_t device) {
     if (!out) return fail(RAGFIN_EINVAL, "out is NULL");
     *out = nullptr;
@@ -1658,11 +1668,12 @@ extern "C" int ragfin_exchange_create(ragfin_exchange_t** out, int32_t rank, int
     x->rank = rank; x->world = world; x->device = device;
     x->record_max = ((size_t)record_bytes_max + 15) / 16 * 16;
     const size_t area = 2 * (size_t)world * x->record_max;
-    x->bytes = area + 2 * (size_t)world * sizeof(uint32_t);
+    x->bytes = area + 2 * (size_t)world * sizeof(uint32_t) + 2 * (size_t)world * kFMaxQ * sizeof(uint32_t);
     cudaError_t e = cudaMalloc((void**)&x->local, x->bytes);
     if (e == cudaSuccess) e = cudaMemset(x->local, 0, x->bytes);
     if (e == cudaSuccess) e = cudaMalloc((void**)&x->d_peer_area, world * sizeof(char*));
     if (e == cudaSuccess) e = cudaMalloc((void**)&x->d_peer_flag, world * sizeof(uint32_t*));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&x->d_peer_qflag, world * sizeof(uint32_t*));
     if (e == cudaSuccess) e = cudaMalloc((void**)&x->d_done, world * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(x->d_done, 0, world * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -1671,6 +1682,7 @@ extern "C" int ragfin_exchange_create(ragfin_exchange_t** out, int32_t rank, int
         if (x->local) cudaFree(x->local);
         if (x->d_peer_area) cudaFree(x->d_peer_area);
         if (x->d_peer_flag) cudaFree(x->d_peer_flag);
+        if (x->d_peer_qflag) cudaFree(x->d_peer_qflag);
         if (x->d_done) cudaFree(x->d_done);
         delete x;
         return fail(RAGFIN_ENOMEM, "exchange allocation failed: %s", cudaGetErrorString(e));
@@ -1697,6 +1709,7 @@ extern "C" int ragfin_exchange_connect(ragfin_exchange_t* x, const void* handles
     const size_t area = 2 * (size_t)x->world * x->record_max;
     char* areas[64];
     uint32_t* flags[64];
+    uint32_t* qflags[64];
     for (int p = 0; p < x->world; ++p) {
         if (p == x->rank) {
             x->peer_base[p] = x->local;
@@ -1714,9 +1727,11 @@ extern "C" int ragfin_exchange_connect(ragfin_exchange_t* x, const void* handles
         }
         areas[p] = x->peer_base[p];
         flags[p] = reinterpret_cast<uint32_t*>(x->peer_base[p] + area);
+        qflags[p] = flags[p] + 2 * (size_t)x->world;
     }
     CU_TRY(cudaMemcpy(x->d_peer_area, areas, x->world * sizeof(char*), cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(x->d_peer_flag, flags, x->world * sizeof(uint32_t*), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(x->d_peer_qflag, qflags, x->world * sizeof(uint32_t*), cudaMemcpyHostToDevice));
     x->connected = true;
     return RAGFIN_OK;
 }
@@ -1749,6 +1764,87 @@ extern "C" int ragfin_exchange_allgather_merge(ragfin_exchange_t* x, const int64
     return RAGFIN_OK;
 }
 
+// Whether (nq, k) on this handle would take the one-kernel search.  Ranks of a sharded search must agree before they use
+// ragfin_search_sharded (shard sizes differ by a row): the host layer reduces this over the ranks once per shape.
+extern "C" int ragfin_fused_eligible(ragfin_t* h, int32_t nq, int32_t k, int32_t* out) {
+    if (!h || !out || nq < 1 || k < 1) return fail(RAGFIN_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    *out = (nq <= kFMaxQ && fused_eligible(h, nq, k)) ? 1 : 0;
+    return RAGFIN_OK;
+}
+
+static int sharded_locked(ragfin* h, ragfin_exchange* x, const float* q_dev, int nq, int k, int64_t* out_ids, float* out_scores,
+                          cudaStream_t st) {
+    if (!x->connected) return fail(RAGFIN_EINVAL, "exchange is not connected");
+    if (x->device != h->device) return fail(RAGFIN_EINVAL, "exchange and collection live on different devices");
+    if (nq > kFMaxQ || !fused_eligible(h, nq, k))
+        return fail(RAGFIN_EUNSUPPORTED, "shape (nq = %d, k = %d) does not take the one-kernel search on this shard", nq, k);
+    const size_t record = (size_t)nq * (((size_t)k * 12 + 15) / 16 * 16);
+    if (record > x->record_max) return fail(RAGFIN_EINVAL, "record of %zu bytes exceeds the exchange's %zu", record, x->record_max);
+    if (x->have_stream && x->stream != st)
+        return fail(RAGFIN_EINVAL, "every step of an exchange must be issued on the same CUDA stream (its double buffering relies on stream order)");
+    x->have_stream = true; x->stream = st;
+    int rc;
+    if ((rc = ensure(h->flags, (size_t)(kMaxQueryBatch + 1) * sizeof(int)))) return rc;
+    int* fl = (int*)h->flags.p;
+    h->stats.launches = 0;
+    const int64_t n_eff = h->count;
+    const uint32_t step = ++x->step;
+    return run_fused(h, q_dev, nq, k, n_eff, out_ids, out_scores, fl, fl + kMaxQueryBatch, st, x, step);
+}
+
+// Row-sharded search in ONE kernel per GPU (sweep_fused.cuh): this rank's shard is swept, the finalizing CTAs push the
+// shard's exact hits into every rank's gather area over NVLink, wait for the other ranks' and write the GLOBAL top-k.
+// Collective: every rank of the exchange must call it with the same (nq, k) and queries, once per step, on one stream.
+extern "C" int ragfin_search_sharded(ragfin_t* h, ragfin_exchange_t* x, const float* q, int32_t nq, int32_t k, int64_t* out_ids,
+                                     float* out_scores, void* stream) {
+    if (!h || !x) return fail(RAGFIN_EINVAL, "NULL handle");
+    if (nq < 1 || !q || !out_ids || !out_scores) return fail(RAGFIN_EINVAL, "NULL buffer");
+    if (k < 1 || k > 16384) return fail(RAGFIN_EINVAL, "k = %d outside [1, 16384]", k);
+    std::lock_guard<std::mutex> lk(h->mu);
+    std::lock_guard<std::mutex> lx(x->mu);
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = wait_prev(h, st))) return rc;
+    if ((rc = sharded_locked(h, x, q, nq, k, out_ids, out_scores, st))) return rc;
+    return mark_done(h, st);
+}
+
+// Same with HOST buffers (what a serving process calls): queries staged through pinned memory, the global hits written by
+// the kernel straight into device-mapped pinned memory, one stream synchronisation.
+extern "C" int ragfin_search_sharded_host(ragfin_t* h, ragfin_exchange_t* x, const float* q_host, int32_t nq, int32_t k,
+                                          int64_t* out_ids_host, float* out_scores_host) {
+    if (!h || !x) return fail(RAGFIN_EINVAL, "NULL handle");
+    if (nq < 1 || !q_host || !out_ids_host || !out_scores_host) return fail(RAGFIN_EINVAL, "NULL buffer");
+    if (k < 1 || k > 16384) return fail(RAGFIN_EINVAL, "k = %d outside [1, 16384]", k);
+    std::lock_guard<std::mutex> lk(h->mu);
+    std::lock_guard<std::mutex> lx(x->mu);
+    DeviceGuard g(h->device);
+    cudaStream_t st = 0;
+    int rc;
+    if ((rc = wait_prev(h, st))) return rc;
+    const size_t qb = (size_t)nq * h->dim * sizeof(float), ib = (size_t)nq * k * sizeof(int64_t), sb = (size_t)nq * k * sizeof(float);
+    if (qb > kHostStageQ || ib + sb > kHostStageOut) return fail(RAGFIN_EUNSUPPORTED, "request too large for the mapped staging");
+    if (!h->hstage && cudaHostAlloc(&h->hstage, kHostStageQ + kHostStageOut, cudaHostAllocMapped) != cudaSuccess) {
+        (void)cudaGetLastError(); h->hstage = nullptr;
+        return fail(RAGFIN_ENOMEM, "pinned staging allocation failed");
+    }
+    void* dptr = nullptr;
+    CU_TRY(cudaHostGetDevicePointer(&dptr, h->hstage, 0));
+    char* hq = (char*)h->hstage;
+    char* ho = hq + kHostStageQ;
+    char* dout = (char*)dptr + kHostStageQ;
+    memcpy(hq, q_host, qb);
+    if ((rc = ensure(h->stage_q, qb))) return rc;
+    CU_TRY(cudaMemcpyAsync(h->stage_q.p, hq, qb, cudaMemcpyHostToDevice, st));
+    if ((rc = sharded_locked(h, x, (const float*)h->stage_q.p, nq, k, (int64_t*)dout, (float*)(dout + ib), st))) return rc;
+    CU_TRY(cudaStreamSynchronize(st));
+    memcpy(out_ids_host, ho, ib);
+    memcpy(out_scores_host, ho + ib, sb);
+    return mark_done(h, st);
+}
+
 extern "C" void ragfin_exchange_destroy(ragfin_exchange_t* x) {
     if (!x) return;
     DeviceGuard g(x->device);
@@ -1758,6 +1854,7 @@ extern "C" void ragfin_exchange_destroy(ragfin_exchange_t* x) {
     if (x->local) cudaFree(x->local);
     if (x->d_peer_area) cudaFree(x->d_peer_area);
     if (x->d_peer_flag) cudaFree(x->d_peer_flag);
+    if (x->d_peer_qflag) cudaFree(x->d_peer_qflag);
     if (x->d_done) cudaFree(x->d_done);
     (void)cudaGetLastError();
     delete x;

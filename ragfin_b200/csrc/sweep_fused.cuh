@@ -25,6 +25,10 @@
 //              histogram-narrowing select of T over the buffer, gather above T - 2 eps, canonical fp64 rescore, sort,
 //              emit; an overflowing buffer (> cap rows within reach of the top k: massive duplication) is answered by
 //              the same CTA with a canonical scan of the whole corpus - slow, exact, and no extra launch.
+//   exchange   row-sharded corpora (one process per GPU): the finalizing CTA of a query stores its k exact hits straight
+//              into every peer's gather area over NVLink (CUDA IPC mappings), publishes a per-(rank, query) flag with
+//              st.release.sys, waits for the W flags of its own area, merges the W x k hits by rank counting and writes
+//              the GLOBAL top-k - the whole sharded search is this one kernel per GPU, no collective call.
 // The control block (counters, published thresholds) is left zeroed by every search.
 #pragma once
 #include "gemm_rows.cuh"
@@ -72,6 +76,13 @@ struct FusedArgs {
     float* out_scores;          // [nq][k]
     int* flags;                 // [nq] 1 = the query took the in-kernel exact scan
     int* flag_count;
+    // cross-shard exchange inside the finalize (row-sharded corpora, one process per GPU; xworld <= 1: off).  Peer gather
+    // areas and flags are mapped through CUDA IPC (ragfin_exchange_*); see "exchange" in the header comment.
+    int xworld, xrank;
+    uint32_t xstep;             // step number of this search: flag value, parity selects the half of the double buffer
+    unsigned long long xrec_max;   // bytes of one rank's record in a gather area
+    char* const* xpeer_area;    // [xworld] base of every rank's gather area: [2][xworld][xrec_max]
+    uint32_t* const* xpeer_qflag;  // [xworld] base of every rank's per-query flags: [2][xworld][kFMaxQ]
 };
 
 // pending area: [nq][pend] appended scores per tile in steady state, [kObsQ][kObsStride] observed scores in the first tile
@@ -488,6 +499,74 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
     u64* sel = reinterpret_cast<u64*>(fsm + (((size_t)ld_al * 4 + 256 * 4 + 16 + 15) / 16) * 16);
     const int sel_cap = (int)((region_bytes - (size_t)(reinterpret_cast<uint8_t*>(sel) - fsm)) / sizeof(u64));
 
+    // Emit the query's hits: fin[0 .. keff) are its exact keys in order (this shard).  Single GPU: write them out.  Sharded:
+    // push them to every rank, wait for every rank's, merge, write the global top-k.  Called by all threads of the CTA.
+    auto emit = [&](int qi, const u64* fin, int nvalid) {
+        long long* oid = a.out_ids + (size_t)qi * k;
+        float* osc = a.out_scores + (size_t)qi * k;
+        if (a.xworld <= 1) {
+            for (int i = tid; i < k; i += kFThreads) {
+                const u64 key = i < nvalid ? fin[i] : 0ull;
+                oid[i] = key ? a.id_base + (long long)key_row(key) : -1;
+                osc[i] = key ? key_score(key) : -INFINITY;
+            }
+            return;
+        }
+        const int W = a.xworld;
+        const size_t rec_q = ((size_t)k * 12 + 15) / 16 * 16;            // one query's hits inside a rank's record
+        const size_t half = (size_t)(a.xstep & 1u) * W;
+        for (int i = tid; i < k * W; i += kFThreads) {                    // 1. my hits -> slot `xrank` of every rank's area
+            const int p = i / k, j = i % k;
+            const u64 key = j < nvalid ? fin[j] : 0ull;
+            char* dst = a.xpeer_area[p] + (half + a.xrank) * a.xrec_max + (size_t)qi * rec_q;
+            reinterpret_cast<long long*>(dst)[j] = key ? a.id_base + (long long)key_row(key) : -1;
+            reinterpret_cast<float*>(dst + (size_t)k * 8)[j] = key ? key_score(key) : -INFINITY;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < W) st_release_sys(a.xpeer_qflag[tid] + (half + a.xrank) * kFMaxQ + qi, a.xstep);
+        const uint32_t* myflags = a.xpeer_qflag[a.xrank] + half * kFMaxQ;
+        bool arrived = true;
+        if (tid < W) {                                                     // 2. every rank's hits for this query have landed
+            const uint32_t* f = myflags + (size_t)tid * kFMaxQ + qi;
+            unsigned long long t0 = 0, now = 0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while (ld_acquire_sys(f) != a.xstep) {
+                __nanosleep(100);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (now - t0 > 4000000000ull) { arrived = false; break; }  // 4 s: a peer is gone; fail the query, not the GPU
+            }
+        }
+        const int all_in = __syncthreads_and(arrived ? 1 : 0);
+        (void)ld_acquire_sys(myflags + (size_t)(tid % W) * kFMaxQ + qi);   // every thread acquires for its own loads below
+        // 3. merge by rank counting: the lists are ordered and all ids are distinct
+        int64_t* mids = reinterpret_cast<int64_t*>(sel);              // [W][k]   (fin is dead: it has been pushed)
+        float* msc = reinterpret_cast<float*>(mids + (size_t)W * k);      // [W][k]
+        const char* area = a.xpeer_area[a.xrank] + half * a.xrec_max;
+        for (int i = tid; i < k * W; i += kFThreads) {
+            const int p = i / k, j = i % k;
+            const char* src = area + (size_t)p * a.xrec_max + (size_t)qi * rec_q;
+            mids[i] = all_in ? (int64_t)__ldcg(reinterpret_cast<const long long*>(src) + j) : (int64_t)-1;
+            msc[i] = all_in ? __ldcg(reinterpret_cast<const float*>(src + (size_t)k * 8) + j) : -INFINITY;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int valid = 0;
+            for (int p = 0; p < W; ++p) valid += count_better<false>(mids + (size_t)p * k, msc + (size_t)p * k, k, -INFINITY, INT64_MAX);
+            for (int i = valid; i < k; ++i) { oid[i] = -1; osc[i] = all_in ? -INFINITY : __int_as_float(0x7FC00000); }   // NaN: exchange timed out
+        }
+        for (int i = tid; i < k * W; i += kFThreads) {
+            const int p = i / k, j = i % k;
+            const int64_t id = mids[i];
+            if (id < 0) continue;
+            const float sc = msc[i];
+            int rank = j;
+            for (int pp = 0; pp < W && rank < k; ++pp)
+                if (pp != p) rank += count_better<false>(mids + (size_t)pp * k, msc + (size_t)pp * k, k, sc, id);
+            if (rank < k) { oid[rank] = id; osc[rank] = sc; }
+        }
+    };
+
     for (int qi = ticket - first_fin; qi < nq; qi += n_fin) {
         // normalised fp32 query (the rescore operand), recomputed: bit-identical to the prologue and to ingest
         {
@@ -508,8 +587,6 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
         const uint32_t m32 = __ldcg(a.ctl->cnt + qi);
         if (tid == 0) { a.ctl->last_cnt[qi] = m32; a.ctl->last_resc[qi] = 0xFFFFFFFFu; }
         const int keff = a.keff;
-        long long* oid = a.out_ids + (size_t)qi * k;
-        float* osc = a.out_scores + (size_t)qi * k;
         const u64* in = a.cand + (size_t)qi * a.cap;
         bool exact_scan = m32 > (uint32_t)a.cap || (int)m32 < keff;   // block-uniform
         if (!exact_scan && keff > 0) {
@@ -542,16 +619,12 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                 for (int i = c2 + tid; i < P2; i += kFThreads) sel[i] = 0ull;
                 __syncthreads();
                 block_bitonic_sort_desc(sel, P2, tid, kFThreads);
-                for (int i = tid; i < k; i += kFThreads) {
-                    const u64 key = i < keff ? sel[i] : 0ull;
-                    oid[i] = key ? a.id_base + (long long)key_row(key) : -1;
-                    osc[i] = key ? key_score(key) : -INFINITY;
-                }
+                emit(qi, sel, keff);
                 if (tid == 0) { a.flags[qi] = 0; a.ctl->last_resc[qi] = (uint32_t)c2; }
             }
             }
         } else if (!exact_scan) {   // keff == 0: nothing to return
-            for (int i = tid; i < k; i += kFThreads) { oid[i] = -1; osc[i] = -INFINITY; }
+            emit(qi, sel, 0);
             if (tid == 0) a.flags[qi] = 0;
         }
         if (exact_scan) {
@@ -578,11 +651,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
             }
             __syncthreads();
             block_bitonic_sort_desc(lists, P2, tid, kFThreads);
-            for (int i = tid; i < k; i += kFThreads) {
-                const u64 key = i < keff ? lists[i] : 0ull;
-                oid[i] = key ? a.id_base + (long long)key_row(key) : -1;
-                osc[i] = key ? key_score(key) : -INFINITY;
-            }
+            emit(qi, lists, keff);
             if (tid == 0) { a.flags[qi] = 1; atomicAdd(a.flag_count, 1); }
         }
         __syncthreads();

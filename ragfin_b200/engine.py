@@ -227,6 +227,12 @@ class Index:
         min_rows > 0 also sets the smallest corpus it serves."""
         _lib.check(self._L.ragfin_set_fused(self._h, 1 if enable else 0, int(min_rows)))
 
+    def fused_eligible(self, nq: int, k: int) -> bool:
+        """Whether (nq, k) takes the one-kernel search on this handle (csrc/sweep_fused.cuh)."""
+        out = ctypes.c_int32()
+        _lib.check(self._L.ragfin_fused_eligible(self._h, int(nq), int(k), ctypes.byref(out)))
+        return bool(out.value)
+
     def fused_counts(self, nq: int):
         """Diagnostics of the last one-kernel search: (rows appended per query, rows rescored per query; -1 = exact scan)."""
         a, r = np.zeros(nq, np.int64), np.zeros(nq, np.int64)
@@ -359,6 +365,30 @@ class PeerExchange:
         _lib.check(self._L.ragfin_exchange_allgather_merge(self._x, ids.data_ptr(), scores.data_ptr(), nq, k,
                                                            out_ids.data_ptr(), out_scores.data_ptr(), _stream_ptr(stream)))
         return out_ids, out_scores
+
+    def search_sharded(self, index, queries, k: int, out_ids=None, out_scores=None, stream=None):
+        """Row-sharded search in one kernel per GPU (ragfin_search_sharded): `queries` CUDA fp32 [nq, dim], the same on
+        every rank; returns the GLOBAL (ids, scores) [nq, k] on every rank.  Collective over the exchange's ranks."""
+        import torch
+        nq = queries.shape[0]
+        if out_ids is None:
+            out_ids = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
+        if out_scores is None:
+            out_scores = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
+        queries = queries.contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.ragfin_search_sharded(index._h, self._x, queries.data_ptr(), nq, int(k), out_ids.data_ptr(),
+                                                     out_scores.data_ptr(), _stream_ptr(stream)))
+        return out_ids, out_scores
+
+    def search_sharded_host(self, index, queries, k: int, out_ids=None, out_scores=None):
+        """Same through host buffers (numpy in, numpy out, synchronous): ragfin_search_sharded_host."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = q.shape[0]
+        ids = out_ids if out_ids is not None else np.empty((nq, k), dtype=np.int64)
+        scores = out_scores if out_scores is not None else np.empty((nq, k), dtype=np.float32)
+        _lib.check(self._L.ragfin_search_sharded_host(index._h, self._x, q.ctypes.data, nq, int(k), ids.ctypes.data, scores.ctypes.data))
+        return ids, scores
 
     def close(self):
         if getattr(self, "_x", None) is not None and self._x:

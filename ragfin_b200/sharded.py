@@ -31,7 +31,7 @@ class ShardedSearcher:
     is a single NCCL all-gather of nq*k*12 bytes."""
 
     def __init__(self, local_search: Callable, merge: Callable, group=None, packed_factory: Optional[Callable] = None,
-                 exchange=None):
+                 exchange=None, index=None):
         import torch.distributed as dist
         self._dist = dist
         self.group = group
@@ -41,6 +41,8 @@ class ShardedSearcher:
         self.merge = merge
         self.packed_factory = packed_factory
         self.exchange = exchange          # PeerExchange: stores over NVLink peer memory instead of the NCCL all-gather
+        self.index = index                # with an exchange: shapes every rank can serve with the one-kernel search take
+        self._fused = {}                  #   ragfin_search_sharded (sweep + exchange + reduce in ONE kernel per GPU)
         self._local = {}
         self._packed = {}
         self._gather_ids = None
@@ -49,16 +51,16 @@ class ShardedSearcher:
     @classmethod
     def for_index(cls, index, group=None, p2p: Optional[bool] = None) -> "ShardedSearcher":
         """GPU wiring.  p2p: True = peer-memory exchange (raises if unavailable), False = NCCL all-gather + reduce,
-        None = NCCL unless env RAGFIN_P2P=1 asks for the peer-memory exchange (falls back to NCCL if it cannot be set
-        up).  Measured on 8 B200s, 10M x 768 bf16, batch 1: 0.376 ms per step with peer stores, 0.373 ms with NCCL -
-        the exchange is not what bounds the step, so the library collective stays the default."""
+        None = peer memory unless env RAGFIN_P2P=0, falling back to NCCL if it cannot be set up.  With peer memory, shapes
+        that every rank serves with the one-kernel search (<= 64 queries, k <= 128) run sweep + exchange + reduce in ONE
+        kernel per GPU (`ragfin_search_sharded`); other shapes use the push / merge kernels or the NCCL all-gather."""
         import os
         import torch.distributed as dist
         from .engine import PackedHits, PeerExchange, merge_topk
         exchange = None
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         if p2p is None:
-            p2p = os.environ.get("RAGFIN_P2P", "0") == "1"
+            p2p = os.environ.get("RAGFIN_P2P", "1") == "1"
             required = False
         else:
             required = bool(p2p)
@@ -68,13 +70,48 @@ class ShardedSearcher:
             except RuntimeError:
                 if required:
                     raise
-        return cls(index.search_device, merge_topk, group, packed_factory=PackedHits, exchange=exchange)
+        return cls(index.search_device, merge_topk, group, packed_factory=PackedHits, exchange=exchange, index=index)
+
+    def fused_ok(self, nq: int, k: int) -> bool:
+        """True when EVERY rank serves (nq, k) with the one-kernel search (decided once per shape by a MIN all-reduce: shard
+        sizes differ by a row, and a rank taking another path would leave its peers waiting in the kernel)."""
+        key = (nq, k)
+        ok = self._fused.get(key)
+        if ok is None:
+            import torch
+            mine = 1 if (self.exchange is not None and self.index is not None and nq * ((k * 12 + 15) // 16 * 16) <= self.exchange.max_record_bytes
+                         and self.index.fused_eligible(nq, k)) else 0
+            t = torch.tensor([mine], dtype=torch.int32, device=torch.device("cuda", self.index.device) if self.index is not None else None)
+            self._dist.all_reduce(t, op=self._dist.ReduceOp.MIN, group=self.group)
+            ok = self._fused[key] = bool(int(t.item()))
+        return ok
+
+    def search_host(self, queries, k: int, out_ids=None, out_scores=None):
+        """Host buffers in and out (numpy), synchronous: the call a serving process makes.  One-kernel path when every rank
+        can take it, else device staging around `search`."""
+        import numpy as np
+        import torch
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if self.world > 1 and self.exchange is not None and self.fused_ok(q.shape[0], k):
+            return self.exchange.search_sharded_host(self.index, q, k, out_ids, out_scores)
+        dev = torch.device("cuda", self.index.device) if self.index is not None else None
+        ids, sc = self.search(torch.from_numpy(q).to(dev), k)
+        ids, sc = ids.cpu().numpy(), sc.cpu().numpy()
+        if out_ids is not None:
+            out_ids[...] = ids
+            ids = out_ids
+        if out_scores is not None:
+            out_scores[...] = sc
+            sc = out_scores
+        return ids, sc
 
     def search(self, queries, k: int):
         import torch
         if self.world == 1:
             return self.local_search(queries, k)
         nq = queries.shape[0]
+        if self.exchange is not None and self.index is not None and self.fused_ok(nq, k):
+            return self.exchange.search_sharded(self.index, queries, k)
         if self.exchange is not None and nq * k * 12 <= self.exchange.max_record_bytes:
             key = (nq, k)
             buf = self._local.get(key)

@@ -19,7 +19,9 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
 for dtype, dim, n, nq, k in [("bf16", 768, 50001, 1, 10), ("f16", 768, 30000, 4, 100), ("f32", 384, 9000, 40, 5),
                              ("bf16", 768, 7, 3, 10), ("bf16", 1024, 40000, 300, 10),
-                             ("bf16", 128, 600000, 40, 10), ("f16", 64, 900000, 5, 100)]:   # shards large enough for append mode
+                             ("bf16", 128, 600000, 40, 10), ("f16", 64, 900000, 5, 100),    # shards large enough for append mode
+                             ("bf16", 768, 200000, 1, 10), ("bf16", 768, 200000, 16, 10), ("f32", 384, 160000, 3, 10),
+                             ("f16", 256, 300000, 64, 5), ("bf16", 768, 100000, 2, 128)]:   # one-kernel sharded search on every rank
     row0, cnt = shard_bounds(n, world, rank)
     idx = ragfin_b200.Index(dim, dtype, capacity=max(cnt, 1), device=local)
     if cnt:
@@ -35,9 +37,12 @@ for dtype, dim, n, nq, k in [("bf16", 768, 50001, 1, 10), ("f16", 768, 30000, 4,
             ids, sc = s.search(qd, k)
             torch.cuda.synchronize()
             same &= np.array_equal(ids.cpu().numpy(), wi) and np.array_equal(sc.cpu().numpy().view(np.uint32), ws.view(np.uint32))
+        hi, hs = s.search_host(q, k)   # host buffers in and out (the serving call)
+        same &= np.array_equal(hi, wi) and np.array_equal(hs.view(np.uint32), ws.view(np.uint32))
         ok &= same
         if rank == 0:
-            how = "peer-memory" if s.exchange is not None else "nccl"
+            how = ("one kernel (sweep + peer exchange + reduce)" if s.exchange is not None and s.fused_ok(nq, k) else
+                   "peer-memory push / merge kernels" if s.exchange is not None else "nccl all-gather + reduce")
             print(f"sharded x{world} {dtype} dim={dim} n={n} nq={nq} k={k} [{how}]: parity={same}", flush=True)
         dist.barrier()
         if s.exchange is not None:
