@@ -69,6 +69,14 @@ int ragfin_add(ragfin_t* h, const float* rows, int64_t n, int32_t src_is_device,
 int ragfin_add_synthetic(ragfin_t* h, uint64_t seed, int64_t row0, int64_t n, int32_t dup_every,
                          int32_t zero_every, void* stream);
 
+/* Bench / test data with the structure of a templated text corpus (the reference's chunks are the same templates filled
+ * with each quarter's figures: FinRag_knowledge_graph/chunks.json): row r = centre(r / topic_rows) + noise(r) * 2^-noise_shift,
+ * centre = row `topic` of the synthetic matrix (seed + RAGFIN_TOPIC_SEED_OFFSET), noise = row r of the synthetic matrix
+ * `seed`; contiguous runs of topic_rows near-duplicates inserted in topic order.  Exact in fp32 (1 <= noise_shift <= 10). */
+#define RAGFIN_TOPIC_SEED_OFFSET 0x7091C5ull
+int ragfin_add_synthetic_topics(ragfin_t* h, uint64_t seed, int64_t row0, int64_t n, int64_t topic_rows, int32_t noise_shift,
+                                void* stream);
+
 /* Number of rows held.  Replaces: Collection.num_entities - vector_rag_mcp/main.py:164. */
 int ragfin_count(const ragfin_t* h, int64_t* n);
 

@@ -16,7 +16,7 @@ SO_PATH = os.environ.get("RAGFIN_LIB") or os.path.join(CSRC, "libragfin.so")
 
 # every symbol include/ragfin.h declares
 SYMBOLS = (
-    "ragfin_abi_version", "ragfin_create", "ragfin_create_view", "ragfin_add", "ragfin_add_synthetic", "ragfin_count", "ragfin_reserve",
+    "ragfin_abi_version", "ragfin_create", "ragfin_create_view", "ragfin_add", "ragfin_add_synthetic", "ragfin_add_synthetic_topics", "ragfin_count", "ragfin_reserve",
     "ragfin_set_id_base", "ragfin_search", "ragfin_search_host", "ragfin_search_filtered", "ragfin_search_filtered_host", "ragfin_merge_topk", "ragfin_read_rows",
     "ragfin_last_search_stats", "ragfin_profile", "ragfin_profile_read", "ragfin_save", "ragfin_load", "ragfin_set_gemm_min_batch", "ragfin_set_gemm_cluster", "ragfin_set_gemm_variant", "ragfin_set_bound_pass", "ragfin_set_scan_variant", "ragfin_set_append_mode", "ragfin_set_fused", "ragfin_debug_fused_counts", "ragfin_debug_gemm_scores", "ragfin_debug_plan", "ragfin_destroy", "ragfin_last_error",
     "ragfin_exchange_create", "ragfin_exchange_handle", "ragfin_exchange_connect", "ragfin_exchange_allgather_merge", "ragfin_fused_eligible", "ragfin_search_sharded", "ragfin_search_sharded_host", "ragfin_exchange_destroy",
@@ -54,6 +54,7 @@ def load() -> ctypes.CDLL:
     L.ragfin_create_view.argtypes = [vp, ctypes.POINTER(vp)]
     L.ragfin_add.argtypes = [vp, vp, i64, i32, vp]
     L.ragfin_add_synthetic.argtypes = [vp, u64, i64, i64, i32, i32, vp]
+    L.ragfin_add_synthetic_topics.argtypes = [vp, u64, i64, i64, i64, i32, vp]
     L.ragfin_count.argtypes = [vp, ctypes.POINTER(i64)]
     L.ragfin_set_id_base.argtypes = [vp, i64]
     L.ragfin_reserve.argtypes = [vp, i64]

@@ -20,11 +20,15 @@ constexpr int kFinWarps = kFinThreads / kWarp;
 // SYNTH: the source row is generated in registers from the counter hash instead of read.
 // dst rows have stride ld (>= dim, multiple of 8); columns [dim, ld) are zero.
 // ---------------------------------------------------------------------------------
+// SYNTH with topic_rows > 0: "templated corpus" generator - row r belongs to topic r / topic_rows and is
+//   centre(topic) + noise(r) * noise_scale     (noise_scale a power of two <= 1/2: the sum is exact in fp32),
+// i.e. contiguous runs of topic_rows near-duplicates (cosine ~0.98 to each other at scale 1/8), inserted in topic order.
 template <int DT, bool SYNTH>
 __global__ void __launch_bounds__(256) ingest_kernel(const float* __restrict__ src, uint64_t synth_key,
                                                      int64_t synth_row0, int dup_every, int zero_every,
                                                      int64_t n, int dim, int ld,
-                                                     typename Store<DT>::T* __restrict__ dst) {
+                                                     typename Store<DT>::T* __restrict__ dst,
+                                                     int64_t topic_rows = 0, uint64_t topic_key = 0, float noise_scale = 0.f) {
     typedef typename Store<DT>::T T;
     const int lane = threadIdx.x & 31;
     const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -41,8 +45,13 @@ __global__ void __launch_bounds__(256) ingest_kernel(const float* __restrict__ s
         } else {
             x = src + r * (int64_t)dim;
         }
+        const uint64_t topic = SYNTH && topic_rows > 0 ? srow / (uint64_t)topic_rows : 0;
         auto elem = [&](int i) -> float {
-            if (SYNTH) return zero ? 0.0f : synth_value(synth_key, srow, dim, i);
+            if (SYNTH) {
+                if (zero) return 0.0f;
+                const float v = synth_value(synth_key, srow, dim, i);
+                return topic_rows > 0 ? __fadd_rn(synth_value(topic_key, topic, dim, i), __fmul_rn(v, noise_scale)) : v;
+            }
             return x[i];
         };
         double acc = 0.0;

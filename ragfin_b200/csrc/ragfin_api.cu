@@ -283,7 +283,8 @@ extern "C" int ragfin_set_id_base(ragfin_t* h, int64_t id_base) {
 // ------------------------------------------------------------------------------
 template <bool SYNTH>
 static int launch_ingest(int dtype, const float* src, uint64_t key, int64_t row0, int dup, int zero, int64_t n,
-                         int dim, int ld, void* dst, int num_sms, cudaStream_t st) {
+                         int dim, int ld, void* dst, int num_sms, cudaStream_t st,
+                         int64_t topic_rows = 0, uint64_t topic_key = 0, float noise_scale = 0.f) {
     if (n == 0) return 0;
     const int threads = 256, wpb = threads / 32;
     int64_t blocks = (n + wpb - 1) / wpb;
@@ -307,9 +308,9 @@ static int launch_ingest(int dtype, const float* src, uint64_t key, int64_t row0
     const int64_t cap = (int64_t)num_sms * 16;
     if (blocks > cap) blocks = cap;
     switch (dtype) {
-        case 0: ingest_kernel<0, SYNTH><<<(int)blocks, threads, 0, st>>>(src, key, row0, dup, zero, n, dim, ld, (float*)dst); break;
-        case 1: ingest_kernel<1, SYNTH><<<(int)blocks, threads, 0, st>>>(src, key, row0, dup, zero, n, dim, ld, (__nv_bfloat16*)dst); break;
-        default: ingest_kernel<2, SYNTH><<<(int)blocks, threads, 0, st>>>(src, key, row0, dup, zero, n, dim, ld, (__half*)dst); break;
+        case 0: ingest_kernel<0, SYNTH><<<(int)blocks, threads, 0, st>>>(src, key, row0, dup, zero, n, dim, ld, (float*)dst, topic_rows, topic_key, noise_scale); break;
+        case 1: ingest_kernel<1, SYNTH><<<(int)blocks, threads, 0, st>>>(src, key, row0, dup, zero, n, dim, ld, (__nv_bfloat16*)dst, topic_rows, topic_key, noise_scale); break;
+        default: ingest_kernel<2, SYNTH><<<(int)blocks, threads, 0, st>>>(src, key, row0, dup, zero, n, dim, ld, (__half*)dst, topic_rows, topic_key, noise_scale); break;
     }
     CU_TRY(cudaGetLastError());
     return 0;
@@ -393,6 +394,33 @@ extern "C" int ragfin_add_synthetic(ragfin_t* h, uint64_t seed, int64_t row0, in
     char* dst = (char*)h->data + (size_t)h->count * h->ld * esize(h->dtype);
     if ((rc = launch_ingest<true>(h->dtype, nullptr, mix64(seed), row0, dup_every, zero_every, n, h->dim, h->ld, dst,
                                   h->num_sms, st)))
+        return rc;
+    h->count += n;
+    return mark_done(h, st);
+}
+
+// "Templated corpus" generator (bench / tests): rows row0..row0+n of a matrix whose row r is
+//   centre(topic = r / topic_rows) + noise(r) * 2^-noise_shift
+// with centre = row `topic` of the synthetic matrix (seed + RAGFIN_TOPIC_SEED_OFFSET) and noise = row r of the synthetic
+// matrix `seed`: contiguous runs of topic_rows near-duplicates in topic order (what repeated templated text looks like to
+// a vector store).  Every value is exact in fp32, so the oracle rebuilds the same rows on the host.
+extern "C" int ragfin_add_synthetic_topics(ragfin_t* h, uint64_t seed, int64_t row0, int64_t n, int64_t topic_rows,
+                                           int32_t noise_shift, void* stream) {
+    if (!h) return fail(RAGFIN_EINVAL, "NULL handle");
+    if (n < 0 || row0 < 0 || topic_rows < 1 || noise_shift < 1 || noise_shift > 10) return fail(RAGFIN_EINVAL, "bad row0 / n / topic_rows / noise_shift");
+    if (n == 0) return RAGFIN_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->is_view) return fail(RAGFIN_EUNSUPPORTED, "a view is read-only: add rows through the handle that owns the matrix");
+    if (h->count + n > h->capacity)
+        return fail(RAGFIN_ENOMEM, "add of %lld rows exceeds capacity (%lld of %lld used)", (long long)n,
+                    (long long)h->count, (long long)h->capacity);
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = wait_prev(h, st))) return rc;
+    char* dst = (char*)h->data + (size_t)h->count * h->ld * esize(h->dtype);
+    if ((rc = launch_ingest<true>(h->dtype, nullptr, mix64(seed), row0, 0, 0, n, h->dim, h->ld, dst, h->num_sms, st, topic_rows,
+                                  mix64(seed + RAGFIN_TOPIC_SEED_OFFSET), ldexpf(1.0f, -noise_shift))))
         return rc;
     h->count += n;
     return mark_done(h, st);

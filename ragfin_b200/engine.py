@@ -126,6 +126,11 @@ class Index:
     def add_synthetic(self, seed: int, row0: int, n: int, dup_every: int = 0, zero_every: int = 0) -> None:
         _lib.check(self._L.ragfin_add_synthetic(self._h, seed, row0, n, dup_every, zero_every, None))
 
+    def add_synthetic_topics(self, seed: int, row0: int, n: int, topic_rows: int, noise_shift: int = 3) -> None:
+        """Templated-corpus generator (bench / tests): row r = centre(r // topic_rows) + noise(r) * 2**-noise_shift, see
+        include/ragfin.h; `ragfin_b200.synthetic.synth_topic_rows` builds the same rows on the host."""
+        _lib.check(self._L.ragfin_add_synthetic_topics(self._h, seed, row0, n, topic_rows, noise_shift, None))
+
     def read_rows(self, row0: int, n: int) -> np.ndarray:
         """Stored rows as fp32 values [n, dim] (test hook for ingest parity)."""
         ld = (self.dim + 7) // 8 * 8

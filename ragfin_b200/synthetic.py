@@ -40,3 +40,19 @@ def synth_rows(seed: int, row0: int, n: int, dim: int, dup_every: int = 0, zero_
             blk[rows % np.uint64(zero_every) == np.uint64(zero_every - 1)] = 0.0
         out[b:b + len(rows)] = blk
     return out
+
+
+TOPIC_SEED_OFFSET = 0x7091C5   # include/ragfin.h RAGFIN_TOPIC_SEED_OFFSET
+
+
+def synth_topic_rows(seed: int, row0: int, n: int, dim: int, topic_rows: int, noise_shift: int = 3, rows_fn=None) -> np.ndarray:
+    """fp32 [n, dim]: rows row0..row0+n of the "templated corpus" behind `Index.add_synthetic_topics`:
+    row r = centre(r // topic_rows) + noise(r) * 2**-noise_shift, centre = row `topic` of synthetic matrix
+    seed + TOPIC_SEED_OFFSET, noise = row r of synthetic matrix `seed`.  Exact in fp32, so bit-identical to the device.
+    `rows_fn(seed, row0, n, dim)` may supply a faster generator with the same contract (the C oracle's in tests / bench)."""
+    gen = rows_fn or synth_rows
+    noise = gen(seed, row0, n, dim)
+    t0, t1 = row0 // topic_rows, (row0 + max(n, 1) - 1) // topic_rows
+    centres = gen(seed + TOPIC_SEED_OFFSET, t0, t1 - t0 + 1, dim)
+    topic = (np.arange(row0, row0 + n, dtype=np.int64) // topic_rows) - t0
+    return (centres[topic] + noise * np.float32(2.0 ** -noise_shift)).astype(np.float32)

@@ -119,3 +119,33 @@ def test_fused_device_api_and_id_base(coracle):
     wi, ws = coracle.cosine_topk(q, coracle.normalize_rows(x, "bf16"), k, id_base=1_000_000)
     assert np.array_equal(ids.cpu().numpy(), wi) and np.array_equal(sc.cpu().numpy().view(np.uint32), ws.view(np.uint32))
     idx.close()
+
+
+def test_templated_corpus_generator_and_search(coracle):
+    """`add_synthetic_topics` (contiguous runs of near-duplicate rows in topic order, the shape of the reference's templated
+    chunks) is bit-identical to the host generator, and queries aimed at one topic - thousands of rows within a hair of the
+    k-th score, none of them in a strided sample - are answered exactly by the one-kernel search without the exact scan."""
+    import ragfin_b200
+    from ragfin_b200.synthetic import synth_topic_rows
+    n, dim, k, topic_rows = 120000, 128, 10, 6000
+    rows_fn = lambda s, r0, m, d: coracle.synth_rows(s, r0, m, d)
+    x = synth_topic_rows(700, 0, n, dim, topic_rows, 3, rows_fn)
+    assert np.array_equal(x, synth_topic_rows(700, 0, n, dim, topic_rows, 3))            # C and numpy generators agree
+    q = synth_topic_rows(700, 7 * topic_rows + 11, 1, dim, topic_rows, 2, rows_fn)       # topic 7's centre + other noise
+    q = np.concatenate([q, synth_topic_rows(701, 3 * topic_rows, 2, dim, topic_rows, 3, rows_fn), coracle.synth_rows(702, 0, 1, dim)])
+    for dtype in ("bf16", "f32"):
+        idx = ragfin_b200.Index(dim, dtype, capacity=n, device=0)
+        idx.add_synthetic_topics(700, 0, 50000, topic_rows, 3)
+        idx.add_synthetic_topics(700, 50000, n - 50000, topic_rows, 3)
+        want_rows = coracle.normalize_rows(x, dtype)
+        assert np.array_equal(idx.read_rows(0, n).view(np.uint32), want_rows.view(np.uint32))
+        idx.set_fused(True, 1)
+        got = idx.search(q, k)
+        st = idx.stats()
+        assert st["path"] == 3 and st["queries_rescanned"] == 0, st
+        wi, ws = coracle.cosine_topk(q, want_rows, k)
+        _same(got, (wi, ws), f"topics {dtype}")
+        assert (wi[0] // topic_rows == 7).all()                                            # the needle topic
+        idx.set_fused(False)
+        _same(idx.search(q, k), (wi, ws), f"topics {dtype}, multi-kernel")
+        idx.close()
