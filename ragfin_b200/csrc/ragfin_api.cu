@@ -1449,6 +1449,19 @@ extern "C" int ragfin_set_append_mode(ragfin_t* h, int32_t enable) {
 
 // Diagnostics of the last one-kernel search: rows appended per query (out_appended[nq]) and rows rescored exactly
 // (out_rescored[nq]; -1 = the query took the in-kernel exact scan).  Synchronises the device.
+// Phase stamps of the last one-kernel search, ns relative to the kernel's start (out[8], see FusedCtl::t).
+extern "C" int ragfin_debug_fused_times(ragfin_t* h, int64_t* out) {
+    if (!h || !out) return fail(RAGFIN_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    if (!h->fctl.p) return fail(RAGFIN_EINVAL, "no one-kernel search has run on this handle");
+    CU_TRY(cudaDeviceSynchronize());
+    FusedCtl c;
+    CU_TRY(cudaMemcpy(&c, h->fctl.p, sizeof(c), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; ++i) out[i] = (int64_t)(c.t[i] - c.t[0]);
+    return RAGFIN_OK;
+}
+
 extern "C" int ragfin_debug_fused_counts(ragfin_t* h, int32_t nq, int64_t* out_appended, int64_t* out_rescored) {
     if (!h || !out_appended || !out_rescored || nq < 1 || nq > kFMaxQ) return fail(RAGFIN_EINVAL, "bad argument");
     std::lock_guard<std::mutex> lk(h->mu);

@@ -50,7 +50,14 @@ struct FusedCtl {
     uint32_t fin_done;        // finalizing CTAs that have finished
     uint32_t last_cnt[kFMaxQ];   // diagnostics of the last search: rows appended per query ...
     uint32_t last_resc[kFMaxQ];  // ... and rows rescored exactly (0xFFFFFFFF: the query took the exact scan)
+    unsigned long long t[8];     // globaltimer stamps of the last search (ns): CTA 0: start, prologue done, first tile done,
+                                 // sweep done; finalizer of query 0: all CTAs arrived, hits selected, rescored, emitted
 };
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 struct FusedArgs {
     uint32_t idesc;             // M = 128, N = NCOL
@@ -90,7 +97,7 @@ __host__ __device__ constexpr size_t fused_pend_words(int nq, int pend) {
     return (size_t)nq * pend > (size_t)kObsQ * kObsStride ? (size_t)nq * pend : (size_t)kObsQ * kObsStride;
 }
 __host__ __device__ constexpr size_t fused_state_bytes(int nq, int k, int pend) {
-    return (size_t)4 * kFMaxQ * 4 + ((size_t)nq * k + fused_pend_words(nq, pend)) * 4 + 64;
+    return (size_t)5 * kFMaxQ * 4 + ((size_t)nq * k + fused_pend_words(nq, pend)) * 4 + 64;
 }
 __host__ __device__ constexpr size_t fused_smem_bytes(int num_kblocks, int ncol, int stages, int nq, int k, int pend) {
     return 1024 + (size_t)num_kblocks * ncol * kGKBytes + (size_t)stages * kBBytes + 256 + fused_state_bytes(nq, k, pend);
@@ -157,10 +164,12 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
     float* eps_s = thr_s + kFMaxQ;                                          // [kFMaxQ]
     int* scnt = reinterpret_cast<int*>(eps_s + kFMaxQ);                     // [kFMaxQ] entries of sorted[q]
     int* pcnt = scnt + kFMaxQ;                                              // [kFMaxQ] entries appended to pend[q] this tile
-    uint32_t* sorted = reinterpret_cast<uint32_t*>(pcnt + kFMaxQ);          // [nq][k] descending ordered-uint scores
+    uint32_t* pub_s = reinterpret_cast<uint32_t*>(pcnt + kFMaxQ);           // [kFMaxQ] what this CTA last published for the query
+    uint32_t* sorted = pub_s + kFMaxQ;                                      // [nq][k] descending ordered-uint scores
     uint32_t* pend = sorted + (size_t)nq * k;                               // [nq][pend]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (blockIdx.x == 0 && tid == 0) a.ctl->t[0] = global_ns();
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
@@ -170,7 +179,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < kFMaxQ; i += kFThreads) { thr_s[i] = i < nq ? -INFINITY : INFINITY; eps_s[i] = 0.f; scnt[i] = 0; pcnt[i] = 0; }
+    for (int i = tid; i < kFMaxQ; i += kFThreads) { thr_s[i] = i < nq ? -INFINITY : INFINITY; eps_s[i] = 0.f; scnt[i] = 0; pcnt[i] = 0; pub_s[i] = 0u; }
     if (blockIdx.x == 0 && tid == 0) *a.flag_count = 0;   // ordered before every finalizer's atomicAdd by the arrival counter
     tc_fence_before();
     __syncthreads();
@@ -205,49 +214,71 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
         for (int i = tid; i < nkb * QTILE / 16; i += kFThreads) qz[i] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
         const int esz = KIND == 1 ? 4 : 2;
-        auto q_addr = [&](int row, int i) -> uint8_t* {   // element i of the padded embedding, MMA column `row`
-            const int kb = i / a.k_elems, c = (i % a.k_elems) * esz;
-            return fsm + (size_t)kb * QTILE + (size_t)(row >> 3) * 1024 + (size_t)(row & 7) * 128 + ((((c >> 4) ^ (row & 7)) << 4) | (c & 15));
-        };
+        // pass 1, one warp per query: canonical sum of squares -> 1 / |q| (fp64), parked in the pending area
+        double* inv_s = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(pend) + 7) & ~(uintptr_t)7);   // [nq]
+        float* d2_s = reinterpret_cast<float*>(inv_s + kFMaxQ);    // [nq] squared rounding residual of the query
         for (int j = warp; j < nq; j += kFThreads / 32) {
             const float* x = a.q + (size_t)j * a.dim;
             double acc = 0.0;
-            for (int i = lane; i < a.dim; i += kWarp) {
-                const double v = (double)x[i];
-                acc = acc + v * v;
+            for (int i0 = lane; i0 < a.dim; i0 += 12 * kWarp) {     // 12 loads in flight; the adds stay in increasing-i order
+                float xv[12];
+#pragma unroll
+                for (int u = 0; u < 12; ++u) xv[u] = i0 + u * kWarp < a.dim ? __ldg(x + i0 + u * kWarp) : 0.0f;
+#pragma unroll
+                for (int u = 0; u < 12; ++u) { const double v = (double)xv[u]; acc = acc + v * v; }   // + 0 for the tail: exact
             }
             const double n2 = warp_butterfly_f64(acc);
-            const double inv = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
-            const int row_hi = SPLIT ? (j >> 3) * 16 + (j & 7) : j;
-            double d2 = 0.0;
-            for (int i = lane; i < a.dim; i += kWarp) {
-                const float y = (float)((double)x[i] * inv);
+            if (lane == 0) { inv_s[j] = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0; d2_s[j] = 0.f; }
+        }
+        __syncthreads();
+        // pass 2, all threads over (query, element): y = RNE_f32(x / |q|) exactly as ingest does, hi / lo split, swizzled store
+        {
+            constexpr int KE = KIND == 1 ? 32 : 64;               // elements per 128-byte k-block
+            const int total = nq * a.dim;
+            int jq = -1;
+            float d2 = 0.f;
+            for (int idx = tid; idx < total; idx += kFThreads) {
+                const int j = idx / a.dim, i = idx - j * a.dim;
+                if (j != jq) { if (jq >= 0 && d2 != 0.f) atomicAdd(d2_s + jq, d2); jq = j; d2 = 0.f; }
+                const float y = (float)((double)__ldg(a.q + idx) * inv_s[j]);
+                const int row_hi = SPLIT ? (j >> 3) * 16 + (j & 7) : j;
+                const int kb = i / KE, c = (i % KE) * esz;
+                uint8_t* p_hi = fsm + (size_t)kb * QTILE + (size_t)(row_hi >> 3) * 1024 + (size_t)(row_hi & 7) * 128 + ((((c >> 4) ^ (row_hi & 7)) << 4) | (c & 15));
                 if (KIND == 1) {
-                    *reinterpret_cast<float*>(q_addr(row_hi, i)) = y;
-                } else if (a.dt == 1) {
-                    const __nv_bfloat16 hi = __float2bfloat16_rn(y);
-                    const float rest = y - __bfloat162float(hi);            // exact: both are fp32 values within a binade or two
-                    const __nv_bfloat16 lo = SPLIT ? __float2bfloat16_rn(rest) : __float2bfloat16_rn(0.f);
-                    *reinterpret_cast<__nv_bfloat16*>(q_addr(row_hi, i)) = hi;
-                    if (SPLIT) *reinterpret_cast<__nv_bfloat16*>(q_addr(row_hi + 8, i)) = lo;
-                    const double d = (double)y - (double)__bfloat162float(hi) - (double)__bfloat162float(lo);
-                    d2 += d * d;
+                    *reinterpret_cast<float*>(p_hi) = y;
                 } else {
-                    const __half hi = __float2half_rn(y);
-                    const float rest = y - __half2float(hi);
-                    const __half lo = SPLIT ? __float2half_rn(rest) : __float2half_rn(0.f);
-                    *reinterpret_cast<__half*>(q_addr(row_hi, i)) = hi;
-                    if (SPLIT) *reinterpret_cast<__half*>(q_addr(row_hi + 8, i)) = lo;
-                    const double d = (double)y - (double)__half2float(hi) - (double)__half2float(lo);
-                    d2 += d * d;
+                    // the lo row is 8 MMA columns further: same 8-row group (rows hi .. hi + 8 share row & 7), next 1024 bytes
+                    uint8_t* p_lo = p_hi + 1024;
+                    float r2;
+                    if (a.dt == 1) {
+                        const __nv_bfloat16 hi = __float2bfloat16_rn(y);
+                        const float rest = y - __bfloat162float(hi);        // exact
+                        const __nv_bfloat16 lo = SPLIT ? __float2bfloat16_rn(rest) : __float2bfloat16_rn(0.f);
+                        *reinterpret_cast<__nv_bfloat16*>(p_hi) = hi;
+                        if (SPLIT) *reinterpret_cast<__nv_bfloat16*>(p_lo) = lo;
+                        r2 = rest - __bfloat162float(lo);                   // exact
+                    } else {
+                        const __half hi = __float2half_rn(y);
+                        const float rest = y - __half2float(hi);
+                        const __half lo = SPLIT ? __float2half_rn(rest) : __float2half_rn(0.f);
+                        *reinterpret_cast<__half*>(p_hi) = hi;
+                        if (SPLIT) *reinterpret_cast<__half*>(p_lo) = lo;
+                        r2 = rest - __half2float(lo);
+                    }
+                    d2 = __fmaf_ru(r2, r2, d2);                             // rounded up: it feeds an error BOUND
                 }
             }
-            d2 = warp_butterfly_f64(d2);
-            // |approx - exact| <= |q - hi - lo|_2 * max |stored row|_2 (<= 1 + 2^-8) + the accumulation allowance
-            if (lane == 0) eps_s[j] = a.eps_const + (KIND == 1 ? 0.0f : (float)(sqrt(d2) * 1.0078125) + 1e-9f);
+            if (jq >= 0 && d2 != 0.f) atomicAdd(d2_s + jq, d2);
         }
+        __syncthreads();
+        // |approx - exact| <= |q - hi - lo|_2 * max |stored row|_2 (<= 1 + 2^-8) + the accumulation allowance
+        for (int j = tid; j < nq; j += kFThreads)
+            eps_s[j] = a.eps_const + (KIND == 1 ? 0.0f : __fmul_ru(__fsqrt_ru(d2_s[j]), 1.0078125f * 1.001f) + 1e-9f);
+        __syncthreads();
+        for (int i = tid; i < 3 * kFMaxQ + 2; i += kFThreads) pend[i] = 0u;   // the parking area goes back to the pending lists
         fence_proxy_async_smem();   // generic-proxy writes above -> visible to the tensor core's async-proxy reads
         __syncthreads();
+        if (blockIdx.x == 0 && tid == 0) a.ctl->t[1] = global_ns();
     }
 
     if (warp == 0) {
@@ -308,7 +339,6 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
         const int quarter = warp & 3;
         const int m = quarter * 32 + lane;          // row of the half tile
         const int et = tid - 64;                    // 0..127 among the epilogue threads; thread et < nq maintains query et
-        const float my_eps = et < nq ? eps_s[et] : 0.f;
         const int npend = a.pend;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -329,37 +359,110 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
 #pragma unroll
             for (int j = 0; j < QPC; ++j) out[j] = SPLIT ? s16[j] + s16[j + 8] : s16[j];
         };
-        // sorted-list insert of one ordered score for the query whose list is sl_ (entries so far: sc_n)
-        auto list_insert = [&](uint32_t* sl_, int& sc_n, uint32_t val) {
-            int j;
-            if (sc_n < k) j = sc_n++;
-            else if (val > sl_[k - 1]) j = k - 1;
-            else return;
-            while (j > 0 && sl_[j - 1] < val) { sl_[j] = sl_[j - 1]; --j; }
-            sl_[j] = val;
-        };
-        // min over the CTA groups of the bound each group has published for query qi (-inf until every group has one): read
-        // NOW, so that the next tile is filtered with the best bound the grid has found
+        // ---- per-query bookkeeping, WARP-cooperative: epilogue warp ew = warp & 3 owns the queries ew, ew + 4, ew + 8, ... ----
+        // (one thread walking a sorted list in shared memory is a chain of dependent ~30-cycle accesses: measured 48 us for
+        // the first tile at k = 10 and 370 us at k = 100; a warp does each step in a handful of instructions.)
+        const int ew = quarter;
         const int my_group = (int)(blockIdx.x % (unsigned)a.groups);
-        uint32_t my_pub = 0u;                          // what this CTA last published for its query (thread et)
-        auto group_bound = [&](int qi) -> float {
-            uint32_t mn = 0xFFFFFFFFu;
-            for (int g = 0; g < a.groups; ++g) {
-                const uint32_t v = __ldcg(&a.ctl->gthr[qi][g]);
-                mn = v < mn ? v : mn;
+        // want-th largest (1-based) of the 256 ordered scores ob[0..256) (0 = empty): bisection on the value bits, the count of
+        // values >= candidate by one warp reduction per bit.  Returns 0 when fewer than `want` entries exist.
+        auto warp_kth_of_tile = [&](const uint32_t* ob, int want) -> uint32_t {
+            uint32_t v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = ob[lane + 32 * i];
+            uint32_t T = 0u;
+#pragma unroll 1
+            for (int bit = 31; bit >= 0; --bit) {
+                const uint32_t cand = T | (1u << bit);
+                int c = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) c += v[i] >= cand;
+                if (__reduce_add_sync(kFull, c) >= want) T = cand;
             }
-            return mn ? ordered_to_float(mn) : -INFINITY;
+            return T;
         };
-        // new threshold of query qi from its sorted list (own k-th best), the published group bounds, and the old value;
-        // publishes this CTA's grank-th best for its group when that improved
-        auto refresh = [&](int qi, const uint32_t* sl_, int sc_n, float old_thr) -> float {
-            float nt = old_thr;
-            if (sc_n >= a.keff && a.keff > 0) nt = fmaxf(nt, thr_below(ordered_to_float(sl_[a.keff - 1]), my_eps));
-            if (sc_n >= a.grank && a.grank > 0) {
-                const uint32_t pv = float_to_ordered(thr_below(ordered_to_float(sl_[a.grank - 1]), my_eps));
-                if (pv > my_pub) { my_pub = pv; atomicMax(&a.ctl->gthr[qi][my_group], pv); __threadfence(); }
+        // sorted[q][0..n) := the n = min(k, valid) largest of the tile's 256 scores, descending; returns n
+        auto warp_seed_list = [&](int q, const uint32_t* ob) -> int {
+            uint32_t* sl_ = sorted + (size_t)q * k;
+            const uint32_t T = warp_kth_of_tile(ob, k);          // k-th largest, or 0: fewer than k valid scores -> take them all
+            int n = 0;
+            for (int pass = 0; pass < 2; ++pass) {                 // pass 0: values > T; pass 1: values == T while room remains
+#pragma unroll 1
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t val = ob[lane + 32 * i];
+                    const bool take = val != 0u && (pass == 0 ? val > T : (val == T && T != 0u));
+                    const unsigned mk = __ballot_sync(kFull, take);
+                    const int pos = n + __popc(mk & ((1u << lane) - 1u));
+                    if (take && pos < k) sl_[pos] = val;
+                    n += __popc(mk);
+                }
             }
-            return fmaxf(nt, group_bound(qi));
+            if (n > k) n = k;
+            __syncwarp();
+            // rank sort in place (n <= 128: at most 4 entries per lane, held in registers across the rewrite)
+            uint32_t e[4];
+            int rk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const int jx = lane + 32 * i; e[i] = jx < n ? sl_[jx] : 0u; rk[i] = 0; }
+            for (int mi = 0; mi < n; ++mi) {
+                const uint32_t o = sl_[mi];                        // broadcast read
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rk[i] += (o > e[i]) || (o == e[i] && mi < lane + 32 * i);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (lane + 32 * i < n) sl_[rk[i]] = e[i];
+            __syncwarp();
+            return n;
+        };
+        // one appended score into the query's sorted list (n entries so far; the smallest falls off a full list); returns n
+        auto warp_list_add = [&](uint32_t* sl_, int n, uint32_t val) -> int {
+            if (n == k && val <= sl_[k - 1]) return n;             // warp-uniform
+            uint32_t e[4];
+            int c = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const int jx = lane + 32 * i; e[i] = jx < n ? sl_[jx] : 0u; c += jx < n && e[i] > val; }
+            const int pos = __reduce_add_sync(kFull, c);           // entries that stay in front of val
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const int jx = lane + 32 * i; if (jx >= pos && jx < n && jx + 1 < k) sl_[jx + 1] = e[i]; }
+            if (lane == 0) sl_[pos] = val;
+            __syncwarp();
+            return n < k ? n + 1 : k;
+        };
+        // New thresholds for this warp's queries: own k-th best, and the minimum over the CTA groups of what each group has
+        // published (read NOW, so that the next tile is filtered with the best bound the grid has found); publishes this
+        // CTA's grank-th best for its group when that improved.  Two queries per step: lanes 0-15 / 16-31 read the 16 words.
+        auto warp_refresh = [&]() {
+            const int half = lane >> 4, gl = lane & 15;
+            uint32_t gw[kFMaxQ / 8];                               // all the loads first: ONE L2 round trip per refresh
+#pragma unroll
+            for (int it = 0; it < kFMaxQ / 8; ++it) {
+                const int q = ew + 8 * it + 4 * half;              // this half-warp's query of step `it` (may be >= nq)
+                gw[it] = (q < nq && gl < a.groups) ? __ldcg(&a.ctl->gthr[q][gl]) : 0xFFFFFFFFu;
+            }
+#pragma unroll
+            for (int it = 0; it < kFMaxQ / 8; ++it) {
+                const int q = ew + 8 * it + 4 * half;
+                if (ew + 8 * it >= nq) break;                      // warp-uniform
+                uint32_t g = gw[it];
+#pragma unroll
+                for (int off = 8; off >= 1; off >>= 1) { const uint32_t o = __shfl_xor_sync(kFull, g, off); g = o < g ? o : g; }
+                if (gl == 0 && q < nq) {
+                    const uint32_t* sl_ = sorted + (size_t)q * k;
+                    const int n = scnt[q];
+                    const float e = eps_s[q];
+                    float nt = thr_s[q];
+                    if (n >= a.keff && a.keff > 0) nt = fmaxf(nt, thr_below(ordered_to_float(sl_[a.keff - 1]), e));
+                    if (n >= a.grank && a.grank > 0) {
+                        const uint32_t pv = float_to_ordered(thr_below(ordered_to_float(sl_[a.grank - 1]), e));
+                        if (pv > pub_s[q]) { pub_s[q] = pv; atomicMax(&a.ctl->gthr[q][my_group], pv); __threadfence(); }
+                    }
+                    if (g != 0u) nt = fmaxf(nt, ordered_to_float(g));   // 0: some group has not published yet
+                    thr_s[q] = nt;
+                }
+            }
+            __syncwarp();
         };
         for (int sl = blockIdx.x; sl < a.S; sl += gridDim.x) {
             long long r0, r1;
@@ -392,32 +495,28 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                             }
                         }
                         named_bar_sync(1, 128);
-                        if (et >= q0 && et < q0 + kObsQ && et < nq) {
-                            uint32_t* sl_ = sorted + (size_t)et * k;
-                            int sc_n = 0;
-                            const uint32_t* ob = pend + (size_t)(et - q0) * kObsStride;
-                            for (int i = 0; i < kGN; ++i) {
-                                const uint32_t val = ob[i];
-                                if (val != 0u) list_insert(sl_, sc_n, val);
-                            }
-                            scnt[et] = sc_n;
-                            thr_s[et] = refresh(et, sl_, sc_n, -INFINITY);
+                        for (int q = q0 + ew; q < q0 + kObsQ && q < nq; q += 4) {
+                            const int n = warp_seed_list(q, pend + (size_t)(q - q0) * kObsStride);
+                            if (lane == 0) scnt[q] = n;
                         }
                         named_bar_sync(2, 128);
                     }
+                    warp_refresh();
                     // Best-effort rendezvous: all CTAs observe their first tile at the same time, so a few microseconds later
                     // every bound is published and the first tile can be filtered with the best of them (on a corpus sorted
                     // by similarity - or with the coarse tf32 error bound - the LOCAL bound admits every row of the tile).
                     // The wait is bounded: a CTA that is not resident yet (another kernel on the device) only costs tightness.
                     // TMA and the tensor core keep running ahead meanwhile (second accumulator, ring).
+                    named_bar_sync(1, 128);                            // every warp's bounds are published
                     if (et == 0) {
                         __threadfence();
                         atomicAdd(&a.ctl->obs_done, 1u);
-                        for (int spins = 0; spins < 256 && ld_acq_gpu(&a.ctl->obs_done) < gridDim.x; ++spins) __nanosleep(40);
+                        const unsigned long long t0 = global_ns();
+                        while (ld_acq_gpu(&a.ctl->obs_done) < gridDim.x && global_ns() - t0 < 4000ull) __nanosleep(100);
                     }
-                    named_bar_sync(1, 128);
-                    if (et < nq) thr_s[et] = fmaxf(thr_s[et], group_bound(et));
                     named_bar_sync(2, 128);
+                    warp_refresh();
+                    named_bar_sync(1, 128);
                 }
                 // ---- append pass: every row whose approximate score reaches the query's current threshold ----
 #pragma unroll 1
@@ -448,23 +547,28 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
                 // ---- threshold maintenance: the tile's appended scores enter the query's sorted list ----
                 named_bar_sync(1, 128);
-                if (et < nq && !warm) {
-                    uint32_t* sl_ = sorted + (size_t)et * k;
-                    int sc_n = scnt[et];
-                    int pc = pcnt[et];
-                    if (pc > 0) {
-                        if (pc > npend) pc = npend;                    // the surplus was dropped: only tightening information is lost
-                        for (int i = 0; i < pc; ++i) list_insert(sl_, sc_n, pend[(size_t)et * npend + i]);
-                        scnt[et] = sc_n;
-                        pcnt[et] = 0;
+                if (!warm) {
+                    for (int q = ew; q < nq; q += 4) {
+                        int pc = pcnt[q];                              // warp-uniform (shared memory, written before the barrier)
+                        if (pc > 0) {
+                            if (pc > npend) pc = npend;                // the surplus was dropped: only tightening information is lost
+                            uint32_t* sl_ = sorted + (size_t)q * k;
+                            int n = scnt[q];
+                            __syncwarp();
+                            for (int i = 0; i < pc; ++i) n = warp_list_add(sl_, n, pend[(size_t)q * npend + i]);
+                            if (lane == 0) { scnt[q] = n; pcnt[q] = 0; }
+                        }
                     }
-                    thr_s[et] = refresh(et, sl_, sc_n, thr_s[et]);
+                    __syncwarp();
+                    warp_refresh();
                 }
+                if (warm && blockIdx.x == 0 && et == 0) a.ctl->t[2] = global_ns();
                 warm = false;
                 named_bar_sync(2, 128);
             }
         }
         __threadfence();   // this thread's appended keys are visible device-wide before the CTA is counted as done
+        if (blockIdx.x == 0 && et == 0) a.ctl->t[3] = global_ns();
     }
     tc_fence_before();
     __syncthreads();
@@ -483,14 +587,9 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
     const int ticket = (int)*s_ticket;
     const int first_fin = (int)gridDim.x - n_fin;
     if (ticket < first_fin) return;
-    if (tid == 0) {
-        while (ld_acq_gpu(&a.ctl->done) < gridDim.x) __nanosleep(64);
-        __threadfence();
-    }
+    // scratch over the query block + ring: qv [ld] fp32 | hist [256] | s3 [3] + c2 | sel [..] u64
     fence_proxy_async_smem();   // the ring was written by TMA and read by the tensor core; from here on plain stores reuse it
     __syncthreads();
-
-    // scratch over the query block + ring: qv [ld] fp32 | hist [256] | s3 [3] + c2 | sel [..] u64
     float* qv = reinterpret_cast<float*>(fsm);
     const int ld_al = (a.ld + 3) / 4 * 4;
     uint32_t* hist = reinterpret_cast<uint32_t*>(qv + ld_al);
@@ -498,6 +597,32 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
     int* s_c2 = reinterpret_cast<int*>(s3 + 3);
     u64* sel = reinterpret_cast<u64*>(fsm + (((size_t)ld_al * 4 + 256 * 4 + 16 + 15) / 16) * 16);
     const int sel_cap = (int)((region_bytes - (size_t)(reinterpret_cast<uint8_t*>(sel) - fsm)) / sizeof(u64));
+    // normalised fp32 query (the rescore operand), recomputed: bit-identical to the prologue and to ingest.  For the CTA's
+    // first query this runs while the rest of the grid is still sweeping.
+    auto make_qv = [&](int qi) {
+        if (warp == 1) {
+            const float* x = a.q + (size_t)qi * a.dim;
+            double acc = 0.0;
+            for (int i0 = lane; i0 < a.dim; i0 += 12 * kWarp) {
+                float xv[12];
+#pragma unroll
+                for (int u = 0; u < 12; ++u) xv[u] = i0 + u * kWarp < a.dim ? __ldg(x + i0 + u * kWarp) : 0.0f;
+#pragma unroll
+                for (int u = 0; u < 12; ++u) { const double v = (double)xv[u]; acc = acc + v * v; }
+            }
+            const double n2 = warp_butterfly_f64(acc);
+            const double inv = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
+            for (int i = lane; i < a.ld; i += kWarp) qv[i] = i < a.dim ? (float)((double)__ldg(x + i) * inv) : 0.0f;
+        }
+    };
+    make_qv(ticket - first_fin);
+    if (tid == 0) {
+        while (ld_acq_gpu(&a.ctl->done) < gridDim.x) __nanosleep(64);
+        __threadfence();
+    }
+    __syncthreads();
+    const bool stamp = ticket - first_fin == 0 && tid == 0;
+    if (stamp) a.ctl->t[4] = global_ns();
 
     // Emit the query's hits: fin[0 .. keff) are its exact keys in order (this shard).  Single GPU: write them out.  Sharded:
     // push them to every rank, wait for every rank's, merge, write the global top-k.  Called by all threads of the CTA.
@@ -568,21 +693,8 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
     };
 
     for (int qi = ticket - first_fin; qi < nq; qi += n_fin) {
-        // normalised fp32 query (the rescore operand), recomputed: bit-identical to the prologue and to ingest
-        {
-            const float* x = a.q + (size_t)qi * a.dim;
-            if (warp == 0) {
-                double acc = 0.0;
-                for (int i = lane; i < a.dim; i += kWarp) {
-                    const double v = (double)x[i];
-                    acc = acc + v * v;
-                }
-                const double n2 = warp_butterfly_f64(acc);
-                const double inv = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
-                for (int i = lane; i < a.ld; i += kWarp) qv[i] = i < a.dim ? (float)((double)x[i] * inv) : 0.0f;
-            }
-            if (tid == 0) *s_c2 = 0;
-        }
+        if (qi != ticket - first_fin) make_qv(qi);
+        if (tid == 0) *s_c2 = 0;
         __syncthreads();
         const uint32_t m32 = __ldcg(a.ctl->cnt + qi);
         if (tid == 0) { a.ctl->last_cnt[qi] = m32; a.ctl->last_resc[qi] = 0xFFFFFFFFu; }
@@ -591,16 +703,43 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
         bool exact_scan = m32 > (uint32_t)a.cap || (int)m32 < keff;   // block-uniform
         if (!exact_scan && keff > 0) {
             const int m = (int)m32;
-            const uint32_t t_ord = block_kth_largest([&](int i) { return (uint32_t)(__ldcg(in + i) >> 32); }, m, (uint32_t)keff, hist, s3);
-            const float cut = thr_below(ordered_to_float(t_ord), eps_s[qi]);
-            for (int i = tid; i < m; i += kFThreads) {
-                const u64 key = __ldcg(in + i);
-                if (key_score(key) >= cut) {
-                    const int pos = atomicAdd(s_c2, 1);
-                    if (pos < sel_cap) sel[pos] = key;
+            constexpr int kSmallM = 2048;
+            if (m <= kSmallM && sel_cap >= 2 * kSmallM) {
+                // the usual case (a few hundred keys): stage them in shared memory once; one warp finds T = keff-th largest
+                // approximate score by bisection on the value bits (a warp reduction per bit), everybody gathers
+                u64* stg = sel + (sel_cap - kSmallM);
+                for (int i = tid; i < m; i += kFThreads) stg[i] = __ldcg(in + i);
+                __syncthreads();
+                if (warp == 0) {
+                    uint32_t T = 0u;
+#pragma unroll 1
+                    for (int bit = 31; bit >= 0; --bit) {
+                        const uint32_t cand = T | (1u << bit);
+                        int c = 0;
+                        for (int i = lane; i < m; i += kWarp) c += (uint32_t)(stg[i] >> 32) >= cand;
+                        if (__reduce_add_sync(kFull, c) >= keff) T = cand;
+                    }
+                    if (lane == 0) s3[0] = T;
+                }
+                __syncthreads();
+                const float cut = thr_below(ordered_to_float(s3[0]), eps_s[qi]);
+                for (int i = tid; i < m; i += kFThreads) {
+                    const u64 key = stg[i];
+                    if (key_score(key) >= cut) sel[atomicAdd(s_c2, 1)] = key;      // <= m <= kSmallM entries: below the staging area
+                }
+            } else {
+                const uint32_t t_ord = block_kth_largest([&](int i) { return (uint32_t)(__ldcg(in + i) >> 32); }, m, (uint32_t)keff, hist, s3);
+                const float cut = thr_below(ordered_to_float(t_ord), eps_s[qi]);
+                for (int i = tid; i < m; i += kFThreads) {
+                    const u64 key = __ldcg(in + i);
+                    if (key_score(key) >= cut) {
+                        const int pos = atomicAdd(s_c2, 1);
+                        if (pos < sel_cap) sel[pos] = key;
+                    }
                 }
             }
             __syncthreads();
+            if (stamp && qi == 0) a.ctl->t[5] = global_ns();
             const int c2 = *s_c2;
             int P2 = 32;
             while (P2 < c2) P2 <<= 1;
@@ -618,8 +757,20 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
             {
                 for (int i = c2 + tid; i < P2; i += kFThreads) sel[i] = 0ull;
                 __syncthreads();
-                block_bitonic_sort_desc(sel, P2, tid, kFThreads);
+                if (stamp && qi == 0) a.ctl->t[6] = global_ns();
+                if (c2 <= kFThreads) {
+                    // a handful of exact keys: rank by counting (keys are unique), one thread per key, two barriers
+                    const u64 mine = tid < c2 ? sel[tid] : 0ull;
+                    int rk = 0;
+                    for (int i = 0; i < c2; ++i) rk += sel[i] > mine;
+                    __syncthreads();
+                    if (tid < c2) sel[rk] = mine;
+                    __syncthreads();
+                } else {
+                    block_bitonic_sort_desc(sel, P2, tid, kFThreads);
+                }
                 emit(qi, sel, keff);
+                if (stamp && qi == 0) a.ctl->t[7] = global_ns();
                 if (tid == 0) { a.flags[qi] = 0; a.ctl->last_resc[qi] = (uint32_t)c2; }
             }
             }

@@ -244,6 +244,13 @@ class Index:
         _lib.check(self._L.ragfin_debug_fused_counts(self._h, int(nq), a.ctypes.data, r.ctypes.data))
         return a, r
 
+    def fused_times(self):
+        """Phase stamps of the last one-kernel search (us since kernel start): start, prologue, first tile, sweep end (CTA 0);
+        all arrived, selected, rescored, emitted (finalizer of query 0)."""
+        t = np.zeros(8, np.int64)
+        _lib.check(self._L.ragfin_debug_fused_times(self._h, t.ctypes.data))
+        return (t / 1e3).round(1).tolist()
+
     def set_append_mode(self, enable: bool) -> None:
         """tcgen05 path: append mode (no lists, threshold from the bound pass) on/off (default on; results identical)."""
         _lib.check(self._L.ragfin_set_append_mode(self._h, 1 if enable else 0))

@@ -197,9 +197,10 @@ def test_config2_1m_f32_1024_queries(coracle):
             assert s_[j] > s_[j + 1] or (s_[j] == s_[j + 1] and i_[j] < i_[j + 1])
         want = coracle.exact_scores(stored[i_], qhat[qi])
         assert np.array_equal(want.view(np.uint32), s_.view(np.uint32)), qi
-    # the one-kernel search (<= 64 queries, kind::tf32 with 32 / 64 query columns) answers the same bits
+    # the one-kernel search (kind::tf32 with 16 / 32 query columns; 64 fp32 query rows of 768 do not fit next to the ring)
+    # answers the same bits
     idx.set_fused(True)
-    for a, b in ((0, 1), (100, 116), (200, 264)):
+    for a, b in ((0, 1), (100, 116), (200, 232)):
         ids_f, sc_f = idx.search(q[a:b], K)
         assert idx.stats()["path"] == 3 and idx.stats()["queries_rescanned"] == 0
         assert np.array_equal(ids_f, ids[a:b]) and np.array_equal(sc_f.view(np.uint32), sc[a:b].view(np.uint32))
