@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--also-batch", type=int, default=4096,
                     help="second regime measured in the same run and reported under 'regimes' (0 = off)")
     ap.add_argument("--gemm-cluster", type=int, default=0, help="tcgen05 path cluster size: 0 auto, 1, 2 or 4")
-    ap.add_argument("--gemm-variant", type=int, default=-1, help="tcgen05 kernel: 0 auto, 1 streaming, 2 A-stationary, 3 swapped roles for <= 16 queries, 4 experimental 2-SM pairs, 5 experimental self-seeded sweep (-1 = library default)")
+    ap.add_argument("--gemm-variant", type=int, default=-1, help="tcgen05 kernel of the multi-kernel path: 0 auto, 1 streaming, 2 A-stationary, 3 swapped roles for <= 16 queries, 4 2-SM MMA pairs (-1 = library default)")
     ap.add_argument("--cpu-rows", type=int, default=0,
                     help="rows of the CPU baseline sample (0 = the whole corpus when MemAvailable >= 1.3 x rows*dim*4, else 2M rows, extrapolated)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -315,9 +315,13 @@ def run_ours(a):
         out_sc = torch.empty((batch, a.k), dtype=torch.float32).pin_memory()
         q_stage = torch.empty((batch, a.dim), dtype=torch.float32, device=dev)
 
+        fused_sharded = world > 1 and searcher.exchange is not None and searcher.fused_ok(batch, a.k)
+
         def e2e_step(i):
             if world == 1:   # the C-ABI host call: H2D + search + D2H + sync inside ragfin_search_host
                 idx.search(q_host[i % nbatches].numpy(), a.k, out_ids=out_ids.numpy(), out_scores=out_sc.numpy())
+            elif fused_sharded:   # ragfin_search_sharded_host: pinned staging, one kernel per GPU (sweep + exchange + reduce), one sync
+                searcher.search_host(q_host[i % nbatches].numpy(), a.k, out_ids=out_ids.numpy(), out_scores=out_sc.numpy())
             else:
                 q_stage.copy_(q_host[i % nbatches], non_blocking=True)
                 ids, sc = searcher.search(q_stage, a.k)
@@ -330,7 +334,9 @@ def run_ours(a):
         for i in range(max(1, warmup // 2)):
             e2e_step(i)
         st = idx.stats()
-        launches_per_step = st["launches"] + (1 if world > 1 else 0)
+        # kernels of ours per step: the search's own launches; sharded without the one-kernel path: + push / merge kernels
+        # (peer memory) or + the reduce kernel after NCCL's all-gather
+        launches_per_step = st["launches"] + (0 if world == 1 or fused_sharded else 2 if searcher.exchange is not None else 1)
 
         sampler = ClockSampler(local)
         if rank == 0:
@@ -368,8 +374,8 @@ def run_ours(a):
             alg = shard_rows * ld * esize
             achieved = alg / (kern_avg_ms * 1e-3) / 1e9
             # <= 16 queries run the swapped-role kernel unless a variant is forced (csrc/gemm_rows.cuh)
-            kname = ("scan_topk_kernel" if st["path"] == 0 else "gemm_rows_kernel" if batch <= 16 and a.gemm_variant in (-1, 0, 3)
-                     else "gemm_rows_seeded_kernel" if batch <= 16 and a.k <= 16 and a.gemm_variant == 5 else "gemm_topk_kernel")
+            kname = ("scan_topk_kernel" if st["path"] == 0 else "sweep_fused_kernel" if st["path"] == 3 else
+                     "gemm_rows_kernel" if batch <= 16 and a.gemm_variant in (-1, 0, 3) else "gemm_topk_kernel")
             roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": achieved / peaks["hbm"], "algorithmic_bytes_per_launch": alg,
                     "frac_of_nominal_8TBps": achieved / 8000.0}
@@ -392,6 +398,9 @@ def run_ours(a):
                     "h2d_bytes_per_step": batch * a.dim * 4, "d2h_bytes_per_step": batch * a.k * 12},
             "gpu_launches": launches_per_step * steps, "roofline": roof,
             "queries_rescanned_last_step": st["queries_rescanned"],
+            "search_path": {0: "scan + finalize", 1: "tensor-core sweep, multi-kernel", 2: "large k", 3: "one kernel (sweep_fused)"}.get(st["path"]),
+            "exchange": None if world == 1 else ("in-kernel peer stores (ragfin_search_sharded)" if fused_sharded else
+                                                 "peer-memory push / merge kernels" if searcher.exchange is not None else "nccl all-gather + reduce kernel"),
         }
 
     def throttled(m):
@@ -515,7 +524,8 @@ def run_ours(a):
             "config": {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "k": a.k, "batch": a.batch,
                        "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
                        "l2": "inputs (corpus shard) larger than L2; no flush needed",
-                       "ingest_s": round(ingest_s, 2), "queries_rescanned_last_step": main["queries_rescanned_last_step"]},
+                       "ingest_s": round(ingest_s, 2), "queries_rescanned_last_step": main["queries_rescanned_last_step"],
+                       "search_path": main["search_path"], "exchange": main["exchange"]},
             "clocks": dict(main["clocks"] or {}, **({"remeasured_after": main["remeasured_after"]} if "remeasured_after" in main else {})),
             "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "roofline": main["roofline"],
             "parity_check": main["parity_check"],

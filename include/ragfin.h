@@ -241,8 +241,9 @@ int ragfin_set_fused(ragfin_t* h, int32_t enable, int64_t min_rows);
  * buffer during the sweep and rows rescored exactly by the finalize (-1: the buffer overflowed and the query was answered
  * by the in-kernel exact scan).  Synchronises. */
 int ragfin_debug_fused_counts(ragfin_t* h, int32_t nq, int64_t* out_appended, int64_t* out_rescored);
-/* Phase stamps of the last one-kernel search in ns since the kernel's start, out[8]: CTA 0 {start, prologue done, first tile
- * done, sweep done}, finalizer of query 0 {all CTAs arrived, hits selected, rescored, emitted}.  Synchronises. */
+/* Phase stamps of the last one-kernel search in ns since the kernel's start, out[16]: CTA 0 {start, prologue done, first tile
+ * done, sweep done}, finalizer of query 0 {all CTAs arrived, hits selected, rescored, emitted}, then finer stamps {setup done,
+ * norms done, count read, keys staged, T found} (csrc/sweep_fused.cuh FusedCtl::t).  Synchronises. */
 int ragfin_debug_fused_times(ragfin_t* h, int64_t* out);
 
 /* Test hook: raw (approximate, fp32-accumulated) tensor-core scores of nq queries against every

@@ -78,6 +78,7 @@ struct ragfin {
     bool fctl_dirty = true;   // set when a launch may have left it non-zero (first use, failed call): re-zeroed before the next launch
     bool use_fused = true;    // <= 64 queries, k <= 128: the one-kernel search (sweep_fused.cuh); RAGFIN_NO_FUSED=1 disables
     int fused_min_rows = 8192;
+    int fused_max_nq = 32;    // kFusedMaxBatch; RAGFIN_FUSED_MAX_NQ overrides (<= 64)
     struct MapSlot { const void* base = nullptr; int64_t rows = 0; int ld = 0, dtype = 0, box_rows = 0; CUtensorMap map; };
     MapSlot map_cache[8];     // tensor maps are pure functions of (base, rows, ld, dtype, box): encode once
     int map_next = 0;
@@ -167,6 +168,7 @@ extern "C" int ragfin_create(ragfin_t** out, int32_t dim, int32_t dtype, int64_t
     h->num_sms = prop.multiProcessorCount;
     { const char* e = getenv("RAGFIN_NO_BOUND_PASS"); if (e && atoi(e)) h->use_bound_pass = false; }
     { const char* e = getenv("RAGFIN_NO_FUSED"); if (e && atoi(e)) h->use_fused = false; }
+    { const char* e = getenv("RAGFIN_FUSED_MAX_NQ"); if (e && atoi(e) >= 1 && atoi(e) <= kFMaxQ) h->fused_max_nq = atoi(e); }
     h->capacity = capacity_rows;
     const size_t bytes = (size_t)capacity_rows * h->ld * esize(dtype);
     e = cudaMalloc(&h->data, bytes);
@@ -1003,9 +1005,11 @@ struct FusedPlan {
 };
 
 // Column count / split / ring depth for nb queries, or ncol = 0 when the shape does not fit one CTA's shared memory.
+// Measured (profiles/r02): up to 32 queries the one-kernel search matches or beats the multi-kernel sweep; at 33-64 queries
+// (64 plain columns, 3-stage ring) its sweep is slower than the query-major kernel's (2.9 vs 2.25 ms on 10M rows).
 static FusedPlan plan_fused(const ragfin* h, int nb, int k) {
     FusedPlan best;
-    if (nb < 1 || nb > kFMaxQ || k > kFMaxK) return best;
+    if (nb < 1 || nb > (h->fused_max_nq < kFMaxQ ? h->fused_max_nq : kFMaxQ) || k > kFMaxK) return best;
     const int es = (int)esize(h->dtype);
     const int k_elems = kGKBytes / es;
     const int nkb = (h->ld + k_elems - 1) / k_elems;
@@ -1160,7 +1164,7 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
     const int steps = round_steps((nvec + 31) / 32);
     const int64_t n_eff = h->cur_allow ? h->cur_allowed : n;   // rows a hit may come from
     if ((rc = ensure(h->flags, (size_t)(kMaxQueryBatch + 1) * sizeof(int)))) return rc;
-    if (nq <= kFMaxQ && fused_eligible(h, nq, k)) {   // the one-kernel search (sweep_fused.cuh): prep, sweep, finalize, exact fallback
+    if (nq <= h->fused_max_nq && fused_eligible(h, nq, k)) {   // the one-kernel search (sweep_fused.cuh): prep, sweep, finalize, exact fallback
         int* fl = (int*)h->flags.p;
         return run_fused(h, q_dev, nq, k, n_eff, out_ids, out_scores, fl, fl + kMaxQueryBatch, st);
     }
@@ -1449,7 +1453,7 @@ extern "C" int ragfin_set_append_mode(ragfin_t* h, int32_t enable) {
 
 // Diagnostics of the last one-kernel search: rows appended per query (out_appended[nq]) and rows rescored exactly
 // (out_rescored[nq]; -1 = the query took the in-kernel exact scan).  Synchronises the device.
-// Phase stamps of the last one-kernel search, ns relative to the kernel's start (out[8], see FusedCtl::t).
+// Phase stamps of the last one-kernel search, ns relative to the kernel's start (out[16], see FusedCtl::t).
 extern "C" int ragfin_debug_fused_times(ragfin_t* h, int64_t* out) {
     if (!h || !out) return fail(RAGFIN_EINVAL, "bad argument");
     std::lock_guard<std::mutex> lk(h->mu);
@@ -1458,7 +1462,7 @@ extern "C" int ragfin_debug_fused_times(ragfin_t* h, int64_t* out) {
     CU_TRY(cudaDeviceSynchronize());
     FusedCtl c;
     CU_TRY(cudaMemcpy(&c, h->fctl.p, sizeof(c), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < 8; ++i) out[i] = (int64_t)(c.t[i] - c.t[0]);
+    for (int i = 0; i < 16; ++i) out[i] = (int64_t)(c.t[i] - c.t[0]);
     return RAGFIN_OK;
 }
 

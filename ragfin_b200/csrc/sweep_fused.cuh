@@ -50,8 +50,9 @@ struct FusedCtl {
     uint32_t fin_done;        // finalizing CTAs that have finished
     uint32_t last_cnt[kFMaxQ];   // diagnostics of the last search: rows appended per query ...
     uint32_t last_resc[kFMaxQ];  // ... and rows rescored exactly (0xFFFFFFFF: the query took the exact scan)
-    unsigned long long t[8];     // globaltimer stamps of the last search (ns): CTA 0: start, prologue done, first tile done,
-                                 // sweep done; finalizer of query 0: all CTAs arrived, hits selected, rescored, emitted
+    unsigned long long t[16];    // globaltimer stamps of the last search (ns): CTA 0: start, prologue done, first tile done,
+                                 // sweep done; finalizer of query 0: all CTAs arrived, hits selected, rescored, emitted;
+                                 // [8..]: finer stamps (setup done, norms done; count read, keys staged, T found)
 };
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
@@ -185,6 +186,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (blockIdx.x == 0 && tid == 0) a.ctl->t[8] = global_ns();
 
     auto slice_tiles = [&](int sl, long long& r0, long long& r1) -> int {
         r0 = (long long)sl * a.rows_per_slice;
@@ -216,66 +218,147 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
         const int esz = KIND == 1 ? 4 : 2;
         // pass 1, one warp per query: canonical sum of squares -> 1 / |q| (fp64), parked in the pending area
         double* inv_s = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(pend) + 7) & ~(uintptr_t)7);   // [nq]
-        float* d2_s = reinterpret_cast<float*>(inv_s + kFMaxQ);    // [nq] squared rounding residual of the query
         for (int j = warp; j < nq; j += kFThreads / 32) {
             const float* x = a.q + (size_t)j * a.dim;
             double acc = 0.0;
-            for (int i0 = lane; i0 < a.dim; i0 += 12 * kWarp) {     // 12 loads in flight; the adds stay in increasing-i order
-                float xv[12];
+            for (int i0 = lane; i0 < a.dim; i0 += 24 * kWarp) {     // 24 loads in flight (a 768-wide query: one round trip);
+                float xv[24];                                       // the adds stay in increasing-i order
 #pragma unroll
-                for (int u = 0; u < 12; ++u) xv[u] = i0 + u * kWarp < a.dim ? __ldg(x + i0 + u * kWarp) : 0.0f;
+                for (int u = 0; u < 24; ++u) xv[u] = i0 + u * kWarp < a.dim ? __ldg(x + i0 + u * kWarp) : 0.0f;
 #pragma unroll
-                for (int u = 0; u < 12; ++u) { const double v = (double)xv[u]; acc = acc + v * v; }   // + 0 for the tail: exact
+                for (int u = 0; u < 24; ++u) { const double v = (double)xv[u]; acc = acc + v * v; }   // + 0 for the tail: exact
             }
             const double n2 = warp_butterfly_f64(acc);
-            if (lane == 0) { inv_s[j] = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0; d2_s[j] = 0.f; }
+            if (lane == 0) inv_s[j] = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
         }
         __syncthreads();
-        // pass 2, all threads over (query, element): y = RNE_f32(x / |q|) exactly as ingest does, hi / lo split, swizzled store
-        {
-            constexpr int KE = KIND == 1 ? 32 : 64;               // elements per 128-byte k-block
-            const int total = nq * a.dim;
-            int jq = -1;
-            float d2 = 0.f;
-            for (int idx = tid; idx < total; idx += kFThreads) {
-                const int j = idx / a.dim, i = idx - j * a.dim;
-                if (j != jq) { if (jq >= 0 && d2 != 0.f) atomicAdd(d2_s + jq, d2); jq = j; d2 = 0.f; }
-                const float y = (float)((double)__ldg(a.q + idx) * inv_s[j]);
-                const int row_hi = SPLIT ? (j >> 3) * 16 + (j & 7) : j;
-                const int kb = i / KE, c = (i % KE) * esz;
-                uint8_t* p_hi = fsm + (size_t)kb * QTILE + (size_t)(row_hi >> 3) * 1024 + (size_t)(row_hi & 7) * 128 + ((((c >> 4) ^ (row_hi & 7)) << 4) | (c & 15));
-                if (KIND == 1) {
-                    *reinterpret_cast<float*>(p_hi) = y;
-                } else {
-                    // the lo row is 8 MMA columns further: same 8-row group (rows hi .. hi + 8 share row & 7), next 1024 bytes
-                    uint8_t* p_lo = p_hi + 1024;
-                    float r2;
-                    if (a.dt == 1) {
-                        const __nv_bfloat16 hi = __float2bfloat16_rn(y);
-                        const float rest = y - __bfloat162float(hi);        // exact
-                        const __nv_bfloat16 lo = SPLIT ? __float2bfloat16_rn(rest) : __float2bfloat16_rn(0.f);
-                        *reinterpret_cast<__nv_bfloat16*>(p_hi) = hi;
-                        if (SPLIT) *reinterpret_cast<__nv_bfloat16*>(p_lo) = lo;
-                        r2 = rest - __bfloat162float(lo);                   // exact
-                    } else {
-                        const __half hi = __float2half_rn(y);
-                        const float rest = y - __half2float(hi);
-                        const __half lo = SPLIT ? __float2half_rn(rest) : __float2half_rn(0.f);
-                        *reinterpret_cast<__half*>(p_hi) = hi;
-                        if (SPLIT) *reinterpret_cast<__half*>(p_lo) = lo;
-                        r2 = rest - __half2float(lo);
+        if (blockIdx.x == 0 && tid == 0) a.ctl->t[9] = global_ns();
+        // pass 2, all threads: y = RNE_f32(x / |q|) exactly as ingest does, hi / lo split, swizzled store.  Work units are runs
+        // of 192 consecutive elements of ONE query (so a unit's threads share the query: the residual is reduced per warp);
+        // the loads of 8 units are issued before anything is computed.
+        constexpr int VE = KIND == 1 ? 4 : 8;                     // elements of one 16-byte chunk of a query row
+        if (a.dim % VE == 0 && (reinterpret_cast<uintptr_t>(a.q) & 15u) == 0) {
+            // fast path: one thread per 16-byte chunk (8 bf16 / fp16 or 4 fp32 elements): 128-bit loads, one 128-bit swizzled
+            // store for the hi row and one for the lo row; the residual is summed per thread, then per warp
+            constexpr int KE = KIND == 1 ? 32 : 64;
+            const int cpq = a.dim / VE;                            // chunks per query
+            const int total = nq * cpq;
+            for (int ch0 = 0; ch0 < total; ch0 += 2 * kFThreads) {
+                float xv[2][8];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int ch = ch0 + u * kFThreads + tid;
+#pragma unroll
+                    for (int v4 = 0; v4 < VE / 4; ++v4) {
+                        const float4 f = ch < total ? __ldg(reinterpret_cast<const float4*>(a.q) + (size_t)ch * (VE / 4) + v4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        xv[u][4 * v4] = f.x; xv[u][4 * v4 + 1] = f.y; xv[u][4 * v4 + 2] = f.z; xv[u][4 * v4 + 3] = f.w;
                     }
-                    d2 = __fmaf_ru(r2, r2, d2);                             // rounded up: it feeds an error BOUND
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int ch = ch0 + u * kFThreads + tid;
+                    const bool live = ch < total;
+                    const int j = live ? ch / cpq : 0, i = (ch - j * cpq) * VE;     // query, first element of the chunk
+                    if (live) {
+                        const double inv = inv_s[j];
+                        const int row_hi = SPLIT ? (j >> 3) * 16 + (j & 7) : j;
+                        const int kb = i / KE, cc = ((i % KE) * esz) >> 4;           // k-block, 16-byte chunk inside the 128-byte row
+                        uint8_t* p_hi = fsm + (size_t)kb * QTILE + (size_t)(row_hi >> 3) * 1024 + (size_t)(row_hi & 7) * 128 + ((cc ^ (row_hi & 7)) << 4);
+                        float y[VE];
+#pragma unroll
+                        for (int e = 0; e < VE; ++e) y[e] = (float)((double)xv[u][e] * inv);
+                        if (KIND == 1) {
+                            *reinterpret_cast<float4*>(p_hi) = make_float4(y[0], y[1], y[2], y[3]);
+                        } else {
+                            uint32_t hw[4], lw[4];
+#pragma unroll
+                            for (int e = 0; e < VE; e += 2) {
+                                uint16_t hb[2], lb[2];
+#pragma unroll
+                                for (int t2 = 0; t2 < 2; ++t2) {
+                                    if (a.dt == 1) {
+                                        const __nv_bfloat16 hi = __float2bfloat16_rn(y[e + t2]);
+                                        const float rest = y[e + t2] - __bfloat162float(hi);             // exact
+                                        const __nv_bfloat16 lo = SPLIT ? __float2bfloat16_rn(rest) : __float2bfloat16_rn(0.f);
+                                        hb[t2] = __bfloat16_as_ushort(hi); lb[t2] = __bfloat16_as_ushort(lo);
+                                    } else {
+                                        const __half hi = __float2half_rn(y[e + t2]);
+                                        const float rest = y[e + t2] - __half2float(hi);
+                                        const __half lo = SPLIT ? __float2half_rn(rest) : __float2half_rn(0.f);
+                                        hb[t2] = __half_as_ushort(hi); lb[t2] = __half_as_ushort(lo);
+                                    }
+                                }
+                                hw[e >> 1] = (uint32_t)hb[0] | ((uint32_t)hb[1] << 16);
+                                lw[e >> 1] = (uint32_t)lb[0] | ((uint32_t)lb[1] << 16);
+                            }
+                            *reinterpret_cast<uint4*>(p_hi) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                            // the lo row is 8 MMA columns further: same position inside the next 8-row group (+1024 bytes)
+                            if (SPLIT) *reinterpret_cast<uint4*>(p_hi + 1024) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        }
+                    }
                 }
             }
-            if (jq >= 0 && d2 != 0.f) atomicAdd(d2_s + jq, d2);
+        } else {
+            constexpr int KE = KIND == 1 ? 32 : 64;               // elements per 128-byte k-block
+            constexpr int UB = 8;
+            const int upq = (a.dim + kFThreads - 1) / kFThreads;  // units per query
+            const int units = nq * upq;
+            for (int u0 = 0; u0 < units; u0 += UB) {
+                float xv[UB];
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int un = u0 + u, j = un / upq, i = (un - j * upq) * kFThreads + tid;
+                    xv[u] = (un < units && i < a.dim) ? __ldg(a.q + (size_t)j * a.dim + i) : 0.0f;
+                }
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int un = u0 + u;
+                    if (un >= units) break;                         // block-uniform
+                    const int j = un / upq, i = (un - j * upq) * kFThreads + tid;
+                    if (i < a.dim) {
+                        const float y = (float)((double)xv[u] * inv_s[j]);
+                        const int row_hi = SPLIT ? (j >> 3) * 16 + (j & 7) : j;
+                        const int kb = i / KE, c = (i % KE) * esz;
+                        uint8_t* p_hi = fsm + (size_t)kb * QTILE + (size_t)(row_hi >> 3) * 1024 + (size_t)(row_hi & 7) * 128 + ((((c >> 4) ^ (row_hi & 7)) << 4) | (c & 15));
+                        if (KIND == 1) {
+                            *reinterpret_cast<float*>(p_hi) = y;
+                        } else {
+                            // the lo row is 8 MMA columns further: same position inside the next 8-row group (+1024 bytes)
+                            uint8_t* p_lo = p_hi + 1024;
+                            if (a.dt == 1) {
+                                const __nv_bfloat16 hi = __float2bfloat16_rn(y);
+                                const float rest = y - __bfloat162float(hi);        // exact
+                                const __nv_bfloat16 lo = SPLIT ? __float2bfloat16_rn(rest) : __float2bfloat16_rn(0.f);
+                                *reinterpret_cast<__nv_bfloat16*>(p_hi) = hi;
+                                if (SPLIT) *reinterpret_cast<__nv_bfloat16*>(p_lo) = lo;
+                            } else {
+                                const __half hi = __float2half_rn(y);
+                                const float rest = y - __half2float(hi);
+                                const __half lo = SPLIT ? __float2half_rn(rest) : __float2half_rn(0.f);
+                                *reinterpret_cast<__half*>(p_hi) = hi;
+                                if (SPLIT) *reinterpret_cast<__half*>(p_lo) = lo;
+                            }
+                        }
+                    }
+                }
+            }
         }
         __syncthreads();
-        // |approx - exact| <= |q - hi - lo|_2 * max |stored row|_2 (<= 1 + 2^-8) + the accumulation allowance
-        for (int j = tid; j < nq; j += kFThreads)
-            eps_s[j] = a.eps_const + (KIND == 1 ? 0.0f : __fmul_ru(__fsqrt_ru(d2_s[j]), 1.0078125f * 1.001f) + 1e-9f);
+        // |approx - exact| <= |q - hi - lo|_2 * max |stored row|_2 + the accumulation allowance.  The residual is bounded a
+        // priori, element by element (round to nearest: half an ulp): bf16 keeps 8 significant bits, so |q - hi| <= 2^-9 |q|
+        // and |q - hi - lo| <= 2^-18 |q|; fp16 keeps 11 (2^-12, 2^-24) but loses relative accuracy below 2^-14, where the
+        // spacing is 2^-24: at most 2^-25 more per element.  |q|_2 <= 1 + 2^-22 and |row|_2 <= 1 + 2^-8: factor 1.0078125.
+        {
+            float eq = 0.f;
+            if (KIND != 1) {
+                const float rel = a.dt == 1 ? (SPLIT ? 3.814697265625e-06f : 1.953125e-03f) : (SPLIT ? 5.9604644775390625e-08f : 2.44140625e-04f);
+                const float sub = a.dt == 1 ? 0.f : __fmul_ru(__fsqrt_ru((float)a.ld), 2.98023223876953125e-08f);
+                eq = __fmul_ru(__fadd_ru(rel, sub), 1.0078125f);
+            }
+            for (int j = tid; j < nq; j += kFThreads) eps_s[j] = __fadd_ru(a.eps_const, eq);
+        }
         __syncthreads();
-        for (int i = tid; i < 3 * kFMaxQ + 2; i += kFThreads) pend[i] = 0u;   // the parking area goes back to the pending lists
+        for (int i = tid; i < 2 * kFMaxQ + 2; i += kFThreads) pend[i] = 0u;   // the parking area goes back to the pending lists
         fence_proxy_async_smem();   // generic-proxy writes above -> visible to the tensor core's async-proxy reads
         __syncthreads();
         if (blockIdx.x == 0 && tid == 0) a.ctl->t[1] = global_ns();
@@ -698,30 +781,75 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
         __syncthreads();
         const uint32_t m32 = __ldcg(a.ctl->cnt + qi);
         if (tid == 0) { a.ctl->last_cnt[qi] = m32; a.ctl->last_resc[qi] = 0xFFFFFFFFu; }
+        if (stamp && qi == 0) a.ctl->t[10] = global_ns();
         const int keff = a.keff;
         const u64* in = a.cand + (size_t)qi * a.cap;
         bool exact_scan = m32 > (uint32_t)a.cap || (int)m32 < keff;   // block-uniform
         if (!exact_scan && keff > 0) {
             const int m = (int)m32;
-            constexpr int kSmallM = 2048;
+            constexpr int kSmallM = 8192;
             if (m <= kSmallM && sel_cap >= 2 * kSmallM) {
-                // the usual case (a few hundred keys): stage them in shared memory once; one warp finds T = keff-th largest
-                // approximate score by bisection on the value bits (a warp reduction per bit), everybody gathers
+                // the usual case (a few hundred to a few thousand keys): stage them in shared memory once, then T = keff-th
+                // largest approximate score by a 4-pass radix select over the ordered score bits (256-bin shared histogram)
                 u64* stg = sel + (sel_cap - kSmallM);
                 for (int i = tid; i < m; i += kFThreads) stg[i] = __ldcg(in + i);
+                if (tid == 0) { s3[0] = 0u; s3[2] = (uint32_t)keff; }
                 __syncthreads();
-                if (warp == 0) {
-                    uint32_t T = 0u;
-#pragma unroll 1
-                    for (int bit = 31; bit >= 0; --bit) {
-                        const uint32_t cand = T | (1u << bit);
-                        int c = 0;
-                        for (int i = lane; i < m; i += kWarp) c += (uint32_t)(stg[i] >> 32) >= cand;
-                        if (__reduce_add_sync(kFull, c) >= keff) T = cand;
+                if (stamp && qi == 0) a.ctl->t[11] = global_ns();
+                if (m <= 2 * kFThreads) {
+                    // a couple of hundred keys (k = 10): count, for one or two keys per thread, the scores above / not below
+                    // it (broadcast reads); the key with #above < keff <= #not-below carries T
+                    uint32_t mine[2];
+                    int gt[2] = {0, 0}, ge[2] = {0, 0};
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) mine[u] = tid + u * kFThreads < m ? (uint32_t)(stg[tid + u * kFThreads] >> 32) : 0xFFFFFFFFu;
+                    for (int i = 0; i < m; ++i) {
+                        const uint32_t o = (uint32_t)(stg[i] >> 32);
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) { gt[u] += o > mine[u]; ge[u] += o >= mine[u]; }
                     }
-                    if (lane == 0) s3[0] = T;
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+                        if (tid + u * kFThreads < m && gt[u] < keff && ge[u] >= keff) s3[0] = mine[u];   // every writer holds the same value
+                    __syncthreads();
+                } else
+#pragma unroll 1
+                for (int shift = 24; shift >= 0; shift -= 8) {
+                    const uint32_t prefix = s3[0], want = s3[2];
+                    for (int i = tid; i < 256; i += kFThreads) hist[i] = 0u;
+                    __syncthreads();
+                    for (int i0 = warp * kWarp; i0 < m; i0 += kFThreads) {     // warp-uniform trip count
+                        const int i = i0 + lane;
+                        const uint32_t hsc = i < m ? (uint32_t)(stg[i] >> 32) : 0u;
+                        const bool in = i < m && (shift == 24 || (hsc >> (shift + 8)) == (prefix >> (shift + 8)));
+                        // scores of one query share their leading bytes: aggregate equal digits inside the warp, one atomic each
+                        const unsigned same = __match_any_sync(kFull, in ? (int)((hsc >> shift) & 255u) : -1);
+                        if (in && lane == __ffs(same) - 1) atomicAdd(&hist[(hsc >> shift) & 255u], (uint32_t)__popc(same));
+                    }
+                    __syncthreads();
+                    if (warp == 0) {   // bin (from the top) in which the cumulative count reaches `want`; lane l owns bins 255-8l .. 248-8l
+                        uint32_t c[8], sum = 0;
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) { c[b] = hist[255 - 8 * lane - b]; sum += c[b]; }
+                        uint32_t incl = sum;
+#pragma unroll
+                        for (int off = 1; off < 32; off <<= 1) {
+                            const uint32_t o = __shfl_up_sync(kFull, incl, off);
+                            if (lane >= off) incl += o;
+                        }
+                        const uint32_t before = incl - sum;
+                        if (before < want && incl >= want) {          // exactly one lane
+                            uint32_t run = before;
+#pragma unroll
+                            for (int b = 0; b < 8; ++b) {
+                                if (run < want && run + c[b] >= want) { s3[0] = prefix | ((uint32_t)(255 - 8 * lane - b) << shift); s3[2] = want - run; }
+                                run += c[b];
+                            }
+                        }
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
+                if (stamp && qi == 0) a.ctl->t[12] = global_ns();
                 const float cut = thr_below(ordered_to_float(s3[0]), eps_s[qi]);
                 for (int i = tid; i < m; i += kFThreads) {
                     const u64 key = stg[i];

@@ -247,7 +247,7 @@ class Index:
     def fused_times(self):
         """Phase stamps of the last one-kernel search (us since kernel start): start, prologue, first tile, sweep end (CTA 0);
         all arrived, selected, rescored, emitted (finalizer of query 0)."""
-        t = np.zeros(8, np.int64)
+        t = np.zeros(16, np.int64)
         _lib.check(self._L.ragfin_debug_fused_times(self._h, t.ctypes.data))
         return (t / 1e3).round(1).tolist()
 

@@ -8,7 +8,7 @@ for rows in (1_250_000, 10_000_000):
     idx = ragfin_b200.Index(768, "bf16", capacity=rows)
     for r in range(0, rows, 1_000_000):
         idx.add_synthetic(1234, r, min(1_000_000, rows - r))
-    for nq, k in ((1, 10), (16, 10), (64, 10), (1, 100), (16, 100)):
+    for nq, k in ((1, 10), (8, 10), (16, 10), (32, 10), (64, 10), (1, 100), (16, 100)):
         q = torch.from_numpy(synth_rows(1235, 0, nq, 768)).cuda()
         for _ in range(3):
             idx.search_device(q, k)

@@ -214,7 +214,7 @@ def test_config2_1m_f32_1024_queries(coracle):
 
 
 def test_full_size_one_kernel_search(corpus, coracle):
-    """The default path for <= 64 queries (csrc/sweep_fused.cuh) at BASELINE's full size: batches of 1, 8, 16, 33 and 64
+    """The default path for <= 32 queries (csrc/sweep_fused.cuh) at BASELINE's full size: batches of 1, 8, 16 and 32
     queries, k = 10 and 100, bit-identical to the multi-kernel tensor-core path (itself pinned above), no in-kernel
     exact scan, needles first."""
     idx, q = corpus
@@ -223,7 +223,7 @@ def test_full_size_one_kernel_search(corpus, coracle):
     ref100 = idx.search(q[:16], 100)
     idx.set_fused(True)
     try:
-        for nq in (1, 8, 16, 33, 64):
+        for nq in (1, 8, 16, 32):
             ids, sc = idx.search(q[:nq], K)
             st = idx.stats()
             assert st["path"] == 3 and st["launches"] == 1 and st["queries_rescanned"] == 0, (nq, st)
