@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--cpu-rows", type=int, default=0,
                     help="rows of the CPU baseline sample (0 = the whole corpus when MemAvailable >= 1.3 x rows*dim*4, else 2M rows, extrapolated)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-regimes", action="store_true", help="skip the clustered-corpus and ingest legs")
     return ap.parse_args()
 
 
@@ -509,12 +510,133 @@ def run_ours(a):
                        "shard) first with their global id, no row of a 200k-row oracle-scored sample beats the k-th hit; "
                        "result hash equal on every rank"}
 
+    def ingest_leg():
+        """K1 (L2-normalise + cast at ingest, "chunking_storing (1).py":379-396) on one rank: rows/s and GB/s of
+        4 * dim (fp32 read) + esize * ld (stored write) bytes per row, kernel time from the library's events.
+        device: source already in HBM (the N2 device feed); host: pinned source through the double-buffered staging."""
+        if rank != 0:
+            return None
+        n_dev, n_host = 2_000_000, 500_000
+        per_row = 4 * a.dim + esize * ld
+        out = {"bytes_per_row": per_row, "kernel": "ingest_vec_kernel" if a.dim % 4 == 0 and ld <= 1024 else "ingest_kernel"}
+        src = torch.randn((n_dev, a.dim), dtype=torch.float32, device=dev)
+        tmp = ragfin_b200.Index(a.dim, a.dtype, capacity=3 * n_dev, device=local)
+        tmp.add(src)                                    # warm-up (first launch, clocks)
+        tmp.profile(True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            tmp.add(src)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        kms, kn = tmp.profile_read()
+        tmp.profile(False)
+        out["device"] = {"rows": 2 * n_dev, "kernel_ms": kms, "launches": kn, "gbps": 2 * n_dev * per_row / (kms * 1e-3) / 1e9,
+                         "frac_of_hbm_peak": 2 * n_dev * per_row / (kms * 1e-3) / 1e9 / peaks["hbm"], "rows_per_s": 2 * n_dev / (kms * 1e-3),
+                         "wall_ms_through_the_api": wall * 1e3}
+        tmp.close()
+        del src
+        hsrc = torch.randn((n_host, a.dim), dtype=torch.float32).pin_memory()
+        tmp = ragfin_b200.Index(a.dim, a.dtype, capacity=2 * n_host, device=local)
+        tmp.add(hsrc.numpy())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tmp.add(hsrc.numpy())
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        out["host"] = {"rows": n_host, "wall_ms": wall * 1e3, "h2d_gbps": n_host * a.dim * 4 / wall / 1e9, "rows_per_s": n_host / wall,
+                       "note": "pinned host source, H2D of slice i + 1 overlaps K1 on slice i (PCIe-bound)"}
+        tmp.close()
+        return out
+
+    def clustered_leg(batch, iid_ms):
+        """The same search over a corpus with the structure of templated text (the reference's chunks are templates filled
+        with each quarter's figures): contiguous runs of `topic_rows` near-duplicate rows in topic order
+        (ragfin_add_synthetic_topics), queries aimed at single topics.  A strided sample never sees the topic, thousands of
+        rows sit within a hair of the k-th score: the case that sends a static-threshold design to its exact fallback."""
+        from oracle import c_oracle
+        from ragfin_b200.synthetic import synth_topic_rows
+        topic_rows, shift, seed = 16384, 3, SEED_CORPUS + 77
+        cidx = ragfin_b200.Index(a.dim, a.dtype, capacity=max(n_local, 1), device=local)
+        for r in range(0, n_local, 1_000_000):
+            cidx.add_synthetic_topics(seed, row0 + r, min(1_000_000, n_local - r), topic_rows, shift)
+        cidx.set_id_base(row0)
+        csearch = ShardedSearcher.for_index(cidx)
+        rows_fn = lambda sd, r0, m, d: c_oracle.synth_rows(sd, r0, m, d)
+        nb = 8
+        n_topics = max(1, a.rows // topic_rows)
+        targets = [((2 * i + 1) * n_topics // (2 * nb * batch)) % n_topics for i in range(nb * batch)]     # spread over the corpus (every shard)
+        from ragfin_b200.synthetic import TOPIC_SEED_OFFSET
+        # a query = its topic's centre + fresh noise at twice the corpus amplitude (not a copy of any row)
+        qh = np.concatenate([c_oracle.synth_rows(seed + TOPIC_SEED_OFFSET, t, 1, a.dim) +
+                             c_oracle.synth_rows(seed + 4242, i, 1, a.dim) * np.float32(2.0 ** -(shift - 1)) for i, t in enumerate(targets)]).astype(np.float32)
+        qd = torch.from_numpy(qh).to(dev).view(nb, batch, a.dim)
+        steps = max(10, min(a.steps, 50))
+        for i in range(3):
+            csearch.search(qd[i % nb], a.k)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(steps):
+            csearch.search(qd[i % nb], a.k)
+        ev1.record()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item()) / steps
+        resc, appended = 0, []
+        results = []
+        for i in range(nb):
+            ids, sc = csearch.search(qd[i], a.k)
+            torch.cuda.synchronize()
+            st = cidx.stats()
+            resc += max(0, st["queries_rescanned"])
+            if st["path"] == 3:
+                appended += cidx.fused_counts(batch)[0].tolist()
+            results.append((ids.cpu().numpy(), sc.cpu().numpy()))
+        t = torch.tensor([resc], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        resc = int(t.item())
+        out = None
+        if rank == 0:
+            fails, checked = [], 0
+            for i, (ids, sc) in enumerate(results):
+                qhat = c_oracle.normalize_rows(qh[i * batch:(i + 1) * batch], "f32")
+                for j in range(min(batch, 4)):
+                    t_q = targets[i * batch + j]
+                    i_, s_ = ids[j], sc[j]
+                    checked += 1
+                    if not all(s_[x] > s_[x + 1] or (s_[x] == s_[x + 1] and i_[x] < i_[x + 1]) for x in range(a.k - 1)):
+                        fails.append(f"q{i}.{j}: order")
+                    # the whole target topic, rebuilt on the host and scored by the oracle: its top-k IS the answer
+                    blk = c_oracle.normalize_rows(synth_topic_rows(seed, t_q * topic_rows, min(topic_rows, a.rows - t_q * topic_rows), a.dim, topic_rows, shift, rows_fn), a.dtype)
+                    ssc = c_oracle.exact_scores(blk, qhat[j])
+                    order = np.lexsort((np.arange(len(ssc)), -ssc.astype(np.float64)))[:a.k]
+                    want_ids = order + t_q * topic_rows
+                    if not (np.array_equal(i_, want_ids) and np.array_equal(s_.view(np.uint32), ssc[order].view(np.uint32))):
+                        fails.append(f"q{i}.{j}: differs from the oracle's top-k of topic {t_q}")
+            out = {"ms_per_step": ms, "value": batch / (ms * 1e-3), "unit": "queries/s", "batch": batch, "steps": steps,
+                   "vs_iid_time": ms / iid_ms, "queries_rescanned": resc,
+                   "rows_appended_per_query": {"mean": float(np.mean(appended)) if appended else None, "max": int(max(appended)) if appended else None},
+                   "corpus": f"{a.rows} rows in runs of {topic_rows} near-duplicates (centre + noise / {2 ** shift}; cosine ~0.98 inside a run), topic order",
+                   "queries": "one topic each (its centre + noise / %d), topics spread over every shard" % 2 ** (shift - 1),
+                   "parity_check": {"ok": not fails, "queries": checked, "failures": fails[:5],
+                                    "how": "ids and score bits equal to the oracle's exact top-k over the query's whole topic (16384 rows rebuilt on the host)"}}
+        if csearch.exchange is not None:
+            csearch.exchange.close()
+        cidx.close()
+        return out
+
     main = measure_checked(a.batch, a.steps, a.warmup)
     main["parity_check"] = parity_check(a.batch)
     other = None
     if a.also_batch and a.also_batch != a.batch:
         other = measure_checked(a.also_batch, max(5, a.steps // 10), a.warmup)
         other["parity_check"] = parity_check(a.also_batch)
+    clustered = clustered_leg(a.batch, main["ms_per_step"]) if not a.no_extra_regimes else None
+    ingest = ingest_leg() if (world == 1 and not a.no_extra_regimes) else None
 
     if rank == 0:
         line = {
@@ -532,6 +654,10 @@ def run_ours(a):
         }
         if other is not None:
             line["regimes"] = {f"batch_{other['batch']}": other}
+        if clustered is not None:
+            line.setdefault("regimes", {})["clustered"] = clustered
+        if ingest is not None:
+            line.setdefault("regimes", {})["ingest"] = ingest
         if world == 1 and not a.no_cpu_baseline:
             del idx
             line["cpu_baseline"] = cpu_baseline(a, budget_s=15.0)[0]
