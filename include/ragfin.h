@@ -245,6 +245,8 @@ int ragfin_debug_fused_counts(ragfin_t* h, int32_t nq, int64_t* out_appended, in
  * done, sweep done}, finalizer of query 0 {all CTAs arrived, hits selected, rescored, emitted}, then finer stamps {setup done,
  * norms done, count read, keys staged, T found} (csrc/sweep_fused.cuh FusedCtl::t).  Synchronises. */
 int ragfin_debug_fused_times(ragfin_t* h, int64_t* out);
+/* Per-CTA diagnostics of the last one-kernel search (arrays of 160): final threshold of query 0, rows appended for it. */
+int ragfin_debug_fused_ctas(ragfin_t* h, float* out_thr, int32_t* out_app);
 
 /* Test hook: raw (approximate, fp32-accumulated) tensor-core scores of nq queries against every
  * stored row, out_scores_dev [nq, count] device memory.  Validates the TMA / tcgen05 plumbing. */

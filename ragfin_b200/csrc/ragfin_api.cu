@@ -1466,6 +1466,21 @@ extern "C" int ragfin_debug_fused_times(ragfin_t* h, int64_t* out) {
     return RAGFIN_OK;
 }
 
+// Per-CTA diagnostics of the last one-kernel search: final threshold of query 0 and rows appended for it (out arrays of 160).
+extern "C" int ragfin_debug_fused_ctas(ragfin_t* h, float* out_thr, int32_t* out_app) {
+    if (!h || !out_thr || !out_app) return fail(RAGFIN_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    if (!h->fctl.p) return fail(RAGFIN_EINVAL, "no one-kernel search has run on this handle");
+    CU_TRY(cudaDeviceSynchronize());
+    FusedCtl* c = new FusedCtl;
+    cudaError_t e = cudaMemcpy(c, h->fctl.p, sizeof(*c), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) for (int i = 0; i < 160; ++i) { out_thr[i] = c->cta_thr[i]; out_app[i] = (int32_t)c->cta_app[i]; }
+    delete c;
+    CU_TRY(e);
+    return RAGFIN_OK;
+}
+
 extern "C" int ragfin_debug_fused_counts(ragfin_t* h, int32_t nq, int64_t* out_appended, int64_t* out_rescored) {
     if (!h || !out_appended || !out_rescored || nq < 1 || nq > kFMaxQ) return fail(RAGFIN_EINVAL, "bad argument");
     std::lock_guard<std::mutex> lk(h->mu);

@@ -44,12 +44,16 @@ constexpr int kObsStride = kGN + 1;   // ... [kObsQ][256 (+1: bank spread)] orde
 
 struct FusedCtl {
     uint32_t cnt[kFMaxQ];     // rows appended per query (may exceed cap: overflow)
-    uint32_t gthr[kFMaxQ][kFGroups];   // published bounds per (query, CTA group), float_to_ordered (0 = none yet)
+    uint32_t gthr[kFMaxQ][kFGroups + 1];   // published bounds per query, float_to_ordered (0 = none yet): one word per CTA group
+                                           // (each CTA's ceil(k / G)-th best) and, in slot kFGroups, the best FULL bound of any CTA
+                                           // (its own k-th best): on clustered data one CTA holds the whole answer
     uint32_t done;            // CTAs that have finished their sweep
     uint32_t obs_done;        // CTAs that have observed their first tile and published its bound
     uint32_t fin_done;        // finalizing CTAs that have finished
     uint32_t last_cnt[kFMaxQ];   // diagnostics of the last search: rows appended per query ...
     uint32_t last_resc[kFMaxQ];  // ... and rows rescored exactly (0xFFFFFFFF: the query took the exact scan)
+    float cta_thr[160];          // diagnostics: every CTA's final threshold of query 0 ...
+    uint32_t cta_app[160];       // ... and the rows it appended for query 0
     unsigned long long t[16];    // globaltimer stamps of the last search (ns): CTA 0: start, prologue done, first tile done,
                                  // sweep done; finalizer of query 0: all CTAs arrived, hits selected, rescored, emitted;
                                  // [8..]: finer stamps (setup done, norms done; count read, keys staged, T found)
@@ -98,7 +102,7 @@ __host__ __device__ constexpr size_t fused_pend_words(int nq, int pend) {
     return (size_t)nq * pend > (size_t)kObsQ * kObsStride ? (size_t)nq * pend : (size_t)kObsQ * kObsStride;
 }
 __host__ __device__ constexpr size_t fused_state_bytes(int nq, int k, int pend) {
-    return (size_t)5 * kFMaxQ * 4 + ((size_t)nq * k + fused_pend_words(nq, pend)) * 4 + 64;
+    return (size_t)6 * kFMaxQ * 4 + ((size_t)nq * k + fused_pend_words(nq, pend)) * 4 + 64;
 }
 __host__ __device__ constexpr size_t fused_smem_bytes(int num_kblocks, int ncol, int stages, int nq, int k, int pend) {
     return 1024 + (size_t)num_kblocks * ncol * kGKBytes + (size_t)stages * kBBytes + 256 + fused_state_bytes(nq, k, pend);
@@ -160,13 +164,15 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
     auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kRMaxStages + 2 + s); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRMaxStages + 4);
     uint32_t* s_ticket = tmem_slot + 1;
+    int* s_app = reinterpret_cast<int*>(tmem_slot + 2);    // diagnostics: rows this CTA appended for query 0
     // per-query threshold state
     float* thr_s = reinterpret_cast<float*>(fsm + region_bytes + 256);     // [kFMaxQ]
     float* eps_s = thr_s + kFMaxQ;                                          // [kFMaxQ]
     int* scnt = reinterpret_cast<int*>(eps_s + kFMaxQ);                     // [kFMaxQ] entries of sorted[q]
     int* pcnt = scnt + kFMaxQ;                                              // [kFMaxQ] entries appended to pend[q] this tile
     uint32_t* pub_s = reinterpret_cast<uint32_t*>(pcnt + kFMaxQ);           // [kFMaxQ] what this CTA last published for the query
-    uint32_t* sorted = pub_s + kFMaxQ;                                      // [nq][k] descending ordered-uint scores
+    uint32_t* pubf_s = pub_s + kFMaxQ;                                      // [kFMaxQ] ... and its last published full bound
+    uint32_t* sorted = pubf_s + kFMaxQ;                                     // [nq][k] descending ordered-uint scores
     uint32_t* pend = sorted + (size_t)nq * k;                               // [nq][pend]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -180,7 +186,8 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < kFMaxQ; i += kFThreads) { thr_s[i] = i < nq ? -INFINITY : INFINITY; eps_s[i] = 0.f; scnt[i] = 0; pcnt[i] = 0; pub_s[i] = 0u; }
+    for (int i = tid; i < kFMaxQ; i += kFThreads) { thr_s[i] = i < nq ? -INFINITY : INFINITY; eps_s[i] = 0.f; scnt[i] = 0; pcnt[i] = 0; pub_s[i] = 0u; pubf_s[i] = 0u; }
+    if (tid == 0) *s_app = 0;
     if (blockIdx.x == 0 && tid == 0) *a.flag_count = 0;   // ordered before every finalizer's atomicAdd by the arrival counter
     tc_fence_before();
     __syncthreads();
@@ -524,6 +531,12 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                 const int q = ew + 8 * it + 4 * half;              // this half-warp's query of step `it` (may be >= nq)
                 gw[it] = (q < nq && gl < a.groups) ? __ldcg(&a.ctl->gthr[q][gl]) : 0xFFFFFFFFu;
             }
+            uint32_t gfull[kFMaxQ / 8];                            // the best full bound any CTA has published (lanes 0 / 16)
+#pragma unroll
+            for (int it = 0; it < kFMaxQ / 8; ++it) {
+                const int q = ew + 8 * it + 4 * half;
+                gfull[it] = (q < nq && gl == 0) ? __ldcg(&a.ctl->gthr[q][kFGroups]) : 0u;
+            }
 #pragma unroll
             for (int it = 0; it < kFMaxQ / 8; ++it) {
                 const int q = ew + 8 * it + 4 * half;
@@ -536,7 +549,13 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                     const int n = scnt[q];
                     const float e = eps_s[q];
                     float nt = thr_s[q];
-                    if (n >= a.keff && a.keff > 0) nt = fmaxf(nt, thr_below(ordered_to_float(sl_[a.keff - 1]), e));
+                    if (n >= a.keff && a.keff > 0) {
+                        const float own = thr_below(ordered_to_float(sl_[a.keff - 1]), e);
+                        nt = fmaxf(nt, own);
+                        const uint32_t po = float_to_ordered(own);
+                        if (po > gfull[it] && po > pubf_s[q]) { pubf_s[q] = po; atomicMax(&a.ctl->gthr[q][kFGroups], po); }
+                    }
+                    if (gfull[it] != 0u) nt = fmaxf(nt, ordered_to_float(gfull[it]));
                     if (n >= a.grank && a.grank > 0) {
                         const uint32_t pv = float_to_ordered(thr_below(ordered_to_float(sl_[a.grank - 1]), e));
                         if (pv > pub_s[q]) { pub_s[q] = pv; atomicMax(&a.ctl->gthr[q][my_group], pv); __threadfence(); }
@@ -614,6 +633,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                             for (int j = 0; j < QPC; ++j) {
                                 const int qi = c * QPC + j;
                                 if (sc[j] >= thr_s[qi]) {              // shared-memory broadcast; padding queries hold +inf
+                                    if (qi == 0) atomicAdd(s_app, 1);
                                     const uint32_t pos = atomicAdd(a.ctl->cnt + qi, 1u);
                                     if (pos < (uint32_t)a.cap) a.cand[(size_t)qi * a.cap + pos] = make_key(sc[j] + 0.0f, (uint32_t)row);
                                     if (!warm) {                       // the first tile's scores are already in the sorted list
@@ -652,6 +672,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
         }
         __threadfence();   // this thread's appended keys are visible device-wide before the CTA is counted as done
         if (blockIdx.x == 0 && et == 0) a.ctl->t[3] = global_ns();
+        if (et == 0 && blockIdx.x < 160) { a.ctl->cta_thr[blockIdx.x] = thr_s[0]; a.ctl->cta_app[blockIdx.x] = (uint32_t)*s_app; }
     }
     tc_fence_before();
     __syncthreads();
@@ -935,7 +956,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
         }
         __syncthreads();
         if (tid == 0) a.ctl->cnt[qi] = 0u;                             // leave the control block clean for the next search
-        if (tid < kFGroups) a.ctl->gthr[qi][tid] = 0u;
+        if (tid <= kFGroups) a.ctl->gthr[qi][tid] = 0u;
     }
     if (tid == 0) {
         __threadfence();

@@ -244,6 +244,12 @@ class Index:
         _lib.check(self._L.ragfin_debug_fused_counts(self._h, int(nq), a.ctypes.data, r.ctypes.data))
         return a, r
 
+    def fused_ctas(self):
+        """Per-CTA diagnostics of the last one-kernel search: (final threshold of query 0, rows appended for it), 160 slots."""
+        t, c = np.zeros(160, np.float32), np.zeros(160, np.int32)
+        _lib.check(self._L.ragfin_debug_fused_ctas(self._h, t.ctypes.data, c.ctypes.data))
+        return t, c
+
     def fused_times(self):
         """Phase stamps of the last one-kernel search (us since kernel start): start, prologue, first tile, sweep end (CTA 0);
         all arrived, selected, rescored, emitted (finalizer of query 0)."""
