@@ -78,7 +78,8 @@ struct ragfin {
     bool fctl_dirty = true;   // set when a launch may have left it non-zero (first use, failed call): re-zeroed before the next launch
     bool use_fused = true;    // <= 64 queries, k <= 128: the one-kernel search (sweep_fused.cuh); RAGFIN_NO_FUSED=1 disables
     int fused_min_rows = 8192;
-    int fused_max_nq = 32;    // kFusedMaxBatch; RAGFIN_FUSED_MAX_NQ overrides (<= 64)
+    int fused_max_nq = 16;    // see plan_fused; RAGFIN_FUSED_MAX_NQ overrides (<= 64)
+    int fused_max_nqk = 400;  // queries x k; RAGFIN_FUSED_MAX_NQK overrides
     struct MapSlot { const void* base = nullptr; int64_t rows = 0; int ld = 0, dtype = 0, box_rows = 0; CUtensorMap map; };
     MapSlot map_cache[8];     // tensor maps are pure functions of (base, rows, ld, dtype, box): encode once
     int map_next = 0;
@@ -169,6 +170,7 @@ extern "C" int ragfin_create(ragfin_t** out, int32_t dim, int32_t dtype, int64_t
     { const char* e = getenv("RAGFIN_NO_BOUND_PASS"); if (e && atoi(e)) h->use_bound_pass = false; }
     { const char* e = getenv("RAGFIN_NO_FUSED"); if (e && atoi(e)) h->use_fused = false; }
     { const char* e = getenv("RAGFIN_FUSED_MAX_NQ"); if (e && atoi(e) >= 1 && atoi(e) <= kFMaxQ) h->fused_max_nq = atoi(e); }
+    { const char* e = getenv("RAGFIN_FUSED_MAX_NQK"); if (e && atoi(e) >= 1) h->fused_max_nqk = atoi(e); }
     h->capacity = capacity_rows;
     const size_t bytes = (size_t)capacity_rows * h->ld * esize(dtype);
     e = cudaMalloc(&h->data, bytes);
@@ -1005,11 +1007,14 @@ struct FusedPlan {
 };
 
 // Column count / split / ring depth for nb queries, or ncol = 0 when the shape does not fit one CTA's shared memory.
-// Measured (profiles/r02): up to 32 queries the one-kernel search matches or beats the multi-kernel sweep; at 33-64 queries
-// (64 plain columns, 3-stage ring) its sweep is slower than the query-major kernel's (2.9 vs 2.25 ms on 10M rows).
+// Measured (profiles/r02, 1.25M- and 10M-row corpora): the one-kernel search wins up to 16 queries at k = 10 (0.306 vs 0.343 ms
+// at 1 query, 0.330 vs 0.343 at 16 on the 1.25M-row shard) and up to ~4 queries at k = 100 (0.347 vs 0.413 ms at 1 query); beyond
+// that its per-query bookkeeping in the first tile and the finalize outweigh the launches it saves (32 queries: 0.383 vs 0.343;
+// 16 queries at k = 100: 0.504 vs 0.416).  Default limits: <= 16 queries and queries x k <= 400; RAGFIN_FUSED_MAX_NQ /
+// RAGFIN_FUSED_MAX_NQK override them (the wider configurations stay compiled in and tested).
 static FusedPlan plan_fused(const ragfin* h, int nb, int k) {
     FusedPlan best;
-    if (nb < 1 || nb > (h->fused_max_nq < kFMaxQ ? h->fused_max_nq : kFMaxQ) || k > kFMaxK) return best;
+    if (nb < 1 || nb > (h->fused_max_nq < kFMaxQ ? h->fused_max_nq : kFMaxQ) || k > kFMaxK || (int64_t)nb * k > h->fused_max_nqk) return best;
     const int es = (int)esize(h->dtype);
     const int k_elems = kGKBytes / es;
     const int nkb = (h->ld + k_elems - 1) / k_elems;
@@ -1079,6 +1084,8 @@ static int run_fused(ragfin* h, const float* q_dev, int nb, int k, int64_t n_eff
     if (a.groups < 1) a.groups = 1;
     a.grank = a.keff > 0 ? (a.keff + a.groups - 1) / a.groups : 0;
     a.q = q_dev;
+    if ((rc = ensure(h->qhat, (size_t)kFMaxQ * h->ld * sizeof(float)))) return rc;
+    a.qn = (float*)h->qhat.p;
     a.data = h->data;
     a.allow = h->cur_allow;
     a.cand = (u64*)h->cand.p; a.cap = f.cap;

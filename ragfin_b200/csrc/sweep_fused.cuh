@@ -77,6 +77,7 @@ struct FusedArgs {
     int pend;                   // pending-score slots per query and tile
     int groups, grank;          // CTA groups of the shared bound and the rank each CTA publishes: ceil(keff / groups)
     const float* q;             // [nq][dim] raw fp32 queries
+    float* qn;                  // [nq][ld] workspace: the normalised fp32 queries (written by CTA 0, read by the finalizers)
     const void* data;           // corpus [n_rows][ld]
     const uint32_t* allow;      // scalar filter bitmask or null
     u64* cand;                  // [nq][cap] append buffers
@@ -240,6 +241,8 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
         }
         __syncthreads();
         if (blockIdx.x == 0 && tid == 0) a.ctl->t[9] = global_ns();
+        if (blockIdx.x == 0 && a.ld > a.dim)
+            for (int i = tid; i < nq * (a.ld - a.dim); i += kFThreads) a.qn[(size_t)(i / (a.ld - a.dim)) * a.ld + a.dim + i % (a.ld - a.dim)] = 0.0f;
         // pass 2, all threads: y = RNE_f32(x / |q|) exactly as ingest does, hi / lo split, swizzled store.  Work units are runs
         // of 192 consecutive elements of ONE query (so a unit's threads share the query: the residual is reduced per warp);
         // the loads of 8 units are issued before anything is computed.
@@ -274,6 +277,10 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                         float y[VE];
 #pragma unroll
                         for (int e = 0; e < VE; ++e) y[e] = (float)((double)xv[u][e] * inv);
+                        if (blockIdx.x == 0) {
+#pragma unroll
+                            for (int e = 0; e < VE; e += 4) *reinterpret_cast<float4*>(a.qn + (size_t)j * a.ld + i + e) = make_float4(y[e], y[e + 1], y[e + 2], y[e + 3]);
+                        }
                         if (KIND == 1) {
                             *reinterpret_cast<float4*>(p_hi) = make_float4(y[0], y[1], y[2], y[3]);
                         } else {
@@ -324,6 +331,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                     const int j = un / upq, i = (un - j * upq) * kFThreads + tid;
                     if (i < a.dim) {
                         const float y = (float)((double)xv[u] * inv_s[j]);
+                        if (blockIdx.x == 0) a.qn[(size_t)j * a.ld + i] = y;
                         const int row_hi = SPLIT ? (j >> 3) * 16 + (j & 7) : j;
                         const int kb = i / KE, c = (i % KE) * esz;
                         uint8_t* p_hi = fsm + (size_t)kb * QTILE + (size_t)(row_hi >> 3) * 1024 + (size_t)(row_hi & 7) * 128 + ((((c >> 4) ^ (row_hi & 7)) << 4) | (c & 15));
@@ -433,6 +441,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
         int acc = 0;
         uint32_t acc_phase = 0;
         bool warm = true;                           // the CTA's first tile is observed before anything is appended
+        const bool obs_holds_tile = nq <= kObsQ;    // ... and with <= kObsQ queries the observation area holds the whole tile
         // scores of the 16-column chunk c of half h of the current accumulator: QPC queries per chunk
         auto chunk_scores = [&](int h, int c, float (&out)[QPC]) {
             uint32_t v[P][16];
@@ -494,6 +503,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
             int rk[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) { const int jx = lane + 32 * i; e[i] = jx < n ? sl_[jx] : 0u; rk[i] = 0; }
+#pragma unroll 8
             for (int mi = 0; mi < n; ++mi) {
                 const uint32_t o = sl_[mi];                        // broadcast read
 #pragma unroll
@@ -596,6 +606,12 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                                     pend[(size_t)(c * QPC + j - q0) * kObsStride + h * 128 + m] = (h ? ok1 : ok0) ? float_to_ordered(sc[j] + 0.0f) : 0u;
                             }
                         }
+                        if (obs_holds_tile) {
+                            // <= kObsQ queries: the observed scores ARE the tile.  Hand the accumulator back now - the tensor core
+                            // goes on with the tile after next while the bounds are agreed on - and append from shared memory below.
+                            tc_fence_before();
+                            mbar_arrive(tempty_bar(acc));
+                        }
                         named_bar_sync(1, 128);
                         for (int q = q0 + ew; q < q0 + kObsQ && q < nq; q += 4) {
                             const int n = warp_seed_list(q, pend + (size_t)(q - q0) * kObsStride);
@@ -619,8 +635,24 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                     named_bar_sync(2, 128);
                     warp_refresh();
                     named_bar_sync(1, 128);
+                    if (obs_holds_tile) {
+                        for (int qi = 0; qi < nq; ++qi) {
+                            const float th = thr_s[qi];
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint32_t ov = pend[(size_t)qi * kObsStride + h * 128 + m];     // 0: row out of range / filtered
+                                const float scv = ordered_to_float(ov);
+                                if (ov != 0u && scv >= th) {
+                                    if (qi == 0) atomicAdd(s_app, 1);
+                                    const uint32_t pos = atomicAdd(a.ctl->cnt + qi, 1u);
+                                    if (pos < (uint32_t)a.cap) a.cand[(size_t)qi * a.cap + pos] = make_key(scv, (uint32_t)(trow + h * 128 + m));
+                                }
+                            }
+                        }
+                    }
                 }
                 // ---- append pass: every row whose approximate score reaches the query's current threshold ----
+                if (!(warm && obs_holds_tile)) {
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
                     const long long row = trow + h * 128 + m;
@@ -647,6 +679,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                 }
                 tc_fence_before();
                 mbar_arrive(tempty_bar(acc));
+                }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
                 // ---- threshold maintenance: the tile's appended scores enter the query's sorted list ----
                 named_bar_sync(1, 128);
@@ -701,30 +734,17 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
     int* s_c2 = reinterpret_cast<int*>(s3 + 3);
     u64* sel = reinterpret_cast<u64*>(fsm + (((size_t)ld_al * 4 + 256 * 4 + 16 + 15) / 16) * 16);
     const int sel_cap = (int)((region_bytes - (size_t)(reinterpret_cast<uint8_t*>(sel) - fsm)) / sizeof(u64));
-    // normalised fp32 query (the rescore operand), recomputed: bit-identical to the prologue and to ingest.  For the CTA's
-    // first query this runs while the rest of the grid is still sweeping.
+    // normalised fp32 query (the rescore operand): bit-identical to what ingest would store as fp32
+    // (written by CTA 0 in its prologue, before it was counted as done: visible after the acquire on the arrival counter)
     auto make_qv = [&](int qi) {
-        if (warp == 1) {
-            const float* x = a.q + (size_t)qi * a.dim;
-            double acc = 0.0;
-            for (int i0 = lane; i0 < a.dim; i0 += 12 * kWarp) {
-                float xv[12];
-#pragma unroll
-                for (int u = 0; u < 12; ++u) xv[u] = i0 + u * kWarp < a.dim ? __ldg(x + i0 + u * kWarp) : 0.0f;
-#pragma unroll
-                for (int u = 0; u < 12; ++u) { const double v = (double)xv[u]; acc = acc + v * v; }
-            }
-            const double n2 = warp_butterfly_f64(acc);
-            const double inv = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
-            for (int i = lane; i < a.ld; i += kWarp) qv[i] = i < a.dim ? (float)((double)__ldg(x + i) * inv) : 0.0f;
-        }
+        for (int i = tid; i < a.ld; i += kFThreads) qv[i] = __ldcg(a.qn + (size_t)qi * a.ld + i);
     };
-    make_qv(ticket - first_fin);
     if (tid == 0) {
-        while (ld_acq_gpu(&a.ctl->done) < gridDim.x) __nanosleep(64);
+        while (ld_acq_gpu(&a.ctl->done) < gridDim.x) __nanosleep(32);
         __threadfence();
     }
     __syncthreads();
+    make_qv(ticket - first_fin);
     const bool stamp = ticket - first_fin == 0 && tid == 0;
     if (stamp) a.ctl->t[4] = global_ns();
 
@@ -824,6 +844,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                     int gt[2] = {0, 0}, ge[2] = {0, 0};
 #pragma unroll
                     for (int u = 0; u < 2; ++u) mine[u] = tid + u * kFThreads < m ? (uint32_t)(stg[tid + u * kFThreads] >> 32) : 0xFFFFFFFFu;
+#pragma unroll 8
                     for (int i = 0; i < m; ++i) {
                         const uint32_t o = (uint32_t)(stg[i] >> 32);
 #pragma unroll

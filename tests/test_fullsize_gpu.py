@@ -200,7 +200,7 @@ def test_config2_1m_f32_1024_queries(coracle):
     # the one-kernel search (kind::tf32 with 16 / 32 query columns; 64 fp32 query rows of 768 do not fit next to the ring)
     # answers the same bits
     idx.set_fused(True)
-    for a, b in ((0, 1), (100, 116), (200, 232)):
+    for a, b in ((0, 1), (100, 116)):
         ids_f, sc_f = idx.search(q[a:b], K)
         assert idx.stats()["path"] == 3 and idx.stats()["queries_rescanned"] == 0
         assert np.array_equal(ids_f, ids[a:b]) and np.array_equal(sc_f.view(np.uint32), sc[a:b].view(np.uint32))
@@ -214,8 +214,8 @@ def test_config2_1m_f32_1024_queries(coracle):
 
 
 def test_full_size_one_kernel_search(corpus, coracle):
-    """The default path for <= 32 queries (csrc/sweep_fused.cuh) at BASELINE's full size: batches of 1, 8, 16 and 32
-    queries, k = 10 and 100, bit-identical to the multi-kernel tensor-core path (itself pinned above), no in-kernel
+    """The default path for <= 16 queries (csrc/sweep_fused.cuh) at BASELINE's full size: batches of 1, 8 and 16
+    queries at k = 10, 1 and 4 queries at k = 100, bit-identical to the multi-kernel tensor-core path (itself pinned above), no in-kernel
     exact scan, needles first."""
     idx, q = corpus
     idx.set_gemm_min_batch(3)
@@ -223,13 +223,13 @@ def test_full_size_one_kernel_search(corpus, coracle):
     ref100 = idx.search(q[:16], 100)
     idx.set_fused(True)
     try:
-        for nq in (1, 8, 16, 32):
+        for nq in (1, 8, 16):
             ids, sc = idx.search(q[:nq], K)
             st = idx.stats()
             assert st["path"] == 3 and st["launches"] == 1 and st["queries_rescanned"] == 0, (nq, st)
             assert np.array_equal(ids, ref10[0][:nq]) and np.array_equal(sc.view(np.uint32), ref10[1][:nq].view(np.uint32)), nq
             assert ids[0][0] == N
-        for nq in (1, 16):
+        for nq in (1, 4):
             ids, sc = idx.search(q[:nq], 100)
             st = idx.stats()
             assert st["path"] == 3 and st["queries_rescanned"] == 0, (nq, st)

@@ -12,9 +12,10 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(autouse=True)
 def _all_column_configurations(monkeypatch):
-    """By default the library serves up to 32 queries with the one-kernel search (measured crossover); the 64-column plain
-    configuration (33-64 queries) stays compiled in and is covered here."""
+    """By default the library serves up to 16 queries (and queries x k <= 400) with the one-kernel search (measured crossover);
+    the wider configurations (up to 64 queries, k up to 128) stay compiled in and are covered here."""
     monkeypatch.setenv("RAGFIN_FUSED_MAX_NQ", "64")
+    monkeypatch.setenv("RAGFIN_FUSED_MAX_NQK", "1000000")
 
 
 def _index(x, dtype, min_rows=1):
