@@ -9,6 +9,7 @@
 #include <mutex>
 #include <new>
 #include <utility>
+#include <vector>
 
 #include "../../include/ragfin.h"
 #include "kernels.cuh"
@@ -62,7 +63,7 @@ struct ragfin {
     bool is_view = false;  // ragfin_create_view: `data` belongs to another handle (read-only here, never freed here)
     std::mutex mu;
     // workspace (grow-only)
-    Buf qhat, q16, eps_q, gtau, bmax, acnt, athr, allow, bk_scores, bk_state, bk_keys, cand, cand_e, flags, stage_q, stage_ids, stage_scores, add_stage;
+    Buf qhat, q16, eps_q, gtau, bmax, acnt, athr, allow, bk_scores, bk_state, bk_keys, bk_rows, cand, cand_e, flags, stage_q, stage_ids, stage_scores, add_stage;
     int gemm_min_nq = 3;      // query batches of at least this many rows take the tcgen05 path (1-2: HBM-bound scan) ...
     int gemm_min_nq_large = 1;   // ... except on corpora of >= kSweepBytes, where the TMA-fed sweep wins from 1 query
     int gemm_cluster = 0;     // 0 = choose by batch size; 1, 2 or 4 = force
@@ -76,6 +77,7 @@ struct ragfin {
                               // 4 = 2-SM MMA pairs (cta_group::2) for >= 2 query tiles in append mode (gemm_pair.cuh)
     Buf fctl;                 // fused sweep: control block (FusedCtl), zero between searches
     bool fctl_dirty = true;   // set when a launch may have left it non-zero (first use, failed call): re-zeroed before the next launch
+    bool use_bigk_batched = true;   // k > 256: batched dump + select pipeline (RAGFIN_NO_BIGK_BATCHED=1: the one-query exact path)
     bool use_fused = true;    // <= 64 queries, k <= 128: the one-kernel search (sweep_fused.cuh); RAGFIN_NO_FUSED=1 disables
     int fused_min_rows = 8192;
     int fused_max_nq = 16;    // see plan_fused; RAGFIN_FUSED_MAX_NQ overrides (<= 64)
@@ -169,6 +171,7 @@ extern "C" int ragfin_create(ragfin_t** out, int32_t dim, int32_t dtype, int64_t
     h->num_sms = prop.multiProcessorCount;
     { const char* e = getenv("RAGFIN_NO_BOUND_PASS"); if (e && atoi(e)) h->use_bound_pass = false; }
     { const char* e = getenv("RAGFIN_NO_FUSED"); if (e && atoi(e)) h->use_fused = false; }
+    { const char* e = getenv("RAGFIN_NO_BIGK_BATCHED"); if (e && atoi(e)) h->use_bigk_batched = false; }
     { const char* e = getenv("RAGFIN_FUSED_MAX_NQ"); if (e && atoi(e) >= 1 && atoi(e) <= kFMaxQ) h->fused_max_nq = atoi(e); }
     { const char* e = getenv("RAGFIN_FUSED_MAX_NQK"); if (e && atoi(e) >= 1) h->fused_max_nqk = atoi(e); }
     h->capacity = capacity_rows;
@@ -221,7 +224,7 @@ extern "C" void ragfin_destroy(ragfin_t* h) {
     if (!h) return;
     DeviceGuard g(h->device);
     (void)cudaDeviceSynchronize();
-    Buf* bufs[] = {&h->qhat, &h->q16, &h->eps_q, &h->gtau, &h->bmax, &h->acnt, &h->athr, &h->allow, &h->bk_scores, &h->bk_state, &h->bk_keys, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage, &h->fctl};
+    Buf* bufs[] = {&h->qhat, &h->q16, &h->eps_q, &h->gtau, &h->bmax, &h->acnt, &h->athr, &h->allow, &h->bk_scores, &h->bk_state, &h->bk_keys, &h->bk_rows, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage, &h->fctl};
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->data && !h->is_view) cudaFree(h->data);
@@ -1159,6 +1162,83 @@ static int search_bigk(ragfin* h, const float* q_dev, int nq, int k, int64_t* ou
     return 0;
 }
 
+// Batched large-k path (bigk.cuh, second half): up to 16 queries per tensor-core sweep, approximate scores dumped, radix
+// select + compaction + exact rescore + rank sort per query with grid.y = query; ONE stream synchronisation at the end to
+// read the overflow flags (flagged queries - thousands of rows within 2 eps of the k-th score - take the exact one-query path).
+static const int kBigChunk = 16;
+static int search_bigk_batched(ragfin* h, const float* q_dev, int nq, int k, int64_t* out_ids, float* out_scores, cudaStream_t st) {
+    int rc;
+    const int64_t n = h->count;
+    const int64_t n_eff = h->cur_allow ? h->cur_allowed : n;
+    const int keff = (int)((int64_t)k < n_eff ? k : n_eff);
+    const int slack = keff / 4 > 4096 ? keff / 4 : 4096;
+    const int cmax = keff + slack;
+    h->stats.path = 2;
+    h->stats.cand_per_query = cmax;
+    h->stats.queries_rescanned = 0;
+    const int nbq = kGM;                                   // the sweep pads the query tile to 128 rows
+    if ((rc = ensure(h->qhat, (size_t)nbq * h->ld * sizeof(float)))) return rc;
+    if ((rc = ensure(h->eps_q, (size_t)nbq * sizeof(float))) || (rc = ensure(h->gtau, (size_t)nbq * sizeof(uint32_t)))) return rc;
+    if (h->dtype != 0 && (rc = ensure(h->q16, (size_t)nbq * h->ld * 2))) return rc;
+    if ((rc = ensure(h->flags, (size_t)(kMaxQueryBatch + 1) * sizeof(int)))) return rc;
+    if ((rc = ensure(h->bk_scores, (size_t)kBigChunk * n * sizeof(float)))) return rc;
+    if ((rc = ensure(h->bk_state, (size_t)nq * sizeof(BkState)))) return rc;
+    if ((rc = ensure(h->bk_rows, (size_t)kBigChunk * cmax * sizeof(uint32_t)))) return rc;
+    if ((rc = ensure(h->bk_keys, (size_t)kBigChunk * cmax * sizeof(u64)))) return rc;
+    float* qhat = (float*)h->qhat.p;
+    float* scores = (float*)h->bk_scores.p;
+    BkState* states = (BkState*)h->bk_state.p;
+    int* flag_count = (int*)h->flags.p + kMaxQueryBatch;
+    CU_TRY(cudaMemsetAsync(states, 0, (size_t)nq * sizeof(BkState), st));
+    const int blocks = h->num_sms * 8;
+    const float eps = eps_gemm_const(h->dtype, h->ld);
+    for (int q0 = 0; q0 < nq; q0 += kBigChunk) {
+        const int nb = nq - q0 < kBigChunk ? nq - q0 : kBigChunk;
+        const int wpb = 8, pblocks = (nbq + wpb - 1) / wpb;
+        const float* qsrc = q_dev + (size_t)q0 * h->dim;
+        switch (h->dtype) {
+            case 0: prep_queries_kernel<0><<<pblocks, wpb * 32, 0, st>>>(qsrc, nb, nbq, h->dim, h->ld, qhat, nullptr, (float*)h->eps_q.p, flag_count, (uint32_t*)h->gtau.p); break;
+            case 1: prep_queries_kernel<1><<<pblocks, wpb * 32, 0, st>>>(qsrc, nb, nbq, h->dim, h->ld, qhat, (__nv_bfloat16*)h->q16.p, (float*)h->eps_q.p, flag_count, (uint32_t*)h->gtau.p); break;
+            default: prep_queries_kernel<2><<<pblocks, wpb * 32, 0, st>>>(qsrc, nb, nbq, h->dim, h->ld, qhat, (__half*)h->q16.p, (float*)h->eps_q.p, flag_count, (uint32_t*)h->gtau.p); break;
+        }
+        CU_TRY(cudaGetLastError());
+        int G = 0;
+        bool ap = false;
+        if ((rc = run_gemm(h, nb, 10, 32, &G, &ap, scores, st, true))) return rc;        // MODE 1: approx[q][row]
+        BkState* stq = states + q0;
+        for (int pass = 0; pass < 4; ++pass)
+            bk_hist_kernel<<<dim3(blocks, nb), 256, 0, st>>>(scores, n, pass, keff, stq, h->cur_allow);
+        bk_compact_kernel<<<dim3(blocks, nb), 256, 0, st>>>(scores, n, keff, eps, (const float*)h->eps_q.p, stq, (uint32_t*)h->bk_rows.p, cmax, h->cur_allow);
+        const dim3 rg((cmax + 7) / 8, nb);
+        switch (h->dtype) {
+            case 0: bk_rescore_kernel<0><<<rg, 256, 0, st>>>(h->data, h->ld, qhat, stq, (const uint32_t*)h->bk_rows.p, cmax, (u64*)h->bk_keys.p); break;
+            case 1: bk_rescore_kernel<1><<<rg, 256, 0, st>>>(h->data, h->ld, qhat, stq, (const uint32_t*)h->bk_rows.p, cmax, (u64*)h->bk_keys.p); break;
+            default: bk_rescore_kernel<2><<<rg, 256, 0, st>>>(h->data, h->ld, qhat, stq, (const uint32_t*)h->bk_rows.p, cmax, (u64*)h->bk_keys.p); break;
+        }
+        const int span = cmax > k ? cmax : k;
+        bk_rank_sort_kernel<<<dim3((span + 255) / 256, nb), 256, 0, st>>>((const u64*)h->bk_keys.p, stq, cmax, k, keff, h->id_base,
+                                                                          out_ids + (size_t)q0 * k, out_scores + (size_t)q0 * k);
+        CU_TRY(cudaGetLastError());
+        h->stats.launches += 9;
+    }
+    // overflow flags: the one host round trip of this path
+    std::vector<BkState> host(nq);
+    CU_TRY(cudaMemcpyAsync(host.data(), states, (size_t)nq * sizeof(BkState), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    int redone = 0;
+    const int launches = h->stats.launches;
+    for (int q = 0; q < nq; ++q) {
+        if (!host[q].overflow) continue;
+        ++redone;
+        if ((rc = search_bigk(h, q_dev + (size_t)q * h->dim, 1, k, out_ids + (size_t)q * k, out_scores + (size_t)q * k, st))) return rc;
+    }
+    h->stats.path = 2;
+    h->stats.cand_per_query = cmax;
+    h->stats.queries_rescanned = redone;
+    h->stats.launches = launches + 20 * redone;
+    return 0;
+}
+
 static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* out_ids, float* out_scores,
                          cudaStream_t st) {
     int rc;
@@ -1179,7 +1259,11 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
     if (kp == 0 && n <= 256) kp = 256;   // every row is a candidate: any k (graph_cons.py:279 asks limit=1000 of 16 rows)
     const int min_nq_all = (size_t)n * h->ld * esize(h->dtype) >= kSweepBytes ? h->gemm_min_nq_large : h->gemm_min_nq;
     const bool ap = append_eligible(h, k) && nq >= min_nq_all;   // tensor-core append mode: no K' lists needed
-    if (kp == 0 && !ap) return search_bigk(h, q_dev, nq, k, out_ids, out_scores, st);
+    if (kp == 0 && !ap) {
+        // k beyond the list / append modes: batched dump + select on corpora worth a tensor-core sweep, else one query at a time
+        if (h->use_bigk_batched && n >= 4096 && gemm_rows_ok(h)) return search_bigk_batched(h, q_dev, nq, k, out_ids, out_scores, st);
+        return search_bigk(h, q_dev, nq, k, out_ids, out_scores, st);
+    }
     if (kp == 0) kp = 256;
     h->stats.cand_per_query = kp;
     int kpe = 32;                                          // tier-2 list length: a power of two (bitonic merges)

@@ -472,6 +472,48 @@ def test_large_k_matches_oracle(coracle, dtype, n, k, nq):
         assert (got[0][:, n:] == -1).all() and np.isneginf(got[1][:, n:]).all()
 
 
+@pytest.mark.parametrize("dtype,dim,n,k,nq", [("bf16", 768, 60000, 1000, 1), ("bf16", 768, 60000, 1000, 16), ("f16", 384, 50000, 300, 19),
+                                              ("f32", 384, 30000, 1000, 5), ("bf16", 100, 70000, 16384, 2), ("f32", 768, 9000, 9000, 3)])
+def test_large_k_batched_pipeline_matches_oracle(coracle, dtype, dim, n, k, nq):
+    """k > 256 on corpora of >= 4096 rows: tensor-core sweep dumping approximate scores of 16 queries at a time, radix select of
+    the k-th approximate score, compaction of every row within 2 eps, exact rescore, rank sort - batched over the queries, one
+    stream synchronisation per call.  Same bits as the oracle and as the one-query exact path."""
+    import ragfin_b200
+    x = O.synth_rows(210, 0, n, dim, dup_every=41, zero_every=997)
+    q = O.synth_rows(211, 0, nq, dim)
+    want = coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), k)
+    idx = _index(x, dtype)
+    got = idx.search(q, k)
+    st = idx.stats()
+    assert st["path"] == 2 and st["queries_rescanned"] == 0 and st["launches"] == 9 * ((nq + 15) // 16), st
+    _assert_same(got, want, f"batched large-k {dtype} dim={dim} n={n} k={k} nq={nq}")
+    idx.close()
+
+
+def test_large_k_batched_pipeline_filters_and_duplicates(coracle, monkeypatch):
+    import ragfin_b200
+    n, dim, k = 40000, 128, 500
+    x = O.synth_rows(220, 0, n, dim)
+    x[1000:9000] = x[999]                       # 8000 identical rows at the top of one query: more candidates than the buffer
+    q = np.concatenate([x[999:1000] * 3.0, O.synth_rows(221, 0, 2, dim)])
+    idx = _index(x, "bf16")
+    stored = coracle.normalize_rows(x, "bf16")
+    got = idx.search(q, k)
+    st = idx.stats()
+    assert st["path"] == 2 and st["queries_rescanned"] == 1, st       # the flagged query took the exact one-query path
+    _assert_same(got, coracle.cosine_topk(q, stored, k), "duplicates")
+    assert list(got[0][0][:3]) == [999, 1000, 1001]
+    allow = np.random.default_rng(5).random(n) < 0.3
+    ids, sc = idx.search(q[1:], k, allow=allow)
+    rows = np.flatnonzero(allow)
+    wi, ws = coracle.cosine_topk(q[1:], stored[rows], k)
+    assert np.array_equal(ids, rows[wi]) and np.array_equal(sc.view(np.uint32), ws.view(np.uint32))
+    monkeypatch.setenv("RAGFIN_NO_BIGK_BATCHED", "1")           # the one-query exact path answers the same bits
+    idx2 = _index(x, "bf16")
+    _assert_same(idx2.search(q[1:], k), coracle.cosine_topk(q[1:], stored, k), "one-query path")
+    assert idx2.stats()["launches"] == 40
+
+
 def test_hybrid_limit_1000_through_the_shim_on_a_larger_collection(coracle):
     """graph_cons.py:275-281 asks limit=1000; on a collection larger than that it must return exactly 1000 ranked hits."""
     from ragfin_b200 import milvus_compat as mc
