@@ -1171,7 +1171,9 @@ static int search_bigk_batched(ragfin* h, const float* q_dev, int nq, int k, int
     const int64_t n = h->count;
     const int64_t n_eff = h->cur_allow ? h->cur_allowed : n;
     const int keff = (int)((int64_t)k < n_eff ? k : n_eff);
-    const int slack = keff / 4 > 4096 ? keff / 4 : 4096;
+    // rows within 2 eps below the k-th score: the score density grows with k (~ +40 % of k at k = 16384 on 10M random rows
+    // with the unsplit 16-bit query's eps)
+    const int slack = keff > 4096 ? keff : 4096;
     const int cmax = keff + slack;
     h->stats.path = 2;
     h->stats.cand_per_query = cmax;

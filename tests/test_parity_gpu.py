@@ -485,7 +485,7 @@ def test_large_k_batched_pipeline_matches_oracle(coracle, dtype, dim, n, k, nq):
     idx = _index(x, dtype)
     got = idx.search(q, k)
     st = idx.stats()
-    assert st["path"] == 2 and st["queries_rescanned"] == 0 and st["launches"] == 9 * ((nq + 15) // 16), st
+    assert st["path"] == 2 and st["queries_rescanned"] == 0 and st["launches"] == 10 * ((nq + 15) // 16), st
     _assert_same(got, want, f"batched large-k {dtype} dim={dim} n={n} k={k} nq={nq}")
     idx.close()
 
