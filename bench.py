@@ -383,7 +383,7 @@ def run_ours(a):
         else:                 # tensor-bound GEMM: algorithmic flops = 2 * nq * shard rows * dim per launch
             alg = 2.0 * batch * shard_rows * a.dim
             achieved = alg / (kern_avg_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "gemm_pair_kernel" if a.gemm_variant == 4 and batch > 128 else "gemm_topk_kernel", "achieved": achieved, "peak": peaks["bf16"],
+            roof = {"bound": "tensor", "kernel": "gemm_pair_kernel" if a.gemm_variant in (-1, 0, 3, 4) and batch > 128 else "gemm_topk_kernel", "achieved": achieved, "peak": peaks["bf16"],
                     "unit": "TFLOP/s", "frac": achieved / peaks["bf16"], "algorithmic_flops_per_launch": alg,
                     "frac_of_sustained_peak": achieved / peaks["bf16_sustained"] if peaks.get("bf16_sustained") else None}
         roof.update({"kernel_ms_avg": kern_avg_ms, "kernel_launches_timed": kern_n, "peak_source": peaks["source"],

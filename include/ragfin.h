@@ -207,10 +207,10 @@ int ragfin_set_gemm_cluster(ragfin_t* h, int32_t cluster);
  * slower); 3 = streaming, and batches of <= 16 queries in append mode run with the operand roles swapped (corpus
  * rows are the MMA's M dimension, the queries its N = 16: a sixteenth of the tensor work per byte, full SM clock);
  * 4 = batches of >= 2 query tiles in append mode sweep with a 2-SM MMA (tcgen05 cta_group::2, M = 256: each CTA of a
- * pair holds its own query tile and half of the corpus tile; csrc/gemm_pair.cuh).  Bit-exact on the GPU
- * (tests/test_parity_gpu.py); measured faster at 256 / 512 / 2048 queries and slower at 1024 / 4096 under the power cap
- * (profiles/r02), so it is not chosen automatically.
- * 0 = automatic (default; currently 3).  Results are identical. */
+ * pair holds its own query tile and half of the corpus tile; csrc/gemm_pair.cuh).
+ * 0 = automatic (default): 3 for <= 16 queries, 4 from 129 queries - measured interleaved on 10M x 768 bf16
+ * (profiles/r02/policy_sweep.log) the 2-SM kernel beats the best single-CTA configuration at every batch from 129 to 4096
+ * queries (4096: 45.3 vs 47.9 ms = 1 390 TFLOP/s).  Results are identical. */
 int ragfin_set_gemm_variant(ragfin_t* h, int32_t variant);
 
 /* Tuning knob: small-batch (1-2 query) scan kernel.  0 = automatic (default; currently 1), 1 = 128-bit register-path

@@ -72,7 +72,7 @@ struct ragfin {
     int scan_variant = 0;         // small-batch scan: 0 = automatic (= 1, measured faster), 1 = LDG kernel, 2 = TMA-fed ring
     bool use_append = true;       // tcgen05 path: append mode (threshold from the bound pass, no lists) when eligible
     bool use_bound_pass = true;   // tcgen05 path: sample pass that seeds the per-query thresholds (RAGFIN_NO_BOUND_PASS=1 disables)
-    int gemm_variant = 0;     // 0 = automatic (= 3), 1 = streaming (A and B through shared memory), 2 = A-stationary (A in TMEM),
+    int gemm_variant = 0;     // 0 = automatic (= 3 for <= 16 queries, 4 from 129 queries), 1 = streaming (A and B through shared memory), 2 = A-stationary (A in TMEM),
                               // 3 = streaming + swapped operand roles for <= 16 queries in append mode (gemm_rows.cuh),
                               // 4 = 2-SM MMA pairs (cta_group::2) for >= 2 query tiles in append mode (gemm_pair.cuh)
     Buf fctl;                 // fused sweep: control block (FusedCtl), zero between searches
@@ -637,10 +637,19 @@ static GemmPlan plan_gemm(int nq, int64_t n, int num_sms, int kp, int C) {
     return p;
 }
 
-// |tensor-core score - exact score| beyond the query rounding term: fp32 accumulation inside the tensor
-// core (bounded generously: truncating adds) and, for tf32, the truncation of both operands to 10 mantissa bits.
+// |tensor-core score - exact score| beyond the query rounding term.
+// Accumulation: the products of two 16-bit (or tf32) operands are exact in fp32; what errs is their summation.  Model: every
+// addend entering an accumulation step - ld products and, per 16-element MMA step, the running sum, i.e. ld * 17 / 16 addends -
+// is aligned to the largest exponent of the step and TRUNCATED there, losing less than one fp32 ulp of a magnitude that never
+// exceeds sum |x_i q_i| <= |x|_2 |q|_2 <= 1.0078 (stored rows: <= 1 + 2^-8; queries: <= 1 + 2^-22): less than 2^-23 * 1.0078
+// each, so |error| < 1.0625 * ld * 2^-23 * 1.0078 (9.8e-5 at ld = 768) for ANY summation order and grouping.  The allowance
+// below is twice that model (2^-22 per element, + 64 elements, + one ulp so that rounding the exact score cannot create a
+// tie); tests/test_parity_gpu.py::test_tensor_core_error_stays_inside_the_allowance measures the real error on adversarial
+// (all-positive, maximal partial sums) and random operands through the raw-score hook and requires it to stay below a
+// quarter of the allowance.  Round 1 used 2^-21 per element.
+// fp32 storage (kind::tf32): both operands are truncated to 10 explicit mantissa bits, 2^-10 relative each.
 static float eps_gemm_const(int dtype, int ld) {
-    double e = (ld + 64) * 4.76837158203125e-07 * 1.0625 + 4.76837158203125e-07;   // (ld+64) * 2^-21
+    double e = (ld + 64) * 2.384185791015625e-07 * 1.0625 + 4.76837158203125e-07;   // (ld + 64) * 2^-22 * 17/16 + 2^-21
     if (dtype == 0) e += 2.0 * 9.765625e-04 * 1.0625;                               // 2 * 2^-10
     return (float)e;
 }
@@ -667,10 +676,11 @@ static bool append_eligible(const ragfin* h, int k) {
            h->count < ((int64_t)1 << 31) - kGN;
 }
 
-// Cluster size by the number of query tiles.  Measured on 10M x 768 bf16 (profiles/r01): pairs use all 148 SMs and win from
-// 1024 queries up (49.7 vs 53.1 ms at 4096); quads strand 16 SMs but read each corpus tile once, which wins at 3-7 query
-// tiles (6.35 vs 6.80 ms at 512).
-static int auto_cluster(int QT0) { return QT0 >= 8 ? 2 : QT0 >= 3 ? 4 : QT0 >= 2 ? 2 : 1; }
+// Cluster size of the single-CTA-MMA kernel by the number of query tiles.  Measured interleaved on 10M x 768 bf16
+// (profiles/r02/policy_sweep.log): pairs beat quads at every batch (512: 6.71 vs 7.67 ms, 768: 9.5 vs 14.5, 4096: 47.9 vs 55.0;
+// round 1's table, measured in separate runs, had quads ahead at 3-7 tiles) and the 2-SM MMA kernel (gemm_pair.cuh) beats both
+// (see run_gemm), so this policy only serves what the pair kernel does not: list mode (filters, small corpora) and fp32 dumps.
+static int auto_cluster(int QT0) { return QT0 >= 2 ? 2 : 1; }
 
 // Sample ("bound") pass geometry: nblk blocks of g sample tiles each; sample tile j is corpus tile j * bstride, so the
 // tiles are distinct and the last (possibly partial) tile is never sampled.  Callers guarantee n_tiles >= 4 * rank.
@@ -712,7 +722,11 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
     // cluster size along the query-tile axis: multicast pays once several query tiles share a slice
     const int QT0 = (nb + kGM - 1) / kGM;
     int C = h->gemm_cluster ? h->gemm_cluster : auto_cluster(QT0);
-    const bool want_pair = h->gemm_variant == 4 && QT0 >= 2;   // 2-SM MMA sweep: pairs of query tiles
+    // 2-SM MMA sweep (gemm_pair.cuh, tcgen05 cta_group::2) for >= 2 query tiles: the default since the interleaved sweep of
+    // profiles/r02/policy_sweep.log - faster than the best single-CTA configuration at every batch from 129 to 4096 queries
+    // (256: 3.07 vs 3.49 ms, 1024: 11.97 vs 14.00, 2048: 21.8 vs 25.4, 4096: 45.3 vs 47.9 = 1 390 TFLOP/s); variant 1 forces
+    // the single-CTA kernel
+    const bool want_pair = (h->gemm_variant == 4 || h->gemm_variant == 0 || h->gemm_variant == 3) && QT0 >= 2;
     if (want_pair) C = 2;
     typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const GemmArgs);
 #define RF_PICK_MODE(KIND, CC) (mode == 0 ? gemm_topk_kernel<KIND, 0, CC> : mode == 1 ? gemm_topk_kernel<KIND, 1, CC> : mode == 2 ? gemm_topk_kernel<KIND, 2, CC> : gemm_topk_kernel<KIND, 3, CC>)

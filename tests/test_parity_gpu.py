@@ -832,3 +832,28 @@ def test_view_shares_the_matrix_and_is_read_only(coracle):
         _assert_same((ids.cpu().numpy(), sc.cpu().numpy()), want, "interleaved")
     v.close()
     idx.close()
+
+
+@pytest.mark.parametrize("dtype,dim", [("bf16", 768), ("f16", 768), ("bf16", 1024), ("bf16", 2048), ("f16", 384)])
+def test_tensor_core_error_stays_inside_the_allowance(dtype, dim):
+    """The accumulation allowance of the tensor-core paths ((ld + 64) * 2^-22 * 17/16 + 2^-21, csrc/ragfin_api.cu
+    eps_gemm_const) against the measured |tensor-core score - exact score| on the operands that maximise it: every product
+    positive, so the partial sums are as large as they can be (|x| . |q| ~ 0.6-0.8), plus random-sign operands.  The
+    tensor core multiplies the STORED rows by the 16-bit-rounded query, so the exact reference uses those operands (the
+    query rounding is a separate, rigorously bounded term).  Required: max error <= allowance / 4."""
+    import torch
+    ld = (dim + 7) // 8 * 8
+    allowance = (ld + 64) * 2.0 ** -22 * 1.0625 + 2.0 ** -21
+    worst = 0.0
+    for positive in (True, False):
+        x = O.synth_rows(510, 0, 4000, dim)
+        q = O.synth_rows(511, 0, 130, dim)
+        if positive:
+            x, q = np.abs(x), np.abs(q)
+        idx = _index(x, dtype)
+        got = idx.debug_gemm_scores(torch.from_numpy(q).cuda()).cpu().numpy().astype(np.float64)
+        stored = idx.read_rows(0, len(x)).astype(np.float64)
+        q16 = O.round_to_storage(O.normalize_rows(q, "f32"), dtype).astype(np.float64)
+        worst = max(worst, float(np.abs(got - q16 @ stored.T).max()))
+        idx.close()
+    assert worst <= allowance / 4, (worst, allowance)
