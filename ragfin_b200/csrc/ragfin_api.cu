@@ -726,7 +726,8 @@ static int run_gemm(ragfin* h, int nb, int k, int kp, int* G, bool* appended, fl
     // profiles/r02/policy_sweep.log - faster than the best single-CTA configuration at every batch from 129 to 4096 queries
     // (256: 3.07 vs 3.49 ms, 1024: 11.97 vs 14.00, 2048: 21.8 vs 25.4, 4096: 45.3 vs 47.9 = 1 390 TFLOP/s); variant 1 forces
     // the single-CTA kernel
-    const bool want_pair = (h->gemm_variant == 4 || h->gemm_variant == 0 || h->gemm_variant == 3) && QT0 >= 2;
+    // the single-CTA kernel, and so does a forced cluster size other than 2
+    const bool want_pair = (h->gemm_variant == 4 || ((h->gemm_variant == 0 || h->gemm_variant == 3) && (h->gemm_cluster == 0 || h->gemm_cluster == 2))) && QT0 >= 2;
     if (want_pair) C = 2;
     typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const GemmArgs);
 #define RF_PICK_MODE(KIND, CC) (mode == 0 ? gemm_topk_kernel<KIND, 0, CC> : mode == 1 ? gemm_topk_kernel<KIND, 1, CC> : mode == 2 ? gemm_topk_kernel<KIND, 2, CC> : gemm_topk_kernel<KIND, 3, CC>)

@@ -51,7 +51,7 @@ def test_slices_cover_every_row_once_and_the_grid_fits(plan, num_sms, cluster):
 
 
 def test_automatic_cluster_size(plan):
-    assert [plan(nq, 10_000_000)["C"] for nq in (1, 128, 129, 256, 257, 384, 896, 897, 1024, 4096)] == [1, 1, 2, 2, 4, 4, 4, 2, 2, 2]
+    assert [plan(nq, 10_000_000)["C"] for nq in (1, 128, 129, 256, 257, 384, 896, 897, 1024, 4096)] == [1, 1, 2, 2, 2, 2, 2, 2, 2, 2]   # pairs from two query tiles up (profiles/r02/policy_sweep.log)
 
 
 def test_bound_pass_samples_distinct_tiles_and_never_the_last(plan):
