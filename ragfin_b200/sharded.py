@@ -81,7 +81,8 @@ class ShardedSearcher:
             import torch
             mine = 1 if (self.exchange is not None and self.index is not None and nq * ((k * 12 + 15) // 16 * 16) <= self.exchange.max_record_bytes
                          and self.index.fused_eligible(nq, k)) else 0
-            t = torch.tensor([mine], dtype=torch.int32, device=torch.device("cuda", self.index.device) if self.index is not None else None)
+            on_gpu = self.index is not None and torch.cuda.is_available()
+            t = torch.tensor([mine], dtype=torch.int32, device=torch.device("cuda", self.index.device) if on_gpu else None)
             self._dist.all_reduce(t, op=self._dist.ReduceOp.MIN, group=self.group)
             ok = self._fused[key] = bool(int(t.item()))
         return ok
@@ -94,8 +95,8 @@ class ShardedSearcher:
         q = np.ascontiguousarray(queries, dtype=np.float32)
         if self.world > 1 and self.exchange is not None and self.fused_ok(q.shape[0], k):
             return self.exchange.search_sharded_host(self.index, q, k, out_ids, out_scores)
-        dev = torch.device("cuda", self.index.device) if self.index is not None else None
-        ids, sc = self.search(torch.from_numpy(q).to(dev), k)
+        dev = torch.device("cuda", self.index.device) if (self.index is not None and torch.cuda.is_available()) else None
+        ids, sc = self.search(torch.from_numpy(q).to(dev) if dev is not None else torch.from_numpy(q), k)
         ids, sc = ids.cpu().numpy(), sc.cpu().numpy()
         if out_ids is not None:
             out_ids[...] = ids

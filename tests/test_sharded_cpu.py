@@ -126,3 +126,92 @@ def test_exchange_branch_and_its_fallback_over_gloo():
     out = mp.get_context("spawn").Manager().dict()
     mp.spawn(_worker_exchange, args=(2, _free_port(), out), nprocs=2, join=True)
     assert dict(out) == {0: 1, 1: 1}
+
+
+class _FakeIndex:
+    """Stand-in with the two members ShardedSearcher reads for the one-kernel decision."""
+    device = 0
+
+    def __init__(self, eligible):
+        self.eligible = eligible
+
+    def fused_eligible(self, nq, k):
+        return self.eligible(nq, k)
+
+
+class _FakeExchange:
+    """Stand-in for PeerExchange: records which entry point a search took; `search_sharded*` answer from the full matrix
+    (what the real kernel's exchange + reduce produces on every rank)."""
+    max_record_bytes = 1 << 20
+
+    def __init__(self, x, log):
+        self.x, self.log = x, log
+
+    def search_sharded(self, index, queries, k, out_ids=None, out_scores=None, stream=None):
+        self.log.append("one-kernel")
+        ids, sc = O.cosine_topk(queries.numpy(), self.x, k)
+        return torch.from_numpy(ids), torch.from_numpy(sc)
+
+    def search_sharded_host(self, index, q, k, out_ids=None, out_scores=None):
+        self.log.append("one-kernel-host")
+        return O.cosine_topk(q, self.x, k)
+
+    def allgather_merge(self, ids, scores, stream=None):
+        self.log.append("push-merge")
+        parts = [torch.empty_like(ids) for _ in range(dist.get_world_size())]
+        sparts = [torch.empty_like(scores) for _ in range(dist.get_world_size())]
+        dist.all_gather(parts, ids.contiguous())
+        dist.all_gather(sparts, scores.contiguous())
+        mi, ms = O.merge_topk([p.numpy() for p in parts], [p.numpy() for p in sparts], ids.shape[1])
+        return torch.from_numpy(mi), torch.from_numpy(ms)
+
+
+def _worker_fused_agreement(rank, world, port, out):
+    """Rank 1's shard is 'too small' for the one-kernel search at k = 5: NO rank may take it for that shape (a rank on another
+    path would leave its peers waiting inside the kernel); at k = 3 every rank is eligible and all of them take it."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n, dim = 300, 32
+        x = O.normalize_rows(O.synth_rows(31, 0, n, dim), "f32")
+        q = O.synth_rows(32, 0, 2, dim)
+        row0, cnt = shard_bounds(n, world, rank)
+        log = []
+
+        def local_search(queries, kk, out_ids=None, out_scores=None):
+            ids, sc = O.cosine_topk(queries.numpy(), x[row0:row0 + cnt], kk, id_base=row0)
+            if out_ids is not None:
+                out_ids.copy_(torch.from_numpy(ids)); out_scores.copy_(torch.from_numpy(sc))
+                return out_ids, out_scores
+            return torch.from_numpy(ids), torch.from_numpy(sc)
+
+        idx = _FakeIndex(lambda nq, k: not (rank == 1 and k == 5))
+        s = ShardedSearcher(local_search, None, exchange=_FakeExchange(x, log), index=idx)
+        ok = True
+        for k, want_path in ((3, "one-kernel"), (5, "push-merge"), (3, "one-kernel")):
+            ids, sc = s.search(torch.from_numpy(q), k)
+            wi, ws = O.cosine_topk(q, x, k)
+            ok &= np.array_equal(ids.numpy(), wi) and np.array_equal(sc.numpy().view(np.uint32), ws.view(np.uint32))
+            ok &= log[-1] == want_path
+        hi, hs = s.search_host(q, 3)
+        ok &= log[-1] == "one-kernel-host" and np.array_equal(hi, O.cosine_topk(q, x, 3)[0])
+        hi, hs = s.search_host(q, 5)               # not eligible everywhere: device staging around search()
+        ok &= log[-1] == "push-merge" and np.array_equal(hi, O.cosine_topk(q, x, 5)[0])
+        ok &= s._fused == {(2, 3): True, (2, 5): False}
+        out[rank] = int(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_one_kernel_path_is_taken_only_when_every_rank_can():
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_fused_agreement, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    assert all(p.exitcode == 0 for p in procs)
+    assert dict(out) == {0: 1, 1: 1}
