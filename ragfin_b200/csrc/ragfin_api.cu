@@ -2010,6 +2010,12 @@ extern "C" int ragfin_search_sharded_host(ragfin_t* h, ragfin_exchange_t* x, con
     CU_TRY(cudaStreamSynchronize(st));
     memcpy(out_ids_host, ho, ib);
     memcpy(out_scores_host, ho + ib, sb);
+    // a finalizing CTA that waited 4 s for a peer's hits gives up and marks the query's empty slots with NaN scores
+    for (size_t i = 0; i < (size_t)nq * k; ++i)
+        if (out_scores_host[i] != out_scores_host[i]) {
+            (void)mark_done(h, st);
+            return fail(RAGFIN_ECUDA, "sharded search: the exchange timed out waiting for a peer rank's hits (query %zu); is every rank calling with the same shape?", i / k);
+        }
     return mark_done(h, st);
 }
 
