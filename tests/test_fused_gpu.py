@@ -157,3 +157,41 @@ def test_templated_corpus_generator_and_search(coracle):
         idx.set_fused(False)
         _same(idx.search(q, k), (wi, ws), f"topics {dtype}, multi-kernel")
         idx.close()
+
+
+def test_fused_zero_query_and_concurrent_callers(coracle):
+    """An all-zero query scores 0 against every row: every row ties, the buffer overflows and the in-kernel exact scan answers
+    with the lowest ids; other queries of the batch are unaffected.  Two host threads sharing one handle (FastMCP runs tools
+    on a worker pool, vector_rag_mcp/main.py:134) serialise on the handle and both get the oracle's answer."""
+    import threading
+    n, dim, k = 30000, 128, 5
+    x = O.synth_rows(360, 0, n, dim)
+    q = O.synth_rows(361, 0, 3, dim)
+    q[1] = 0.0
+    idx = _index(x, "bf16")
+    stored = coracle.normalize_rows(x, "bf16")
+    want = coracle.cosine_topk(q, stored, k)
+    got = idx.search(q, k)
+    st = idx.stats()
+    assert st["path"] == 3 and st["queries_rescanned"] == 1, st
+    _same(got, want, "zero query")
+    assert list(got[0][1]) == list(range(k)) and not got[1][1].any()
+    results, errors = {}, []
+
+    def worker(t):
+        try:
+            for i in range(20):
+                results[(t, i)] = idx.search(q[[0, 2]], k)
+        except Exception as e:   # noqa: BLE001
+            errors.append(e)
+
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors
+    w2 = coracle.cosine_topk(q[[0, 2]], stored, k)
+    for r in results.values():
+        _same(r, w2, "concurrent")
+    idx.close()
