@@ -67,6 +67,7 @@ struct ragfin {
     int gemm_min_nq = 3;      // query batches of at least this many rows take the tcgen05 path (1-2: HBM-bound scan) ...
     int gemm_min_nq_large = 1;   // ... except on corpora of >= kSweepBytes, where the TMA-fed sweep wins from 1 query
     int gemm_cluster = 0;     // 0 = choose by batch size; 1, 2 or 4 = force
+    bool cur_pipelined = false;            // the search in flight came through an asynchronous entry point (ragfin_search)
     const uint32_t* cur_allow = nullptr;   // scalar filter of the search in flight (device bitmask), else null
     int64_t cur_allowed = 0;               // rows it allows
     int scan_variant = 0;         // small-batch scan: 0 = automatic (= 1, measured faster), 1 = LDG kernel, 2 = TMA-fed ring
@@ -75,7 +76,10 @@ struct ragfin {
     int gemm_variant = 0;     // 0 = automatic (= 3 for <= 16 queries, 4 from 129 queries), 1 = streaming (A and B through shared memory), 2 = A-stationary (A in TMEM),
                               // 3 = streaming + swapped operand roles for <= 16 queries in append mode (gemm_rows.cuh),
                               // 4 = 2-SM MMA pairs (cta_group::2) for >= 2 query tiles in append mode (gemm_pair.cuh)
-    Buf fctl;                 // fused sweep: control block (FusedCtl), zero between searches
+    Buf fctl;                 // fused sweep: TWO control blocks (FusedCtl), zero between searches; consecutive searches alternate
+    Buf fcand, fqn, fflags;   //   ... and so do their append buffers, normalised queries and overflow flags: a pipelined search
+    uint32_t fused_seq = 0;   //   (ragfin_search / ragfin_search_sharded) may start while its predecessor is still finalizing
+    int fused_last = 0;       // half used by the last search (diagnostics, stats)
     bool fctl_dirty = true;   // set when a launch may have left it non-zero (first use, failed call): re-zeroed before the next launch
     bool use_bigk_batched = true;   // k > 256: batched dump + select pipeline (RAGFIN_NO_BIGK_BATCHED=1: the one-query exact path)
     bool use_fused = true;    // <= 64 queries, k <= 128: the one-kernel search (sweep_fused.cuh); RAGFIN_NO_FUSED=1 disables
@@ -91,6 +95,8 @@ struct ragfin {
     void* hstage = nullptr;   // pinned, device-mapped staging for small host calls: kernels read the queries and write the hits
                               // straight through PCIe, no copy engine launches (ragfin_search_host)
     cudaEvent_t last_done = nullptr;
+    bool have_pending = false;            // pipelined searches enqueued on pending_stream since the last event record
+    cudaStream_t pending_stream = nullptr;
     ragfin_search_stats stats = {0, 0, 0, 0};
     // measurement hook (ragfin_profile): event pairs around the dominant kernel
     bool profiling = false;
@@ -224,7 +230,7 @@ extern "C" void ragfin_destroy(ragfin_t* h) {
     if (!h) return;
     DeviceGuard g(h->device);
     (void)cudaDeviceSynchronize();
-    Buf* bufs[] = {&h->qhat, &h->q16, &h->eps_q, &h->gtau, &h->bmax, &h->acnt, &h->athr, &h->allow, &h->bk_scores, &h->bk_state, &h->bk_keys, &h->bk_rows, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage, &h->fctl};
+    Buf* bufs[] = {&h->qhat, &h->q16, &h->eps_q, &h->gtau, &h->bmax, &h->acnt, &h->athr, &h->allow, &h->bk_scores, &h->bk_state, &h->bk_keys, &h->bk_rows, &h->cand, &h->cand_e, &h->flags, &h->stage_q, &h->stage_ids, &h->stage_scores, &h->add_stage, &h->fctl, &h->fcand, &h->fqn, &h->fflags};
     for (Buf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->data && !h->is_view) cudaFree(h->data);
@@ -323,8 +329,24 @@ static int launch_ingest(int dtype, const float* src, uint64_t key, int64_t row0
     return 0;
 }
 
-static int wait_prev(ragfin* h, cudaStream_t st) { CU_TRY(cudaStreamWaitEvent(st, h->last_done, 0)); return 0; }
-static int mark_done(ragfin* h, cudaStream_t st) { CU_TRY(cudaEventRecord(h->last_done, st)); return 0; }
+// Ordering of the handle's operations across streams: every operation waits for the previous one's completion event.  An event
+// record between two kernels of one stream would also cut the programmatic dependency that lets a pipelined search start while
+// its predecessor finalizes, so pipelined searches only NOTE their stream; the event is recorded later, on that stream, when an
+// operation on another stream (or a non-pipelined one) needs it - a record covers everything enqueued before it.
+static int wait_prev(ragfin* h, cudaStream_t st, bool pipelined = false) {
+    if (h->have_pending) {
+        if (pipelined && st == h->pending_stream) return 0;          // same stream: stream order is the dependency
+        CU_TRY(cudaEventRecord(h->last_done, h->pending_stream));
+        h->have_pending = false;
+    }
+    CU_TRY(cudaStreamWaitEvent(st, h->last_done, 0));
+    return 0;
+}
+static int mark_done(ragfin* h, cudaStream_t st, bool pipelined = false) {
+    if (pipelined) { h->have_pending = true; h->pending_stream = st; return 0; }
+    CU_TRY(cudaEventRecord(h->last_done, st));
+    return 0;
+}
 
 extern "C" int ragfin_add(ragfin_t* h, const float* rows, int64_t n, int32_t src_is_device, void* stream) {
     if (!h) return fail(RAGFIN_EINVAL, "NULL handle");
@@ -1054,6 +1076,7 @@ static FusedPlan plan_fused(const ragfin* h, int nb, int k) {
                 if (region < hdr + 4096 * sizeof(u64)) continue;      // the finalize's scratch (rows within 2 eps of the k-th score)
                 // every CTA appends ~k rows of its first tile, so the buffer scales with k (148 CTAs x 128 = 19 k rows)
                 const int cap = k <= 16 ? kAppendCap : 4 * kAppendCap;
+                if ((size_t)nb * cap > (size_t)kFMaxQ * kAppendCap) continue;   // one half of the double-buffered append workspace
                 FusedPlan f;
                 f.ncol = ncol; f.split = split; f.stages = stages; f.pend = pend; f.cap = cap; f.smem = smem;
                 return f;
@@ -1074,16 +1097,25 @@ static fused_fn pick_fused(int dtype, int ncol, bool split) {
     return ncol == 16 ? sweep_fused_kernel<0, 16, false> : ncol == 32 ? sweep_fused_kernel<0, 32, false> : sweep_fused_kernel<0, 64, false>;
 }
 
+// pipelined: the asynchronous entry points.  The launch carries programmatic stream serialization, the kernel triggers its
+// dependents at the end of its sweep, and one SM is left free for the predecessor's finalizing CTA, so back-to-back searches
+// overlap one search's finalize / exchange (one CTA busy, 147 SMs idle) with the next one's prologue and sweep.  Synchronous
+// host calls (one search, then a stream synchronisation) use the whole device and a plain launch.
 static int run_fused(ragfin* h, const float* q_dev, int nb, int k, int64_t n_eff, int64_t* out_ids, float* out_scores,
-                     int* flags, int* flag_count, cudaStream_t st, ragfin_exchange* x = nullptr, uint32_t xstep = 0) {
+                     cudaStream_t st, bool pipelined, ragfin_exchange* x = nullptr, uint32_t xstep = 0) {
     int rc;
     const FusedPlan f = plan_fused(h, nb, k);
     if (f.ncol == 0) return fail(RAGFIN_EUNSUPPORTED, "no fused sweep for %d queries, k = %d", nb, k);
     const int64_t n = h->count;
-    if ((rc = ensure(h->cand, (size_t)nb * f.cap * sizeof(u64)))) return rc;
-    if (!h->fctl.p) { if ((rc = ensure(h->fctl, sizeof(FusedCtl)))) return rc; h->fctl_dirty = true; }
-    if (h->fctl_dirty) { CU_TRY(cudaMemsetAsync(h->fctl.p, 0, sizeof(FusedCtl), st)); h->fctl_dirty = false; }
-    const GemmPlan p = plan_gemm(nb, n, h->num_sms, 32, 1);
+    const size_t cand_half = (size_t)kFMaxQ * 4 * kAppendCap * sizeof(u64) / 4;   // per half: up to 16 queries x 65 536 keys (= 64 x 16 384)
+    const size_t qn_half = (size_t)kFMaxQ * h->ld * sizeof(float);
+    if ((size_t)nb * f.cap * sizeof(u64) > cand_half) return fail(RAGFIN_EUNSUPPORTED, "append buffers of %d queries x %d keys exceed the workspace half", nb, f.cap);
+    if ((rc = ensure(h->fcand, 2 * cand_half)) || (rc = ensure(h->fqn, 2 * qn_half)) || (rc = ensure(h->fflags, 2 * (kFMaxQ + 1) * sizeof(int)))) return rc;
+    if (!h->fctl.p) { if ((rc = ensure(h->fctl, 2 * sizeof(FusedCtl)))) return rc; h->fctl_dirty = true; }
+    if (h->fctl_dirty) { CU_TRY(cudaMemsetAsync(h->fctl.p, 0, 2 * sizeof(FusedCtl), st)); h->fctl_dirty = false; }
+    const int half = (int)(h->fused_seq++ & 1u);
+    h->fused_last = half;
+    const GemmPlan p = plan_gemm(nb, n, pipelined && h->num_sms > 8 ? h->num_sms - 1 : h->num_sms, 32, 1);
     CUtensorMap tmB;
     if ((rc = cached_map(h, &tmB, h->dtype, h->data, n, h->ld, kGN))) return rc;
     FusedArgs a;
@@ -1102,16 +1134,15 @@ static int run_fused(ragfin* h, const float* q_dev, int nb, int k, int64_t n_eff
     if (a.groups < 1) a.groups = 1;
     a.grank = a.keff > 0 ? (a.keff + a.groups - 1) / a.groups : 0;
     a.q = q_dev;
-    if ((rc = ensure(h->qhat, (size_t)kFMaxQ * h->ld * sizeof(float)))) return rc;
-    a.qn = (float*)h->qhat.p;
+    a.qn = (float*)((char*)h->fqn.p + half * qn_half);
     a.data = h->data;
     a.allow = h->cur_allow;
-    a.cand = (u64*)h->cand.p; a.cap = f.cap;
-    a.ctl = (FusedCtl*)h->fctl.p;
+    a.cand = (u64*)((char*)h->fcand.p + half * cand_half); a.cap = f.cap;
+    a.ctl = (FusedCtl*)h->fctl.p + half;
     a.eps_const = eps_gemm_const(h->dtype, h->ld);
     a.id_base = h->id_base;
     a.out_ids = (long long*)out_ids; a.out_scores = out_scores;
-    a.flags = flags; a.flag_count = flag_count;
+    a.flags = (int*)h->fflags.p + half * (kFMaxQ + 1); a.flag_count = a.flags + kFMaxQ;
     a.xworld = 0; a.xrank = 0; a.xstep = 0; a.xrec_max = 0; a.xpeer_area = nullptr; a.xpeer_qflag = nullptr;
     if (x != nullptr && x->world > 1) {
         a.xworld = x->world; a.xrank = x->rank; a.xstep = xstep; a.xrec_max = x->record_max;
@@ -1120,8 +1151,14 @@ static int run_fused(ragfin* h, const float* q_dev, int nb, int k, int64_t n_eff
     fused_fn fn = pick_fused(h->dtype, f.ncol, f.split);
     if ((rc = set_dyn_smem(h->device, (const void*)fn, f.smem))) return rc;
     h->fctl_dirty = true;          // until the launch is known to have been accepted
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.grid); cfg.blockDim = dim3(kFThreads); cfg.dynamicSmemBytes = f.smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pipelined ? 1 : 0;
     prof_begin(h, st);
-    fn<<<p.grid, kFThreads, f.smem, st>>>(tmB, a);
+    CU_TRY(cudaLaunchKernelEx(&cfg, fn, tmB, a));
     prof_end(h, st);
     CU_TRY(cudaGetLastError());
     h->fctl_dirty = false;
@@ -1269,8 +1306,7 @@ static int search_locked(ragfin* h, const float* q_dev, int nq, int k, int64_t* 
     const int64_t n_eff = h->cur_allow ? h->cur_allowed : n;   // rows a hit may come from
     if ((rc = ensure(h->flags, (size_t)(kMaxQueryBatch + 1) * sizeof(int)))) return rc;
     if (nq <= h->fused_max_nq && fused_eligible(h, nq, k)) {   // the one-kernel search (sweep_fused.cuh): prep, sweep, finalize, exact fallback
-        int* fl = (int*)h->flags.p;
-        return run_fused(h, q_dev, nq, k, n_eff, out_ids, out_scores, fl, fl + kMaxQueryBatch, st);
+        return run_fused(h, q_dev, nq, k, n_eff, out_ids, out_scores, st, h->cur_pipelined);
     }
     int kp = cand_per_query(k);
     if (kp == 0 && n <= 256) kp = 256;   // every row is a candidate: any k (graph_cons.py:279 asks limit=1000 of 16 rows)
@@ -1569,7 +1605,7 @@ extern "C" int ragfin_debug_fused_times(ragfin_t* h, int64_t* out) {
     if (!h->fctl.p) return fail(RAGFIN_EINVAL, "no one-kernel search has run on this handle");
     CU_TRY(cudaDeviceSynchronize());
     FusedCtl c;
-    CU_TRY(cudaMemcpy(&c, h->fctl.p, sizeof(c), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(&c, (FusedCtl*)h->fctl.p + h->fused_last, sizeof(c), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 16; ++i) out[i] = (int64_t)(c.t[i] - c.t[0]);
     return RAGFIN_OK;
 }
@@ -1582,7 +1618,7 @@ extern "C" int ragfin_debug_fused_ctas(ragfin_t* h, float* out_thr, int32_t* out
     if (!h->fctl.p) return fail(RAGFIN_EINVAL, "no one-kernel search has run on this handle");
     CU_TRY(cudaDeviceSynchronize());
     FusedCtl* c = new FusedCtl;
-    cudaError_t e = cudaMemcpy(c, h->fctl.p, sizeof(*c), cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(c, (FusedCtl*)h->fctl.p + h->fused_last, sizeof(*c), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) for (int i = 0; i < 160; ++i) { out_thr[i] = c->cta_thr[i]; out_app[i] = (int32_t)c->cta_app[i]; }
     delete c;
     CU_TRY(e);
@@ -1596,7 +1632,7 @@ extern "C" int ragfin_debug_fused_counts(ragfin_t* h, int32_t nq, int64_t* out_a
     if (!h->fctl.p) return fail(RAGFIN_EINVAL, "no one-kernel search has run on this handle");
     CU_TRY(cudaDeviceSynchronize());
     FusedCtl c;
-    CU_TRY(cudaMemcpy(&c, h->fctl.p, sizeof(c), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(&c, (FusedCtl*)h->fctl.p + h->fused_last, sizeof(c), cudaMemcpyDeviceToHost));
     for (int i = 0; i < nq; ++i) {
         out_appended[i] = c.last_cnt[i];
         out_rescored[i] = c.last_resc[i] == 0xFFFFFFFFu ? -1 : (int64_t)c.last_resc[i];
@@ -1650,9 +1686,13 @@ extern "C" int ragfin_search(ragfin_t* h, const float* q, int32_t nq, int32_t k,
     DeviceGuard g(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    if ((rc = wait_prev(h, st))) return rc;
-    if ((rc = search_locked(h, q, nq, k, out_ids, out_scores, st))) return rc;
-    return mark_done(h, st);
+    const bool pipe = nq <= h->fused_max_nq && fused_eligible(h, nq, k);   // the one-kernel search: pipelined launch
+    if ((rc = wait_prev(h, st, pipe))) return rc;
+    h->cur_pipelined = pipe;
+    rc = search_locked(h, q, nq, k, out_ids, out_scores, st);
+    h->cur_pipelined = false;
+    if (rc) return rc;
+    return mark_done(h, st, pipe);
 }
 
 extern "C" int ragfin_search_host(ragfin_t* h, const float* q_host, int32_t nq, int32_t k, int64_t* out_ids_host,
@@ -1766,7 +1806,12 @@ extern "C" int ragfin_last_search_stats(ragfin_t* h, ragfin_search_stats* out) {
     if (!h || !out) return fail(RAGFIN_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard g(h->device);
-    if (h->flags.p && h->stats.path != 2) {
+    if (h->stats.path == 3 && h->fflags.p) {
+        CU_TRY(cudaDeviceSynchronize());
+        int fc = 0;
+        CU_TRY(cudaMemcpy(&fc, (int*)h->fflags.p + h->fused_last * (kFMaxQ + 1) + kFMaxQ, sizeof(int), cudaMemcpyDeviceToHost));
+        h->stats.queries_rescanned = fc;
+    } else if (h->flags.p && h->stats.path != 2) {
         CU_TRY(cudaDeviceSynchronize());
         int fc = 0;
         CU_TRY(cudaMemcpy(&fc, (int*)h->flags.p + kMaxQueryBatch, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1942,7 +1987,7 @@ extern "C" int ragfin_fused_eligible(ragfin_t* h, int32_t nq, int32_t k, int32_t
 }
 
 static int sharded_locked(ragfin* h, ragfin_exchange* x, const float* q_dev, int nq, int k, int64_t* out_ids, float* out_scores,
-                          cudaStream_t st) {
+                          cudaStream_t st, bool pipelined) {
     if (!x->connected) return fail(RAGFIN_EINVAL, "exchange is not connected");
     if (x->device != h->device) return fail(RAGFIN_EINVAL, "exchange and collection live on different devices");
     if (nq > kFMaxQ || !fused_eligible(h, nq, k))
@@ -1954,11 +1999,10 @@ static int sharded_locked(ragfin* h, ragfin_exchange* x, const float* q_dev, int
     x->have_stream = true; x->stream = st;
     int rc;
     if ((rc = ensure(h->flags, (size_t)(kMaxQueryBatch + 1) * sizeof(int)))) return rc;
-    int* fl = (int*)h->flags.p;
     h->stats.launches = 0;
     const int64_t n_eff = h->count;
     const uint32_t step = ++x->step;
-    return run_fused(h, q_dev, nq, k, n_eff, out_ids, out_scores, fl, fl + kMaxQueryBatch, st, x, step);
+    return run_fused(h, q_dev, nq, k, n_eff, out_ids, out_scores, st, pipelined, x, step);
 }
 
 // Row-sharded search in ONE kernel per GPU (sweep_fused.cuh): this rank's shard is swept, the finalizing CTAs push the
@@ -1974,9 +2018,9 @@ extern "C" int ragfin_search_sharded(ragfin_t* h, ragfin_exchange_t* x, const fl
     DeviceGuard g(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    if ((rc = wait_prev(h, st))) return rc;
-    if ((rc = sharded_locked(h, x, q, nq, k, out_ids, out_scores, st))) return rc;
-    return mark_done(h, st);
+    if ((rc = wait_prev(h, st, true))) return rc;
+    if ((rc = sharded_locked(h, x, q, nq, k, out_ids, out_scores, st, true))) return rc;
+    return mark_done(h, st, true);
 }
 
 // Same with HOST buffers (what a serving process calls): queries staged through pinned memory, the global hits written by
@@ -2006,7 +2050,7 @@ extern "C" int ragfin_search_sharded_host(ragfin_t* h, ragfin_exchange_t* x, con
     memcpy(hq, q_host, qb);
     if ((rc = ensure(h->stage_q, qb))) return rc;
     CU_TRY(cudaMemcpyAsync(h->stage_q.p, hq, qb, cudaMemcpyHostToDevice, st));
-    if ((rc = sharded_locked(h, x, (const float*)h->stage_q.p, nq, k, (int64_t*)dout, (float*)(dout + ib), st))) return rc;
+    if ((rc = sharded_locked(h, x, (const float*)h->stage_q.p, nq, k, (int64_t*)dout, (float*)(dout + ib), st, false))) return rc;
     CU_TRY(cudaStreamSynchronize(st));
     memcpy(out_ids_host, ho, ib);
     memcpy(out_scores_host, ho + ib, sb);

@@ -750,6 +750,10 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
     const int n_fin = nq < (int)gridDim.x ? nq : (int)gridDim.x;
     if (tid == 0) {
         __threadfence();
+        // Pipelined launches (programmatic stream serialization, see run_fused): once every CTA is past its sweep the NEXT
+        // search's grid may start on the SMs this one has vacated - its prologue and sweep overlap this search's finalize and
+        // exchange.  It works on the other half of the double-buffered control block / buffers and never reads this search's.
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         *s_ticket = atomicAdd(&a.ctl->done, 1u);
     }
     __syncthreads();
@@ -785,6 +789,9 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
     auto emit = [&](int qi, const u64* fin, int nvalid) {
         long long* oid = a.out_ids + (size_t)qi * k;
         float* osc = a.out_scores + (size_t)qi * k;
+        // the previous search on this stream (which this grid may have overtaken) has completed and its writes are visible
+        // before this one touches the caller's output buffers: results land in stream order
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         if (a.xworld <= 1) {
             for (int i = tid; i < k; i += kFThreads) {
                 const u64 key = i < nvalid ? fin[i] : 0ull;

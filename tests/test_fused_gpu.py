@@ -195,3 +195,41 @@ def test_fused_zero_query_and_concurrent_callers(coracle):
     for r in results.values():
         _same(r, w2, "concurrent")
     idx.close()
+
+
+def test_fused_pipelined_back_to_back_searches(coracle):
+    """The asynchronous entry point launches the one-kernel search with programmatic stream serialization: a search may start
+    while its predecessor is still finalizing (they alternate between two halves of the control block and buffers).  Sixty
+    searches of varying shape enqueued without any synchronisation, then every result is checked; interleaved with host calls
+    and an add() on another stream."""
+    import torch
+    n, dim = 60000, 128
+    x = O.synth_rows(370, 0, n, dim, dup_every=301)
+    stored = coracle.normalize_rows(x, "bf16")
+    idx = _index(x[:50000], "bf16")
+    idx.reserve(n)
+    shapes = [(1, 10), (2, 5), (16, 10), (1, 100), (3, 1), (8, 25)]
+    qs = [O.synth_rows(371 + i, 0, nq, dim) for i, (nq, _) in enumerate(shapes)]
+    qd = [torch.from_numpy(q).cuda() for q in qs]
+    outs = []
+    for rep in range(10):
+        for i, (nq, k) in enumerate(shapes):
+            outs.append((i, 50000, idx.search_device(qd[i], k)))
+    torch.cuda.synchronize()
+    assert idx.stats()["path"] == 3
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        idx.add(torch.from_numpy(x[50000:]).cuda(), stream=side)          # orders itself after the pipelined searches
+    for rep in range(3):
+        for i, (nq, k) in enumerate(shapes):
+            outs.append((i, n, idx.search_device(qd[i], k)))
+        h = idx.search(qs[0], 10)                                          # synchronous host call in between
+        _same(h, coracle.cosine_topk(qs[0], stored, 10), "host call between pipelined searches")
+    torch.cuda.synchronize()
+    want = {}
+    for i, rows, (ids, sc) in outs:
+        key = (i, rows)
+        if key not in want:
+            want[key] = coracle.cosine_topk(qs[i], stored[:rows], shapes[i][1])
+        _same((ids.cpu().numpy(), sc.cpu().numpy()), want[key], f"pipelined shape {shapes[i]} rows {rows}")
+    idx.close()
