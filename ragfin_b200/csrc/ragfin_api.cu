@@ -1097,10 +1097,10 @@ static fused_fn pick_fused(int dtype, int ncol, bool split) {
     return ncol == 16 ? sweep_fused_kernel<0, 16, false> : ncol == 32 ? sweep_fused_kernel<0, 32, false> : sweep_fused_kernel<0, 64, false>;
 }
 
-// pipelined: the asynchronous entry points.  The launch carries programmatic stream serialization, the kernel triggers its
-// dependents at the end of its sweep, and one SM is left free for the predecessor's finalizing CTA, so back-to-back searches
-// overlap one search's finalize / exchange (one CTA busy, 147 SMs idle) with the next one's prologue and sweep.  Synchronous
-// host calls (one search, then a stream synchronisation) use the whole device and a plain launch.
+// pipelined: the asynchronous entry points.  The launch carries programmatic stream serialization and the kernel releases its
+// dependents when it starts, so the CTAs of the next search on the stream take over the SMs one by one as this search's CTAs
+// finish: one search's prologue, tail skew, finalize and exchange overlap the next one's sweep.  Synchronous host calls (one
+// search, then a stream synchronisation) use a plain launch.
 static int run_fused(ragfin* h, const float* q_dev, int nb, int k, int64_t n_eff, int64_t* out_ids, float* out_scores,
                      cudaStream_t st, bool pipelined, ragfin_exchange* x = nullptr, uint32_t xstep = 0) {
     int rc;
@@ -1112,10 +1112,11 @@ static int run_fused(ragfin* h, const float* q_dev, int nb, int k, int64_t n_eff
     if ((size_t)nb * f.cap * sizeof(u64) > cand_half) return fail(RAGFIN_EUNSUPPORTED, "append buffers of %d queries x %d keys exceed the workspace half", nb, f.cap);
     if ((rc = ensure(h->fcand, 2 * cand_half)) || (rc = ensure(h->fqn, 2 * qn_half)) || (rc = ensure(h->fflags, 2 * (kFMaxQ + 1) * sizeof(int)))) return rc;
     if (!h->fctl.p) { if ((rc = ensure(h->fctl, 2 * sizeof(FusedCtl)))) return rc; h->fctl_dirty = true; }
-    if (h->fctl_dirty) { CU_TRY(cudaMemsetAsync(h->fctl.p, 0, 2 * sizeof(FusedCtl), st)); h->fctl_dirty = false; }
-    const int half = (int)(h->fused_seq++ & 1u);
+    if (h->fctl_dirty) { CU_TRY(cudaMemsetAsync(h->fctl.p, 0, 2 * sizeof(FusedCtl), st)); h->fctl_dirty = false; h->fused_seq = 0; }
+    const uint32_t seq = h->fused_seq++;
+    const int half = (int)(seq & 1u);
     h->fused_last = half;
-    const GemmPlan p = plan_gemm(nb, n, pipelined && h->num_sms > 8 ? h->num_sms - 1 : h->num_sms, 32, 1);
+    const GemmPlan p = plan_gemm(nb, n, h->num_sms, 32, 1);
     CUtensorMap tmB;
     if ((rc = cached_map(h, &tmB, h->dtype, h->data, n, h->ld, kGN))) return rc;
     FusedArgs a;
@@ -1133,6 +1134,7 @@ static int run_fused(ragfin* h, const float* q_dev, int nb, int k, int64_t n_eff
     if (a.keff > 0 && a.groups > a.keff) a.groups = a.keff;
     if (a.groups < 1) a.groups = 1;
     a.grank = a.keff > 0 ? (a.keff + a.groups - 1) / a.groups : 0;
+    a.seq_on_half = seq >> 1;
     a.q = q_dev;
     a.qn = (float*)((char*)h->fqn.p + half * qn_half);
     a.data = h->data;

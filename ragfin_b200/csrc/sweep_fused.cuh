@@ -50,6 +50,7 @@ struct FusedCtl {
     uint32_t done;            // CTAs that have finished their sweep
     uint32_t obs_done;        // CTAs that have observed their first tile and published its bound
     uint32_t fin_done;        // finalizing CTAs that have finished
+    uint32_t n_done;          // searches that have completely finished with this control block (pipelined launches, see below)
     uint32_t last_cnt[kFMaxQ];   // diagnostics of the last search: rows appended per query ...
     uint32_t last_resc[kFMaxQ];  // ... and rows rescored exactly (0xFFFFFFFF: the query took the exact scan)
     float cta_thr[160];          // diagnostics: every CTA's final threshold of query 0 ...
@@ -76,6 +77,7 @@ struct FusedArgs {
     int k, keff;                // keff = min(k, rows a hit may come from)
     int pend;                   // pending-score slots per query and tile
     int groups, grank;          // CTA groups of the shared bound and the rank each CTA publishes: ceil(keff / groups)
+    uint32_t seq_on_half;       // searches launched on this half of the double-buffered workspace before this one
     const float* q;             // [nq][dim] raw fp32 queries
     float* qn;                  // [nq][ld] workspace: the normalised fp32 queries (written by CTA 0, read by the finalizers)
     const void* data;           // corpus [n_rows][ld]
@@ -207,6 +209,17 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
     uint32_t* pend = sorted + (size_t)nq * k;                               // [nq][pend]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // Pipelined launches (programmatic stream serialization, see run_fused): the NEXT search's grid may be scheduled as soon as
+    // every CTA of this one has started, so its CTAs take over the SMs one by one as this search's CTAs finish their slices -
+    // the prologue, the tail skew, the finalize and the exchange of one search overlap the sweep of the next, and HBM never
+    // idles between back-to-back searches.  Consecutive searches alternate between two halves of the workspace and never read
+    // each other's; the only shared thing is the caller's output buffer, ordered by griddepcontrol.wait before the emit.
+    if (tid == 0) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        // the search before the previous one used this half: it must be completely done with it (it always is when the grid
+        // fills the device - its last CTA has to exit before the previous search's last CTA can even start)
+        while (ld_acq_gpu(&a.ctl->n_done) != a.seq_on_half) __nanosleep(200);
+    }
     if (blockIdx.x == 0 && tid == 0) a.ctl->t[0] = global_ns();
     // the prologue's first global accesses are the queries (cold): start pulling them in while barriers and tensor memory are set up
     for (int ln = tid; ln * 32 < a.nq * a.dim; ln += kFThreads) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.q + (size_t)ln * 32));
@@ -750,10 +763,6 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
     const int n_fin = nq < (int)gridDim.x ? nq : (int)gridDim.x;
     if (tid == 0) {
         __threadfence();
-        // Pipelined launches (programmatic stream serialization, see run_fused): once every CTA is past its sweep the NEXT
-        // search's grid may start on the SMs this one has vacated - its prologue and sweep overlap this search's finalize and
-        // exchange.  It works on the other half of the double-buffered control block / buffers and never reads this search's.
-        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         *s_ticket = atomicAdd(&a.ctl->done, 1u);
     }
     __syncthreads();
@@ -1045,6 +1054,8 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
             a.ctl->done = 0u;
             a.ctl->obs_done = 0u;
             a.ctl->fin_done = 0u;
+            __threadfence();
+            a.ctl->n_done = a.seq_on_half + 1u;      // this half is free for the search after the next
         }
     }
 }
