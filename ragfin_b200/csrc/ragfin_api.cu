@@ -79,6 +79,7 @@ struct ragfin {
     Buf fctl;                 // fused sweep: TWO control blocks (FusedCtl), zero between searches; consecutive searches alternate
     Buf fcand, fqn, fflags;   //   ... and so do their append buffers, normalised queries and overflow flags: a pipelined search
     uint32_t fused_seq = 0;   //   (ragfin_search / ragfin_search_sharded) may start while its predecessor is still finalizing
+    uint32_t host_seq = 0;    // sequence number of synchronous host calls (value of the mapped completion word)
     int fused_last = 0;       // half used by the last search (diagnostics, stats)
     bool fctl_dirty = true;   // set when a launch may have left it non-zero (first use, failed call): re-zeroed before the next launch
     bool use_bigk_batched = true;   // k > 256: batched dump + select pipeline (RAGFIN_NO_BIGK_BATCHED=1: the one-query exact path)
@@ -546,6 +547,7 @@ static int cand_per_query(int k) {
 static float eps_fp32_accumulate(int ld) { return (float)((ld + 64) * 5.9604644775390625e-08 * 1.0625 + 4.76837158203125e-07); }
 
 static const size_t kHostStageQ = 64 << 10, kHostStageOut = 64 << 10;   // mapped staging of ragfin_search_host (small requests)
+static const size_t kHostStageFlag = 64;                                // ... + the completion word the one-kernel search sets
 static const int kMaxQueryBatch = 4096;  // queries per pass through the pipeline (bounds the workspace)
 
 // ------------------------------------------------------------------------------
@@ -1090,7 +1092,7 @@ static bool fused_eligible(const ragfin* h, int nb, int k) {
     return h->use_fused && h->count >= h->fused_min_rows && gemm_rows_ok(h) && plan_fused(h, nb, k).ncol != 0;
 }
 
-typedef void (*fused_fn)(const CUtensorMap, const FusedArgs);
+typedef void (*fused_fn)(const CUtensorMap, const FusedArgs, const FusedInlineQ);
 static fused_fn pick_fused(int dtype, int ncol, bool split) {
     if (dtype == 0) return ncol == 16 ? sweep_fused_kernel<1, 16, false> : ncol == 32 ? sweep_fused_kernel<1, 32, false> : sweep_fused_kernel<1, 64, false>;
     if (split) return ncol == 16 ? sweep_fused_kernel<0, 16, true> : ncol == 32 ? sweep_fused_kernel<0, 32, true> : sweep_fused_kernel<0, 64, true>;
@@ -1101,8 +1103,11 @@ static fused_fn pick_fused(int dtype, int ncol, bool split) {
 // dependents when it starts, so the CTAs of the next search on the stream take over the SMs one by one as this search's CTAs
 // finish: one search's prologue, tail skew, finalize and exchange overlap the next one's sweep.  Synchronous host calls (one
 // search, then a stream synchronisation) use a plain launch.
+// q_inline_host != null: the queries are host memory and travel in the launch's parameter space (no copy in front of the kernel);
+// host_flag_dev != null: the last finalizer sets that device-mapped word to host_seq (synchronous host calls poll it).
 static int run_fused(ragfin* h, const float* q_dev, int nb, int k, int64_t n_eff, int64_t* out_ids, float* out_scores,
-                     cudaStream_t st, bool pipelined, ragfin_exchange* x = nullptr, uint32_t xstep = 0) {
+                     cudaStream_t st, bool pipelined, ragfin_exchange* x = nullptr, uint32_t xstep = 0,
+                     const float* q_inline_host = nullptr, uint32_t* host_flag_dev = nullptr, uint32_t host_seq = 0) {
     int rc;
     const FusedPlan f = plan_fused(h, nb, k);
     if (f.ncol == 0) return fail(RAGFIN_EUNSUPPORTED, "no fused sweep for %d queries, k = %d", nb, k);
@@ -1135,7 +1140,8 @@ static int run_fused(ragfin* h, const float* q_dev, int nb, int k, int64_t n_eff
     if (a.groups < 1) a.groups = 1;
     a.grank = a.keff > 0 ? (a.keff + a.groups - 1) / a.groups : 0;
     a.seq_on_half = seq >> 1;
-    a.q = q_dev;
+    a.q = q_inline_host ? nullptr : q_dev;
+    a.host_flag = host_flag_dev; a.host_seq = host_seq;
     a.qn = (float*)((char*)h->fqn.p + half * qn_half);
     a.data = h->data;
     a.allow = h->cur_allow;
@@ -1159,8 +1165,10 @@ static int run_fused(ragfin* h, const float* q_dev, int nb, int k, int64_t n_eff
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pipelined ? 1 : 0;
+    static thread_local FusedInlineQ qin;          // 12 KB: copied into the launch only up to what the queries occupy matters
+    if (q_inline_host) memcpy(qin.v, q_inline_host, (size_t)nb * h->dim * sizeof(float));
     prof_begin(h, st);
-    CU_TRY(cudaLaunchKernelEx(&cfg, fn, tmB, a));
+    CU_TRY(cudaLaunchKernelEx(&cfg, fn, tmB, a, qin));
     prof_end(h, st);
     CU_TRY(cudaGetLastError());
     h->fctl_dirty = false;
@@ -1697,6 +1705,65 @@ extern "C" int ragfin_search(ragfin_t* h, const float* q, int32_t nq, int32_t k,
     return mark_done(h, st, pipe);
 }
 
+// Synchronous host calls of the one-kernel search: wait for the completion word the last finalizing CTA writes into
+// device-mapped pinned memory (a posted PCIe write, ~1 us after the hits) instead of for the stream (kernel teardown + driver
+// wake-up).  The stream is queried now and then so that a failed launch cannot spin forever.
+static int poll_host_flag(const volatile uint32_t* flag, uint32_t seq, cudaStream_t st) {
+    for (unsigned spins = 1;; ++spins) {
+        if (*flag == seq) { __atomic_thread_fence(__ATOMIC_ACQUIRE); return 0; }
+        __builtin_ia32_pause();
+        if ((spins & 0x3FFFu) == 0) {
+            const cudaError_t e = cudaStreamQuery(st);
+            if (e == cudaSuccess) return *flag == seq ? 0 : fail(RAGFIN_ECUDA, "the search kernel finished without publishing its results");
+            if (e != cudaErrorNotReady) { (void)cudaGetLastError(); return fail(RAGFIN_ECUDA, "search kernel failed: %s", cudaGetErrorString(e)); }
+        }
+    }
+}
+
+// The fused-path body of the two synchronous host entry points (hstage = mapped staging: [queries | hits | flag]).
+static int fused_host_call(ragfin* h, ragfin_exchange* x, const float* q_host, int nq, int k, int64_t* out_ids_host, float* out_scores_host,
+                           cudaStream_t st) {
+    int rc;
+    const size_t qb = (size_t)nq * h->dim * sizeof(float), ib = (size_t)nq * k * sizeof(int64_t), sb = (size_t)nq * k * sizeof(float);
+    void* dptr = nullptr;
+    CU_TRY(cudaHostGetDevicePointer(&dptr, h->hstage, 0));
+    char* hq = (char*)h->hstage;
+    char* ho = hq + kHostStageQ;
+    volatile uint32_t* hflag = (volatile uint32_t*)(ho + kHostStageOut);
+    char* dout = (char*)dptr + kHostStageQ;
+    uint32_t* dflag = (uint32_t*)(dout + kHostStageOut);
+    const float* q_dev = nullptr;
+    const float* q_inline = nullptr;
+    if ((size_t)nq * h->dim <= (size_t)kFInlineFloats) {
+        q_inline = q_host;                                   // the queries ride in the launch: no transfer in front of the kernel
+    } else {
+        // every CTA reads the queries: one small copy-engine transfer into HBM instead of ~150 reads of the same bytes over PCIe
+        memcpy(hq, q_host, qb);
+        if ((rc = ensure(h->stage_q, qb))) return rc;
+        CU_TRY(cudaMemcpyAsync(h->stage_q.p, hq, qb, cudaMemcpyHostToDevice, st));
+        q_dev = (const float*)h->stage_q.p;
+    }
+    const uint32_t seq = ++h->host_seq;
+    h->stats.launches = 0;
+    h->stats.queries_rescanned = -1;
+    if (x != nullptr) {
+        if (!x->connected) return fail(RAGFIN_EINVAL, "exchange is not connected");
+        if (x->have_stream && x->stream != st)
+            return fail(RAGFIN_EINVAL, "every step of an exchange must be issued on the same CUDA stream (its double buffering relies on stream order)");
+        x->have_stream = true; x->stream = st;
+        const uint32_t step = ++x->step;
+        rc = run_fused(h, q_dev, nq, k, h->count, (int64_t*)dout, (float*)(dout + ib), st, false, x, step, q_inline, dflag, seq);
+    } else {
+        const int64_t n_eff = h->cur_allow ? h->cur_allowed : h->count;
+        rc = run_fused(h, q_dev, nq, k, n_eff, (int64_t*)dout, (float*)(dout + ib), st, false, nullptr, 0, q_inline, dflag, seq);
+    }
+    if (rc) return rc;
+    if ((rc = poll_host_flag(hflag, seq, st))) return rc;
+    memcpy(out_ids_host, ho, ib);
+    memcpy(out_scores_host, ho + ib, sb);
+    return 0;
+}
+
 extern "C" int ragfin_search_host(ragfin_t* h, const float* q_host, int32_t nq, int32_t k, int64_t* out_ids_host,
                                   float* out_scores_host) {
     if (!h) return fail(RAGFIN_EINVAL, "NULL handle");
@@ -1713,23 +1780,20 @@ extern "C" int ragfin_search_host(ragfin_t* h, const float* q_host, int32_t nq, 
         // small request: three copy-engine launches (~20 us) would cost more than the bytes; the kernels read the queries
         // from, and write the hits to, device-mapped pinned memory
         if (!h->hstage) {
-            if (cudaHostAlloc(&h->hstage, kHostStageQ + kHostStageOut, cudaHostAllocMapped) != cudaSuccess) { (void)cudaGetLastError(); h->hstage = nullptr; }
+            if (cudaHostAlloc(&h->hstage, kHostStageQ + kHostStageOut + kHostStageFlag, cudaHostAllocMapped) != cudaSuccess) { (void)cudaGetLastError(); h->hstage = nullptr; }
         }
         void* dptr = nullptr;
         if (h->hstage && cudaHostGetDevicePointer(&dptr, h->hstage, 0) == cudaSuccess) {
+            if (nq <= h->fused_max_nq && fused_eligible(h, nq, k)) {
+                if ((rc = fused_host_call(h, nullptr, q_host, nq, k, out_ids_host, out_scores_host, st))) return rc;
+                return mark_done(h, st);
+            }
             char* hq = (char*)h->hstage;
             char* ho = hq + kHostStageQ;
             memcpy(hq, q_host, qb);
             char* dq = (char*)dptr;
             char* dout = dq + kHostStageQ;
             const float* qsrc = (const float*)dq;
-            if (nq <= kFMaxQ && fused_eligible(h, nq, k)) {
-                // the one-kernel search reads the queries from every CTA: one small copy-engine transfer into HBM instead
-                // of ~150 reads of the same bytes over PCIe; the hits are still written straight into the mapped staging
-                if ((rc = ensure(h->stage_q, qb))) return rc;
-                CU_TRY(cudaMemcpyAsync(h->stage_q.p, hq, qb, cudaMemcpyHostToDevice, st));
-                qsrc = (const float*)h->stage_q.p;
-            }
             if ((rc = search_locked(h, qsrc, nq, k, (int64_t*)dout, (float*)(dout + ib), st))) return rc;
             CU_TRY(cudaStreamSynchronize(st));
             memcpy(out_ids_host, ho, ib);
@@ -2040,22 +2104,15 @@ extern "C" int ragfin_search_sharded_host(ragfin_t* h, ragfin_exchange_t* x, con
     if ((rc = wait_prev(h, st))) return rc;
     const size_t qb = (size_t)nq * h->dim * sizeof(float), ib = (size_t)nq * k * sizeof(int64_t), sb = (size_t)nq * k * sizeof(float);
     if (qb > kHostStageQ || ib + sb > kHostStageOut) return fail(RAGFIN_EUNSUPPORTED, "request too large for the mapped staging");
-    if (!h->hstage && cudaHostAlloc(&h->hstage, kHostStageQ + kHostStageOut, cudaHostAllocMapped) != cudaSuccess) {
+    if (x->device != h->device) return fail(RAGFIN_EINVAL, "exchange and collection live on different devices");
+    if (nq > h->fused_max_nq || !fused_eligible(h, nq, k))
+        return fail(RAGFIN_EUNSUPPORTED, "shape (nq = %d, k = %d) does not take the one-kernel search on this shard", nq, k);
+    if ((size_t)nq * (((size_t)k * 12 + 15) / 16 * 16) > x->record_max) return fail(RAGFIN_EINVAL, "record exceeds the exchange's %zu bytes", x->record_max);
+    if (!h->hstage && cudaHostAlloc(&h->hstage, kHostStageQ + kHostStageOut + kHostStageFlag, cudaHostAllocMapped) != cudaSuccess) {
         (void)cudaGetLastError(); h->hstage = nullptr;
         return fail(RAGFIN_ENOMEM, "pinned staging allocation failed");
     }
-    void* dptr = nullptr;
-    CU_TRY(cudaHostGetDevicePointer(&dptr, h->hstage, 0));
-    char* hq = (char*)h->hstage;
-    char* ho = hq + kHostStageQ;
-    char* dout = (char*)dptr + kHostStageQ;
-    memcpy(hq, q_host, qb);
-    if ((rc = ensure(h->stage_q, qb))) return rc;
-    CU_TRY(cudaMemcpyAsync(h->stage_q.p, hq, qb, cudaMemcpyHostToDevice, st));
-    if ((rc = sharded_locked(h, x, (const float*)h->stage_q.p, nq, k, (int64_t*)dout, (float*)(dout + ib), st, false))) return rc;
-    CU_TRY(cudaStreamSynchronize(st));
-    memcpy(out_ids_host, ho, ib);
-    memcpy(out_scores_host, ho + ib, sb);
+    if ((rc = fused_host_call(h, x, q_host, nq, k, out_ids_host, out_scores_host, st))) return rc;
     // a finalizing CTA that waited 4 s for a peer's hits gives up and marks the query's empty slots with NaN scores
     for (size_t i = 0; i < (size_t)nq * k; ++i)
         if (out_scores_host[i] != out_scores_host[i]) {

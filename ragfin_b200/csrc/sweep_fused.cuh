@@ -65,6 +65,11 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
+// Queries of a small synchronous host call travel INSIDE the launch (kernel parameter space) instead of through a copy-engine
+// transfer in front of the kernel: up to kFInlineFloats floats (4 queries of 768, 3 of 1024).
+constexpr int kFInlineFloats = 3072;
+struct FusedInlineQ { float v[kFInlineFloats]; };
+
 struct FusedArgs {
     uint32_t idesc;             // M = 128, N = NCOL
     int num_kblocks, k_elems;   // k-blocks of 128 bytes; elements per k-block (64 for 16-bit storage, 32 for fp32)
@@ -78,7 +83,7 @@ struct FusedArgs {
     int pend;                   // pending-score slots per query and tile
     int groups, grank;          // CTA groups of the shared bound and the rank each CTA publishes: ceil(keff / groups)
     uint32_t seq_on_half;       // searches launched on this half of the double-buffered workspace before this one
-    const float* q;             // [nq][dim] raw fp32 queries
+    const float* q;             // [nq][dim] raw fp32 queries; null: they are in the launch's FusedInlineQ parameter
     float* qn;                  // [nq][ld] workspace: the normalised fp32 queries (written by CTA 0, read by the finalizers)
     const void* data;           // corpus [n_rows][ld]
     const uint32_t* allow;      // scalar filter bitmask or null
@@ -91,6 +96,8 @@ struct FusedArgs {
     float* out_scores;          // [nq][k]
     int* flags;                 // [nq] 1 = the query took the in-kernel exact scan
     int* flag_count;
+    uint32_t* host_flag;        // synchronous host calls: device-mapped pinned word the last finalizer sets to host_seq once every
+    uint32_t host_seq;          //   query's hits are in the (mapped) output buffers - the host polls it instead of waiting for the stream
     // cross-shard exchange inside the finalize (row-sharded corpora, one process per GPU; xworld <= 1: off).  Peer gather
     // areas and flags are mapped through CUDA IPC (ragfin_exchange_*); see "exchange" in the header comment.
     int xworld, xrank;
@@ -172,7 +179,8 @@ __device__ __forceinline__ void canonical_dot_two_rows(const void* data, uint32_
 
 template <int KIND, int NCOL, bool SPLIT>
 __global__ void __launch_bounds__(kFThreads, 1)
-sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
+sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a, const __grid_constant__ FusedInlineQ qin) {
+    const float* const qsrc = a.q != nullptr ? a.q : qin.v;
     constexpr int P = NCOL <= 32 ? 4 : 2;                      // partial accumulators per half tile
     constexpr int kAcc = 2 * P * NCOL;                         // TMEM columns of one tile buffer
     constexpr int kTmemCols = 2 * kAcc <= 256 ? 256 : 512;
@@ -222,7 +230,8 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
     }
     if (blockIdx.x == 0 && tid == 0) a.ctl->t[0] = global_ns();
     // the prologue's first global accesses are the queries (cold): start pulling them in while barriers and tensor memory are set up
-    for (int ln = tid; ln * 32 < a.nq * a.dim; ln += kFThreads) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.q + (size_t)ln * 32));
+    if (a.q != nullptr)
+        for (int ln = tid; ln * 32 < a.nq * a.dim; ln += kFThreads) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.q + (size_t)ln * 32));
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
@@ -272,12 +281,12 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
         // pass 1, one warp per query: canonical sum of squares -> 1 / |q| (fp64), parked in the pending area
         double* inv_s = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(pend) + 7) & ~(uintptr_t)7);   // [nq]
         for (int j = warp; j < nq; j += kFThreads / 32) {
-            const float* x = a.q + (size_t)j * a.dim;
+            const float* x = qsrc + (size_t)j * a.dim;
             double acc = 0.0;
             for (int i0 = lane; i0 < a.dim; i0 += 24 * kWarp) {     // 24 loads in flight (a 768-wide query: one round trip);
                 float xv[24];                                       // the adds stay in increasing-i order
 #pragma unroll
-                for (int u = 0; u < 24; ++u) xv[u] = i0 + u * kWarp < a.dim ? __ldg(x + i0 + u * kWarp) : 0.0f;
+                for (int u = 0; u < 24; ++u) xv[u] = i0 + u * kWarp < a.dim ? x[i0 + u * kWarp] : 0.0f;
 #pragma unroll
                 for (int u = 0; u < 24; ++u) { const double v = (double)xv[u]; acc = acc + v * v; }   // + 0 for the tail: exact
             }
@@ -292,7 +301,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
         // of 192 consecutive elements of ONE query (so a unit's threads share the query: the residual is reduced per warp);
         // the loads of 8 units are issued before anything is computed.
         constexpr int VE = KIND == 1 ? 4 : 8;                     // elements of one 16-byte chunk of a query row
-        if (a.dim % VE == 0 && (reinterpret_cast<uintptr_t>(a.q) & 15u) == 0) {
+        if (a.dim % VE == 0 && (reinterpret_cast<uintptr_t>(qsrc) & 15u) == 0) {
             // fast path: one thread per 16-byte chunk (8 bf16 / fp16 or 4 fp32 elements): 128-bit loads, one 128-bit swizzled
             // store for the hi row and one for the lo row; the residual is summed per thread, then per warp
             constexpr int KE = KIND == 1 ? 32 : 64;
@@ -305,7 +314,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
                     const int ch = ch0 + u * kFThreads + tid;
 #pragma unroll
                     for (int v4 = 0; v4 < VE / 4; ++v4) {
-                        const float4 f = ch < total ? __ldg(reinterpret_cast<const float4*>(a.q) + (size_t)ch * (VE / 4) + v4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 f = ch < total ? reinterpret_cast<const float4*>(qsrc)[(size_t)ch * (VE / 4) + v4] : make_float4(0.f, 0.f, 0.f, 0.f);
                         xv[u][4 * v4] = f.x; xv[u][4 * v4 + 1] = f.y; xv[u][4 * v4 + 2] = f.z; xv[u][4 * v4 + 3] = f.w;
                     }
                 }
@@ -367,7 +376,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
 #pragma unroll
                 for (int u = 0; u < UB; ++u) {
                     const int un = u0 + u, j = un / upq, i = (un - j * upq) * kFThreads + tid;
-                    xv[u] = (un < units && i < a.dim) ? __ldg(a.q + (size_t)j * a.dim + i) : 0.0f;
+                    xv[u] = (un < units && i < a.dim) ? qsrc[(size_t)j * a.dim + i] : 0.0f;
                 }
 #pragma unroll
                 for (int u = 0; u < UB; ++u) {
@@ -1049,13 +1058,14 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a) {
         if (tid <= kFGroups) a.ctl->gthr[qi][tid] = 0u;
     }
     if (tid == 0) {
-        __threadfence();
+        if (a.host_flag != nullptr) __threadfence_system(); else __threadfence();   // this CTA's hits are visible (to the host) first
         if (atomicAdd(&a.ctl->fin_done, 1u) == (uint32_t)n_fin - 1u) {   // last finalizer: counters back to zero
             a.ctl->done = 0u;
             a.ctl->obs_done = 0u;
             a.ctl->fin_done = 0u;
             __threadfence();
             a.ctl->n_done = a.seq_on_half + 1u;      // this half is free for the search after the next
+            if (a.host_flag != nullptr) { __threadfence_system(); *reinterpret_cast<volatile uint32_t*>(a.host_flag) = a.host_seq; }
         }
     }
 }
