@@ -233,3 +233,22 @@ def test_fused_pipelined_back_to_back_searches(coracle):
             want[key] = coracle.cosine_topk(qs[i], stored[:rows], shapes[i][1])
         _same((ids.cpu().numpy(), sc.cpu().numpy()), want[key], f"pipelined shape {shapes[i]} rows {rows}")
     idx.close()
+
+
+def test_fused_thousands_of_rows_tied_at_the_top(coracle):
+    """9 000 copies of the best row (more than the staged select holds, fewer than the append buffer): the finalize falls back
+    to the global-memory select, rescans all of them and returns the lowest ids - without the exact scan."""
+    n, dim, k = 80000, 64, 10
+    x = O.synth_rows(380, 0, n, dim)
+    x[20000:29000] = x[19999]
+    q = np.concatenate([x[19999:20000] * 2.0, O.synth_rows(381, 0, 1, dim)])
+    for dtype in ("bf16", "f32"):
+        idx = _index(x, dtype)
+        got = idx.search(q, k)
+        st = idx.stats()
+        a, r = idx.fused_counts(2)
+        assert st["path"] == 3 and st["queries_rescanned"] == 0, (st, a, r)
+        assert a[0] >= 9001 and r[0] >= 9001, (a, r)
+        _same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), k), f"tied top {dtype}")
+        assert list(got[0][0]) == list(range(19999, 19999 + k))
+        idx.close()
