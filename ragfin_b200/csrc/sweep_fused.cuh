@@ -1,35 +1,44 @@
-// K3f: the whole small-batch search in ONE kernel (<= 64 queries, k <= 128) - query preparation, tensor-core sweep with
-// self-tightening thresholds, exact finalize.  sm_100a only.
+// K3f: the whole small-batch search in ONE kernel (<= 64 queries, k <= 128; by default <= 16 queries and queries x k <= 400,
+// the measured crossover) - query preparation, tensor-core sweep with self-tightening thresholds, exact finalize and, on a
+// row-sharded corpus, the cross-GPU exchange and reduce.  sm_100a only.
 //
-// Round 1 served these batches with six launches (query prep, bound pass, bound select, sweep, append finalize, two gated
-// tier-2 launches): ~65-90 us of latency-bound head and tail around a 0.27-2.1 ms sweep, which is what held the 8-GPU
+// Round 1 served these batches with seven launches (query prep, bound sweep, bound select, sweep, append finalize, two gated
+// tier-2 launches): 65-90 us of latency-bound head and tail around a 0.27-2.1 ms sweep, which is what held the 8-GPU
 // strong-scaling efficiency at 0.74.  Here:
 //
-//   prologue   every CTA normalises the <= 64 queries itself (canonical fp64 arithmetic, bit-identical to ingest) and
-//              writes them straight into its shared memory in the tensor core's K-major SWIZZLE_128B layout, while the
-//              TMA producer already streams corpus tiles.  16-bit storage: every query is split into hi = round(q) and
-//              lo = round(q - hi), two MMA columns summed in the epilogue, so the query rounding error that dominated the
-//              rigorous error bound drops from ~1.6e-3 to ~8e-6 (SPLIT).
+//   prologue   every CTA prepares the queries itself: one warp per query computes 1 / |q| with the canonical fp64 reduction,
+//              then all threads scale 16-byte chunks exactly as ingest does and store them straight into shared memory in the
+//              tensor core's K-major SWIZZLE_128B layout, while the TMA producer already has a ring-full of corpus bytes in
+//              flight.  16-bit storage: every query enters as TWO columns, hi = round(q) and lo = round(q - hi), summed in
+//              the epilogue, so the query term of the error bound drops from ~1.6e-3 to an a-priori 2^-18 (SPLIT).
 //   sweep      as gemm_rows.cuh: corpus rows are the MMA's M (two 128-row halves per 256-row tile), the query block its
-//              N = 16 / 32 / 64, P partial accumulators per half so that no MMA waits on its predecessor.
-//   threshold  NO bound pass.  A row is appended to its query's buffer when approx >= thr[q]; thr[q] starts at -inf
-//              and only rises: every CTA keeps, per query, the sorted k best approximate scores among the rows IT has
-//              appended (k distinct rows, so the k-th is a lower bound of T, the k-th best approximate score of the
-//              corpus) and sets thr = kth - 2 eps.  CTAs cooperate through G = 16 words per query: CTA c publishes its
-//              ceil(k / G)-th best score (minus 2 eps) into word c % G by atomicMax; the MINIMUM of the G words is a valid
-//              bound too (G different CTAs each hold ceil(k / G) distinct rows at or above their word) and a much tighter
-//              one for large k - a CTA only has to find k / 16 good rows, not k.  Re-read every tile.  Every row of the exact top-k satisfies approx >= T - 2 eps >= thr at
-//              any time, so it is in the buffer (DESIGN.md 2.4 with a moving threshold).  Tiles of a slice are visited in
-//              a strided permutation, so a corpus sorted by similarity cannot make every row beat the running bound.
-//   finalize   the last nq CTAs to finish wait for the grid-wide arrival counter and finalize one query each in place:
-//              histogram-narrowing select of T over the buffer, gather above T - 2 eps, canonical fp64 rescore, sort,
-//              emit; an overflowing buffer (> cap rows within reach of the top k: massive duplication) is answered by
-//              the same CTA with a canonical scan of the whole corpus - slow, exact, and no extra launch.
-//   exchange   row-sharded corpora (one process per GPU): the finalizing CTA of a query stores its k exact hits straight
-//              into every peer's gather area over NVLink (CUDA IPC mappings), publishes a per-(rank, query) flag with
-//              st.release.sys, waits for the W flags of its own area, merges the W x k hits by rank counting and writes
-//              the GLOBAL top-k - the whole sharded search is this one kernel per GPU, no collective call.
-// The control block (counters, published thresholds) is left zeroed by every search.
+//              N = 16 / 32 / 64, P partial accumulators per half so that no MMA waits on its predecessor.  Tiles of a slice are
+//              visited in a strided permutation starting mid-slice, so a corpus sorted by similarity cannot make every row
+//              beat the running bound.
+//   threshold  NO bound pass.  A row is appended to its query's buffer when approx >= thr[q]; thr[q] starts at -inf and only
+//              rises, always from a value that k DISTINCT rows are known to reach (a lower bound of T, the k-th best
+//              approximate score), minus 2 eps: (1) the CTA's own sorted list of the k best scores it has appended; (2) the
+//              best such full bound of ANY CTA, one atomicMax word per query (on a templated corpus one CTA holds the whole
+//              answer); (3) G = 16 words per query, word g = max over the CTAs of group g of their ceil(k / G)-th best: the
+//              MINIMUM of the G words is a bound (G different CTAs, ceil(k / G) distinct rows each) and a far tighter one for
+//              large k.  Every row of the exact top-k has approx >= T - 2 eps >= thr whenever it is scored, so it is in the
+//              buffer.  The CTA's FIRST tile is observed before anything is appended (with thr = -inf
+//              148 x 256 rows per query would land on one counter): its scores go to shared memory, one warp per query finds
+//              its k best, the bounds are published and, after a bounded rendezvous, the tile is appended against the best
+//              bound of the grid.  Per-query bookkeeping is warp-cooperative (epilogue warp w owns queries w, w + 4, ...).
+//   finalize   the last nq CTAs to bump the grid's arrival counter wait for it and finalize one query each: the buffer is
+//              pre-filtered with the CTA's own final threshold and staged in shared memory (the ring is free), T by rank
+//              counting or a shared-memory radix select, gather above T - 2 eps, canonical fp64 rescore (two rows in flight
+//              per warp), rank sort, emit.  A buffer that overflowed (> cap rows ever within reach of the top k: massive
+//              duplication) is answered by the same CTA with a canonical scan of the whole corpus - slow, exact, no launch.
+//   exchange   row-sharded corpora (one process per GPU): the finalizing CTA stores its k exact hits straight into every
+//              rank's gather area over NVLink (CUDA IPC mappings), publishes a per-(rank, query) flag with st.release.sys,
+//              waits for the W flags of its own area, merges the W x k hits by rank counting and writes the GLOBAL top-k - a
+//              sharded search is this one kernel per GPU, no collective call.
+//   pipelining asynchronous entry points launch with programmatic stream serialization and the kernel releases its
+//              dependents when it starts: the next search's CTAs take over SMs as this one's finish, so back-to-back
+//              searches overlap one search's tail with the next one's sweep.  Consecutive searches alternate between two
+//              halves of the workspace; every search leaves its control block zeroed.
 #pragma once
 #include "gemm_rows.cuh"
 
