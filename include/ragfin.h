@@ -245,6 +245,9 @@ int ragfin_debug_fused_counts(ragfin_t* h, int32_t nq, int64_t* out_appended, in
  * done, sweep done}, finalizer of query 0 {all CTAs arrived, hits selected, rescored, emitted}, then finer stamps {setup done,
  * norms done, count read, keys staged, T found} (csrc/sweep_fused.cuh FusedCtl::t).  Synchronises. */
 int ragfin_debug_fused_times(ragfin_t* h, int64_t* out);
+/* Test hook, no device needed: the order in which the one-kernel search visits the n_tiles tiles of a slice (out[n_tiles]); the
+ * CPU suite checks that it is a permutation for every slice length (every tile scored exactly once) and starts mid-slice. */
+int ragfin_debug_fused_tile_order(int32_t n_tiles, int32_t* out);
 /* Per-CTA diagnostics of the last one-kernel search (arrays of 160): final threshold of query 0, rows appended for it. */
 int ragfin_debug_fused_ctas(ragfin_t* h, float* out_thr, int32_t* out_app);
 

@@ -1607,6 +1607,15 @@ extern "C" int ragfin_set_append_mode(ragfin_t* h, int32_t enable) {
 
 // Diagnostics of the last one-kernel search: rows appended per query (out_appended[nq]) and rows rescored exactly
 // (out_rescored[nq]; -1 = the query took the in-kernel exact scan).  Synchronises the device.
+// Test hook, pure host arithmetic (no device needed): the order in which the one-kernel search visits the n tiles of a slice
+// (out[n]).  Exactness rests on it being a permutation - every tile scored exactly once.
+extern "C" int ragfin_debug_fused_tile_order(int32_t n_tiles, int32_t* out) {
+    if (!out || n_tiles < 1) return fail(RAGFIN_EINVAL, "bad argument");
+    const int mult = perm_mult(n_tiles);
+    for (int t = 0; t < n_tiles; ++t) out[t] = perm_tile(t, mult, n_tiles);
+    return RAGFIN_OK;
+}
+
 // Phase stamps of the last one-kernel search, ns relative to the kernel's start (out[16], see FusedCtl::t).
 extern "C" int ragfin_debug_fused_times(ragfin_t* h, int64_t* out) {
     if (!h || !out) return fail(RAGFIN_EINVAL, "bad argument");

@@ -77,7 +77,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // Queries of a small synchronous host call travel INSIDE the launch (kernel parameter space) instead of through a copy-engine
 // transfer in front of the kernel: up to kFInlineFloats floats (4 queries of 768, 3 of 1024).
 constexpr int kFInlineFloats = 3072;
-struct FusedInlineQ { float v[kFInlineFloats]; };
+struct alignas(16) FusedInlineQ { float v[kFInlineFloats]; };   // 16-byte aligned: the prologue reads it with 128-bit loads
 
 struct FusedArgs {
     uint32_t idesc;             // M = 128, N = NCOL
@@ -143,9 +143,9 @@ __device__ __forceinline__ float thr_below(float value, float eps) {
 // Tiles of a slice are visited in the order perm_tile(t) = (n / 2 + t * mult) % n: a stride near 0.618 n (coprime with n, so
 // every tile is visited once) starting in the middle, so that the first few tiles sample the whole slice - on a corpus sorted
 // by similarity a sequential sweep would see every row beat the running k-th score.
-__device__ __forceinline__ int perm_tile(int t, int mult, int n) { return (int)(((long long)t * mult + n / 2) % n); }
+__host__ __device__ __forceinline__ int perm_tile(int t, int mult, int n) { return (int)(((long long)t * mult + n / 2) % n); }
 // multiplier of the tile permutation: odd, near 0.618 n, coprime with n
-__device__ __forceinline__ int perm_mult(int n) {
+__host__ __device__ __forceinline__ int perm_mult(int n) {
     if (n <= 2) return 1;
     int m = (int)(0.6180339887 * n) | 1;
     for (;; m += 2) {
@@ -306,13 +306,11 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a, c
         if (blockIdx.x == 0 && tid == 0) a.ctl->t[9] = global_ns();
         if (blockIdx.x == 0 && a.ld > a.dim)
             for (int i = tid; i < nq * (a.ld - a.dim); i += kFThreads) a.qn[(size_t)(i / (a.ld - a.dim)) * a.ld + a.dim + i % (a.ld - a.dim)] = 0.0f;
-        // pass 2, all threads: y = RNE_f32(x / |q|) exactly as ingest does, hi / lo split, swizzled store.  Work units are runs
-        // of 192 consecutive elements of ONE query (so a unit's threads share the query: the residual is reduced per warp);
-        // the loads of 8 units are issued before anything is computed.
+        // pass 2, all threads: y = RNE_f32(x / |q|) exactly as ingest does, hi / lo split, swizzled store
         constexpr int VE = KIND == 1 ? 4 : 8;                     // elements of one 16-byte chunk of a query row
         if (a.dim % VE == 0 && (reinterpret_cast<uintptr_t>(qsrc) & 15u) == 0) {
             // fast path: one thread per 16-byte chunk (8 bf16 / fp16 or 4 fp32 elements): 128-bit loads, one 128-bit swizzled
-            // store for the hi row and one for the lo row; the residual is summed per thread, then per warp
+            // store for the hi row and one for the lo row
             constexpr int KE = KIND == 1 ? 32 : 64;
             const int cpq = a.dim / VE;                            // chunks per query
             const int total = nq * cpq;

@@ -91,3 +91,22 @@ def test_plan_rejects_bad_arguments():
     assert L.ragfin_debug_plan(0, 10, 148, 10, 0, out) == _lib.EINVAL
     assert L.ragfin_debug_plan(1, 10, 148, 10, 3, out) == _lib.EINVAL
     assert L.ragfin_debug_plan(1, 10, 148, 10, 0, None) == _lib.EINVAL
+
+
+def test_fused_sweep_visits_every_tile_of_a_slice_exactly_once():
+    """csrc/sweep_fused.cuh visits the tiles of a slice in a strided permutation starting mid-slice (so that a corpus sorted by
+    similarity cannot make every row beat the running bound).  The library's own function, run on the host for every slice
+    length up to 3 000 tiles and a few large ones: a permutation of 0 .. n - 1, first tile n // 2, consecutive visits far apart."""
+    import numpy as np
+    from ragfin_b200 import _lib
+    L = _lib.load()
+    for n in list(range(1, 3001)) + [39063, 48829, 65536, 100003, 390625]:
+        out = np.empty(n, np.int32)
+        _lib.check(L.ragfin_debug_fused_tile_order(n, out.ctypes.data))
+        assert np.array_equal(np.sort(out), np.arange(n)), n
+        assert out[0] == n // 2
+        if n >= 16:
+            step = np.abs(np.diff(out.astype(np.int64)))
+            step = np.minimum(step, n - step)
+            assert step.min() >= n // 4, (n, step.min())          # no two consecutive visits close to each other
+    assert L.ragfin_debug_fused_tile_order(0, None) == _lib.EINVAL
