@@ -902,12 +902,16 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a, c
                 const float thr_loc = thr_s[qi];
                 if (tid == 0) { s3[1] = 0u; s3[0] = 0u; s3[2] = (uint32_t)keff; }
                 __syncthreads();
-                for (int i = tid; i < m; i += kFThreads) {
-                    const u64 key = __ldcg(in + i);
-                    if (key_score(key) >= thr_loc) {
-                        const uint32_t p_ = atomicAdd(&s3[1], 1u);
-                        if (p_ < (uint32_t)kSmallM) stg[p_] = key;
-                    }
+                for (int i0 = tid; i0 < m; i0 += 4 * kFThreads) {       // four loads in flight per thread (the buffer is in L2)
+                    u64 key[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) key[u] = i0 + u * kFThreads < m ? __ldcg(in + i0 + u * kFThreads) : 0ull;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (key[u] != 0ull && key_score(key[u]) >= thr_loc) {
+                            const uint32_t p_ = atomicAdd(&s3[1], 1u);
+                            if (p_ < (uint32_t)kSmallM) stg[p_] = key[u];
+                        }
                 }
                 __syncthreads();
                 m1 = (int)s3[1];
