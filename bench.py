@@ -326,11 +326,13 @@ def run_ours(a):
 
         fused_sharded = world > 1 and searcher.exchange is not None and searcher.fused_ok(batch, a.k)
 
+        q_batches = [q_host[b] for b in range(nbatches)]   # the caller's own pinned buffers, handed over as they are
+
         def e2e_step(i):
             if world == 1:   # the C-ABI host call: H2D + search + D2H + sync inside ragfin_search_host
-                idx.search(q_host[i % nbatches].numpy(), a.k, out_ids=out_ids.numpy(), out_scores=out_sc.numpy())
+                idx.search(q_batches[i % nbatches], a.k, out_ids=out_ids, out_scores=out_sc)
             elif fused_sharded:   # ragfin_search_sharded_host: pinned staging, one kernel per GPU (sweep + exchange + reduce), one sync
-                searcher.search_host(q_host[i % nbatches].numpy(), a.k, out_ids=out_ids.numpy(), out_scores=out_sc.numpy())
+                searcher.search_host(q_batches[i % nbatches], a.k, out_ids=out_ids, out_scores=out_sc)
             else:
                 q_stage.copy_(q_host[i % nbatches], non_blocking=True)
                 ids, sc = searcher.search(q_stage, a.k)

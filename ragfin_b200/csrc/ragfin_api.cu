@@ -85,6 +85,7 @@ struct ragfin {
     bool use_bigk_batched = true;   // k > 256: batched dump + select pipeline (RAGFIN_NO_BIGK_BATCHED=1: the one-query exact path)
     bool use_fused = true;    // <= 64 queries, k <= 128: the one-kernel search (sweep_fused.cuh); RAGFIN_NO_FUSED=1 disables
     int fused_min_rows = 8192;
+    int fused_refresh_every = 4, fused_stage_cap = kRMaxStages;   // experiment knobs (RAGFIN_FUSED_REFRESH_EVERY / _STAGES)
     int fused_max_nq = 16;    // see plan_fused; RAGFIN_FUSED_MAX_NQ overrides (<= 64)
     int fused_max_nqk = 400;  // queries x k; RAGFIN_FUSED_MAX_NQK overrides
     struct MapSlot { const void* base = nullptr; int64_t rows = 0; int ld = 0, dtype = 0, box_rows = 0; CUtensorMap map; };
@@ -147,6 +148,17 @@ struct DeviceGuard {
     }
 };
 
+// Environment knobs, read when a handle (or a view) is created.
+static void read_env_knobs(ragfin* h) {
+    { const char* e = getenv("RAGFIN_NO_BOUND_PASS"); if (e && atoi(e)) h->use_bound_pass = false; }
+    { const char* e = getenv("RAGFIN_NO_FUSED"); if (e && atoi(e)) h->use_fused = false; }
+    { const char* e = getenv("RAGFIN_NO_BIGK_BATCHED"); if (e && atoi(e)) h->use_bigk_batched = false; }
+    { const char* e = getenv("RAGFIN_FUSED_MAX_NQ"); if (e && atoi(e) >= 1 && atoi(e) <= kFMaxQ) h->fused_max_nq = atoi(e); }
+    { const char* e = getenv("RAGFIN_FUSED_MAX_NQK"); if (e && atoi(e) >= 1) h->fused_max_nqk = atoi(e); }
+    { const char* e = getenv("RAGFIN_FUSED_REFRESH_EVERY"); if (e && atoi(e) >= 1) h->fused_refresh_every = atoi(e); }
+    { const char* e = getenv("RAGFIN_FUSED_STAGES"); if (e && atoi(e) >= 2 && atoi(e) <= kRMaxStages) h->fused_stage_cap = atoi(e); }
+}
+
 extern "C" int ragfin_create(ragfin_t** out, int32_t dim, int32_t dtype, int64_t capacity_rows, int32_t device) {
     if (!out) return fail(RAGFIN_EINVAL, "out is NULL");
     *out = nullptr;
@@ -176,11 +188,7 @@ extern "C" int ragfin_create(ragfin_t** out, int32_t dim, int32_t dtype, int64_t
     h->dtype = dtype;
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
-    { const char* e = getenv("RAGFIN_NO_BOUND_PASS"); if (e && atoi(e)) h->use_bound_pass = false; }
-    { const char* e = getenv("RAGFIN_NO_FUSED"); if (e && atoi(e)) h->use_fused = false; }
-    { const char* e = getenv("RAGFIN_NO_BIGK_BATCHED"); if (e && atoi(e)) h->use_bigk_batched = false; }
-    { const char* e = getenv("RAGFIN_FUSED_MAX_NQ"); if (e && atoi(e) >= 1 && atoi(e) <= kFMaxQ) h->fused_max_nq = atoi(e); }
-    { const char* e = getenv("RAGFIN_FUSED_MAX_NQK"); if (e && atoi(e) >= 1) h->fused_max_nqk = atoi(e); }
+    read_env_knobs(h);
     h->capacity = capacity_rows;
     const size_t bytes = (size_t)capacity_rows * h->ld * esize(dtype);
     e = cudaMalloc(&h->data, bytes);
@@ -218,6 +226,10 @@ extern "C" int ragfin_create_view(ragfin_t* parent, ragfin_t** out) {
     h->gemm_min_nq = parent->gemm_min_nq; h->gemm_min_nq_large = parent->gemm_min_nq_large; h->gemm_cluster = parent->gemm_cluster;
     h->scan_variant = parent->scan_variant; h->use_append = parent->use_append; h->use_bound_pass = parent->use_bound_pass;
     h->gemm_variant = parent->gemm_variant;
+    h->use_fused = parent->use_fused; h->use_bigk_batched = parent->use_bigk_batched; h->fused_min_rows = parent->fused_min_rows;
+    h->fused_max_nq = parent->fused_max_nq; h->fused_max_nqk = parent->fused_max_nqk;
+    h->fused_refresh_every = parent->fused_refresh_every; h->fused_stage_cap = parent->fused_stage_cap;
+    read_env_knobs(h);
     cudaError_t e = cudaEventCreateWithFlags(&h->last_done, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         delete h;
@@ -1070,7 +1082,7 @@ static FusedPlan plan_fused(const ragfin* h, int nb, int k) {
         for (int ci = 0; ci < 3; ++ci) {
             const int ncol = split ? cols_split[ci] : cols_plain[ci];
             if ((split ? ncol / 2 : ncol) < nb) continue;
-            for (int stages = kRMaxStages; stages >= 3; --stages) {
+            for (int stages = h->fused_stage_cap; stages >= 2; --stages) {
                 const size_t smem = fused_smem_bytes(nkb, ncol, stages, nb, k, pend);
                 if (smem > (size_t)227 * 1024) continue;
                 const size_t region = (size_t)nkb * ncol * kGKBytes + (size_t)stages * kBBytes;
@@ -1140,6 +1152,7 @@ static int run_fused(ragfin* h, const float* q_dev, int nb, int k, int64_t n_eff
     if (a.groups < 1) a.groups = 1;
     a.grank = a.keff > 0 ? (a.keff + a.groups - 1) / a.groups : 0;
     a.seq_on_half = seq >> 1;
+    a.refresh_every = h->fused_refresh_every;
     a.q = q_inline_host ? nullptr : q_dev;
     a.host_flag = host_flag_dev; a.host_seq = host_seq;
     a.qn = (float*)((char*)h->fqn.p + half * qn_half);
@@ -1625,7 +1638,8 @@ extern "C" int ragfin_debug_fused_times(ragfin_t* h, int64_t* out) {
     CU_TRY(cudaDeviceSynchronize());
     FusedCtl c;
     CU_TRY(cudaMemcpy(&c, (FusedCtl*)h->fctl.p + h->fused_last, sizeof(c), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < 16; ++i) out[i] = (int64_t)(c.t[i] - c.t[0]);
+    for (int i = 0; i < 13; ++i) out[i] = (int64_t)(c.t[i] - c.t[0]);
+    for (int i = 13; i < 16; ++i) out[i] = (int64_t)c.t[i];   // sums over CTA 0's tiles, not stamps
     return RAGFIN_OK;
 }
 

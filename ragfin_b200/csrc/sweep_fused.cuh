@@ -92,6 +92,8 @@ struct FusedArgs {
     int pend;                   // pending-score slots per query and tile
     int groups, grank;          // CTA groups of the shared bound and the rank each CTA publishes: ceil(keff / groups)
     uint32_t seq_on_half;       // searches launched on this half of the double-buffered workspace before this one
+    int refresh_every;          // thresholds are re-read from the grid every tile for the first 8 tiles of a slice, then every n-th
+                                // tile (and whenever one of the warp's own lists changed); a stale threshold only admits more rows
     const float* q;             // [nq][dim] raw fp32 queries; null: they are in the launch's FusedInlineQ parameter
     float* qn;                  // [nq][ld] workspace: the normalised fp32 queries (written by CTA 0, read by the finalizers)
     const void* data;           // corpus [n_rows][ld]
@@ -128,6 +130,29 @@ __host__ __device__ constexpr size_t fused_smem_bytes(int num_kblocks, int ncol,
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+// named barrier that also ORs a flag over its threads (one instruction: "did any thread of the epilogue append this tile?")
+__device__ __forceinline__ bool named_bar_or(int id, int threads, bool flag) {
+    uint32_t out;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(out) : "r"((uint32_t)flag), "r"(id), "r"(threads) : "memory");
+    return out != 0u;
+}
+// tcgen05.ld without the wait: several loads in flight, then ONE tmem_ld_wait(), then tmem_ld_fence16() on every destination
+// array (an empty volatile asm that names the registers in/out: no use of them can be scheduled above the wait).
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_fence16(uint32_t (&r)[16]) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                      "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]) :: "memory");
+}
 __device__ __forceinline__ uint32_t ld_acq_gpu(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -237,7 +262,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a, c
         // fills the device - its last CTA has to exit before the previous search's last CTA can even start)
         while (ld_acq_gpu(&a.ctl->n_done) != a.seq_on_half) __nanosleep(200);
     }
-    if (blockIdx.x == 0 && tid == 0) a.ctl->t[0] = global_ns();
+    if (blockIdx.x == 0 && tid == 0) { a.ctl->t[0] = global_ns(); a.ctl->t[13] = 0; a.ctl->t[14] = 0; a.ctl->t[15] = 0; }
     // the prologue's first global accesses are the queries (cold): start pulling them in while barriers and tensor memory are set up
     if (a.q != nullptr)
         for (int ln = tid; ln * 32 < a.nq * a.dim; ln += kFThreads) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.q + (size_t)ln * 32));
@@ -504,11 +529,17 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a, c
         bool warm = true;                           // the CTA's first tile is observed before anything is appended
         const bool obs_holds_tile = nq <= kObsQ;    // ... and with <= kObsQ queries the observation area holds the whole tile
         // scores of the 16-column chunk c of half h of the current accumulator: QPC queries per chunk
-        auto chunk_scores = [&](int h, int c, float (&out)[QPC]) {
-            uint32_t v[P][16];
+        // the P partial accumulators of chunk c of half h: P loads in flight, no wait
+        auto chunk_load = [&](int h, int c, uint32_t (&v)[P][16]) {
 #pragma unroll
             for (int p = 0; p < P; ++p)
-                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kAcc + (uint32_t)h * (P * NCOL) + (uint32_t)p * NCOL + (uint32_t)c * 16, v[p]);
+                tmem_ld16_async(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kAcc + (uint32_t)h * (P * NCOL) + (uint32_t)p * NCOL + (uint32_t)c * 16, v[p]);
+        };
+        auto chunk_fence = [&](uint32_t (&v)[P][16]) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) tmem_ld_fence16(v[p]);
+        };
+        auto chunk_reduce = [&](const uint32_t (&v)[P][16], float (&out)[QPC]) {
             float s16[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -518,6 +549,13 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a, c
             }
 #pragma unroll
             for (int j = 0; j < QPC; ++j) out[j] = SPLIT ? s16[j] + s16[j + 8] : s16[j];
+        };
+        auto chunk_scores = [&](int h, int c, float (&out)[QPC]) {
+            uint32_t v[P][16];
+            chunk_load(h, c, v);
+            tmem_ld_wait();
+            chunk_fence(v);
+            chunk_reduce(v, out);
         };
         // ---- per-query bookkeeping, WARP-cooperative: epilogue warp ew = warp & 3 owns the queries ew, ew + 4, ew + 8, ... ----
         // (one thread walking a sorted list in shared memory is a chain of dependent ~30-cycle accesses: measured 48 us for
@@ -644,8 +682,12 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a, c
             for (int t = 0; t < ntiles; ++t) {
                 const int tp = perm_tile(t, mult, ntiles);
                 const long long trow = r0 + (long long)tp * kGN;
+                const bool stamp_tile = blockIdx.x == 0 && et == 0;
+                unsigned long long ts0 = 0, ts1 = 0, ts2 = 0;
+                if (stamp_tile) ts0 = global_ns();
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
+                if (stamp_tile) ts1 = global_ns();
                 // rows past the slice / corpus (zero-filled by TMA) and filtered rows never qualify
                 const long long row_h0 = trow + m, row_h1 = trow + 128 + m;
                 const bool ok0 = row_h0 < r1 && (a.allow == nullptr || row_allowed(a.allow, row_h0));
@@ -713,55 +755,108 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a, c
                     }
                 }
                 // ---- append pass: every row whose approximate score reaches the query's current threshold ----
+                // Almost every tile has no such row: thresholds come in by vector loads, a chunk's compares fold into one mask
+                // and only a non-zero mask branches (one threshold load, compare and branch per score in program order, behind
+                // P serialized tensor-memory round trips per chunk, measured 3.6-6.3 us per tile at 64 columns against a tile
+                // period of 7.8 us: the epilogue, not HBM, set the pace of the wide configurations).
+                bool hit = false;
                 if (!(warm && obs_holds_tile)) {
-#pragma unroll 1
-                for (int h = 0; h < 2; ++h) {
-                    const long long row = trow + h * 128 + m;
+                    auto append_hits = [&](unsigned mask, const float (&sc)[QPC], int c, long long row) {
+#pragma unroll
+                        for (int j = 0; j < QPC; ++j) {
+                            if (mask >> j & 1u) {
+                                const int qi = c * QPC + j;
+                                if (qi == 0) atomicAdd(s_app, 1);
+                                const uint32_t pos = atomicAdd(a.ctl->cnt + qi, 1u);
+                                if (pos < (uint32_t)a.cap) a.cand[(size_t)qi * a.cap + pos] = make_key(sc[j] + 0.0f, (uint32_t)row);
+                                if (!warm) {                           // the first tile's scores are already in the sorted list
+                                    const int lp = atomicAdd(pcnt + qi, 1);
+                                    if (lp < npend) pend[(size_t)qi * npend + lp] = float_to_ordered(sc[j] + 0.0f);
+                                }
+                            }
+                        }
+                    };
 #pragma unroll 1
                     for (int c = 0; c < NCOL / 16; ++c) {
-                        float sc[QPC];
-                        chunk_scores(h, c, sc);
-                        if (h ? ok1 : ok0) {
+                        float th[QPC];                                 // padding queries hold +inf
 #pragma unroll
-                            for (int j = 0; j < QPC; ++j) {
-                                const int qi = c * QPC + j;
-                                if (sc[j] >= thr_s[qi]) {              // shared-memory broadcast; padding queries hold +inf
-                                    if (qi == 0) atomicAdd(s_app, 1);
-                                    const uint32_t pos = atomicAdd(a.ctl->cnt + qi, 1u);
-                                    if (pos < (uint32_t)a.cap) a.cand[(size_t)qi * a.cap + pos] = make_key(sc[j] + 0.0f, (uint32_t)row);
-                                    if (!warm) {                       // the first tile's scores are already in the sorted list
-                                        const int lp = atomicAdd(pcnt + qi, 1);
-                                        if (lp < npend) pend[(size_t)qi * npend + lp] = float_to_ordered(sc[j] + 0.0f);
-                                    }
+                        for (int j = 0; j < QPC; j += 4) {
+                            const float4 t4 = *reinterpret_cast<const float4*>(thr_s + c * QPC + j);
+                            th[j] = t4.x; th[j + 1] = t4.y; th[j + 2] = t4.z; th[j + 3] = t4.w;
+                        }
+                        if (P == 2) {                                  // both halves of the tile in flight: one wait per chunk
+                            uint32_t v0[P][16], v1[P][16];
+                            chunk_load(0, c, v0);
+                            chunk_load(1, c, v1);
+                            tmem_ld_wait();
+                            chunk_fence(v0);
+                            chunk_fence(v1);
+                            float sc0[QPC], sc1[QPC];
+                            chunk_reduce(v0, sc0);
+                            chunk_reduce(v1, sc1);
+                            unsigned m0 = 0u, m1 = 0u;
+#pragma unroll
+                            for (int j = 0; j < QPC; ++j) { m0 |= (unsigned)(sc0[j] >= th[j]) << j; m1 |= (unsigned)(sc1[j] >= th[j]) << j; }
+                            if (!ok0) m0 = 0u;
+                            if (!ok1) m1 = 0u;
+                            if (m0 | m1) {
+                                hit = true;
+                                append_hits(m0, sc0, c, row_h0);
+                                append_hits(m1, sc1, c, row_h1);
+                            }
+                        } else {
+#pragma unroll 1
+                            for (int h = 0; h < 2; ++h) {
+                                float sc[QPC];
+                                chunk_scores(h, c, sc);
+                                unsigned mk = 0u;
+#pragma unroll
+                                for (int j = 0; j < QPC; ++j) mk |= (unsigned)(sc[j] >= th[j]) << j;
+                                if (!(h ? ok1 : ok0)) mk = 0u;
+                                if (mk) {
+                                    hit = true;
+                                    append_hits(mk, sc, c, h ? row_h1 : row_h0);
                                 }
                             }
                         }
                     }
-                }
-                tc_fence_before();
-                mbar_arrive(tempty_bar(acc));
+                    tc_fence_before();
+                    mbar_arrive(tempty_bar(acc));
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                if (stamp_tile) ts2 = global_ns();
                 // ---- threshold maintenance: the tile's appended scores enter the query's sorted list ----
-                named_bar_sync(1, 128);
-                if (!warm) {
-                    for (int q = ew; q < nq; q += 4) {
-                        int pc = pcnt[q];                              // warp-uniform (shared memory, written before the barrier)
-                        if (pc > 0) {
-                            if (pc > npend) pc = npend;                // the surplus was dropped: only tightening information is lost
-                            uint32_t* sl_ = sorted + (size_t)q * k;
-                            int n = scnt[q];
-                            __syncwarp();
-                            for (int i = 0; i < pc; ++i) n = warp_list_add(sl_, n, pend[(size_t)q * npend + i]);
-                            if (lane == 0) { scnt[q] = n; pcnt[q] = 0; }
+                // One barrier that also tells whether ANY epilogue thread appended; a tile without appended rows that is not a
+                // refresh tile ends here (nothing was written that the next tile reads).
+                const bool refresh_tile = t < 8 || t % a.refresh_every == 0;
+                const bool any = named_bar_or(1, 128, hit);
+                if (warm) {
+                    if (blockIdx.x == 0 && et == 0) a.ctl->t[2] = global_ns();
+                    named_bar_sync(2, 128);
+                } else if (any || refresh_tile) {
+                    bool changed = false;
+                    if (any) {
+                        for (int q = ew; q < nq; q += 4) {
+                            int pc = pcnt[q];                          // warp-uniform (shared memory, written before the barrier)
+                            if (pc > 0) {
+                                changed = true;
+                                if (pc > npend) pc = npend;            // the surplus was dropped: only tightening information is lost
+                                uint32_t* sl_ = sorted + (size_t)q * k;
+                                int n = scnt[q];
+                                __syncwarp();
+                                for (int i = 0; i < pc; ++i) n = warp_list_add(sl_, n, pend[(size_t)q * npend + i]);
+                                if (lane == 0) { scnt[q] = n; pcnt[q] = 0; }
+                            }
                         }
+                        __syncwarp();
                     }
-                    __syncwarp();
-                    warp_refresh();
+                    if (changed || refresh_tile) warp_refresh();
+                    named_bar_sync(2, 128);
                 }
-                if (warm && blockIdx.x == 0 && et == 0) a.ctl->t[2] = global_ns();
+                if (stamp_tile && !warm) {   // CTA 0's epilogue, summed over its tiles: waiting for the tensor core, append pass, bookkeeping
+                    a.ctl->t[13] += ts1 - ts0; a.ctl->t[14] += ts2 - ts1; a.ctl->t[15] += global_ns() - ts2;
+                }
                 warm = false;
-                named_bar_sync(2, 128);
             }
         }
         __threadfence();   // this thread's appended keys are visible device-wide before the CTA is counted as done

@@ -92,9 +92,12 @@ class ShardedSearcher:
         can take it, else device staging around `search`."""
         import numpy as np
         import torch
-        q = np.ascontiguousarray(queries, dtype=np.float32)
-        if self.world > 1 and self.exchange is not None and self.fused_ok(q.shape[0], k):
-            return self.exchange.search_sharded_host(self.index, q, k, out_ids, out_scores)
+        nq = queries.shape[0] if getattr(queries, "ndim", 0) == 2 else 1
+        if self.world > 1 and self.exchange is not None and self.fused_ok(nq, k):
+            return self.exchange.search_sharded_host(self.index, queries, k, out_ids, out_scores)   # numpy or torch CPU buffers
+        q = queries.numpy() if hasattr(queries, "data_ptr") else np.ascontiguousarray(queries, dtype=np.float32)
+        out_ids = out_ids.numpy() if hasattr(out_ids, "data_ptr") else out_ids
+        out_scores = out_scores.numpy() if hasattr(out_scores, "data_ptr") else out_scores
         dev = torch.device("cuda", self.index.device) if (self.index is not None and torch.cuda.is_available()) else None
         ids, sc = self.search(torch.from_numpy(q).to(dev) if dev is not None else torch.from_numpy(q), k)
         ids, sc = ids.cpu().numpy(), sc.cpu().numpy()

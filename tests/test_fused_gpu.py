@@ -252,3 +252,31 @@ def test_fused_thousands_of_rows_tied_at_the_top(coracle):
         _same(got, coracle.cosine_topk(q, coracle.normalize_rows(x, dtype), k), f"tied top {dtype}")
         assert list(got[0][0]) == list(range(19999, 19999 + k))
         idx.close()
+
+
+def test_host_call_with_pinned_torch_buffers(coracle):
+    """Index.search takes the caller's own pinned torch buffers (queries in, ids / scores out) as well as numpy arrays: same
+    bits, and the results land in the buffers that were passed."""
+    import torch
+    n, dim, k = 30000, 768, 10
+    x = O.synth_rows(390, 0, n, dim)
+    q = O.synth_rows(391, 0, 3, dim)
+    idx = _index(x, "bf16")
+    want = coracle.cosine_topk(q, coracle.normalize_rows(x, "bf16"), k)
+    qt = torch.from_numpy(q).pin_memory()
+    ids, sc = torch.full((3, k), -7, dtype=torch.int64).pin_memory(), torch.zeros((3, k), dtype=torch.float32).pin_memory()
+    got = idx.search(qt, k, out_ids=ids, out_scores=sc)
+    assert got[0] is ids and got[1] is sc and idx.stats()["path"] == 3
+    _same((ids.numpy(), sc.numpy()), want, "pinned torch buffers")
+    one = idx.search(qt[1], k)                                  # a single query, fresh numpy results
+    _same(one, (want[0][1:2], want[1][1:2]), "one query")
+    keep = np.ones(n, bool)
+    keep[want[0][:, 0]] = False
+    got = idx.search(qt, k, out_ids=ids, out_scores=sc, allow=keep)
+    x2 = coracle.normalize_rows(x, "bf16")
+    rows = np.flatnonzero(keep)
+    wi, ws = coracle.cosine_topk(q, x2[rows], k)
+    _same((ids.numpy(), sc.numpy()), (rows[wi], ws), "filtered, pinned torch buffers")
+    with pytest.raises(ValueError):
+        idx.search(qt, k, out_ids=ids.cuda(), out_scores=sc)
+    idx.close()

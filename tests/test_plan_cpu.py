@@ -110,3 +110,41 @@ def test_fused_sweep_visits_every_tile_of_a_slice_exactly_once():
             step = np.minimum(step, n - step)
             assert step.min() >= n // 4, (n, step.min())          # no two consecutive visits close to each other
     assert L.ragfin_debug_fused_tile_order(0, None) == _lib.EINVAL
+
+
+def test_host_buffers_numpy_and_torch():
+    """engine._host_queries / _host_out: what Index.search and PeerExchange.search_sharded_host hand to the C ABI.  numpy and
+    torch CPU buffers give the address of the caller's own memory; anything the library could not write into is refused."""
+    import numpy as np
+    import torch
+    from ragfin_b200 import engine
+    qn = np.arange(2 * 8, dtype=np.float32).reshape(2, 8)
+    obj, ptr, nq = engine._host_queries(qn, 8)
+    assert obj is qn and ptr == qn.ctypes.data and nq == 2
+    obj, ptr, nq = engine._host_queries(qn[0].tolist(), 8)                  # one query as a list
+    assert nq == 1 and obj.shape == (1, 8) and obj.dtype == np.float32
+    qt = torch.from_numpy(qn)
+    obj, ptr, nq = engine._host_queries(qt, 8)
+    assert obj is qt and ptr == qt.data_ptr() == qn.ctypes.data and nq == 2
+    obj, ptr, nq = engine._host_queries(qt.double()[:, :], 8)               # wrong dtype: converted, not reinterpreted
+    assert obj.dtype == torch.float32 and torch.equal(obj, qt) and ptr == obj.data_ptr()
+    obj, ptr, nq = engine._host_queries(qt.t().contiguous().t(), 8)         # not contiguous: compacted
+    assert obj.is_contiguous() and torch.equal(obj, qt)
+    obj, ptr, nq = engine._host_queries(qt[1], 8)
+    assert nq == 1 and tuple(obj.shape) == (1, 8)
+    for bad in (np.zeros((2, 7), np.float32), torch.zeros(2, 9), np.zeros((2, 2, 8), np.float32)):
+        with pytest.raises(ValueError):
+            engine._host_queries(bad, 8)
+
+    out, p = engine._host_out(None, 2, 5, np.int64, "out_ids")
+    assert out.shape == (2, 5) and out.dtype == np.int64 and p == out.ctypes.data
+    mine = torch.empty((2, 5), dtype=torch.int64)
+    out, p = engine._host_out(mine, 2, 5, np.int64, "out_ids")
+    assert out is mine and p == mine.data_ptr()
+    mine = np.empty((2, 5), np.float32)
+    out, p = engine._host_out(mine, 2, 5, np.float32, "out_scores")
+    assert out is mine and p == mine.ctypes.data
+    for bad in (torch.empty((2, 5), dtype=torch.int32), torch.empty((5, 2), dtype=torch.int64), torch.empty((2, 10), dtype=torch.int64)[:, ::2],
+                np.empty((2, 5), np.int32), np.empty((2, 10), np.int64)[:, ::2], np.empty((3, 5), np.int64)):
+        with pytest.raises(ValueError):
+            engine._host_out(bad, 2, 5, np.int64, "out_ids")
