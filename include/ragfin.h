@@ -237,6 +237,17 @@ int ragfin_set_append_mode(ragfin_t* h, int32_t enable);
  * Replaces: the same Collection.search call sites; this is the batch-1 path of vector_rag_mcp/main.py:51-57. */
 int ragfin_set_fused(ragfin_t* h, int32_t enable, int64_t min_rows);
 
+/* Opt-in pipelining of consecutive one-kernel searches issued through ragfin_search / ragfin_search_sharded on ONE stream
+ * (default off; RAGFIN_PIPELINED=1 turns it on for new handles): search n + 1 is launched with programmatic stream
+ * serialization and starts sweeping while search n finalizes and exchanges hits; results land in stream order.  Contract: a
+ * pipelined search may begin before the operation enqueued just ahead of it on the stream has completed, so its query buffer
+ * must already hold the queries when the PREVIOUS search on this handle was enqueued (written by work ordered before that
+ * search, or by the host).  Queries produced by a kernel enqueued between two searches need pipelining off.  Only a search
+ * that directly follows this handle's own one-kernel search on the same stream is launched this way; after an add, a filter,
+ * another path or another stream the launch is an ordinary one.  Results are identical either way.
+ * Replaces: nothing in the reference (its searches are sequential gRPC calls - vector_rag_mcp/main.py:51-57). */
+int ragfin_set_pipelined(ragfin_t* h, int32_t enable);
+
 /* Test / bench hook: per-query diagnostics of the last one-kernel search on this handle - rows appended to the query's
  * buffer during the sweep and rows rescored exactly by the finalize (-1: the buffer overflowed and the query was answered
  * by the in-kernel exact scan).  Synchronises. */

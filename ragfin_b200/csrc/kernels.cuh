@@ -706,12 +706,18 @@ __global__ void merge_topk_kernel(const int64_t* __restrict__ ids, const float* 
 // NCCL all-gather, every rank STORES its packed hit record {ids[nq*k] | scores[nq*k]} straight into slot `rank` of
 // every peer's gather area and then publishes the step number in that peer's flag word (release, system scope); the
 // reduce kernel spins (acquire) until all `world` flags of its own area carry the step number, then merges.
-// Gather areas and flags are double-buffered by step parity: a rank can be at most one step ahead of a peer (its
-// step t+1 reduce needs the peer's step t+1 record, sent after the peer's step t reduce in stream order).
-//   peer_area[p]  base of rank p's gather area: [2][world][record_bytes]
-//   peer_flag[p]  base of rank p's flags:       [2][world] uint32
+// Gather areas and flags form a ring of kXSlots = 4 slots indexed by step % 4.  With these stream-ordered kernels a rank can
+// be at most one step ahead of a peer (its step t+1 reduce needs the peer's step t+1 record, sent after the peer's step t
+// reduce in stream order), so two slots would do; the one-kernel search (sweep_fused.cuh) shares the ring and, when
+// pipelined, keeps two searches of a rank in flight: rank A's step t+3 push can only happen after A's step t+1 search has
+// completed (a search starts only when the one before its predecessor has finished with its control block), which needs
+// peer B's step t+1 hits, pushed by B's step t+1 search, which could only start once B's step t-1 search - the last
+// reader of slot (t+3) % 4 - had completely finished.
+//   peer_area[p]  base of rank p's gather area: [kXSlots][world][record_bytes]
+//   peer_flag[p]  base of rank p's flags:       [kXSlots][world] uint32
 // grid = (chunks, world); blockIdx.y = destination peer.
 // ---------------------------------------------------------------------------------
+constexpr uint32_t kXSlots = 4;
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -725,7 +731,7 @@ exchange_push_kernel(const int64_t* __restrict__ ids, const float* __restrict__ 
                      int rank, int world, size_t record_bytes, uint32_t step, char* const* __restrict__ peer_area,
                      uint32_t* const* __restrict__ peer_flag, unsigned int* __restrict__ done /*[world]*/) {
     const int p = blockIdx.y;
-    char* dst = peer_area[p] + ((size_t)(step & 1u) * world + rank) * record_bytes;
+    char* dst = peer_area[p] + ((size_t)(step % kXSlots) * world + rank) * record_bytes;
     int64_t* dids = reinterpret_cast<int64_t*>(dst);
     float* dsc = reinterpret_cast<float*>(dst + (size_t)n_hits * 8);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_hits; i += (int64_t)gridDim.x * blockDim.x) {
@@ -738,7 +744,7 @@ exchange_push_kernel(const int64_t* __restrict__ ids, const float* __restrict__ 
         if (atomicAdd(&done[p], 1u) == gridDim.x - 1) {   // last CTA of this destination: publish
             done[p] = 0u;
             __threadfence_system();
-            st_release_sys(peer_flag[p] + (size_t)(step & 1u) * world + rank, step);
+            st_release_sys(peer_flag[p] + (size_t)(step % kXSlots) * world + rank, step);
         }
     }
 }
@@ -746,12 +752,12 @@ __global__ void exchange_merge_kernel(const char* area, const uint32_t* flags, i
                                       int k, size_t record_bytes, uint32_t step, int64_t* __restrict__ out_ids,
                                       float* __restrict__ out_scores) {
     if (threadIdx.x < world) {
-        const uint32_t* f = flags + (size_t)(step & 1u) * world + threadIdx.x;
+        const uint32_t* f = flags + (size_t)(step % kXSlots) * world + threadIdx.x;
         while (ld_acquire_sys(f) != step) __nanosleep(20);
     }
     __syncthreads();
-    (void)ld_acquire_sys(flags + (size_t)(step & 1u) * world + threadIdx.x % world);   // every thread acquires for its own loads
-    const char* base = area + (size_t)(step & 1u) * world * record_bytes;
+    (void)ld_acquire_sys(flags + (size_t)(step % kXSlots) * world + threadIdx.x % world);   // every thread acquires for its own loads
+    const char* base = area + (size_t)(step % kXSlots) * world * record_bytes;
     merge_topk_body<true>(reinterpret_cast<const int64_t*>(base), reinterpret_cast<const float*>(base + (size_t)nq * k * 8), nq, world, k,
                     (int64_t)(record_bytes / 8), (int64_t)(record_bytes / 4), (int64_t)k, out_ids, out_scores);
 }

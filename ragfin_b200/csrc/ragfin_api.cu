@@ -67,6 +67,7 @@ struct ragfin {
     int gemm_min_nq = 3;      // query batches of at least this many rows take the tcgen05 path (1-2: HBM-bound scan) ...
     int gemm_min_nq_large = 1;   // ... except on corpora of >= kSweepBytes, where the TMA-fed sweep wins from 1 query
     int gemm_cluster = 0;     // 0 = choose by batch size; 1, 2 or 4 = force
+    bool allow_pipelined = false;          // ragfin_set_pipelined: consecutive one-kernel searches on one stream may overlap (see there)
     bool cur_pipelined = false;            // the search in flight came through an asynchronous entry point (ragfin_search)
     const uint32_t* cur_allow = nullptr;   // scalar filter of the search in flight (device bitmask), else null
     int64_t cur_allowed = 0;               // rows it allows
@@ -155,6 +156,7 @@ static void read_env_knobs(ragfin* h) {
     { const char* e = getenv("RAGFIN_NO_BIGK_BATCHED"); if (e && atoi(e)) h->use_bigk_batched = false; }
     { const char* e = getenv("RAGFIN_FUSED_MAX_NQ"); if (e && atoi(e) >= 1 && atoi(e) <= kFMaxQ) h->fused_max_nq = atoi(e); }
     { const char* e = getenv("RAGFIN_FUSED_MAX_NQK"); if (e && atoi(e) >= 1) h->fused_max_nqk = atoi(e); }
+    { const char* e = getenv("RAGFIN_PIPELINED"); if (e) h->allow_pipelined = atoi(e) != 0; }
     { const char* e = getenv("RAGFIN_FUSED_REFRESH_EVERY"); if (e && atoi(e) >= 1) h->fused_refresh_every = atoi(e); }
     { const char* e = getenv("RAGFIN_FUSED_STAGES"); if (e && atoi(e) >= 2 && atoi(e) <= kRMaxStages) h->fused_stage_cap = atoi(e); }
 }
@@ -227,7 +229,7 @@ extern "C" int ragfin_create_view(ragfin_t* parent, ragfin_t** out) {
     h->scan_variant = parent->scan_variant; h->use_append = parent->use_append; h->use_bound_pass = parent->use_bound_pass;
     h->gemm_variant = parent->gemm_variant;
     h->use_fused = parent->use_fused; h->use_bigk_batched = parent->use_bigk_batched; h->fused_min_rows = parent->fused_min_rows;
-    h->fused_max_nq = parent->fused_max_nq; h->fused_max_nqk = parent->fused_max_nqk;
+    h->fused_max_nq = parent->fused_max_nq; h->fused_max_nqk = parent->fused_max_nqk; h->allow_pipelined = parent->allow_pipelined;
     h->fused_refresh_every = parent->fused_refresh_every; h->fused_stage_cap = parent->fused_stage_cap;
     read_env_knobs(h);
     cudaError_t e = cudaEventCreateWithFlags(&h->last_done, cudaEventDisableTiming);
@@ -1046,7 +1048,7 @@ struct ragfin_exchange {
     unsigned int* d_done = nullptr;
     uint32_t step = 0;
     bool connected = false;
-    bool have_stream = false;            // the double-buffer argument (a rank is at most one step ahead of a peer) holds only
+    bool have_stream = false;            // the slot-ring argument (kernels.cuh: how far a rank can run ahead of a peer) holds only
     cudaStream_t stream = nullptr;       // if every step of this rank is issued on ONE stream: recorded at step 1, checked after
     std::mutex mu;
 };
@@ -1129,7 +1131,11 @@ static int run_fused(ragfin* h, const float* q_dev, int nb, int k, int64_t n_eff
     if ((size_t)nb * f.cap * sizeof(u64) > cand_half) return fail(RAGFIN_EUNSUPPORTED, "append buffers of %d queries x %d keys exceed the workspace half", nb, f.cap);
     if ((rc = ensure(h->fcand, 2 * cand_half)) || (rc = ensure(h->fqn, 2 * qn_half)) || (rc = ensure(h->fflags, 2 * (kFMaxQ + 1) * sizeof(int)))) return rc;
     if (!h->fctl.p) { if ((rc = ensure(h->fctl, 2 * sizeof(FusedCtl)))) return rc; h->fctl_dirty = true; }
-    if (h->fctl_dirty) { CU_TRY(cudaMemsetAsync(h->fctl.p, 0, 2 * sizeof(FusedCtl), st)); h->fctl_dirty = false; h->fused_seq = 0; }
+    if (h->fctl_dirty) {
+        CU_TRY(cudaMemsetAsync(h->fctl.p, 0, 2 * sizeof(FusedCtl), st));
+        h->fctl_dirty = false; h->fused_seq = 0;
+        pipelined = false;     // the kernel reads the control block from its first instruction: full dependency on the memset
+    }
     const uint32_t seq = h->fused_seq++;
     const int half = (int)(seq & 1u);
     h->fused_last = half;
@@ -1683,6 +1689,21 @@ extern "C" int ragfin_set_fused(ragfin_t* h, int32_t enable, int64_t min_rows) {
     return RAGFIN_OK;
 }
 
+// Opt-in: consecutive one-kernel searches issued through the asynchronous entry points (ragfin_search, ragfin_search_sharded)
+// on ONE stream are launched with programmatic stream serialization - search n + 1 starts sweeping while search n finalizes
+// (and, sharded, exchanges hits), so HBM never idles between them; results still land in stream order.  The price is a
+// contract: such a search may begin BEFORE the operation enqueued just ahead of it on the stream has completed, so its query
+// buffer must already hold the queries when the PREVIOUS search on this handle was enqueued (written by a copy or kernel
+// ordered before that search, or by the host) - a kernel that produces the queries between two searches needs pipelining off
+// (the default), or its own stream synchronisation.  The corpus, filters and workspaces are the library's own business: a
+// search that follows anything but this handle's previous one-kernel search on the same stream is launched normally.
+extern "C" int ragfin_set_pipelined(ragfin_t* h, int32_t enable) {
+    if (!h) return fail(RAGFIN_EINVAL, "NULL handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->allow_pipelined = enable != 0;
+    return RAGFIN_OK;
+}
+
 // Tuning knob: small-batch scan kernel.  0 = automatic, 1 = register-path loads (scan_topk_kernel), 2 = TMA-fed ring
 // (scan_tma_kernel; 1-2 queries).  Results are identical.
 extern "C" int ragfin_set_scan_variant(ragfin_t* h, int32_t variant) {
@@ -1719,9 +1740,13 @@ extern "C" int ragfin_search(ragfin_t* h, const float* q, int32_t nq, int32_t k,
     DeviceGuard g(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    const bool pipe = nq <= h->fused_max_nq && fused_eligible(h, nq, k);   // the one-kernel search: pipelined launch
+    // Pipelined launch of the one-kernel search (opt-in, ragfin_set_pipelined): only behind this handle's own previous
+    // one-kernel search on the same stream - after an add, a filter, another path or another stream the launch is an ordinary
+    // one (a programmatic launch does not wait for its predecessor's memory flush, and this kernel reads its inputs at once).
+    const bool pipe = h->allow_pipelined && nq <= h->fused_max_nq && fused_eligible(h, nq, k);
+    const bool chained = pipe && h->have_pending && st == h->pending_stream;
     if ((rc = wait_prev(h, st, pipe))) return rc;
-    h->cur_pipelined = pipe;
+    h->cur_pipelined = chained;
     rc = search_locked(h, q, nq, k, out_ids, out_scores, st);
     h->cur_pipelined = false;
     if (rc) return rc;
@@ -1772,7 +1797,7 @@ static int fused_host_call(ragfin* h, ragfin_exchange* x, const float* q_host, i
     if (x != nullptr) {
         if (!x->connected) return fail(RAGFIN_EINVAL, "exchange is not connected");
         if (x->have_stream && x->stream != st)
-            return fail(RAGFIN_EINVAL, "every step of an exchange must be issued on the same CUDA stream (its double buffering relies on stream order)");
+            return fail(RAGFIN_EINVAL, "every step of an exchange must be issued on the same CUDA stream (its slot ring relies on stream order)");
         x->have_stream = true; x->stream = st;
         const uint32_t step = ++x->step;
         rc = run_fused(h, q_dev, nq, k, h->count, (int64_t*)dout, (float*)(dout + ib), st, false, x, step, q_inline, dflag, seq);
@@ -1969,8 +1994,8 @@ extern "C" int ragfin_exchange_create(ragfin_exchange_t** out, int32_t rank, int
     if (!x) return fail(RAGFIN_ENOMEM, "host allocation failed");
     x->rank = rank; x->world = world; x->device = device;
     x->record_max = ((size_t)record_bytes_max + 15) / 16 * 16;
-    const size_t area = 2 * (size_t)world * x->record_max;
-    x->bytes = area + 2 * (size_t)world * sizeof(uint32_t) + 2 * (size_t)world * kFMaxQ * sizeof(uint32_t);
+    const size_t area = kXSlots * (size_t)world * x->record_max;
+    x->bytes = area + kXSlots * (size_t)world * sizeof(uint32_t) + kXSlots * (size_t)world * kFMaxQ * sizeof(uint32_t);
     cudaError_t e = cudaMalloc((void**)&x->local, x->bytes);
     if (e == cudaSuccess) e = cudaMemset(x->local, 0, x->bytes);
     if (e == cudaSuccess) e = cudaMalloc((void**)&x->d_peer_area, world * sizeof(char*));
@@ -2008,7 +2033,7 @@ extern "C" int ragfin_exchange_connect(ragfin_exchange_t* x, const void* handles
     std::lock_guard<std::mutex> lk(x->mu);
     if (x->connected) return fail(RAGFIN_EINVAL, "exchange is already connected");
     DeviceGuard g(x->device);
-    const size_t area = 2 * (size_t)x->world * x->record_max;
+    const size_t area = kXSlots * (size_t)x->world * x->record_max;
     char* areas[64];
     uint32_t* flags[64];
     uint32_t* qflags[64];
@@ -2029,7 +2054,7 @@ extern "C" int ragfin_exchange_connect(ragfin_exchange_t* x, const void* handles
         }
         areas[p] = x->peer_base[p];
         flags[p] = reinterpret_cast<uint32_t*>(x->peer_base[p] + area);
-        qflags[p] = flags[p] + 2 * (size_t)x->world;
+        qflags[p] = flags[p] + kXSlots * (size_t)x->world;
     }
     CU_TRY(cudaMemcpy(x->d_peer_area, areas, x->world * sizeof(char*), cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(x->d_peer_flag, flags, x->world * sizeof(uint32_t*), cudaMemcpyHostToDevice));
@@ -2050,7 +2075,7 @@ extern "C" int ragfin_exchange_allgather_merge(ragfin_exchange_t* x, const int64
     DeviceGuard g(x->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (x->have_stream && x->stream != st)
-        return fail(RAGFIN_EINVAL, "every step of an exchange must be issued on the same CUDA stream (its double buffering relies on stream order)");
+        return fail(RAGFIN_EINVAL, "every step of an exchange must be issued on the same CUDA stream (its slot ring relies on stream order)");
     x->have_stream = true; x->stream = st;
     const uint32_t step = ++x->step;
     int chunks = (int)((n_hits + 255) / 256);
@@ -2059,7 +2084,7 @@ extern "C" int ragfin_exchange_allgather_merge(ragfin_exchange_t* x, const int64
                                                                  x->d_peer_area, x->d_peer_flag, x->d_done);
     CU_TRY(cudaGetLastError());
     const int64_t total = n_hits * x->world;
-    const uint32_t* flags = reinterpret_cast<const uint32_t*>(x->local + 2 * (size_t)x->world * x->record_max);
+    const uint32_t* flags = reinterpret_cast<const uint32_t*>(x->local + kXSlots * (size_t)x->world * x->record_max);
     exchange_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x->local, flags, nq, x->world, k, x->record_max, step,
                                                                            out_ids, out_scores);
     CU_TRY(cudaGetLastError());
@@ -2084,7 +2109,7 @@ static int sharded_locked(ragfin* h, ragfin_exchange* x, const float* q_dev, int
     const size_t record = (size_t)nq * (((size_t)k * 12 + 15) / 16 * 16);
     if (record > x->record_max) return fail(RAGFIN_EINVAL, "record of %zu bytes exceeds the exchange's %zu", record, x->record_max);
     if (x->have_stream && x->stream != st)
-        return fail(RAGFIN_EINVAL, "every step of an exchange must be issued on the same CUDA stream (its double buffering relies on stream order)");
+        return fail(RAGFIN_EINVAL, "every step of an exchange must be issued on the same CUDA stream (its slot ring relies on stream order)");
     x->have_stream = true; x->stream = st;
     int rc;
     if ((rc = ensure(h->flags, (size_t)(kMaxQueryBatch + 1) * sizeof(int)))) return rc;
@@ -2107,9 +2132,11 @@ extern "C" int ragfin_search_sharded(ragfin_t* h, ragfin_exchange_t* x, const fl
     DeviceGuard g(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    if ((rc = wait_prev(h, st, true))) return rc;
-    if ((rc = sharded_locked(h, x, q, nq, k, out_ids, out_scores, st, true))) return rc;
-    return mark_done(h, st, true);
+    const bool pipe = h->allow_pipelined;
+    const bool chained = pipe && h->have_pending && st == h->pending_stream;   // as in ragfin_search
+    if ((rc = wait_prev(h, st, pipe))) return rc;
+    if ((rc = sharded_locked(h, x, q, nq, k, out_ids, out_scores, st, chained))) return rc;
+    return mark_done(h, st, pipe);
 }
 
 // Same with HOST buffers (what a serving process calls): queries staged through pinned memory, the global hits written by

@@ -112,10 +112,10 @@ struct FusedArgs {
     // cross-shard exchange inside the finalize (row-sharded corpora, one process per GPU; xworld <= 1: off).  Peer gather
     // areas and flags are mapped through CUDA IPC (ragfin_exchange_*); see "exchange" in the header comment.
     int xworld, xrank;
-    uint32_t xstep;             // step number of this search: flag value, parity selects the half of the double buffer
+    uint32_t xstep;             // step number of this search: flag value, xstep % kXSlots selects the slot of the gather ring
     unsigned long long xrec_max;   // bytes of one rank's record in a gather area
-    char* const* xpeer_area;    // [xworld] base of every rank's gather area: [2][xworld][xrec_max]
-    uint32_t* const* xpeer_qflag;  // [xworld] base of every rank's per-query flags: [2][xworld][kFMaxQ]
+    char* const* xpeer_area;    // [xworld] base of every rank's gather area: [kXSlots][xworld][xrec_max]
+    uint32_t* const* xpeer_qflag;  // [xworld] base of every rank's per-query flags: [kXSlots][xworld][kFMaxQ]
 };
 
 // pending area: [nq][pend] appended scores per tile in steady state, [kObsQ][kObsStride] observed scores in the first tile
@@ -922,7 +922,7 @@ sweep_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs a, c
         }
         const int W = a.xworld;
         const size_t rec_q = ((size_t)k * 12 + 15) / 16 * 16;            // one query's hits inside a rank's record
-        const size_t half = (size_t)(a.xstep & 1u) * W;
+        const size_t half = (size_t)(a.xstep % kXSlots) * W;             // slot of the 4-deep ring (kernels.cuh: why 4 is enough)
         for (int i = tid; i < k * W; i += kFThreads) {                    // 1. my hits -> slot `xrank` of every rank's area
             const int p = i / k, j = i % k;
             const u64 key = j < nvalid ? fin[j] : 0ull;

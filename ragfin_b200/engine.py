@@ -261,6 +261,13 @@ class Index:
         min_rows > 0 also sets the smallest corpus it serves."""
         _lib.check(self._L.ragfin_set_fused(self._h, 1 if enable else 0, int(min_rows)))
 
+    def set_pipelined(self, enable: bool) -> None:
+        """Opt-in: consecutive one-kernel searches issued through `search_device` (or the sharded device call) on one stream
+        overlap - the next one sweeps while this one finalizes; results land in stream order.  Contract (include/ragfin.h,
+        ragfin_set_pipelined): the query tensor must already hold its values when the PREVIOUS search on this index was
+        issued - do not enable it when a kernel enqueued between two searches produces the queries.  Default off."""
+        _lib.check(self._L.ragfin_set_pipelined(self._h, 1 if enable else 0))
+
     def fused_eligible(self, nq: int, k: int) -> bool:
         """Whether (nq, k) takes the one-kernel search on this handle (csrc/sweep_fused.cuh)."""
         out = ctypes.c_int32()

@@ -17,11 +17,12 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
-for dtype, dim, n, nq, k in [("bf16", 768, 50001, 1, 10), ("f16", 768, 30000, 4, 100), ("f32", 384, 9000, 40, 5),
-                             ("bf16", 768, 7, 3, 10), ("bf16", 1024, 40000, 300, 10),
-                             ("bf16", 128, 600000, 40, 10), ("f16", 64, 900000, 5, 100),    # shards large enough for append mode
-                             ("bf16", 768, 200000, 1, 10), ("bf16", 768, 200000, 16, 10), ("f32", 384, 160000, 3, 10),
-                             ("f16", 256, 300000, 64, 5), ("bf16", 768, 100000, 2, 128)]:   # one-kernel sharded search on every rank
+CASES = [("bf16", 768, 50001, 1, 10), ("f16", 768, 30000, 4, 100), ("f32", 384, 9000, 40, 5),
+         ("bf16", 768, 7, 3, 10), ("bf16", 1024, 40000, 300, 10),
+         ("bf16", 128, 600000, 40, 10), ("f16", 64, 900000, 5, 100),    # shards large enough for append mode
+         ("bf16", 768, 200000, 1, 10), ("bf16", 768, 200000, 16, 10), ("f32", 384, 160000, 3, 10),
+         ("f16", 256, 300000, 64, 5), ("bf16", 768, 100000, 2, 128)]   # one-kernel sharded search on every rank
+for dtype, dim, n, nq, k in CASES * int(os.environ.get("SHARDED_CHECK_REPEAT", "1")):   # repeats: hunting intermittent failures
     row0, cnt = shard_bounds(n, world, rank)
     idx = ragfin_b200.Index(dim, dtype, capacity=max(cnt, 1), device=local)
     if cnt:
@@ -33,12 +34,36 @@ for dtype, dim, n, nq, k in [("bf16", 768, 50001, 1, 10), ("f16", 768, 30000, 4,
     for p2p in (True, False):      # peer-memory exchange (CUDA IPC + NVLink stores), then NCCL all-gather + reduce
         s = ShardedSearcher.for_index(idx, p2p=p2p)
         same = True
-        for _ in range(3):         # several steps: the exchange double-buffers by step parity
+
+        def check(gi, gs, what):
+            good = np.array_equal(gi, wi) and np.array_equal(gs.view(np.uint32), ws.view(np.uint32))
+            if not good:           # say where: which call, which rank, the first query that differs
+                bad = [j for j in range(nq) if not (np.array_equal(gi[j], wi[j]) and np.array_equal(gs[j].view(np.uint32), ws[j].view(np.uint32)))]
+                j = bad[0]
+                col = [c for c in range(k) if gi[j, c] != wi[j, c] or gs[j, c].view(np.uint32) != ws[j, c].view(np.uint32)]
+                print(f"  MISMATCH rank {rank} {what} p2p={p2p}: {len(bad)}/{nq} queries differ; query {j} columns {col[:8]}: got ids {gi[j, col[:6]].tolist()} "
+                      f"scores {gs[j, col[:6]].tolist()} want ids {wi[j, col[:6]].tolist()} scores {ws[j, col[:6]].tolist()}", flush=True)
+            return good
+
+        for step in range(3):      # several steps: the exchange double-buffers by step parity
             ids, sc = s.search(qd, k)
             torch.cuda.synchronize()
-            same &= np.array_equal(ids.cpu().numpy(), wi) and np.array_equal(sc.cpu().numpy().view(np.uint32), ws.view(np.uint32))
+            same &= check(ids.cpu().numpy(), sc.cpu().numpy(), f"device call {step}")
         hi, hs = s.search_host(q, k)   # host buffers in and out (the serving call)
-        same &= np.array_equal(hi, wi) and np.array_equal(hs.view(np.uint32), ws.view(np.uint32))
+        same &= check(hi, hs, "host call")
+        hit = torch.empty((nq, k), dtype=torch.int64).pin_memory()   # ... and with the caller's pinned torch buffers
+        hst = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+        s.search_host(torch.from_numpy(q).pin_memory(), k, out_ids=hit, out_scores=hst)
+        same &= check(hit.numpy(), hst.numpy(), "host call, pinned torch buffers")
+        if s.exchange is not None and s.fused_ok(nq, k):
+            # pipelined: a burst of searches with no synchronisation in between - two searches of a rank in flight, ranks drifting
+            # apart by up to a step, tiny shards (the sweep is shorter than the finalize): the gather ring's worst case
+            idx.set_pipelined(True)
+            burst = [s.search(qd, k) for _ in range(24)]
+            torch.cuda.synchronize()
+            for step, (ids, sc) in enumerate(burst):
+                same &= check(ids.cpu().numpy(), sc.cpu().numpy(), f"pipelined burst call {step}")
+            idx.set_pipelined(False)
         ok &= same
         if rank == 0:
             how = ("one kernel (sweep + peer exchange + reduce)" if s.exchange is not None and s.fused_ok(nq, k) else

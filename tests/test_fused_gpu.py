@@ -197,17 +197,19 @@ def test_fused_zero_query_and_concurrent_callers(coracle):
     idx.close()
 
 
-def test_fused_pipelined_back_to_back_searches(coracle):
-    """The asynchronous entry point launches the one-kernel search with programmatic stream serialization: a search may start
-    while its predecessor is still finalizing (they alternate between two halves of the control block and buffers).  Sixty
-    searches of varying shape enqueued without any synchronisation, then every result is checked; interleaved with host calls
-    and an add() on another stream."""
+@pytest.mark.parametrize("pipelined", [True, False])
+def test_fused_pipelined_back_to_back_searches(coracle, pipelined):
+    """With Index.set_pipelined(True) the asynchronous entry point launches the one-kernel search with programmatic stream
+    serialization: a search may start while its predecessor is still finalizing (they alternate between two halves of the
+    control block and buffers).  Sixty searches of varying shape enqueued without any synchronisation, then every result is
+    checked; interleaved with host calls and an add() on another stream.  Same run with the default (ordinary launches)."""
     import torch
     n, dim = 60000, 128
     x = O.synth_rows(370, 0, n, dim, dup_every=301)
     stored = coracle.normalize_rows(x, "bf16")
     idx = _index(x[:50000], "bf16")
     idx.reserve(n)
+    idx.set_pipelined(pipelined)
     shapes = [(1, 10), (2, 5), (16, 10), (1, 100), (3, 1), (8, 25)]
     qs = [O.synth_rows(371 + i, 0, nq, dim) for i, (nq, _) in enumerate(shapes)]
     qd = [torch.from_numpy(q).cuda() for q in qs]
