@@ -151,7 +151,9 @@ int ragfin_fused_eligible(ragfin_t* h, int32_t nq, int32_t k, int32_t* out);
  * the shard's exact hits into every rank's gather area over NVLink (the exchange's CUDA IPC mappings), wait for the other
  * ranks' hits and write the GLOBAL top-k into out_ids / out_scores on every rank - no collective call, no separate reduce
  * kernel.  Collective: every rank calls it once per step with the same (nq <= 64, k <= 128) and the same queries, always
- * on the same stream; fails with RAGFIN_EUNSUPPORTED when the shape does not take the one-kernel search on this shard.
+ * on the same stream and with the same handle (one exchange serves one collection: its four-slot gather ring is safe because
+ * a handle never has more than two searches in flight); fails with RAGFIN_EUNSUPPORTED when the shape does not take the
+ * one-kernel search on this shard.
  * _host: host buffers, queries staged through pinned memory, hits written by the kernel into device-mapped pinned memory,
  * one stream synchronisation.
  * Replaces: the querynode -> proxy reduce behind Collection.search on a sharded Milvus deployment
