@@ -1048,6 +1048,7 @@ struct ragfin_exchange {
     unsigned int* d_done = nullptr;
     uint32_t step = 0;
     bool connected = false;
+    const void* owner = nullptr;         // the collection whose one-kernel searches use this exchange (first one to do so)
     bool have_stream = false;            // the slot-ring argument (kernels.cuh: how far a rank can run ahead of a peer) holds only
     cudaStream_t stream = nullptr;       // if every step of this rank is issued on ONE stream: recorded at step 1, checked after
     std::mutex mu;
@@ -1798,6 +1799,9 @@ static int fused_host_call(ragfin* h, ragfin_exchange* x, const float* q_host, i
         if (!x->connected) return fail(RAGFIN_EINVAL, "exchange is not connected");
         if (x->have_stream && x->stream != st)
             return fail(RAGFIN_EINVAL, "every step of an exchange must be issued on the same CUDA stream (its slot ring relies on stream order)");
+        if (x->owner != nullptr && x->owner != h)
+            return fail(RAGFIN_EINVAL, "an exchange serves the one-kernel searches of ONE collection (its gather ring counts on a handle's limit of two searches in flight)");
+        x->owner = h;
         x->have_stream = true; x->stream = st;
         const uint32_t step = ++x->step;
         rc = run_fused(h, q_dev, nq, k, h->count, (int64_t*)dout, (float*)(dout + ib), st, false, x, step, q_inline, dflag, seq);
@@ -2110,6 +2114,9 @@ static int sharded_locked(ragfin* h, ragfin_exchange* x, const float* q_dev, int
     if (record > x->record_max) return fail(RAGFIN_EINVAL, "record of %zu bytes exceeds the exchange's %zu", record, x->record_max);
     if (x->have_stream && x->stream != st)
         return fail(RAGFIN_EINVAL, "every step of an exchange must be issued on the same CUDA stream (its slot ring relies on stream order)");
+    if (x->owner != nullptr && x->owner != h)
+        return fail(RAGFIN_EINVAL, "an exchange serves the one-kernel searches of ONE collection (its gather ring counts on a handle's limit of two searches in flight)");
+    x->owner = h;
     x->have_stream = true; x->stream = st;
     int rc;
     if ((rc = ensure(h->flags, (size_t)(kMaxQueryBatch + 1) * sizeof(int)))) return rc;

@@ -88,14 +88,20 @@ class ShardedSearcher:
         return ok
 
     def search_host(self, queries, k: int, out_ids=None, out_scores=None):
-        """Host buffers in and out (numpy), synchronous: the call a serving process makes.  One-kernel path when every rank
-        can take it, else device staging around `search`."""
+        """Host buffers in and out (numpy arrays, lists or torch CPU tensors; results come back in `out_ids` / `out_scores`
+        when given, else as numpy), synchronous: the call a serving process makes.  One-kernel path when every rank can take
+        it, else device staging around `search`."""
         import numpy as np
         import torch
-        nq = queries.shape[0] if getattr(queries, "ndim", 0) == 2 else 1
+        if not hasattr(queries, "shape"):
+            queries = np.asarray(queries, dtype=np.float32)
+        nq = queries.shape[0] if len(queries.shape) == 2 else 1
         if self.world > 1 and self.exchange is not None and self.fused_ok(nq, k):
             return self.exchange.search_sharded_host(self.index, queries, k, out_ids, out_scores)   # numpy or torch CPU buffers
-        q = queries.numpy() if hasattr(queries, "data_ptr") else np.ascontiguousarray(queries, dtype=np.float32)
+        q = (queries.detach().to("cpu", torch.float32).numpy() if hasattr(queries, "data_ptr")
+             else np.ascontiguousarray(queries, dtype=np.float32))
+        if q.ndim == 1:
+            q = q[None, :]
         out_ids = out_ids.numpy() if hasattr(out_ids, "data_ptr") else out_ids
         out_scores = out_scores.numpy() if hasattr(out_scores, "data_ptr") else out_scores
         dev = torch.device("cuda", self.index.device) if (self.index is not None and torch.cuda.is_available()) else None

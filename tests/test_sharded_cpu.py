@@ -154,7 +154,12 @@ class _FakeExchange:
 
     def search_sharded_host(self, index, q, k, out_ids=None, out_scores=None):
         self.log.append("one-kernel-host")
-        return O.cosine_topk(q, self.x, k)
+        ids, sc = O.cosine_topk(np.asarray(q), self.x, k)          # numpy or torch CPU buffers, as the real one
+        if out_ids is not None:
+            np.asarray(out_ids)[...] = ids
+            np.asarray(out_scores)[...] = sc
+            return out_ids, out_scores
+        return ids, sc
 
     def allgather_merge(self, ids, scores, stream=None):
         self.log.append("push-merge")
@@ -197,7 +202,18 @@ def _worker_fused_agreement(rank, world, port, out):
         ok &= log[-1] == "one-kernel-host" and np.array_equal(hi, O.cosine_topk(q, x, 3)[0])
         hi, hs = s.search_host(q, 5)               # not eligible everywhere: device staging around search()
         ok &= log[-1] == "push-merge" and np.array_equal(hi, O.cosine_topk(q, x, 5)[0])
-        ok &= s._fused == {(2, 3): True, (2, 5): False}
+        # the caller's own torch CPU buffers (what bench.py's e2e leg passes), both branches: results land in them
+        for k, want_path in ((3, "one-kernel-host"), (5, "push-merge")):
+            oi, osc = torch.full((2, k), -9, dtype=torch.int64), torch.zeros((2, k), dtype=torch.float32)
+            ri, rs = s.search_host(torch.from_numpy(q), k, out_ids=oi, out_scores=osc)
+            wi, ws = O.cosine_topk(q, x, k)
+            ok &= log[-1] == want_path and np.array_equal(oi.numpy(), wi) and np.array_equal(osc.numpy().view(np.uint32), ws.view(np.uint32))
+            ok &= np.array_equal(np.asarray(ri), wi) and np.array_equal(np.asarray(rs).view(np.uint32), ws.view(np.uint32))
+        one = s.search_host(q[0], 3)                 # a single query as a 1-D array ...
+        ok &= np.array_equal(np.asarray(one[0]), O.cosine_topk(q[:1], x, 3)[0])
+        one = s.search_host(q[0].tolist(), 5)        # ... and as a plain list, on the staging branch
+        ok &= one[0].shape == (1, 5) and np.array_equal(one[0], O.cosine_topk(q[:1], x, 5)[0])
+        ok &= s._fused == {(2, 3): True, (2, 5): False, (1, 3): True, (1, 5): False}
         out[rank] = int(ok)
     finally:
         dist.destroy_process_group()
