@@ -22,7 +22,8 @@ kernels or NCCL all-gather + reduce kernel): total work is fixed, so scaling = "
   cpu_baseline  the reference's CPU retrieval path (oracle/fast_cpu.py port) on this box's cores, over the
             whole corpus when the host has the memory
 
-`--impl reference` times only that CPU path (rank 0), same metric/config.
+`--impl reference` times only that CPU path (rank 0), same metric and the same `config` object (job_config); what an
+arm did on that config (search path, exchange, pipelining, rescans) is printed beside it under `run`.
 Clocks and throttle reasons are sampled through NVML during the timed regions; a region that saw hw_slowdown,
 hw_thermal_slowdown or sw_thermal_slowdown is rejected and measured once more (`clocks.remeasured_after`); sw_power_cap
 is kept and reported.
@@ -254,6 +255,13 @@ def cpu_baseline(a, budget_s: float, steps: int | None = None):
             "ms_per_call_on_sample": per_call * 1e3}, len(times), per_call
 
 
+def job_config(a, world):
+    """The workload both arms are measured on: printed identically by `--impl ours` and `--impl reference`."""
+    return {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "k": a.k, "batch": a.batch,
+            "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
+            "l2": "inputs (corpus shard) larger than L2; no flush needed"}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -264,8 +272,9 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "queries/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": a.batch / base["value"] * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "k": a.k, "batch": a.batch,
-                   "note": "reference CPU retrieval path (Milvus/knowhere brute-force COSINE restated: oracle/fast_cpu.py)"},
+        "config": job_config(a, a.gpus),      # our arm's config, key for key (the reference arm runs "on your arm's config")
+        "run": {"note": "reference CPU retrieval path (Milvus/knowhere brute-force COSINE restated: oracle/fast_cpu.py), "
+                        "rank 0's host cores only; the corpus is held as fp32 in host memory, far larger than any cache"},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -670,13 +679,12 @@ def run_ours(a):
             "metric": METRIC, "value": main["value"], "unit": "queries/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
-            "config": {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "k": a.k, "batch": a.batch,
-                       "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
-                       "l2": "inputs (corpus shard) larger than L2; no flush needed",
-                       "ingest_s": round(ingest_s, 2), "queries_rescanned_last_step": main["queries_rescanned_last_step"],
-                       "search_path": main["search_path"], "exchange": main["exchange"],
-                       "pipelined": "value: ragfin_set_pipelined(1), consecutive searches of one stream overlap (queries resident before the "
-                                    "timed region); e2e: one synchronous call at a time"},
+            "config": job_config(a, world),
+            # what THIS arm did on that config (kept out of `config` so that both arms print the same config object)
+            "run": {"ingest_s": round(ingest_s, 2), "queries_rescanned_last_step": main["queries_rescanned_last_step"],
+                    "search_path": main["search_path"], "exchange": main["exchange"],
+                    "pipelined": "value: ragfin_set_pipelined(1), consecutive searches of one stream overlap (queries resident before the "
+                                 "timed region); e2e: one synchronous call at a time"},
             "clocks": dict(main["clocks"] or {}, **({"remeasured_after": main["remeasured_after"]} if "remeasured_after" in main else {})),
             "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "roofline": main["roofline"],
             "parity_check": main["parity_check"],

@@ -8,7 +8,7 @@ timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --mas
 import json
 try:
     d = json.loads(open("gpurun_out/r02_bench_$N.json").read().strip().splitlines()[-1])
-    print("value", round(d["value"], 1), "q/s  ms/step", round(d["ms_per_step"], 4), " e2e", round(d["e2e"]["value"], 1), " path", d["config"].get("search_path"), "|", d["config"].get("exchange"))
+    print("value", round(d["value"], 1), "q/s  ms/step", round(d["ms_per_step"], 4), " e2e", round(d["e2e"]["value"], 1), " path", d.get("run", d["config"]).get("search_path"), "|", d.get("run", d["config"]).get("exchange"))
     print("parity", d["parity_check"]["ok"], d["parity_check"]["failures"], " kernel ms", round(d["roofline"]["kernel_ms_avg"], 4), "frac", round(d["roofline"]["frac"], 3))
     r = d.get("regimes", {}).get("batch_4096")
     if r: print("batch 4096:", round(r["value"]), "q/s parity", r["parity_check"]["ok"], r["exchange"])
