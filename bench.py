@@ -671,8 +671,22 @@ def run_ours(a):
     if a.also_batch and a.also_batch != a.batch:
         other = measure_checked(a.also_batch, max(5, a.steps // 10), a.warmup)
         other["parity_check"] = parity_check(a.also_batch)
-    clustered = clustered_leg(a.batch, main["ms_per_step"]) if not a.no_extra_regimes else None
-    ingest = ingest_leg() if (world == 1 and not a.no_extra_regimes) else None
+    def side_leg(fn, *args):
+        """The side regimes must not cost the headline line: on one GPU a failure is reported in place of the leg's figures
+        (with several ranks it propagates - a rank that skipped a leg would leave the others waiting in its collectives)."""
+        if world > 1:
+            return fn(*args)
+        try:
+            return fn(*args)
+        except Exception as e:                                     # noqa: BLE001 - reported, never hidden
+            try:
+                torch.cuda.synchronize()
+            except Exception:                                      # noqa: BLE001
+                pass
+            return {"error": f"{type(e).__name__}: {e}"[:400]}
+
+    clustered = side_leg(clustered_leg, a.batch, main["ms_per_step"]) if not a.no_extra_regimes else None
+    ingest = side_leg(ingest_leg) if (world == 1 and not a.no_extra_regimes) else None
 
     if rank == 0:
         line = {
@@ -697,7 +711,10 @@ def run_ours(a):
             line.setdefault("regimes", {})["ingest"] = ingest
         if world == 1 and not a.no_cpu_baseline:
             del idx
-            line["cpu_baseline"] = cpu_baseline(a, budget_s=15.0)[0]
+            try:
+                line["cpu_baseline"] = cpu_baseline(a, budget_s=15.0)[0]
+            except Exception as e:                                 # noqa: BLE001 - e.g. the host cannot hold the fp32 corpus
+                line["cpu_baseline"] = {"value": None, "unit": "queries/s", "kind": "port", "error": f"{type(e).__name__}: {e}"[:400]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
