@@ -12,7 +12,7 @@ ap.add_argument("--dtype", default="bf16")
 ap.add_argument("--k", default="10", help="comma-separated k values")
 ap.add_argument("--cluster", default="0", help="comma-separated tcgen05 cluster sizes (0 = automatic)")
 ap.add_argument("--out", default="gpurun_out/batch_sweep.json")
-ap.add_argument("--variant", default="0", help="comma-separated tcgen05 kernel variants (0 automatic, 1 streaming, 2 A-stationary, 3 swapped roles for <= 16 queries, 4 experimental 2-SM pairs, 5 experimental self-seeded sweep)")
+ap.add_argument("--variant", default="0", help="comma-separated tcgen05 kernel variants (0 automatic, 1 streaming, 2 A-stationary, 3 swapped roles for <= 16 queries, 4 2-SM MMA pairs)")
 ap.add_argument("--batches", default="1,2,3,4,5,6,8,9,12,16,32,64,128,256,512,1024,2048,4096")
 ap.add_argument("--paths", default="auto")
 a = ap.parse_args()

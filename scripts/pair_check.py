@@ -1,4 +1,5 @@
-"""First GPU run of the experimental 2-SM MMA sweep (gemm variant 4, csrc/gemm_pair.cuh).
+"""First GPU run of the 2-SM MMA sweep (gemm variant 4, csrc/gemm_pair.cuh) - passed at the start of round 2
+(`profiles/r02/experiment_pair_kernel_first_run.log`); the kernel is the default from 129 queries since.
 
 The kernel was written without a GPU at hand, so every stage runs in its own child process under a timeout: a hang
 (barrier protocol wrong) ends that stage, not the gpurun call.  Stages:

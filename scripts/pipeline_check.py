@@ -1,4 +1,5 @@
-"""Views (ragfin_create_view) and pipelined batch-1 searches: NOT yet run on a GPU (written after round 1's GPU budget).
+"""Views (ragfin_create_view) and pipelined batch-1 searches.  Written after round 1's GPU budget; first run at the start of
+round 2 (`profiles/r02/experiment_views_pipeline_first_run.log`: equal results, 0.284 ms per query on three streams vs 0.327).
 
   parity   searches through a view return exactly what the parent returns (and the oracle), a view rejects add()
   overlap  10M x 768 and 1.25M x 768 bf16, batch 1: K calls back to back on one stream against the same K calls
