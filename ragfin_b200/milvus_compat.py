@@ -146,7 +146,35 @@ class _Store:
         self.index = None
         self.metric: Optional[str] = None
         self.pk_to_row: Dict[Any, int] = {}
+        # value -> ascending rows, per scalar field, built on the first filter over that field and kept current by
+        # insert(): a filtered search costs the matching rows, not a pass over every row of the column
+        self.scalar_index: Dict[str, Dict[Any, List[int]]] = {}
         self.lock = threading.RLock()
+
+    def rows_with(self, field: str, wanted, n: int) -> List[int]:
+        """Rows (ascending) among the first n whose `field` equals one of `wanted`."""
+        with self.lock:
+            inv = self.scalar_index.get(field)
+            if inv is None:
+                inv = {}
+                for r, v in enumerate(self.columns[field]):
+                    inv.setdefault(v, []).append(r)
+                self.scalar_index[field] = inv
+            lists = []
+            for w in dict.fromkeys(wanted):                          # a literal listed twice selects its rows once
+                try:
+                    rows = inv.get(w)
+                except TypeError:                                    # unhashable literal: matches nothing
+                    rows = None
+                if rows:
+                    lists.append(rows)
+            if not lists:
+                return []
+            out = lists[0] if len(lists) == 1 else sorted(r for rows in lists for r in rows)
+            if out and out[-1] >= n:
+                import bisect
+                out = out[:bisect.bisect_left(out, n)]
+            return list(out)
 
     def flush(self):
         """Upload the pending blocks through K1.  The collection keeps NO host copy of the embeddings: when the rows
@@ -195,6 +223,7 @@ def load_collection(name: str, directory: str, device: int = 0, using: str = "de
     col = Collection(name, CollectionSchema(fields, meta["description"]), using=using, storage_dtype=meta["storage_dtype"], device=device)
     st = col._st
     st.columns = meta["columns"]
+    st.scalar_index = {}
     st.n_inserted = int(meta["n"])
     st.metric = meta["metric"]
     pk = st.schema.primary_field.name
@@ -392,6 +421,10 @@ class Collection:
             # ---- commit
             for name, c in staged.items():
                 st.columns[name].extend(c)
+                inv = st.scalar_index.get(name)
+                if inv is not None:
+                    for j, v in enumerate(c):
+                        inv.setdefault(v, []).append(st.n_inserted + j)
             for j, pk in enumerate(pks):
                 st.pk_to_row[pk] = st.n_inserted + j
             if n:
@@ -485,8 +518,7 @@ class Collection:
             raise MilvusException(message=f"field {field} not exist")
         if field == pk_name:
             return sorted(r for r in (st.pk_to_row.get(w) for w in wanted) if r is not None and r < n)
-        ws = set(wanted)
-        return [r for r in range(n) if st.columns[field][r] in ws]
+        return st.rows_with(field, wanted, n)
 
     # -- scalar lookups (host side; "next" row N1) --------------------------------------
     def query(self, expr: str = "", output_fields: Optional[List[str]] = None, partition_names=None,

@@ -272,3 +272,51 @@ def test_collection_grows_without_a_host_copy_of_the_embeddings():
     assert [c for c in calls if isinstance(c, tuple)] == [("reserve", 32), ("reserve", 64)]
     res = col.search(x[17:18], "embedding", {"metric_type": "COSINE"}, 3)
     assert res[0][0].id == "k17"
+
+
+def test_scalar_filter_index_stays_current_and_equals_a_column_scan():
+    """`field == literal` / `field in [...]` on a scalar field are answered from a value -> rows index built on first use and
+    kept current by later inserts (a filtered search costs the matching rows, not a pass over the column).  Checked against
+    a plain scan of the columns: ascending rows, literals listed twice, numeric fields, rows inserted after the first
+    filter, unflushed rows invisible to query(), and a failed insert leaving the index untouched."""
+    import random
+    mc.connections.connect("default", host="localhost", port="19530")
+    if mc.utility.has_collection("scalars"):
+        mc.utility.drop_collection("scalars")
+    F, D = mc.FieldSchema, mc.DataType
+    fields = [F("id", D.VARCHAR, max_length=20, is_primary=True), F("embedding", D.FLOAT_VECTOR, dim=8),
+              F("period", D.VARCHAR, max_length=8), F("bucket", D.INT64)]
+    col = mc.Collection("scalars", mc.CollectionSchema(fields, ""), index_factory=OracleIndex)
+    rng = random.Random(7)
+    periods, total = ["Q1", "Q2", "Q3", "Q4"], 0
+
+    def insert(n):
+        nonlocal total
+        rows = [[f"r{total + i}" for i in range(n)], O.synth_rows(40 + total, 0, n, 8).tolist(),
+                [rng.choice(periods) for _ in range(n)], [rng.randrange(5) for _ in range(n)]]
+        total += n
+        col.insert(rows)
+
+    def scan(pred):
+        st = col._st
+        return [st.columns["id"][r] for r in range(col.num_entities) if pred(st.columns["period"][r], st.columns["bucket"][r])]
+
+    insert(300)
+    col.flush()
+    assert [r["id"] for r in col.query(expr='period == "Q3"')] == scan(lambda p, b: p == "Q3")
+    assert "period" in col._st.scalar_index and "bucket" not in col._st.scalar_index
+    insert(200)                                                          # pending: indexed, but not yet visible to query()
+    assert [r["id"] for r in col.query(expr='period in ["Q1", "Q4", "Q1"]')] == scan(lambda p, b: p in ("Q1", "Q4"))
+    assert len(col.query(expr='period in ["Q1", "Q4", "Q1"]')) < sum(p in ("Q1", "Q4") for p in col._st.columns["period"])
+    col.flush()
+    assert [r["id"] for r in col.query(expr='period in ["Q1", "Q4"]')] == scan(lambda p, b: p in ("Q1", "Q4"))
+    assert [r["id"] for r in col.query(expr="bucket in [0, 3]")] == scan(lambda p, b: b in (0, 3))
+    assert [r["id"] for r in col.query(expr="bucket == 4")] == scan(lambda p, b: b == 4)
+    assert col.query(expr='period == "Q9"') == [] and col.query(expr="bucket in []") == []
+    before = {f: {v: list(r) for v, r in inv.items()} for f, inv in col._st.scalar_index.items()}
+    with pytest.raises(mc.MilvusException):
+        col.insert([["x1", "r0"], O.synth_rows(1, 0, 2, 8).tolist(), ["Q1", "Q2"], [1, 2]])      # duplicate primary key
+    assert col._st.scalar_index == before
+    q = O.synth_rows(99, 0, 1, 8)
+    hits = col.search(q, "embedding", {"metric_type": "COSINE"}, 500, expr="bucket == 2", output_fields=["bucket"])[0]
+    assert sorted(h.id for h in hits) == sorted(scan(lambda p, b: b == 2)) and all(h.entity.bucket == 2 for h in hits)
