@@ -253,25 +253,38 @@ utility = _Utility()
 
 
 class Entity:
-    """hit.entity: attribute access (retrieve.py:40-42) and .get() (graph_cons.py:288-291)."""
+    """hit.entity: attribute access (retrieve.py:40-42) and .get() (graph_cons.py:288-291).
 
-    def __init__(self, fields: Dict[str, Any]):
-        self.__dict__["fields"] = fields
+    A view of one row of the collection's scalar columns restricted to the requested output fields: values are looked up
+    when they are read (rows are append-only, so a row's values never change), which keeps a `limit=1000` result
+    (graph_cons.py:275-281) from costing a dict of every field of every hit before the caller has looked at one."""
+    __slots__ = ("_cols", "_row", "_names")
+
+    def __init__(self, fields, row: Optional[int] = None, names=None):
+        if row is None:                                   # Entity({"field": value, ...}): a detached record
+            self._cols, self._row, self._names = {k: (v,) for k, v in fields.items()}, 0, tuple(fields)
+        else:                                             # Entity(columns, row, names): row `row` of the collection
+            self._cols, self._row, self._names = fields, row, names
+
+    @property
+    def fields(self) -> Dict[str, Any]:
+        return {f: self._cols[f][self._row] for f in self._names}
 
     def __getattr__(self, name):
-        try:
-            return self.__dict__["fields"][name]
-        except KeyError:
-            raise MilvusException(message=f"Field {name} is not in return entity") from None
+        if name.startswith("_"):                          # an unset slot (copy / pickle protocols probing): not a field
+            raise AttributeError(name)
+        if name in self._names:
+            return self._cols[name][self._row]
+        raise MilvusException(message=f"Field {name} is not in return entity")
 
     def get(self, name, default=None):
-        return self.__dict__["fields"].get(name, default)
+        return self._cols[name][self._row] if name in self._names else default
 
     def to_dict(self):
-        return dict(self.__dict__["fields"])
+        return self.fields
 
     def __repr__(self):
-        return f"Entity({self.__dict__['fields']!r})"
+        return f"Entity({self.fields!r})"
 
 
 class Hit:
@@ -489,14 +502,14 @@ class Collection:
             else:
                 ids, scores = st.index.search(q, int(limit))
             pk_col = st.columns[st.schema.primary_field.name]
+            cols, names = st.columns, tuple(out_fields)
             for qi in range(q.shape[0]):
-                hits = Hits()
-                for row, sc in zip(ids[qi].tolist(), scores[qi].tolist()):
-                    if row < 0:
-                        break
-                    d = float(sc) if round_decimal < 0 else round(float(sc), round_decimal)
-                    hits.append(Hit(pk_col[row], d, Entity({f: st.columns[f][row] for f in out_fields})))
-                res.append(hits)
+                rows_q, sc_q = ids[qi].tolist(), scores[qi].tolist()      # Python ints / floats (fp32 scores widened exactly)
+                if rows_q and rows_q[-1] < 0:                            # padded: fewer than `limit` rows (or allowed rows)
+                    rows_q = rows_q[:next(i for i, r in enumerate(rows_q) if r < 0)]
+                if round_decimal >= 0:
+                    sc_q = [round(s_, round_decimal) for s_ in sc_q]
+                res.append(Hits([Hit(pk_col[row], sc, Entity(cols, row, names)) for row, sc in zip(rows_q, sc_q)]))
             return res
 
     def _rows_matching(self, expr: str, n: int) -> List[int]:

@@ -320,3 +320,33 @@ def test_scalar_filter_index_stays_current_and_equals_a_column_scan():
     q = O.synth_rows(99, 0, 1, 8)
     hits = col.search(q, "embedding", {"metric_type": "COSINE"}, 500, expr="bucket == 2", output_fields=["bucket"])[0]
     assert sorted(h.id for h in hits) == sorted(scan(lambda p, b: b == 2)) and all(h.entity.bucket == 2 for h in hits)
+
+
+def test_hit_entity_is_a_view_of_the_requested_fields_only():
+    """hit.entity resolves the requested output fields when they are read (rows are append-only): requested fields by
+    attribute and .get(), anything else raises / returns the default exactly as a pymilvus entity does, values survive
+    later inserts and a drop of the collection, round_decimal rounds the score, k > N returns N hits."""
+    import copy
+    col, g = build_collection()
+    q = O.synth_rows(g["seed"] + 1, 0, 2, 384)
+    res = col.search(q, "embedding", {"metric_type": "COSINE"}, 50, output_fields=["id", "period"])
+    assert len(res) == 2 and len(res[0]) == 16 and len(res[1]) == 16            # padded slots never become hits
+    h = res[0][0]
+    row = [c["id"] for c in g["chunks"]].index(h.id)
+    assert h.entity.id == h.id and h.entity.period == g["chunks"][row]["period"] == h.entity.get("period")
+    assert h.entity.get("text") is None and h.entity.get("text", "dflt") == "dflt"
+    with pytest.raises(mc.MilvusException):
+        h.entity.text
+    assert h.entity.to_dict() == {"id": h.id, "period": g["chunks"][row]["period"]} == h.entity.fields
+    assert h.to_dict() == {"id": h.id, "distance": h.distance, "entity": h.entity.to_dict()} and h.score == h.distance
+    assert copy.copy(h.entity).period == h.entity.period and "period" in repr(h)
+    assert mc.Entity({"a": 1, "b": "x"}).b == "x" and mc.Entity({"a": 1}).get("zz", 5) == 5     # detached record
+    scores = [x.distance for x in res[0]]
+    assert scores == sorted(scores, reverse=True) and res[0].ids == [x.id for x in res[0]] and res[0].distances == scores
+    rounded = col.search(q[:1], "embedding", {"metric_type": "COSINE"}, 3, round_decimal=2)[0]
+    assert [x.distance for x in rounded] == [round(s_, 2) for s_ in scores[:3]]
+    col.insert([["late"], ["late text"], O.synth_rows(77, 0, 1, 384).tolist(), ["Q9"], ["t"], ["s"], [1.0]])
+    col.flush()
+    assert h.entity.period == g["chunks"][row]["period"]
+    mc.utility.drop_collection(col.name)
+    assert h.entity.period == g["chunks"][row]["period"]
