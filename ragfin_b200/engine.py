@@ -425,6 +425,8 @@ class PeerExchange:
         """Row-sharded search in one kernel per GPU (ragfin_search_sharded): `queries` CUDA fp32 [nq, dim], the same on
         every rank; returns the GLOBAL (ids, scores) [nq, k] on every rank.  Collective over the exchange's ranks."""
         import torch
+        if not queries.is_cuda or queries.dtype != torch.float32 or queries.dim() != 2 or queries.shape[1] != index.dim:
+            raise ValueError(f"queries must be a CUDA fp32 tensor [nq, {index.dim}]")
         nq = queries.shape[0]
         if out_ids is None:
             out_ids = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
