@@ -62,3 +62,36 @@ def test_view_argument_validation_without_device(lib):
     out = ctypes.c_void_p()
     assert lib.ragfin_create_view(None, ctypes.byref(out)) == -1       # EINVAL: no parent
     assert out.value is None
+
+
+def test_ctypes_prototypes_match_the_header(lib):
+    """Every entry point's ctypes argtypes agree with its prototype in include/ragfin.h, parameter by parameter: pointer,
+    32-bit or 64-bit integer.  (A Python int passed without argtypes is truncated to 32 bits - a device pointer would not
+    survive it - and a miscounted parameter shifts everything behind it.)"""
+    from ragfin_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "ragfin.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    hdr = re.sub(r"//[^\n]*", " ", hdr)
+    protos = dict(re.findall(r"\b(ragfin_[a-z_]+)\s*\(([^()]*)\)\s*;", hdr))
+    assert set(protos) == set(_lib.SYMBOLS)
+
+    def kind_of_c(param):
+        p = " ".join(param.split())
+        if p in ("void", ""):
+            return None
+        if "*" in p:
+            return "ptr"
+        base = p.replace("const ", "").split(" ")[0]
+        return {"int32_t": "i32", "int": "i32", "uint32_t": "i32", "int64_t": "i64", "uint64_t": "i64", "size_t": "i64"}[base]
+
+    def kind_of_ctypes(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or issubclass(t, ctypes._Pointer):
+            return "ptr"
+        return {4: "i32", 8: "i64"}[ctypes.sizeof(t)]
+
+    for name, params in protos.items():
+        want = [k for k in (kind_of_c(p) for p in params.split(",")) if k is not None]
+        fn = getattr(lib, name)
+        assert fn.argtypes is not None, f"{name}: no argtypes"
+        got = [kind_of_ctypes(t) for t in fn.argtypes]
+        assert got == want, f"{name}: header {want}, ctypes {got}"
