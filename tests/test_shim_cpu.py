@@ -350,3 +350,72 @@ def test_hit_entity_is_a_view_of_the_requested_fields_only():
     assert h.entity.period == g["chunks"][row]["period"]
     mc.utility.drop_collection(col.name)
     assert h.entity.period == g["chunks"][row]["period"]
+
+
+def test_concurrent_inserts_and_searches_on_one_collection():
+    """FastMCP runs its sync tools on worker threads and an ingest may run beside them: inserts, flushes,
+    plain and filtered searches and scalar queries from several threads on ONE collection.  Every search must see a
+    consistent prefix of the rows (pk, columns, scalar index and embeddings in step), and the end state must equal a
+    sequential ingest."""
+    import threading
+    mc.connections.connect("default", host="localhost", port="19530")
+    if mc.utility.has_collection("mt"):
+        mc.utility.drop_collection("mt")
+    F, D = mc.FieldSchema, mc.DataType
+    fields = [F("id", D.VARCHAR, max_length=20, is_primary=True), F("embedding", D.FLOAT_VECTOR, dim=16), F("tag", D.VARCHAR, max_length=4)]
+    col = mc.Collection("mt", mc.CollectionSchema(fields, ""), index_factory=OracleIndex)
+    n_writers, per_writer, block = 3, 20, 7
+    x = O.synth_rows(500, 0, n_writers * per_writer * block, 16)
+    q = O.synth_rows(501, 0, 2, 16)
+    errors, stop = [], threading.Event()
+
+    def writer(w):
+        try:
+            for b in range(per_writer):
+                r0 = (w * per_writer + b) * block
+                col.insert([[f"r{r0 + i}" for i in range(block)], x[r0:r0 + block].tolist(), [f"t{(r0 + i) % 3}" for i in range(block)]])
+                if b % 4 == 3:
+                    col.flush()
+        except Exception as e:   # noqa: BLE001
+            errors.append(f"writer {w}: {e!r}")
+
+    def reader(t):
+        try:
+            while not stop.is_set():
+                for hits in col.search(q, "embedding", {"metric_type": "COSINE"}, 5, output_fields=["id", "tag"]):
+                    for h in hits:
+                        row = int(h.id[1:])
+                        if h.entity.id != h.id or h.entity.tag != f"t{row % 3}":
+                            errors.append(f"reader {t}: hit {h.id} carries the columns of another row")
+                    if [h.distance for h in hits] != sorted((h.distance for h in hits), reverse=True):
+                        errors.append(f"reader {t}: hits out of order")
+                for h in col.search(q[:1], "embedding", {"metric_type": "COSINE"}, 4, expr='tag == "t1"', output_fields=["tag"])[0]:
+                    if h.entity.tag != "t1" or int(h.id[1:]) % 3 != 1:
+                        errors.append(f"reader {t}: filtered hit {h.id} has tag {h.entity.tag}")
+                for r in col.query(expr='tag in ["t0", "t2"]', output_fields=["tag"]):
+                    if r["tag"] != f"t{int(r['id'][1:]) % 3}":
+                        errors.append(f"reader {t}: query row {r}")
+        except Exception as e:   # noqa: BLE001
+            errors.append(f"reader {t}: {e!r}")
+
+    readers = [threading.Thread(target=reader, args=(t,)) for t in range(3)]
+    writers = [threading.Thread(target=writer, args=(w,)) for w in range(n_writers)]
+    for th in readers + writers:
+        th.start()
+    for th in writers:
+        th.join()
+    stop.set()
+    for th in readers:
+        th.join()
+    assert not errors, errors[:5]
+    col.flush()
+    n = len(x)
+    assert col.num_entities == n and len(col._st.pk_to_row) == n
+    # end state == sequential semantics: the row a pk maps to holds that pk's embedding (blocks may interleave between writers)
+    order = [int(pk[1:]) for pk in col._st.columns["id"]]
+    assert sorted(order) == list(range(n))
+    want_ids, want_sc = O.cosine_topk(q, O.normalize_rows(x[order], "f32"), 5)
+    got = col.search(q, "embedding", {"metric_type": "COSINE"}, 5)
+    assert [[h.id for h in hits] for hits in got] == [[f"r{order[i]}" for i in row] for row in want_ids]
+    assert [[h.distance for h in hits] for hits in got] == [[float(s) for s in row] for row in want_sc]
+    assert sorted(r["id"] for r in col.query(expr='tag == "t2"')) == sorted(f"r{i}" for i in range(n) if i % 3 == 2)
