@@ -461,7 +461,8 @@ class Collection:
     @property
     def num_entities(self) -> int:
         st = self._st
-        return st.n_inserted - sum(len(b) for b in st.pending)
+        with st.lock:                                         # a flush on another thread swaps `pending` under the same lock
+            return st.n_inserted - sum(len(b) for b in st.pending)
 
     @property
     def is_empty(self) -> bool:
